@@ -1,0 +1,103 @@
+"""The parity rule of BASELINE.json's north_star, as executable code.
+
+* ``jpvt`` and the block sizes ``ncols`` must match the reference exactly on the *trusted
+  prefix*: the leading blocks whose |R_jj| all stay above the rounding-noise floor
+  ``10 * max(m,n) * eps * max|R_jj|`` and (when margins are supplied) whose data-dependent
+  decisions were separated by more than 1e-12 relative margin.  Past the true numerical rank the
+  trailing matrix is implementation-specific rounding noise and no two summation orders agree.
+* the revealed rank must agree at that prefix; |diag R| to 1e-10 relative there.
+* the whole output is graded by invariants: jpvt is a permutation, ||AP-QR||/||A|| and
+  ||I-Q'Q|| <= 10 n eps.
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.linalg as sla
+
+EPS = np.finfo(np.float64).eps / 2  # unit roundoff 2^-53 = LAPACK dlamch('e')
+MARGIN = 1e-12
+DIAG_RTOL = 1e-10
+
+
+def trusted_prefix(exp_ncols, exp_diag, shape, margins=None):
+    """(number of trusted blocks, number of trusted columns)."""
+    m, n = shape
+    d = np.abs(np.asarray(exp_diag))
+    floor = 10.0 * max(m, n) * 2 * EPS * (d.max() if d.size else 0.0)
+    nblk = int(np.count_nonzero(exp_ncols))
+    col = 0
+    for it in range(nblk):
+        k = int(exp_ncols[it])
+        blk = d[col:col + k]
+        if blk.size and blk.min() <= floor:
+            return it, col
+        if margins is not None and np.min(margins[it]) <= MARGIN:
+            return it, col
+        col += k
+    return nblk, col
+
+
+def check_against(got, exp, shape, margins=None, exact=False):
+    """got/exp: dicts with info, jpvt, ncols, tau, diagR (or A).  Raises AssertionError."""
+    m, n = shape
+    assert int(got["info"]) == int(exp["info"]), f"info {got['info']} != {exp['info']}"
+    if int(exp["info"]) != 0:
+        return dict(blocks=0, cols=0)
+    gd = np.diag(got["A"])[: min(m, n)] if "diagR" not in got else got["diagR"]
+    ed = np.diag(exp["A"])[: min(m, n)] if "diagR" not in exp else exp["diagR"]
+    if exact:
+        nblk, ncol = int(np.count_nonzero(exp["ncols"])), int(np.sum(exp["ncols"]))
+    else:
+        nblk, ncol = trusted_prefix(exp["ncols"], ed, shape, margins)
+    assert np.array_equal(got["ncols"][:nblk], exp["ncols"][:nblk]), \
+        f"block sizes differ on trusted prefix: {got['ncols'][:nblk]} vs {exp['ncols'][:nblk]}"
+    assert np.array_equal(got["jpvt"][:ncol], exp["jpvt"][:ncol]), "jpvt differs on trusted prefix"
+    a, b = np.abs(gd[:ncol]), np.abs(ed[:ncol])
+    rel = np.abs(a - b) / np.maximum(b, np.finfo(float).tiny)
+    assert rel.size == 0 or rel.max() <= DIAG_RTOL, f"|diag R| rel diff {rel.max():.3e}"
+    if exact or nblk == int(np.count_nonzero(exp["ncols"])):
+        assert int(np.sum(got["ncols"])) == int(np.sum(exp["ncols"])), "revealed rank differs"
+        assert np.array_equal(got["jpvt"], exp["jpvt"]), "jpvt differs"
+    else:
+        # revealed rank at the prefix: both must go on past it, into the noise
+        assert int(np.sum(got["ncols"])) >= ncol
+    assert sorted(np.asarray(got["jpvt"]).tolist()) == list(range(1, n + 1)), "jpvt is not a permutation"
+    return dict(blocks=nblk, cols=ncol)
+
+
+def qr_invariants(A0, out):
+    """(||A P - Q R||_F/||A||_F, ||I - Q'Q||_F) of a dgeqrdm result, the metrics of the
+    reference's auxil.checkQR (auxil.py:20-105) for the column-major call.  r = sum(ncols)
+    reflectors; columns >= r of the factored array hold the Q'-updated R12/R22."""
+    A0 = np.asarray(A0)
+    m, n = A0.shape
+    F = np.asarray(out["A"])
+    r = int(np.sum(out["ncols"]))
+    tau = np.asarray(out["tau"])[:r]
+    R = np.zeros((m, n))
+    R[:, :r] = np.triu(F[:, :r])
+    R[:, r:] = F[:, r:]
+    if r < n:
+        R[r:, r:] = F[r:, r:]
+    # Q R = H_0 .. H_{r-1} R applied with LAPACK dormqr on the host (verification only)
+    QR, info = _ormqr(F, tau, R, r)
+    assert info == 0
+    P = np.asarray(out["jpvt"]) - 1
+    nrm = np.linalg.norm(A0)
+    res = np.linalg.norm(A0[:, P] - QR) / (nrm if nrm > 0 else 1.0)
+    Q, info = _ormqr(F, tau, np.eye(m), r)
+    orth = np.linalg.norm(np.eye(m) - Q.T @ Q)
+    return res, orth
+
+
+def _ormqr(F, tau, C, r):
+    if r == 0:
+        return C.copy(), 0
+    lw = sla.lapack.dormqr("L", "N", np.asfortranarray(F[:, :r]), tau, np.asfortranarray(C), -1)[1][0]
+    cq, work, info = sla.lapack.dormqr("L", "N", np.asfortranarray(F[:, :r]), tau, np.asfortranarray(C),
+                                       int(lw))
+    return cq, info
+
+
+def invariant_tol(shape):
+    return 10.0 * max(shape) * 2 * EPS
