@@ -1,0 +1,105 @@
+/* qrdm_b200.h — C ABI of libqrdm_b200.so: the B200-native (sm_100a) drop-in for the
+ * factorisation hot path of mdessole/qrdm.
+ *
+ * The first two entry points are exactly what the reference exports and what its only caller
+ * (the CPython wrapper, reference QRDM_wrapper.c:96) binds; the rest are additions for
+ * device-resident timing, multi-GPU and statistics.  Plain C linkage, plain pointers and sizes,
+ * `int` = the reference's `lapack_int` (reference include/lapacke_config.h:46-50).
+ *
+ * There is no CPU fallback: every numeric stage runs as a CUDA kernel; without a usable device the
+ * calls return QRDM_ERR_CUDA.
+ */
+#ifndef QRDM_B200_H_
+#define QRDM_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QRDM_COL_MAJOR 102 /* reference include/cblas.h:10, src/dgeqrdm_work.c:17-18 */
+#define QRDM_ROW_MAJOR 101 /* accepted by the reference's check but never worked there: rejected */
+#define QRDM_NB_MAX 64     /* largest supported block size / candidate count */
+
+/* error codes beyond the reference's (0, -1 bad argument, -8/-6/-13 NaN screens of
+ * LAPACKE_dlarft / LAPACKE_dlarfb_mia, reference src/dlarfb.c:73-86) */
+#define QRDM_ERR_CUDA (-100)       /* CUDA runtime failure (no device, launch error, OOM) */
+#define QRDM_ERR_COMM (-101)       /* NCCL failure in the row-sharded path */
+#define QRDM_ERR_UNSUPPORTED (-102) /* jpvt[j] != 0 on entry (fixed columns), nb > QRDM_NB_MAX */
+
+/* Replaces: reference include/QRDM.h:19-22, src/dgeqrdm.c:5-16.
+ * QR factorisation with Deviation-Maximisation block pivoting, A P = Q R, FP64.
+ *   matrix_layout  QRDM_COL_MAJOR (102)
+ *   a              m x n, column-major, lda >= m, HOST memory; overwritten with R (upper
+ *                  triangle of the first r = sum(ncols) columns), the Householder vectors below
+ *                  it (dgeqrf convention) and the Q'-updated R12/R22 in columns >= r
+ *   jpvt[n]        in: all zero (free columns).  out: 1-based permutation
+ *   tau[min(m,n)]  out: reflector scalars, first r entries
+ *   ncols[n]       in: ncols[0] = stop rule (0 none, 1 eps*n, 2 eps*sqrt(n), 3 thres[2]);
+ *                  out: ncols[it] = columns triangularised in iteration it; revealed rank = sum
+ *   thres          thres[0] = delta (cosine bound), thres[1] = tau_ (norm fraction), [2] = eta
+ *   nb             maximum block size / number of candidates, 1..QRDM_NB_MAX
+ * Returns info as the reference does (0; -1 after an xerbla-style message for bad arguments;
+ * -8/-6/-13 when NaNs reach the block reflector). */
+int dgeqrdm(int matrix_layout, int m, int n, double *a, int lda, int *jpvt, double *tau, int *ncols,
+            double *thres, int nb);
+
+/* Replaces: reference src/dgeqrdm_work.c:420-425 (same contract; dgeqrdm forwards to it). */
+int dgeqrdm_work(int matrix_layout, int m, int n, double *a, int lda, int *jpvt, double *tau,
+                 int *ncols, double *thres, int nb);
+
+/* Addition: device-resident variant used for compute-only timing and by callers that already
+ * hold A in HBM.  d_a, d_jpvt (n ints) and d_tau (min(m,n) doubles) are DEVICE pointers on the
+ * current device; ncols and thres are HOST arrays.  d_jpvt need not be initialised (treated as
+ * all-free).  `stream` is a cudaStream_t passed as void* (NULL = default stream).  The call
+ * returns after the factorisation has completed on the stream. */
+int dgeqrdm_dev(int m, int n, double *d_a, int lda, int *d_jpvt, double *d_tau, int *ncols,
+                const double *thres, int nb, void *stream);
+
+/* Addition: per-call statistics of the last dgeqrdm*() on this thread's device. */
+typedef struct qrdm_b200_stats {
+  int iterations;        /* DM iterations (= number of ncols entries written) */
+  int rank;              /* sum of ncols */
+  long long launches;    /* CUDA kernels launched by the call */
+  double ms_total;       /* device time of the factorisation proper (CUDA events) */
+  double ms_h2d, ms_d2h; /* host<->device copies of the host-pointer entry points */
+  /* per-stage device time in ms, only filled when profiling is enabled (QRDM_B200_PROFILE=1
+   * or qrdm_b200_set_profile(1)): stage order = QRDM_STAGE_* */
+  double ms_stage[12];
+  long long stage_launches[12];
+  double trailing_flops; /* FLOPs executed by the trailing-update kernels (4*rows*cols*k summed) */
+  double panel_cols;     /* total panel columns processed */
+} qrdm_b200_stats;
+
+enum {
+  QRDM_STAGE_NORM_INIT = 0,
+  QRDM_STAGE_SELECT,
+  QRDM_STAGE_GRAM,
+  QRDM_STAGE_PICK,
+  QRDM_STAGE_PERMUTE,
+  QRDM_STAGE_PANEL,
+  QRDM_STAGE_VTV,
+  QRDM_STAGE_VTC,
+  QRDM_STAGE_WSOLVE,
+  QRDM_STAGE_RANKK,
+  QRDM_STAGE_NORM_UPDATE,
+  QRDM_STAGE_SYNC,
+  QRDM_STAGE_COUNT
+};
+
+void qrdm_b200_get_stats(qrdm_b200_stats *out);
+void qrdm_b200_set_profile(int on);
+
+/* Optional: create / release the per-process device workspace ahead of the first call
+ * (otherwise created lazily and grown on demand).  init returns 0 or QRDM_ERR_CUDA. */
+int qrdm_b200_init(int device);
+void qrdm_b200_shutdown(void);
+
+/* Micro-benchmarks used by bench.py for the roofline denominators (measured live, on the stream
+ * given): FP64 FMA-pipe peak in TFLOP/s, and a device-to-device copy in GB/s. */
+double qrdm_b200_measure_fp64_peak(int use_dmma, void *stream);
+const char *qrdm_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QRDM_B200_H_ */

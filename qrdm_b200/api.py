@@ -1,0 +1,59 @@
+"""Convenience layer over the C ABI (no numerics here)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def _params(n, thres, stop_mode):
+    ncols = np.zeros(max(n, 1), dtype=np.int32)
+    ncols[0] = stop_mode
+    th = np.zeros(3, dtype=np.float64)
+    th[: len(thres)] = thres
+    return ncols, th
+
+
+def dgeqrdm(A, thres=(0.9, 0.15), nb=64, stop_mode=0, layout=102, lda=None, inplace=False):
+    """Factor a host matrix through the reference-facing entry point ``dgeqrdm`` (host pointers;
+    H2D/D2H inside the call).  Returns dict(info, A, jpvt, tau, ncols) like the oracle loaders."""
+    A = np.asarray(A, dtype=np.float64)
+    if not (inplace and A.flags.f_contiguous):
+        A = np.array(A, dtype=np.float64, order="F", copy=True)
+    m, n = A.shape
+    jpvt = np.zeros(n, dtype=np.int32)
+    tau = np.zeros(min(m, n), dtype=np.float64)
+    ncols, th = _params(n, thres, stop_mode)
+    info = _lib.lib.dgeqrdm(int(layout), m, n, A.ctypes.data, int(m if lda is None else lda),
+                            jpvt.ctypes.data, tau.ctypes.data, ncols.ctypes.data, th.ctypes.data, int(nb))
+    return dict(info=int(info), A=A, jpvt=jpvt, tau=tau, ncols=ncols)
+
+
+def dgeqrdm_device(dA, m, n, lda, d_jpvt, d_tau, thres=(0.9, 0.15), nb=64, stop_mode=0, stream=None):
+    """Factor a device-resident column-major matrix in place (``dgeqrdm_dev``).  ``dA``, ``d_jpvt``
+    (int32, n) and ``d_tau`` (float64, min(m,n)) are torch CUDA tensors (or raw device pointers);
+    returns (info, ncols) with ncols a host int32 array."""
+    def ptr(x):
+        return int(x.data_ptr()) if hasattr(x, "data_ptr") else int(x)
+    ncols, th = _params(n, thres, stop_mode)
+    if stream is None:
+        import torch
+        stream = torch.cuda.current_stream().cuda_stream
+    info = _lib.lib.dgeqrdm_dev(int(m), int(n), ptr(dA), int(lda), ptr(d_jpvt), ptr(d_tau),
+                                ncols.ctypes.data, th.ctypes.data, int(nb), C.c_void_p(int(stream)))
+    return int(info), ncols
+
+
+def stats():
+    return _lib.stats()
+
+
+def set_profile(on: bool):
+    _lib.lib.qrdm_b200_set_profile(1 if on else 0)
+
+
+def fp64_peak(use_dmma=True, stream=0):
+    """Measured FP64 peak of this GPU in TFLOP/s (DMMA.8x8x4 or DFMA chains on every SM)."""
+    return float(_lib.lib.qrdm_b200_measure_fp64_peak(1 if use_dmma else 0, C.c_void_p(int(stream))))

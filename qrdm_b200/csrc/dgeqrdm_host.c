@@ -1,0 +1,329 @@
+/* dgeqrdm_host.c — host orchestration of the B200-native dgeqrdm, plain C over the thin CUDA
+ * C-ABI layer of qrdm_dev.h (BASELINE.json north_star: "Host orchestration stays in C").
+ *
+ * Replaces the driver of the reference: dgeqrdm (src/dgeqrdm.c:5-16) and dgeqrdm_work
+ * (src/dgeqrdm_work.c:420-838): argument checks (:559-589), stop-rule set-up (:531-543, 684),
+ * the main block loop (:694-787) and its exit test (:782-785).  Every numeric stage is a CUDA
+ * kernel; there is no CPU fallback.  The loop's only host<->device synchronisation is one 64-byte
+ * mailbox copy per iteration (block size, error flag, max partial norm), needed because the block
+ * size — hence the trip count and the stop rule — is data dependent.
+ */
+#include <float.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/qrdm_b200.h"
+#include "qrdm_dev.h"
+
+#define QRDM_VERSION "qrdm_b200 0.1 (round 1)"
+
+typedef struct {
+  int ready, sm_count;
+  /* capacities */
+  int cap_m, cap_n;
+  size_t cap_a_bytes;
+  /* device buffers */
+  qrdm_ctrl *ctrl;
+  double *vn1, *vn2, *gram_part, *gram, *panel_part, *panel_row, *vc, *wp, *w2, *nrm_part;
+  int *flag_list;
+  size_t wp_elems;
+  int ldv, ldw, nrm_splits;
+  /* staging for the host-pointer entry points */
+  double *d_a, *d_tau;
+  int *d_jpvt;
+  size_t cap_tau, cap_jpvt;
+  /* pinned mailbox + events */
+  qrdm_ctrl *mailbox;
+  void *ev[4];
+  void *ev_stage[2];
+} qrdm_workspace;
+
+static qrdm_workspace g_ws;
+static qrdm_b200_stats g_stats;
+static int g_profile = -1;
+
+static int roundup(int x, int a) { return (x + a - 1) / a * a; }
+
+#define CU(call)                                                                          \
+  do {                                                                                    \
+    int e__ = (call);                                                                     \
+    if (e__ != 0) {                                                                       \
+      fprintf(stderr, "qrdm_b200: CUDA error %d (%s) at %s:%d\n", e__, qrdm_rt_errstr(e__), \
+              __FILE__, __LINE__);                                                        \
+      return QRDM_ERR_CUDA;                                                               \
+    }                                                                                     \
+  } while (0)
+
+const char *qrdm_b200_version(void) { return QRDM_VERSION; }
+void qrdm_b200_get_stats(qrdm_b200_stats *out) { *out = g_stats; }
+void qrdm_b200_set_profile(int on) { g_profile = on ? 1 : 0; }
+double qrdm_b200_measure_fp64_peak(int use_dmma, void *stream) { return qrdm_rt_fp64_peak(use_dmma, stream); }
+
+static void ws_free_sized(qrdm_workspace *w) {
+  void *bufs[] = {w->vn1, w->vn2, w->vc, w->wp, w->w2, w->nrm_part, w->flag_list};
+  for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); ++i)
+    if (bufs[i]) qrdm_rt_free(bufs[i]);
+  w->vn1 = w->vn2 = w->vc = w->wp = w->w2 = w->nrm_part = NULL;
+  w->flag_list = NULL;
+  w->cap_m = w->cap_n = 0;
+}
+
+void qrdm_b200_shutdown(void) {
+  qrdm_workspace *w = &g_ws;
+  if (!w->ready) return;
+  ws_free_sized(w);
+  void *fixed[] = {w->ctrl, w->gram_part, w->gram, w->panel_part, w->panel_row, w->d_a, w->d_tau, w->d_jpvt};
+  for (size_t i = 0; i < sizeof(fixed) / sizeof(fixed[0]); ++i)
+    if (fixed[i]) qrdm_rt_free(fixed[i]);
+  if (w->mailbox) qrdm_rt_host_free(w->mailbox);
+  memset(w, 0, sizeof(*w));
+}
+
+int qrdm_b200_init(int device) {
+  qrdm_workspace *w = &g_ws;
+  if (device >= 0) CU(qrdm_rt_set_device(device));
+  if (w->ready) return 0;
+  size_t freeb = 0;
+  CU(qrdm_rt_device_info(&w->sm_count, &freeb));
+  CU(qrdm_rt_malloc((void **)&w->ctrl, sizeof(qrdm_ctrl)));
+  CU(qrdm_rt_malloc((void **)&w->gram_part, sizeof(double) * 4096 * QRDM_GRAM_MAXCTA));
+  CU(qrdm_rt_malloc((void **)&w->gram, sizeof(double) * 4096));
+  CU(qrdm_rt_malloc((void **)&w->panel_part, sizeof(double) * 2 * QRDM_PANEL_MAXCTA * 64));
+  CU(qrdm_rt_malloc((void **)&w->panel_row, sizeof(double) * 2 * 64));
+  CU(qrdm_rt_host_alloc((void **)&w->mailbox, sizeof(qrdm_ctrl)));
+  for (int i = 0; i < 4; ++i) CU(qrdm_rt_event_create(&w->ev[i]));
+  for (int i = 0; i < 2; ++i) CU(qrdm_rt_event_create(&w->ev_stage[i]));
+  w->ready = 1;
+  if (g_profile < 0) {
+    const char *e = getenv("QRDM_B200_PROFILE");
+    g_profile = (e && atoi(e) > 0) ? 1 : 0;
+  }
+  return 0;
+}
+
+static int ws_ensure(int m, int n) {
+  qrdm_workspace *w = &g_ws;
+  int rc = qrdm_b200_init(-1);
+  if (rc) return rc;
+  if (m <= w->cap_m && n <= w->cap_n) return 0;
+  int cm = m > w->cap_m ? m : w->cap_m, cn = n > w->cap_n ? n : w->cap_n;
+  ws_free_sized(w);
+  w->ldv = roundup(cm, QRDM_ROWALIGN) + 128; /* k_rankk row tiles may overhang by < 128 rows */
+  w->ldw = roundup(cn, 128) + 128;           /* k_rankk / k_vtc column tiles overhang likewise */
+  w->nrm_splits = 64;
+  /* partial-W capacity: enough splits for ~2 CTAs per SM at any trailing width (see k_trailing) */
+  w->wp_elems = (size_t)64 * w->ldw * 3 + (size_t)64 * 256 * (2 * (size_t)w->sm_count + 2);
+  CU(qrdm_rt_malloc((void **)&w->vn1, sizeof(double) * cn));
+  CU(qrdm_rt_malloc((void **)&w->vn2, sizeof(double) * cn));
+  CU(qrdm_rt_malloc((void **)&w->vc, sizeof(double) * (size_t)w->ldv * 64));
+  CU(qrdm_rt_malloc((void **)&w->wp, sizeof(double) * w->wp_elems));
+  CU(qrdm_rt_malloc((void **)&w->w2, sizeof(double) * (size_t)w->ldw * 64));
+  CU(qrdm_rt_malloc((void **)&w->nrm_part, sizeof(double) * (size_t)cn * w->nrm_splits));
+  CU(qrdm_rt_malloc((void **)&w->flag_list, sizeof(int) * (size_t)cn));
+  w->cap_m = cm;
+  w->cap_n = cn;
+  return 0;
+}
+
+/* xerbla-style message of the reference (src/dgeqrdm_work.c:577-581) */
+static int bad_argument(int pos) {
+  fprintf(stderr, " ** On entry to DGEQRDM parameter number %2d had an illegal value\n", pos);
+  return -1;
+}
+
+static int check_args(int matrix_layout, int m, int n, int lda, const double *thres, int nb) {
+  if (matrix_layout != QRDM_COL_MAJOR) return bad_argument(1); /* 101 never worked upstream */
+  if (m <= 0) return bad_argument(2);
+  if (n <= 0) return bad_argument(3);
+  if (lda < (m > 1 ? m : 1)) return bad_argument(5);
+  if (thres[0] < 0.0 || thres[0] > 1.0) return bad_argument(9);
+  if (thres[1] < 0.0 || thres[1] > 1.0) return bad_argument(9);
+  if (nb <= 0) return bad_argument(10);
+  if (nb > QRDM_NB_MAX) {
+    fprintf(stderr, "qrdm_b200: nb = %d > %d is not supported\n", nb, QRDM_NB_MAX);
+    return QRDM_ERR_UNSUPPORTED;
+  }
+  return 0;
+}
+
+static int stage_begin(void *stream) {
+  if (g_profile > 0) return qrdm_rt_event_record(g_ws.ev_stage[0], stream);
+  return 0;
+}
+static int stage_end(int stage, long long launches_before, void *stream) {
+  if (g_profile > 0) {
+    int e = qrdm_rt_event_record(g_ws.ev_stage[1], stream);
+    if (e) return e;
+    e = qrdm_rt_event_sync(g_ws.ev_stage[1]);
+    if (e) return e;
+    g_stats.ms_stage[stage] += qrdm_rt_event_ms(g_ws.ev_stage[0], g_ws.ev_stage[1]);
+    g_stats.stage_launches[stage] += qrdm_rt_launch_count() - launches_before;
+  }
+  return 0;
+}
+#define STAGE(id, call)                               \
+  do {                                                \
+    long long lb__ = qrdm_rt_launch_count();          \
+    CU(stage_begin(stream));                          \
+    CU(call);                                         \
+    CU(stage_end(id, lb__, stream));                  \
+  } while (0)
+
+static int read_mailbox(const qrdm_prob *p, void *stream) {
+  CU(qrdm_rt_d2h(g_ws.mailbox, p->ctrl, QRDM_MAILBOX_BYTES, stream));
+  CU(qrdm_rt_sync(stream));
+  return 0;
+}
+
+/* The factorisation proper on device-resident data. */
+static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double *d_tau, int *ncols,
+                         const double *thres, int nb, void *stream) {
+  qrdm_workspace *w = &g_ws;
+  const double eps = DBL_EPSILON * 0.5; /* dlamch('e'), src/dgeqrdm_work.c:528 */
+  const int minmn = m < n ? m : n;
+  int stop_mode = 0;
+  double eta = 0.0;
+  if (ncols[0] == 1) { stop_mode = 1; eta = eps * n; }                    /* :531-534 */
+  else if (ncols[0] == 2) { stop_mode = 2; eta = eps * sqrt((double)n); } /* :535-538 */
+  else if (ncols[0] == 3) { stop_mode = 3; eta = thres[2]; }              /* :539-543 */
+
+  int rc = ws_ensure(m, n);
+  if (rc) return rc;
+
+  qrdm_prob P;
+  memset(&P, 0, sizeof(P));
+  P.m = m; P.n = n; P.lda = lda; P.nb = nb;
+  P.delta = thres[0]; P.tau_ = thres[1];
+  P.a = d_a; P.jpvt = d_jpvt; P.tau = d_tau;
+  P.vn1 = w->vn1; P.vn2 = w->vn2; P.ctrl = w->ctrl;
+  P.gram_part = w->gram_part; P.gram = w->gram;
+  P.panel_part = w->panel_part; P.panel_row = w->panel_row;
+  P.vc = w->vc; P.ldv = w->ldv;
+  P.wp = w->wp; P.wp_elems = w->wp_elems; P.w2 = w->w2; P.ldw = w->ldw;
+  P.nrm_part = w->nrm_part; P.nrm_splits = w->nrm_splits; P.flag_list = w->flag_list;
+  P.sm_count = w->sm_count;
+  P.vec16 = (((size_t)d_a & 15) == 0 && (lda & 1) == 0) ? 1 : 0;
+
+  memset(&g_stats, 0, sizeof(g_stats));
+  const long long launches0 = qrdm_rt_launch_count();
+  CU(qrdm_rt_event_record(w->ev[0], stream));
+  CU(qrdm_rt_memset(w->ctrl, 0, sizeof(qrdm_ctrl), stream));
+  CU(qrdm_rt_memset(w->vc, 0, sizeof(double) * (size_t)w->ldv * 64, stream));
+
+  STAGE(QRDM_STAGE_NORM_INIT, qrdm_k_colnorm(&P, 0, stream));   /* :672-682 */
+  STAGE(QRDM_STAGE_SELECT, qrdm_k_select(&P, stream));
+  rc = read_mailbox(&P, stream);
+  if (rc) return rc;
+  eta *= w->mailbox->maxnrm; /* :684 */
+
+  int info = 0, it = 0, j = 0;
+  while (j < minmn) { /* :694 */
+    const int cols = n - j;
+    STAGE(QRDM_STAGE_GRAM, qrdm_k_gram(&P, 0, m - j, stream));
+    STAGE(QRDM_STAGE_PICK, qrdm_k_pick(&P, stream));
+    STAGE(QRDM_STAGE_PERMUTE, qrdm_k_permute(&P, stream));
+    STAGE(QRDM_STAGE_PANEL, qrdm_k_panel(&P, j, stream));
+    STAGE(QRDM_STAGE_VTV, qrdm_k_gram(&P, 1, m - j, stream));
+    STAGE(QRDM_STAGE_VTC, qrdm_k_trailing(&P, j, stream));
+    STAGE(QRDM_STAGE_NORM_UPDATE, qrdm_k_norm_update(&P, j, stream));
+    STAGE(QRDM_STAGE_SELECT, qrdm_k_select(&P, stream)); /* next iteration's prologue + max norm */
+    {
+      long long lb = qrdm_rt_launch_count();
+      CU(stage_begin(stream));
+      rc = read_mailbox(&P, stream);
+      if (rc) return rc;
+      CU(stage_end(QRDM_STAGE_SYNC, lb, stream));
+    }
+    const qrdm_ctrl *mb = w->mailbox;
+    const int k = mb->last_k;
+    ncols[it++] = k; /* :740 */
+    g_stats.panel_cols += k;
+    if (mb->err != 0) { info = mb->err; break; }
+    if (k <= 0 || mb->j != j + k) {
+      fprintf(stderr, "qrdm_b200: internal error, block size %d at j=%d (device j=%d)\n", k, j, mb->j);
+      info = QRDM_ERR_INTERNAL;
+      break;
+    }
+    g_stats.trailing_flops += 4.0 * (double)(m - j) * (double)(cols - k) * (double)k;
+    j += k;
+    if (stop_mode && mb->maxnrm * sqrt((double)(cols - k)) <= eta) break; /* :782-785 */
+  }
+  CU(qrdm_rt_event_record(w->ev[1], stream));
+  CU(qrdm_rt_event_sync(w->ev[1]));
+  g_stats.ms_total = qrdm_rt_event_ms(w->ev[0], w->ev[1]);
+  g_stats.iterations = it;
+  g_stats.rank = j;
+  g_stats.launches = qrdm_rt_launch_count() - launches0;
+  if (info == -8) fprintf(stderr, "LAPACK dlarft failed, info =%d \n", info);        /* :755-758 */
+  else if (info == -13) fprintf(stderr, "LAPACK dlarfb failed, info =%d \n", info); /* :768-771 */
+  return info;
+}
+
+int dgeqrdm_dev(int m, int n, double *d_a, int lda, int *d_jpvt, double *d_tau, int *ncols,
+                const double *thres, int nb, void *stream) {
+  int rc = check_args(QRDM_COL_MAJOR, m, n, lda, thres, nb);
+  if (rc) return rc;
+  return factor_device(m, n, d_a, lda, d_jpvt, d_tau, ncols, thres, nb, stream);
+}
+
+int dgeqrdm_work(int matrix_layout, int m, int n, double *a, int lda, int *jpvt, double *tau,
+                 int *ncols, double *thres, int nb) {
+  qrdm_workspace *w = &g_ws;
+  int rc = check_args(matrix_layout, m, n, lda, thres, nb);
+  if (rc) return rc;
+  for (int c = 0; c < n; ++c)
+    if (jpvt[c] != 0) {
+      /* fixed columns: the reference's own path is broken for nfxd > 0 */
+      fprintf(stderr, "qrdm_b200: jpvt[%d] != 0 on entry (fixed columns) is not supported\n", c);
+      return QRDM_ERR_UNSUPPORTED;
+    }
+  rc = qrdm_b200_init(-1);
+  if (rc) return rc;
+  void *stream = NULL;
+  const int minmn = m < n ? m : n;
+  const int ldd = (m + 1) & ~1; /* even leading dimension on the device: 16-byte aligned columns */
+  const size_t a_bytes = sizeof(double) * (size_t)ldd * n;
+  if (a_bytes > w->cap_a_bytes) {
+    if (w->d_a) qrdm_rt_free(w->d_a);
+    w->d_a = NULL;
+    w->cap_a_bytes = 0;
+    CU(qrdm_rt_malloc((void **)&w->d_a, a_bytes));
+    w->cap_a_bytes = a_bytes;
+  }
+  if ((size_t)minmn > w->cap_tau) {
+    if (w->d_tau) qrdm_rt_free(w->d_tau);
+    w->cap_tau = 0;
+    CU(qrdm_rt_malloc((void **)&w->d_tau, sizeof(double) * minmn));
+    w->cap_tau = minmn;
+  }
+  if ((size_t)n > w->cap_jpvt) {
+    if (w->d_jpvt) qrdm_rt_free(w->d_jpvt);
+    w->cap_jpvt = 0;
+    CU(qrdm_rt_malloc((void **)&w->d_jpvt, sizeof(int) * n));
+    w->cap_jpvt = n;
+  }
+  CU(qrdm_rt_event_record(w->ev[2], stream));
+  if (ldd != m && ((size_t)ldd * n > (size_t)m * n)) CU(qrdm_rt_memset(w->d_a, 0, a_bytes, stream));
+  CU(qrdm_rt_h2d_2d(w->d_a, sizeof(double) * ldd, a, sizeof(double) * lda, sizeof(double) * m, n, stream));
+  CU(qrdm_rt_h2d(w->d_tau, tau, sizeof(double) * minmn, stream)); /* entries >= rank stay as given */
+  CU(qrdm_rt_event_record(w->ev[3], stream));
+  int info = factor_device(m, n, w->d_a, ldd, w->d_jpvt, w->d_tau, ncols, thres, nb, stream);
+  if (info <= QRDM_ERR_CUDA) return info;
+  const double ms_h2d = qrdm_rt_event_ms(w->ev[2], w->ev[3]);
+  CU(qrdm_rt_event_record(w->ev[2], stream));
+  CU(qrdm_rt_d2h_2d(a, sizeof(double) * lda, w->d_a, sizeof(double) * ldd, sizeof(double) * m, n, stream));
+  CU(qrdm_rt_d2h(jpvt, w->d_jpvt, sizeof(int) * n, stream));
+  CU(qrdm_rt_d2h(tau, w->d_tau, sizeof(double) * minmn, stream));
+  CU(qrdm_rt_event_record(w->ev[3], stream));
+  CU(qrdm_rt_sync(stream));
+  g_stats.ms_h2d = ms_h2d;
+  g_stats.ms_d2h = qrdm_rt_event_ms(w->ev[2], w->ev[3]);
+  return info;
+}
+
+int dgeqrdm(int matrix_layout, int m, int n, double *a, int lda, int *jpvt, double *tau, int *ncols,
+            double *thres, int nb) {
+  return dgeqrdm_work(matrix_layout, m, n, a, lda, jpvt, tau, ncols, thres, nb);
+}

@@ -1,0 +1,123 @@
+// k_norms.cu — K1 (column-norm initialisation) and K2 (partial-norm downdate with the
+// dgeqp3-style recompute guard), the fused HBM-bound pass of BASELINE.json's north_star.
+//
+// Replaces: reference src/dgeqrdm_work.c:672-682 (initial cblas_dnrm2 loop) and
+//           norm_update, src/dgeqrdm_work.c:36-122.
+// Algorithmic bytes: K1 8*m*n; K2 8*k*n_r (+ 8*m_r per recomputed column).
+#include "common.cuh"
+
+// Sum of squares of A[r0:m, c] for the columns of a list (or all columns c0..n-1), rows split in
+// `nsplit` contiguous segments (gridDim.y) so tall matrices fill the machine; partial results go
+// to part[split * n + idx] and are combined in fixed order by k_colnorm_finalize (deterministic;
+// in the row-sharded build the all-reduce sits between the two kernels).
+__global__ void __launch_bounds__(256) k_colnorm_partial(qrdm_prob P, int use_list) {
+  __shared__ double scratch[32];
+  const qrdm_ctrl* ctrl = P.ctrl;
+  int r0, c0, count;
+  if (use_list) {
+    count = ctrl->nflag;
+    r0 = ctrl->j + ctrl->fjb_cmp;  // rows below the block just factored
+    c0 = 0;
+  } else {
+    count = P.n;
+    r0 = 0;
+    c0 = 0;
+  }
+  const int len = P.m - r0;
+  const int nsplit = gridDim.y, split = blockIdx.y;
+  int seg = (len + nsplit - 1) / nsplit;
+  seg = (seg + 1) & ~1;
+  const int lo = min(len, split * seg), hi = min(len, lo + seg);
+  for (int idx = blockIdx.x; idx < count; idx += gridDim.x) {
+    const int c = use_list ? P.flag_list[idx] : c0 + idx;
+    const double* col = P.a + (size_t)c * P.lda + r0;
+    double s0 = 0.0, s1 = 0.0;
+    int i = lo + threadIdx.x * 2;
+    // 16-byte vector loads when the segment start is 16B aligned, scalar otherwise
+    if (((uintptr_t)(col + lo) & 15) == 0) {
+      for (; i + 1 < hi; i += 2 * blockDim.x) {
+        const double2 v = *reinterpret_cast<const double2*>(col + i);
+        s0 = fma(v.x, v.x, s0);
+        s1 = fma(v.y, v.y, s1);
+      }
+      if (i < hi) s0 = fma(col[i], col[i], s0);
+    } else {
+      for (int q = lo + threadIdx.x; q < hi; q += blockDim.x) s0 = fma(col[q], col[q], s0);
+    }
+    const double t = block_sum(s0 + s1, scratch);
+    if (threadIdx.x == 0) P.nrm_part[(size_t)split * P.n + idx] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_colnorm_finalize(qrdm_prob P, int use_list, int nsplit) {
+  const int count = use_list ? P.ctrl->nflag : P.n;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= count) return;
+  double s = 0.0;
+  for (int q = 0; q < nsplit; ++q) s += P.nrm_part[(size_t)q * P.n + idx];
+  const double v = sqrt(s);
+  const int c = use_list ? P.flag_list[idx] : idx;
+  P.vn1[c] = v;
+  P.vn2[c] = v;
+  if (!use_list) P.jpvt[c] = c + 1;  // src/dgeqrdm_work.c:596-609 with every column free
+}
+
+extern "C" int qrdm_k_colnorm(const qrdm_prob* p, int use_list, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  // rows per column segment >= 4096 so each CTA streams >= 32 KB; enough CTAs for ~4 per SM
+  const int len = p->m;
+  int nsplit = 1;
+  const long target = 4L * p->sm_count;
+  if (p->n < target) nsplit = (int)min((long)p->nrm_splits, max(1L, min(target / max(1, p->n), (long)(len / 4096))));
+  if (nsplit < 1) nsplit = 1;
+  const int gx = (int)min((long)p->n, max(1L, target / nsplit));
+  k_colnorm_partial<<<dim3(gx, nsplit), 256, 0, s>>>(*p, use_list);
+  QRDM_LAUNCH_CHECK();
+  k_colnorm_finalize<<<(p->n + 255) / 256, 256, 0, s>>>(*p, use_list, nsplit);
+  QRDM_LAUNCH_CHECK();
+  return 0;
+}
+
+// K2: one warp per active column c >= j + k.  d = sum of squares of the k new R rows of that
+// column; t = max(0,(1+d/vn1)(1-d/vn1)); if t*(vn1/vn2)^2 <= sqrt(eps) the column goes on the
+// exact-recompute list, else vn1 *= sqrt(t)  (reference src/dgeqrdm_work.c:81-108).
+__global__ void __launch_bounds__(256) k_norm_update(qrdm_prob P, double tol3z) {
+  qrdm_ctrl* ctrl = P.ctrl;
+  const int j = ctrl->j, k = ctrl->fjb_cmp;
+  const int lane = threadIdx.x & 31;
+  const int c = j + k + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= P.n) return;
+  const double v1 = P.vn1[c];
+  if (v1 == 0.0) return;
+  const double* col = P.a + (size_t)c * P.lda + j;
+  double d = 0.0;
+  for (int r = lane; r < k; r += 32) d = fma(col[r], col[r], d);
+  d = warp_sum(d);
+  if (lane == 0) {
+    double t = sqrt(fabs(d)) / v1;
+    t = (t + 1.0) * (1.0 - t);
+    t = (0.0 >= t) ? 0.0 : t;
+    const double q = v1 / P.vn2[c];
+    const double t2 = t * (q * q);
+    if (t2 <= tol3z) {
+      if (P.m - (j + k) > 0) {
+        const int slot = atomicAdd(&ctrl->nflag, 1);
+        P.flag_list[slot] = c;
+      } else {
+        P.vn1[c] = 0.0;
+        P.vn2[c] = 0.0;
+      }
+    } else {
+      P.vn1[c] = v1 * sqrt(t);
+    }
+  }
+}
+
+extern "C" int qrdm_k_norm_update(const qrdm_prob* p, int j_host, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  const int maxcols = p->n - j_host - 1;  // k >= 1
+  if (maxcols <= 0) return 0;
+  k_norm_update<<<(maxcols + 7) / 8, 256, 0, s>>>(*p, 1.0536712127723509e-08 /* tol3z = sqrt(dlamch('e')) = sqrt(2^-53), src/dgeqrdm_work.c:528-529 */);
+  QRDM_LAUNCH_CHECK();
+  return qrdm_k_colnorm(p, 1, stream);
+}

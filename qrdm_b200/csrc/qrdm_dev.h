@@ -1,0 +1,108 @@
+/* qrdm_dev.h — the thin CUDA C-ABI layer under the host C driver (dgeqrdm_host.c).
+ * Every function launches one kernel (or does one runtime call) on the given stream and returns
+ * a cudaError_t as int (0 = success).  No C++ types cross this boundary. */
+#ifndef QRDM_DEV_H_
+#define QRDM_DEV_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QRDM_KMAX 64       /* max block size / candidates (QRDM_NB_MAX) */
+#define QRDM_MAXEX 160     /* max column exchanges planned per iteration (<= 2*KMAX, see k_pick) */
+#define QRDM_MAXPOS 320    /* max column positions touched by those exchanges */
+#define QRDM_SELCAP 1024   /* capacity of the top-k candidate list in k_select */
+#define QRDM_GRAM_MAXCTA 148
+#define QRDM_PANEL_MAXCTA 148
+#define QRDM_ERR_INTERNAL (-103) /* planner overflow: cannot happen for nb <= QRDM_KMAX */
+#define QRDM_ROWALIGN 32   /* row tiles of the trailing kernels start at multiples of this */
+
+/* Device-resident control block.  The first QRDM_MAILBOX_BYTES are mirrored into a pinned host
+ * mailbox once per iteration; that copy is the only host<->device synchronisation of the loop. */
+typedef struct qrdm_ctrl {
+  int j;        /* columns triangularised so far = first active row/column (0-based) */
+  int last_k;   /* block size of the iteration that just finished (-> ncols[it]) */
+  int kmax;     /* min(nb, rows, cols) of the iteration being prepared (0 = nothing left) */
+  int nc;       /* candidates that passed the norm filter */
+  int fjb;      /* columns selected by the greedy cosine pick */
+  int fjb_cmp;  /* columns the panel actually triangularised (early stop) */
+  int ncyc;     /* permutation cycles to apply to the columns of A */
+  int nflag;    /* columns whose partial norm must be recomputed exactly */
+  int err;      /* 0, or the reference's info code (-8 tau NaN, -6 V NaN, -13 C NaN) */
+  int it;       /* iterations completed */
+  int pad_[2];
+  double maxnrm; /* max partial column norm of the active columns (stop rule) */
+  double pad2_;
+  /* ---- device-only part ---- */
+  unsigned int panel_bar; /* grid barrier counter of k_panel */
+  int pad3_[3];
+  int cand[QRDM_KMAX];        /* candidate column offsets (relative to j), by norm descending */
+  double candnrm[QRDM_KMAX];  /* their partial norms */
+  int sel[QRDM_KMAX];         /* accepted offsets, acceptance order */
+  int cyc_start[QRDM_MAXPOS + 1];
+  int cyc_pos[QRDM_MAXPOS];   /* cycle c: new[p_k] = old[p_{k+1}], new[p_last] = old[p_0] */
+} qrdm_ctrl;
+#define QRDM_MAILBOX_BYTES 64
+
+/* Problem + workspace descriptor passed by value to every launcher. */
+typedef struct qrdm_prob {
+  int m, n, lda, nb;
+  double delta, tau_; /* thres[0] (cosine bound), thres[1] (norm fraction) */
+  double *a;          /* m x n column-major, device */
+  int *jpvt;          /* n, device, 1-based on exit */
+  double *tau;        /* min(m,n), device */
+  double *vn1, *vn2;  /* n each: partial norms / norms at last exact recompute */
+  qrdm_ctrl *ctrl;
+  double *gram_part;  /* [QRDM_GRAM_MAXCTA][64*64] partial Gram blocks */
+  double *gram;       /* [64*64] reduced Gram (candidates, then V'V) */
+  double *panel_part; /* [2][QRDM_PANEL_MAXCTA][64] */
+  double *panel_row;  /* [2][64] */
+  double *vc;         /* ldv x 64 clean copy of V (unit diagonal, zeros above), rows = global rows */
+  int ldv;            /* multiple of QRDM_ROWALIGN, >= roundup(m, QRDM_ROWALIGN) */
+  double *wp;         /* [splits][64][ldw] partial W = V'C */
+  size_t wp_elems;
+  double *w2;         /* [64][ldw]  T'W, row-major */
+  int ldw;            /* multiple of 4, >= n */
+  double *nrm_part;   /* [nsplit][n] partial sums of squares */
+  int nrm_splits;
+  int *flag_list;     /* n */
+  int sm_count;
+  int vec16;          /* 1 if a is 16-byte aligned and lda is even (fast cp.async path) */
+} qrdm_prob;
+
+int qrdm_k_colnorm(const qrdm_prob *p, int use_flag_list, void *stream);   /* K1 / K2 recompute */
+int qrdm_k_select(const qrdm_prob *p, void *stream);                        /* K3a */
+int qrdm_k_gram(const qrdm_prob *p, int of_v, int rows_hint, void *stream); /* K3b / K5 */
+int qrdm_k_pick(const qrdm_prob *p, void *stream);                          /* K3c + plan */
+int qrdm_k_permute(const qrdm_prob *p, void *stream);                       /* K3d */
+int qrdm_k_panel(const qrdm_prob *p, int j_host, void *stream);             /* K4 */
+int qrdm_k_trailing(const qrdm_prob *p, int j_host, void *stream);          /* K6: vtc, wsolve, rankk */
+int qrdm_k_norm_update(const qrdm_prob *p, int j_host, void *stream);       /* K2 */
+
+/* runtime helpers so that the host driver stays plain C */
+int qrdm_rt_malloc(void **ptr, size_t bytes);
+int qrdm_rt_free(void *ptr);
+int qrdm_rt_host_alloc(void **ptr, size_t bytes);
+int qrdm_rt_host_free(void *ptr);
+int qrdm_rt_memset(void *ptr, int v, size_t bytes, void *stream);
+int qrdm_rt_h2d(void *dst, const void *src, size_t bytes, void *stream);
+int qrdm_rt_d2h(void *dst, const void *src, size_t bytes, void *stream);
+int qrdm_rt_h2d_2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height, void *stream);
+int qrdm_rt_d2h_2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height, void *stream);
+int qrdm_rt_sync(void *stream);
+int qrdm_rt_event_create(void **ev);
+int qrdm_rt_event_record(void *ev, void *stream);
+int qrdm_rt_event_sync(void *ev);
+double qrdm_rt_event_ms(void *ev0, void *ev1);
+int qrdm_rt_device_info(int *sm_count, size_t *free_bytes);
+int qrdm_rt_set_device(int dev);
+const char *qrdm_rt_errstr(int code);
+long long qrdm_rt_launch_count(void);
+double qrdm_rt_fp64_peak(int use_dmma, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

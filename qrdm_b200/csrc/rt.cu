@@ -1,0 +1,109 @@
+// rt.cu — CUDA runtime wrappers with C linkage so the host driver (dgeqrdm_host.c) stays plain C,
+// plus the FP64 peak micro-benchmark bench.py uses as the roofline denominator of K6.
+#include <cstdio>
+
+#include "common.cuh"
+
+long long g_qrdm_launches = 0;
+
+extern "C" {
+
+int qrdm_rt_malloc(void** ptr, size_t bytes) { return (int)cudaMalloc(ptr, bytes); }
+int qrdm_rt_free(void* ptr) { return (int)cudaFree(ptr); }
+int qrdm_rt_host_alloc(void** ptr, size_t bytes) { return (int)cudaMallocHost(ptr, bytes); }
+int qrdm_rt_host_free(void* ptr) { return (int)cudaFreeHost(ptr); }
+int qrdm_rt_memset(void* ptr, int v, size_t bytes, void* stream) {
+  return (int)cudaMemsetAsync(ptr, v, bytes, (cudaStream_t)stream);
+}
+int qrdm_rt_h2d(void* dst, const void* src, size_t bytes, void* stream) {
+  return (int)cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream);
+}
+int qrdm_rt_d2h(void* dst, const void* src, size_t bytes, void* stream) {
+  return (int)cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+}
+int qrdm_rt_h2d_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, void* stream) {
+  return (int)cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyHostToDevice, (cudaStream_t)stream);
+}
+int qrdm_rt_d2h_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, void* stream) {
+  return (int)cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+}
+int qrdm_rt_sync(void* stream) { return (int)cudaStreamSynchronize((cudaStream_t)stream); }
+int qrdm_rt_event_create(void** ev) { return (int)cudaEventCreate((cudaEvent_t*)ev); }
+int qrdm_rt_event_record(void* ev, void* stream) { return (int)cudaEventRecord((cudaEvent_t)ev, (cudaStream_t)stream); }
+int qrdm_rt_event_sync(void* ev) { return (int)cudaEventSynchronize((cudaEvent_t)ev); }
+double qrdm_rt_event_ms(void* ev0, void* ev1) {
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, (cudaEvent_t)ev0, (cudaEvent_t)ev1) != cudaSuccess) return -1.0;
+  return (double)ms;
+}
+int qrdm_rt_device_info(int* sm_count, size_t* free_bytes) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) return (int)e;
+  if (prop.major < 10) {
+    fprintf(stderr, "qrdm_b200: device %s is sm_%d%d; this library is built for sm_100a only\n", prop.name, prop.major, prop.minor);
+    return (int)cudaErrorInvalidDevice;
+  }
+  *sm_count = prop.multiProcessorCount;
+  size_t tot = 0;
+  e = cudaMemGetInfo(free_bytes, &tot);
+  return (int)e;
+}
+int qrdm_rt_set_device(int dev) { return (int)cudaSetDevice(dev); }
+const char* qrdm_rt_errstr(int code) { return cudaGetErrorString((cudaError_t)code); }
+long long qrdm_rt_launch_count(void) { return g_qrdm_launches; }
+
+}  // extern "C"
+
+// ---- FP64 peak: dependent-free chains of DFMA or DMMA.8x8x4 on every SM ----
+template <bool DMMA>
+__global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, double a, double b) {
+  double c[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { c[i][0] = threadIdx.x; c[i][1] = i; }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (DMMA) dmma884(c[i][0], c[i][1], a, b);
+      else { c[i][0] = fma(c[i][0], a, b); c[i][1] = fma(c[i][1], a, b); }
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+extern "C" double qrdm_rt_fp64_peak(int use_dmma, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  double* out = nullptr;
+  if (cudaMalloc(&out, sizeof(double) * sms * 2 * 256) != cudaSuccess) return -1.0;
+  const int iters = 8000, grid = sms * 2;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0, s);
+    if (use_dmma) k_fp64_peak<true><<<grid, 256, 0, s>>>(out, iters, 1.0000001, 1e-9);
+    else k_fp64_peak<false><<<grid, 256, 0, s>>>(out, iters, 1.0000001, 1e-9);
+    cudaEventRecord(e1, s);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  if (cudaGetLastError() != cudaSuccess) return -1.0;
+  const double flops = use_dmma ? 2.0 * 256 * 8 * (double)iters * 8.0 * grid   /* 8 warps x 8 mma x 256 fma */
+                                : 2.0 * 16 * (double)iters * 256.0 * grid;
+  return flops / (best * 1e-3) / 1e12;
+}
