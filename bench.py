@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py — the dgeqrdm FP64 hot path on B200, one JSON line (driver contract).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C3|C2|C1|C4] [--impl reference]
+
+A "step" is one complete dgeqrdm factorisation of one synthetic matrix.  N = 1 runs the
+workload on one GPU; N > 1 (under torchrun) runs N independent replicas, one matrix per rank
+("batched mode spreads independent matrices across GPUs": no data-path collective, weak scaling).
+
+value   = whole-job GFLOP/s with A resident in HBM (dgeqrdm_dev, CUDA events, max over ranks);
+          algorithmic FLOPs F(m,n,r) = 4mnr - 2(m+n)r^2 + (4/3)r^3, r = sum(ncols).
+e2e     = the same metric through the reference-facing C ABI `dgeqrdm` with PINNED HOST buffers:
+          H2D of A, the factorisation, D2H of A/jpvt/tau all inside the timed region.
+roofline= the trailing update (K6: k_vtc + k_wsolve + k_rankk, FP64 DMMA) timed with CUDA events
+          on the launching stream inside the same timed steps, against the FP64 DMMA peak measured
+          live by the library's micro-benchmark (MEASURED_PEAKS.json carries no FP64 figure).
+cpu_baseline / --impl reference = the UNMODIFIED reference (oracle/_ref, compiled from
+          /root/reference, OpenBLAS on all host cores) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (m, n, generator, stop_mode, description = the BASELINE.json config it is)
+    "C1": (1000, 1000, "gaussian", 0, "1000x1000 random Gaussian double matrix (configs[0])"),
+    "C2": (4096, 4096, "graded", 1, "4096x4096 graded-spectrum rank-deficient (rank 2048) (configs[1])"),
+    "C3": (16384, 16384, "gaussian", 0, "16384x16384 dense Gaussian FP64 (configs[2], trailing-GEMM roofline case)"),
+    "C4s": (250000, 512, "gaussian", 0, "tall-skinny 250000x512 slice of configs[3] (one GPU's share at 8 GPUs)"),
+}
+THRES = (0.9, 0.15)
+NB = 64
+
+
+def flops(m, n, r):
+    m, n, r = float(m), float(n), float(r)
+    return 4 * m * n * r - 2 * (m + n) * r * r + (4.0 / 3.0) * r ** 3
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                 f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_matrix_torch(torch, m, n, kind, seed, device):
+    """Synthetic input generated on the device (float64, column-major = a (n, m) row-major tensor)."""
+    gen = torch.Generator(device=device)
+    gen.manual_seed(1234 + seed)
+    if kind == "gaussian":
+        return torch.randn((n, m), dtype=torch.float64, device=device, generator=gen)  # At[c, r] = A[r, c]
+    if kind == "graded":
+        # test.ipynb cell 3 recipe: X = U diag(sv) V', sv_i = 2^(1-i)+1e-17, sv[:r] += .01 (r-i)
+        k = min(m, n)
+        r = k // 2
+        U, _ = torch.linalg.qr(torch.randn((m, m), dtype=torch.float64, device=device, generator=gen))
+        V, _ = torch.linalg.qr(torch.randn((n, n), dtype=torch.float64, device=device, generator=gen))
+        i = torch.arange(1, k + 1, dtype=torch.float64, device=device)
+        sv = torch.pow(2.0, 1.0 - i) + 1e-17
+        sv[:r] += 0.01 * (r - i[:r])
+        X = (U[:, :k] * sv) @ V[:, :k].T          # m x n
+        return X.T.contiguous()                    # stored as (n, m) row-major = column-major m x n
+    raise ValueError(kind)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref) on the
+    box's host cores, on a bounded sample of the workload.  Rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import ref
+    m, n, kind, stop_mode, desc = WORKLOADS[args.workload]
+    cores = len(os.sched_getaffinity(0))
+    line = {"impl": "reference", "metric": "dgeqrdm_fp64_gflops", "unit": "GFLOP/s", "higher_is_better": True,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "dtype": "f64", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None}
+    if not ref.have_ref():
+        line["unavailable"] = "oracle/_ref/libqrdm_ref.so not present (build it where /root/reference exists)"
+        print(json.dumps(line))
+        return
+    ref.set_ref_threads(cores)
+    # bounded sample: the leading sm x sn block of the same matrix family, sized for a few s per step
+    sm_, sn_ = (min(m, args.ref_sample), min(n, args.ref_sample)) if n > 1024 else (m, n)
+    if args.workload == "C4s":
+        sm_, sn_ = min(m, 100000), n
+    from qrdm_b200 import generators as g
+    A0 = g.gaussian(sm_, sn_, 0) if kind == "gaussian" else g.graded(sn_, seed=0, m=sm_)
+    times, rk = [], 0
+    for s in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        out = ref.ref_dgeqrdm(A0, thres=THRES, nb=NB, stop_mode=stop_mode)
+        dt = time.perf_counter() - t0
+        rk = int(out["ncols"].sum())
+        if s >= args.warmup:
+            times.append(dt)
+        if s == 0 and dt * (args.warmup + args.steps) > 240:  # keep the arm within a few minutes
+            times = [dt]
+            break
+    tot = sum(times)
+    val = flops(sm_, sn_, rk) * len(times) / tot / 1e9
+    sample = (f"reference dgeqrdm (oracle/_ref, unmodified sources, OpenBLAS {cores} threads) on a "
+              f"{sm_}x{sn_} {kind} matrix (leading-block sample of {desc}), rank {rk}, {len(times)} timed runs")
+    line.update({"value": val, "ms_per_step": tot / len(times) * 1e3,
+                 "config": {"workload": desc, "sample_shape": [sm_, sn_], "thres": list(THRES), "nb": NB,
+                            "stop_mode": stop_mode},
+                 "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": cores, "kind": "reference",
+                                  "sample": sample},
+                 "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(line))
+
+
+def cpu_baseline(args, m, n, kind, stop_mode, desc):
+    """Bounded CPU sample on rank 0 at N=1: the unmodified reference where its .so travelled with
+    the snapshot, else the plain-C port."""
+    from oracle import ref
+    from qrdm_b200 import generators as g
+    cores = len(os.sched_getaffinity(0))
+    if ref.have_ref():
+        ref.set_ref_threads(cores)
+        sm_, sn_ = (min(m, args.cpu_sample), min(n, args.cpu_sample)) if n > 1024 else (m, n)
+        if args.workload == "C4s":
+            sm_, sn_ = min(m, 100000), n
+        A0 = g.gaussian(sm_, sn_, 0) if kind == "gaussian" else g.graded(sn_, seed=0, m=sm_)
+        ref.ref_dgeqrdm(g.gaussian(512, 512, 1))  # warm the BLAS threads
+        t0 = time.perf_counter()
+        out = ref.ref_dgeqrdm(A0, thres=THRES, nb=NB, stop_mode=stop_mode)
+        dt = time.perf_counter() - t0
+        rk = int(out["ncols"].sum())
+        t1 = time.perf_counter()
+        ref.ref_dgeqp3(A0)
+        dt3 = time.perf_counter() - t1
+        return {"value": flops(sm_, sn_, rk) / dt / 1e9, "unit": "GFLOP/s", "cores": cores, "kind": "reference",
+                "seconds": dt, "dgeqp3_seconds": dt3,
+                "dgeqp3_gflops": flops(sm_, sn_, min(sm_, sn_)) / dt3 / 1e9,
+                "sample": f"one run of the unmodified reference dgeqrdm (oracle/_ref, OpenBLAS {cores} threads) on a "
+                          f"{sm_}x{sn_} {kind} matrix = leading-block sample of {desc}; rank {rk}; "
+                          f"LAPACK dgeqp3 on the same sample timed beside it"}
+    sm_ = min(m, 1024)
+    sn_ = min(n, 1024)
+    A0 = g.gaussian(sm_, sn_, 0)
+    t0 = time.perf_counter()
+    out = ref.port_dgeqrdm(A0, thres=THRES, nb=NB, stop_mode=stop_mode)
+    dt = time.perf_counter() - t0
+    rk = int(out["ncols"].sum())
+    return {"value": flops(sm_, sn_, rk) / dt / 1e9, "unit": "GFLOP/s", "cores": 1, "kind": "port",
+            "seconds": dt, "sample": f"scalar C port (oracle/qrdm_port.c) on a {sm_}x{sn_} Gaussian sample"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=6144, help="edge of the CPU-baseline sample block")
+    ap.add_argument("--ref-sample", type=int, default=6144, help="edge of the --impl reference sample block")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = max(args.warmup, 1)  # contract says W >= 3; honour smaller only for ncu captures
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import qrdm_b200  # fails loudly if libqrdm_b200.so is missing: there is no fallback
+    from qrdm_b200 import _lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if _lib.lib.qrdm_b200_init(local_rank) != 0:
+        raise SystemExit("qrdm_b200_init failed")
+
+    m, n, kind, stop_mode, desc = WORKLOADS[args.workload]
+    minmn = min(m, n)
+    stream = torch.cuda.current_stream()
+
+    # ---- synthetic input, resident in HBM; (n, m) row-major tensor == m x n column-major ----
+    A0 = make_matrix_torch(torch, m, n, kind, seed=rank, device=dev)
+    A = torch.empty_like(A0)
+    d_jpvt = torch.zeros(n, dtype=torch.int32, device=dev)
+    d_tau = torch.zeros(minmn, dtype=torch.float64, device=dev)
+    peak_dmma = qrdm_b200.fp64_peak(True, stream.cuda_stream)
+    peak_dfma = qrdm_b200.fp64_peak(False, stream.cuda_stream)
+
+    def one_step():
+        A.copy_(A0)  # restore the input (D2D, 8mn bytes read + written; inside the timed region)
+        info, ncols = qrdm_b200.dgeqrdm_device(A, m, n, m, d_jpvt, d_tau, thres=THRES, nb=NB,
+                                               stop_mode=stop_mode, stream=stream.cuda_stream)
+        if info != 0:
+            raise SystemExit(f"dgeqrdm_dev failed: info={info}")
+        return ncols
+
+    qrdm_b200.set_profile(2)  # light: event pairs around panel + trailing stages, no syncs
+    for _ in range(args.warmup):
+        one_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    trailing_ms = panel_ms = trailing_flops = 0.0
+    trailing_launches = 0
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(args.steps):
+        ncols = one_step()
+        st = qrdm_b200.stats()
+        launches += st["launches"]
+        trailing_ms += st["ms_stage"]["trailing"]
+        panel_ms += st["ms_stage"]["panel"]
+        trailing_flops += st["trailing_flops"]
+        trailing_launches += st["stage_launches"]["trailing"]
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    rk = int(ncols.sum())
+    iters = int(np.count_nonzero(ncols))
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * args.steps * flops(m, n, rk) / (ms * 1e-3) / 1e9
+    qrdm_b200.set_profile(0)
+
+    # ---- end to end through the reference-facing C ABI with pinned host buffers ----
+    hA0 = torch.empty((n, m), dtype=torch.float64, pin_memory=True)
+    hA0.copy_(A0)
+    hA = torch.empty((n, m), dtype=torch.float64, pin_memory=True)
+    h_jpvt = np.zeros(n, dtype=np.int32)
+    h_tau = np.zeros(minmn, dtype=np.float64)
+    h_ncols = np.zeros(n, dtype=np.int32)
+    th = np.array([THRES[0], THRES[1], 0.0])
+    e2e_steps = max(1, min(args.steps, 3))
+
+    def e2e_step():
+        hA.copy_(hA0)          # host-side restore, NOT timed
+        h_jpvt[:] = 0
+        h_ncols[:] = 0
+        h_ncols[0] = stop_mode
+        t0 = time.perf_counter()
+        info = _lib.lib.dgeqrdm(102, m, n, hA.data_ptr(), m, h_jpvt.ctypes.data, h_tau.ctypes.data,
+                                h_ncols.ctypes.data, th.ctypes.data, NB)
+        dt = time.perf_counter() - t0
+        if info != 0:
+            raise SystemExit(f"dgeqrdm failed: info={info}")
+        return dt
+
+    e2e_step()
+    if world > 1:
+        dist.barrier()
+    e2e_t = sum(e2e_step() for _ in range(e2e_steps))
+    if world > 1:
+        t = torch.tensor([e2e_t], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_t = float(t.item())
+    e2e_rank = int(h_ncols.sum())
+    e2e_val = world * e2e_steps * flops(m, n, e2e_rank) / e2e_t / 1e9
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks_file = {}
+    try:
+        peaks_file = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    achieved = trailing_flops / (trailing_ms * 1e-3) / 1e12 if trailing_ms > 0 else None
+    line = {
+        "metric": "dgeqrdm_fp64_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": desc, "shape": [m, n], "thres": list(THRES), "nb": NB, "stop_mode": stop_mode,
+                   "revealed_rank": rk, "iterations": iters, "parallelism": f"replicas x{world}" if world > 1 else "1 GPU",
+                   "l2": "input 8mn bytes >> 126 MB L2 and restored from HBM every step (no flush needed)"
+                         if 8 * m * n > 4 * 126e6 else "input restored by a D2D copy every step; fits L2 partially",
+                   "timed_region": "K x (D2D restore of A + dgeqrdm_dev), CUDA events on the launching stream"},
+        "e2e": {"value": e2e_val, "unit": "GFLOP/s", "h2d_bytes_per_step": 8 * m * n + 8 * minmn,
+                "d2h_bytes_per_step": 8 * m * n + 8 * minmn + 4 * n, "ms_per_step": e2e_t / e2e_steps * 1e3,
+                "steps": e2e_steps, "api": "dgeqrdm (C ABI, pinned host buffers, wall clock around the blocking call)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"kernel": "K6 trailing update: k_vtc + k_wsolve + k_rankk (DMMA.8x8x4)", "bound": "tensor",
+                     "achieved": achieved, "peak": peak_dmma, "unit": "TFLOP/s",
+                     "frac": (achieved / peak_dmma) if achieved else None,
+                     "peak_source": "FP64 DMMA peak measured live by qrdm_b200_measure_fp64_peak "
+                                    f"(DFMA pipe: {peak_dfma:.2f}); MEASURED_PEAKS.json has no FP64 entry "
+                                    f"(hbm_gbs={peaks_file.get('hbm_gbs')})",
+                     "algorithmic_flops_per_step": trailing_flops / args.steps,
+                     "launches_per_step": trailing_launches / args.steps,
+                     "ms_per_step": trailing_ms / args.steps, "share_of_step": trailing_ms / ms,
+                     "traffic": None},
+        "stages": {"panel_ms_per_step": panel_ms / args.steps, "trailing_ms_per_step": trailing_ms / args.steps},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_baseline(args, m, n, kind, stop_mode, desc)
+        except Exception as exc:  # the baseline must never sink the measurement
+            line["cpu_baseline"] = {"value": None, "error": str(exc)[:200]}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -87,7 +87,7 @@ enum {
 };
 
 void qrdm_b200_get_stats(qrdm_b200_stats *out);
-void qrdm_b200_set_profile(int on);
+void qrdm_b200_set_profile(int mode); /* 0 off, 1 per-stage with syncs, 2 light (panel + trailing, no syncs) */
 
 /* Optional: create / release the per-process device workspace ahead of the first call
  * (otherwise created lazily and grown on demand).  init returns 0 or QRDM_ERR_CUDA. */

@@ -50,8 +50,9 @@ def stats():
     return _lib.stats()
 
 
-def set_profile(on: bool):
-    _lib.lib.qrdm_b200_set_profile(1 if on else 0)
+def set_profile(mode: int):
+    """0 off; 1 every stage timed (syncs after each stage); 2 light: panel + trailing only, no syncs."""
+    _lib.lib.qrdm_b200_set_profile(int(mode))
 
 
 def fp64_peak(use_dmma=True, stream=0):
