@@ -47,15 +47,22 @@ __global__ void __launch_bounds__(256) k_gram_partial(qrdm_prob P, int of_v) {
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
 
-  for (int r0 = my_lo; r0 < my_hi; r0 += GR_ROWS) {
-    // stage 32 rows x 64 columns, lanes along rows (coalesced), warps over columns
-    for (int c = wid; c < 64; c += 8) {
-      double v = 0.0;
-      const int r = r0 + lane;
-      if (c < nc && r < my_hi) v = base[(size_t)scol[c] * ld + r];
-      tile[lane * GR_LD + c] = v;
+  // software pipeline: the global loads of sub-chunk i+1 are in flight while sub-chunk i is
+  // multiplied out of shared memory (warps over columns, lanes along rows: coalesced)
+  double pre[8];
+  auto fetch = [&](int r0) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int c = wid + 8 * q, r = r0 + lane;
+      pre[q] = (c < nc && r < my_hi) ? base[(size_t)scol[c] * ld + r] : 0.0;
     }
+  };
+  if (my_lo < my_hi) fetch(my_lo);
+  for (int r0 = my_lo; r0 < my_hi; r0 += GR_ROWS) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) tile[lane * GR_LD + wid + 8 * q] = pre[q];
     __syncthreads();
+    if (r0 + GR_ROWS < my_hi) fetch(r0 + GR_ROWS);
 #pragma unroll 4
     for (int r = 0; r < GR_ROWS; ++r) {
       const double2 a01 = *reinterpret_cast<const double2*>(&tile[r * GR_LD + 4 * ty]);
@@ -78,24 +85,32 @@ __global__ void __launch_bounds__(256) k_gram_partial(qrdm_prob P, int of_v) {
     for (int b = 0; b < 4; ++b) out[(4 * ty + a) * 64 + 4 * tx + b] = acc[a][b];
 }
 
-__global__ void __launch_bounds__(256) k_gram_reduce(qrdm_prob P, int of_v, int nparts) {
+__global__ void __launch_bounds__(64) k_gram_reduce(qrdm_prob P, int of_v, int nparts) {
   if (!of_v && P.ctrl->nc <= 1) return;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;  // 4096 entries
-  double s = 0.0;
-  for (int q = 0; q < nparts; ++q) s += P.gram_part[(size_t)q * 4096 + e];
-  P.gram[e] = s;
+  const double* src = P.gram_part + e;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int q = 0;
+  for (; q + 3 < nparts; q += 4) {  // fixed association order: deterministic
+    s0 += src[(size_t)q * 4096];
+    s1 += src[(size_t)(q + 1) * 4096];
+    s2 += src[(size_t)(q + 2) * 4096];
+    s3 += src[(size_t)(q + 3) * 4096];
+  }
+  for (; q < nparts; ++q) s0 += src[(size_t)q * 4096];
+  P.gram[e] = (s0 + s1) + (s2 + s3);
 }
 
 // rows_hint: host-side upper bound of the number of rows (m - j) used to size the grid.
 extern "C" int qrdm_k_gram(const qrdm_prob* p, int of_v, int rows_hint, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
-  int g = (rows_hint + 127) / 128;
+  int g = (rows_hint + 63) / 64;
   if (g < 1) g = 1;
   if (g > QRDM_GRAM_MAXCTA) g = QRDM_GRAM_MAXCTA;
-  if (g > p->sm_count) g = p->sm_count;
+  if (g > 2 * p->sm_count) g = 2 * p->sm_count;
   k_gram_partial<<<g, 256, 0, s>>>(*p, of_v);
   QRDM_LAUNCH_CHECK();
-  k_gram_reduce<<<16, 256, 0, s>>>(*p, of_v, g);
+  k_gram_reduce<<<64, 64, 0, s>>>(*p, of_v, g);
   QRDM_LAUNCH_CHECK();
   return 0;
 }

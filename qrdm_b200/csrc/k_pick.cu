@@ -13,30 +13,25 @@
 struct PickShared {
   double cosm[64 * 65];
   double inv[64];
-  double tmpn[QRDM_MAXPOS];
-  int tmpj[QRDM_MAXPOS];
+  int cand[64];
   int selpos[64];
-  int mk[64];
-  int ex_p[QRDM_MAXEX], ex_q[QRDM_MAXEX];
-  int pos[QRDM_MAXPOS], cur[QRDM_MAXPOS];
-  int visited[QRDM_MAXPOS];
-  int fjb, nex, npos;
+  int sel[64];
+  int hi_pos[64];  // current position of selected column s when it sits at a position >= 64, else -1
+  int cyc_start[QRDM_MAXEX + 2];
+  int cyc_pos[2 * QRDM_MAXEX + 4];
+  int fjb, ncyc;
 };
 
-__device__ __forceinline__ bool wl_marked(const int* mk, int fjb, int x, int lane) {
-  bool f = false;
-  for (int s = lane; s < fjb; s += 32) f |= (mk[s] == x);
-  return __any_sync(0xffffffffu, f);
-}
-__device__ __forceinline__ int wl_find(const int* pos, int npos, int x, int lane) {
-  for (int base = 0; base < npos; base += 32) {
-    const int i = base + lane;
-    const unsigned b = __ballot_sync(0xffffffffu, i < npos && pos[i] == x);
-    if (b) return base + __ffs(b) - 1;
-  }
-  return -1;
-}
-
+// The exchange sequence of permute_marked has a simple structure (derivation in DESIGN.md):
+//  * "tail phase": if the LAST active column is selected it is exchanged with slot jb (0, then
+//    the first unselected slot) — at most two exchanges, one 2- or 3-cycle; this is the only
+//    place where two selected columns can be swapped "pointlessly" (e.g. identity -> jpvt 16,1,2..);
+//  * every selected column sitting at a position >= fjb is exchanged, in acceptance order, with
+//    the successive unselected slots among the leading positions: disjoint 2-cycles; selected
+//    columns already inside the leading fjb slots stay where they are.
+// One thread replays the reference's loop verbatim on a 64-bit mask of the leading slots (every
+// exchange has jb < 64), so the plan costs a few hundred instructions instead of a warp-wide
+// search per flag lookup.
 __global__ void __launch_bounds__(256) k_pick(qrdm_prob P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PickShared& S = *reinterpret_cast<PickShared*>(smem_raw);
@@ -45,9 +40,12 @@ __global__ void __launch_bounds__(256) k_pick(qrdm_prob P) {
   const int j = ctrl->j, kmax = ctrl->kmax, nc = ctrl->nc, cols = P.n - j;
   if (kmax == 0) return;
 
-  if (nc > 1) {
+  if (tid < 64) {
+    S.cand[tid] = tid < kmax ? ctrl->cand[tid] : -1;
     if (tid < nc) S.inv[tid] = 1.0 / ctrl->candnrm[tid];  // cc = 1/norm, src/dgeqrdm_work.c:366
-    __syncthreads();
+  }
+  __syncthreads();
+  if (nc > 1) {
     for (int e = tid; e < nc * nc; e += blockDim.x) {
       const int s = e / nc, t = e - s * nc;
       S.cosm[s * 65 + t] = P.gram[s * 64 + t] * S.inv[s] * S.inv[t];
@@ -56,7 +54,7 @@ __global__ void __launch_bounds__(256) k_pick(qrdm_prob P) {
   __syncthreads();
 
   if (wid == 0) {
-    // ---- greedy pick (all lanes in lock-step, scalars are warp-uniform) ----
+    // ---- greedy pick (lock-step warp, scalars warp-uniform), src/dgeqrdm_work.c:382-403 ----
     int fjb = 1;
     if (lane == 0) S.selpos[0] = 0;
     __syncwarp();
@@ -71,101 +69,102 @@ __global__ void __launch_bounds__(256) k_pick(qrdm_prob P) {
       __syncwarp();
     }
     for (int s = lane; s < fjb; s += 32) {
-      const int c = ctrl->cand[S.selpos[s]];
-      S.mk[s] = c;
+      const int c = S.cand[S.selpos[s]];
+      S.sel[s] = c;
+      S.hi_pos[s] = c >= 64 ? c : -1;
       ctrl->sel[s] = c;
     }
     __syncwarp();
 
-    // ---- exchange plan = permute_marked ----
-    int jb = 0, nex = 0;
-    const int jt = cols - 1;
-    bool overflow = false;
-    auto exchange = [&](int p, int q) {
-      const bool mp = wl_marked(S.mk, fjb, p, lane), mq = wl_marked(S.mk, fjb, q, lane);
-      if (mp != mq) {
-        const int from = mp ? p : q, to = mp ? q : p;
-        for (int s = lane; s < fjb; s += 32)
-          if (S.mk[s] == from) S.mk[s] = to;
+    if (lane == 0) {
+      // ---- exchange plan = permute_marked (src/dgeqrdm_work.c:149-262), replayed serially ----
+      unsigned long long low = 0ull;
+      for (int s = 0; s < fjb; ++s)
+        if (S.sel[s] < 64) low |= 1ull << S.sel[s];
+      auto marked = [&](int x) -> bool {
+        if (x < 64) return (low >> x) & 1ull;
+        for (int s = 0; s < fjb; ++s)
+          if (S.hi_pos[s] == x) return true;
+        return false;
+      };
+      auto skip = [&](int jb) -> int {  // while (jb < cols && marked[jb]) ++jb
+        while (jb < cols && marked(jb)) {
+          if (jb < 64) {
+            const unsigned long long freebits = ~low >> jb;
+            jb = freebits ? jb + __ffsll((long long)freebits) - 1 : 64;
+          } else {
+            ++jb;
+          }
+        }
+        return jb;
+      };
+      auto unmark_hi = [&](int x) {
+        for (int s = 0; s < fjb; ++s)
+          if (S.hi_pos[s] == x) S.hi_pos[s] = -1;
+      };
+      int jb = 0, ncyc = 0, total = 0;
+      const int jt = cols - 1;
+      bool overflow = false;
+      // tail phase (can only fire on the first pass of the reference's outer loop)
+      int tail[3], ntail = 0;
+      while (jb < jt && marked(jt) && ntail < 3) {
+        if (jb >= 64) { overflow = true; break; }  // cannot happen: see header comment
+        const bool mb = (low >> jb) & 1ull;
+        if (ntail == 0) { tail[0] = jb; tail[1] = jt; ntail = 2; } else { tail[ntail++] = jb; }
+        if (!mb) {  // flags differ: the selected column moves from jt to jb
+          low |= 1ull << jb;
+          if (jt < 64) low &= ~(1ull << jt); else unmark_hi(jt);
+        }
+        jb = skip(jb);
       }
-      if (nex < QRDM_MAXEX) {
-        if (lane == 0) { S.ex_p[nex] = p; S.ex_q[nex] = q; }
-        ++nex;
-      } else {
-        overflow = true;
+      if (ntail >= 2) {  // exchanges (jt,a)[,(jt,b)] compose to the cycle a <- jt [<- b]
+        S.cyc_start[ncyc++] = total;
+        for (int q = 0; q < ntail; ++q) S.cyc_pos[total++] = tail[q];
       }
-      __syncwarp();
-    };
-    for (int s = 0; s < fjb; ++s) {
-      const int jc = ctrl->sel[s];
-      while (jb < jt && wl_marked(S.mk, fjb, jt, lane)) {
-        exchange(jt, jb);
-        while (jb < cols && wl_marked(S.mk, fjb, jb, lane)) ++jb;
-      }
-      if (wl_marked(S.mk, fjb, jc, lane)) {
-        while (jb < cols && wl_marked(S.mk, fjb, jb, lane)) ++jb;
+      for (int s = 0; s < fjb; ++s) {
+        const int jc = S.sel[s];
+        const bool m = jc < 64 ? ((low >> jc) & 1ull) : (S.hi_pos[s] == jc);
+        if (!m) continue;
+        jb = skip(jb);
         if (jc <= jb || jc < fjb) continue;
-        if (jb < cols && !wl_marked(S.mk, fjb, jb, lane)) {
-          exchange(jc, jb);
+        if (jb < cols && !marked(jb)) {
+          if (jb >= 64 || ncyc >= QRDM_MAXEX) { overflow = true; break; }
+          low |= 1ull << jb;
+          if (jc < 64) low &= ~(1ull << jc); else S.hi_pos[s] = -1;
+          S.cyc_start[ncyc++] = total;
+          S.cyc_pos[total++] = jc;
+          S.cyc_pos[total++] = jb;
           ++jb;
         }
       }
-    }
-
-    // ---- compose exchanges: cur[i] = original position whose column ends up at pos[i] ----
-    int npos = 0;
-    auto slot_of = [&](int x) {
-      int i = wl_find(S.pos, npos, x, lane);
-      if (i < 0) {
-        i = npos;
-        if (lane == 0) { S.pos[i] = x; S.cur[i] = x; S.visited[i] = 0; }
-        ++npos;
-        __syncwarp();
-      }
-      return i;
-    };
-    for (int e = 0; e < nex; ++e) {
-      const int ip = slot_of(S.ex_p[e]), iq = slot_of(S.ex_q[e]);
-      if (lane == 0) { const int t = S.cur[ip]; S.cur[ip] = S.cur[iq]; S.cur[iq] = t; }
-      __syncwarp();
-    }
-    // ---- cycles: new[p_k] = old[p_{k+1}], new[p_last] = old[p_0] ----
-    int ncyc = 0, total = 0;
-    for (int i = 0; i < npos; ++i) {
-      if (S.visited[i] || S.cur[i] == S.pos[i]) continue;
-      if (lane == 0) ctrl->cyc_start[ncyc] = total;
-      const int start = S.pos[i];
-      int idx = i;
-      while (true) {
-        if (lane == 0) { S.visited[idx] = 1; ctrl->cyc_pos[total] = S.pos[idx]; }
-        ++total;
-        __syncwarp();
-        const int nxt = S.cur[idx];
-        if (nxt == start) break;
-        idx = wl_find(S.pos, npos, nxt, lane);
-      }
-      ++ncyc;
-    }
-    if (lane == 0) {
-      ctrl->cyc_start[ncyc] = total;
+      S.cyc_start[ncyc] = total;
+      S.ncyc = ncyc;
+      S.fjb = fjb;
       ctrl->ncyc = ncyc;
       ctrl->fjb = fjb;
       ctrl->panel_bar = 0u;
       if (overflow) ctrl->err = QRDM_ERR_INTERNAL;
-      S.fjb = fjb; S.nex = nex; S.npos = npos;
     }
   }
   __syncthreads();
-  // ---- apply the composed permutation to jpvt and vn1 (NOT vn2: reference quirk) ----
-  const int npos = S.npos;
-  for (int i = tid; i < npos; i += blockDim.x) {
-    S.tmpj[i] = P.jpvt[j + S.cur[i]];
-    S.tmpn[i] = P.vn1[j + S.cur[i]];
-  }
-  __syncthreads();
-  for (int i = tid; i < npos; i += blockDim.x) {
-    P.jpvt[j + S.pos[i]] = S.tmpj[i];
-    P.vn1[j + S.pos[i]] = S.tmpn[i];
+  // ---- publish the cycles; rotate jpvt and vn1 along them (NOT vn2: reference quirk) ----
+  // cycle (p_0 .. p_{L-1}): new[p_k] = old[p_{k+1}], new[p_{L-1}] = old[p_0]
+  const int ncyc = S.ncyc;
+  for (int c = tid; c <= ncyc; c += blockDim.x) ctrl->cyc_start[c] = S.cyc_start[c];
+  for (int e = tid; e < S.cyc_start[ncyc]; e += blockDim.x) ctrl->cyc_pos[e] = S.cyc_pos[e];
+  for (int c = tid; c < ncyc; c += blockDim.x) {
+    const int b = S.cyc_start[c], e = S.cyc_start[c + 1];
+    const int p0 = j + S.cyc_pos[b];
+    const int j0 = P.jpvt[p0];
+    const double n0 = P.vn1[p0];
+    for (int q = b; q < e - 1; ++q) {
+      const int dst = j + S.cyc_pos[q], src = j + S.cyc_pos[q + 1];
+      P.jpvt[dst] = P.jpvt[src];
+      P.vn1[dst] = P.vn1[src];
+    }
+    const int last = j + S.cyc_pos[e - 1];
+    P.jpvt[last] = j0;
+    P.vn1[last] = n0;
   }
 }
 

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(WS_THREADS) k_wsolve(qrdm_prob P, int splits) 
   const int c = blockIdx.x * WS_THREADS + tid;
   if (blockIdx.x * WS_THREADS >= nc || k <= 0) return;
   const int kpad = (k + 7) & ~7;
-  for (int e = tid; e < k * 64; e += WS_THREADS) G[e] = P.gram[e];
+  for (int e = tid; e < 4096; e += WS_THREADS) G[e] = (e >> 6) < k ? P.gram[e] : 0.0;
   if (tid < 64) taus[tid] = tid < k ? P.tau[j + tid] : 0.0;
   if (c < nc) {
     for (int i = 0; i < k; ++i) {
@@ -154,98 +154,174 @@ __global__ void __launch_bounds__(WS_THREADS) k_wsolve(qrdm_prob P, int splits) 
   __syncthreads();
   if (c >= nc) return;
   bool bad = false;
-  for (int i = 0; i < k; ++i) {
-    double a0 = ys[i * WS_THREADS + tid], a1 = 0.0;
-    int s = 0;
-    for (; s + 1 < i; s += 2) {
-      a0 = fma(-G[s * 64 + i], ys[s * WS_THREADS + tid], a0);
-      a1 = fma(-G[(s + 1) * 64 + i], ys[(s + 1) * WS_THREADS + tid], a1);
+  // blocked forward substitution, 16 reflectors at a time: the contributions of the earlier blocks
+  // are 16 independent FMA chains (ILP), only the 16x16 triangle is a dependent recurrence
+  for (int b0 = 0; b0 < k; b0 += 16) {
+    double a[16], y[16];
+#pragma unroll
+    for (int ii = 0; ii < 16; ++ii) a[ii] = (b0 + ii < k) ? ys[(b0 + ii) * WS_THREADS + tid] : 0.0;
+    for (int s = 0; s < b0; ++s) {
+      const double ysv = ys[s * WS_THREADS + tid];
+      const double2* grow = reinterpret_cast<const double2*>(G + s * 64 + b0);
+#pragma unroll
+      for (int ii = 0; ii < 8; ++ii) {
+        const double2 gv = grow[ii];
+        a[2 * ii] = fma(-gv.x, ysv, a[2 * ii]);
+        a[2 * ii + 1] = fma(-gv.y, ysv, a[2 * ii + 1]);
+      }
     }
-    if (s < i) a0 = fma(-G[s * 64 + i], ys[s * WS_THREADS + tid], a0);
-    const double y = taus[i] * (a0 + a1);
-    bad |= (y != y);
-    ys[i * WS_THREADS + tid] = y;
-    P.w2[(size_t)i * P.ldw + c] = y;
+#pragma unroll
+    for (int ii = 0; ii < 16; ++ii) {
+      double acc = a[ii];
+#pragma unroll
+      for (int s2 = 0; s2 < ii; ++s2) acc = fma(-G[(b0 + s2) * 64 + b0 + ii], y[s2], acc);
+      y[ii] = taus[(b0 + ii) & 63] * acc;
+    }
+#pragma unroll
+    for (int ii = 0; ii < 16; ++ii) {
+      if (b0 + ii < k) {
+        bad |= (y[ii] != y[ii]);
+        ys[(b0 + ii) * WS_THREADS + tid] = y[ii];
+        P.w2[(size_t)(b0 + ii) * P.ldw + c] = -y[ii];  // negated: k_rankk computes C + V (-T'W)
+      }
+    }
   }
   for (int i = k; i < kpad; ++i) P.w2[(size_t)i * P.ldw + c] = 0.0;
   if (bad) atomicCAS(&ctrl->err, 0, -13);  // LAPACKE_dlarfb_mia: NaN in C (src/dlarfb.c:73-75)
 }
 
 // ------------------------------------------------------------------ k_rankk
+// Persistent: one CTA per SM walks a contiguous range of (row block, column tile) units; the
+// 128 x k tile of V stays resident in smem while the column tiles of one row block stream by, the
+// next W tile arrives by cp.async during the current tile's MMAs, and the next C tile is
+// prefetched into registers, so HBM latency is never exposed.  k_wsolve stores -T'W, which lets
+// the accumulators be initialised with C itself: C_new = C + V (-T'W) comes straight out of DMMA.
 #define RK_BM 128  // rows
 #define RK_BN 64   // columns
 #define RK_LDV (RK_BM + 4)
 #define RK_LDW (RK_BN + 4)
-#define RK_SMEM ((64 * RK_LDV + 64 * RK_LDW) * 8)
+#define RK_SMEM ((64 * RK_LDV + 2 * 64 * RK_LDW) * 8)
 
 template <bool VEC16>
-__global__ void __launch_bounds__(256, 2) k_rankk(qrdm_prob P) {
+__global__ void __launch_bounds__(256, 1) k_rankk(qrdm_prob P) {
   extern __shared__ __align__(16) double sm[];
   double* Vs = sm;                 // [q][RK_LDV]
-  double* Ws = sm + 64 * RK_LDV;   // [q][RK_LDW]
+  double* Wsb = sm + 64 * RK_LDV;  // 2 x [q][RK_LDW]
   const qrdm_ctrl* ctrl = P.ctrl;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
   const int j = ctrl->j, fjb = ctrl->fjb, k = ctrl->fjb_cmp;
   const int nc = P.n - j - fjb;
-  const int c0 = blockIdx.x * RK_BN;
-  const int jal = j & ~(QRDM_ROWALIGN - 1);
-  const int R0 = jal + blockIdx.y * RK_BM;
-  if (c0 >= nc || R0 >= P.m || k <= 0) return;
+  if (nc <= 0 || k <= 0) return;
   const int kpad = (k + 7) & ~7;
+  const int jal = j & ~(QRDM_ROWALIGN - 1);
+  const int RB = (P.m - jal + RK_BM - 1) / RK_BM, CT = (nc + RK_BN - 1) / RK_BN;
+  const long long U = (long long)RB * CT;
+  const long long lo = U * blockIdx.x / gridDim.x, hi = U * (blockIdx.x + 1) / gridDim.x;
+  if (lo >= hi) return;
   double* Cg = P.a + (size_t)(j + fjb) * P.lda;
-
-  for (int id = tid; id < kpad * (RK_BM / 2); id += 256) {
-    const int q = id / (RK_BM / 2), rp = (id % (RK_BM / 2)) * 2;
-    cp_async16(Vs + q * RK_LDV + rp, P.vc + (size_t)q * P.ldv + R0 + rp, 16);  // ldv covers the tile
-  }
-  for (int id = tid; id < kpad * (RK_BN / 2); id += 256) {
-    const int q = id / (RK_BN / 2), cp = (id % (RK_BN / 2)) * 2;
-    cp_async16(Ws + q * RK_LDW + cp, P.w2 + (size_t)q * P.ldw + c0 + cp, 16);
-  }
-  cp_async_commit();
-  cp_async_wait<0>();
-  __syncthreads();
-
   const int wr = wid & 3, wc = wid >> 2;  // warp tile: rows wr*32.., cols wc*32..
-  double acc[4][4][2];
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
-  const double* ap = Ws + t * RK_LDW + wc * 32 + g;   // A[m=c][k=q]
-  const double* bp = Vs + t * RK_LDV + wr * 32 + g;   // B[k=q][n=r]
-  for (int ks = 0; ks < kpad / 4; ++ks) {
-    double a[4], b[4];
-#pragma unroll
-    for (int x = 0; x < 4; ++x) {
-      a[x] = ap[ks * 4 * RK_LDW + x * 8];
-      b[x] = bp[ks * 4 * RK_LDV + x * 8];
+
+  auto issue_w = [&](long long u, int buf) {
+    const int c0 = (int)(u % CT) * RK_BN;
+    double* Ws = Wsb + buf * 64 * RK_LDW;
+    for (int id = tid; id < kpad * (RK_BN / 2); id += 256) {
+      const int q = id / (RK_BN / 2), cp = (id % (RK_BN / 2)) * 2;
+      cp_async16(Ws + q * RK_LDW + cp, P.w2 + (size_t)q * P.ldw + c0 + cp, 16);
     }
+  };
+  auto issue_v = [&](int rb) {
+    const int R0 = jal + rb * RK_BM;
+    for (int id = tid; id < kpad * (RK_BM / 2); id += 256) {
+      const int q = id / (RK_BM / 2), rp = (id % (RK_BM / 2)) * 2;
+      cp_async16(Vs + q * RK_LDV + rp, P.vc + (size_t)q * P.ldv + R0 + rp, 16);  // ldv covers the tile
+    }
+  };
+  // element (mt, nt, e) of a unit: column c0 + wc*32 + mt*8 + g, rows R0 + wr*32 + nt*8 + 2t + e
+  auto load_c = [&](long long u, double (&dst)[4][4][2]) {
+    const int R0 = jal + (int)(u / CT) * RK_BM, c0 = (int)(u % CT) * RK_BN;
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
+    for (int mt = 0; mt < 4; ++mt) {
+      const int c = c0 + wc * 32 + mt * 8 + g;
+      const double* col = Cg + (size_t)c * P.lda;
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
-  }
-  // C[r, c] -= acc ; lane holds (c = ..+g, r = ..+2t, 2t+1)
+      for (int nt = 0; nt < 4; ++nt) {
+        const int r = R0 + wr * 32 + nt * 8 + 2 * t;
+        double v0 = 0.0, v1 = 0.0;
+        if (c < nc) {
+          if (VEC16 && r >= j && r + 1 < P.m) {
+            const double2 v = *reinterpret_cast<const double2*>(col + r);
+            v0 = v.x; v1 = v.y;
+          } else {
+            if (r >= j && r < P.m) v0 = col[r];
+            if (r + 1 >= j && r + 1 < P.m) v1 = col[r + 1];
+          }
+        }
+        dst[mt][nt][0] = v0; dst[mt][nt][1] = v1;
+      }
+    }
+  };
+  auto store_c = [&](long long u, const double (&src)[4][4][2]) {
+    const int R0 = jal + (int)(u / CT) * RK_BM, c0 = (int)(u % CT) * RK_BN;
 #pragma unroll
-  for (int mt = 0; mt < 4; ++mt) {
-    const int c = c0 + wc * 32 + mt * 8 + g;
-    if (c >= nc) continue;
-    double* col = Cg + (size_t)c * P.lda;
+    for (int mt = 0; mt < 4; ++mt) {
+      const int c = c0 + wc * 32 + mt * 8 + g;
+      if (c >= nc) continue;
+      double* col = Cg + (size_t)c * P.lda;
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      const int r = R0 + wr * 32 + nt * 8 + 2 * t;
-      if (VEC16) {
-        if (r >= j && r + 1 < P.m) {
-          double2 v = *reinterpret_cast<double2*>(col + r);
-          v.x -= acc[mt][nt][0];
-          v.y -= acc[mt][nt][1];
-          *reinterpret_cast<double2*>(col + r) = v;
-          continue;
+      for (int nt = 0; nt < 4; ++nt) {
+        const int r = R0 + wr * 32 + nt * 8 + 2 * t;
+        if (VEC16 && r >= j && r + 1 < P.m) {
+          *reinterpret_cast<double2*>(col + r) = make_double2(src[mt][nt][0], src[mt][nt][1]);
+        } else {
+          if (r >= j && r < P.m) col[r] = src[mt][nt][0];
+          if (r + 1 >= j && r + 1 < P.m) col[r + 1] = src[mt][nt][1];
         }
       }
-      if (r >= j && r < P.m) col[r] -= acc[mt][nt][0];
-      if (r + 1 >= j && r + 1 < P.m) col[r + 1] -= acc[mt][nt][1];
+    }
+  };
+
+  double acc[4][4][2], nxt[4][4][2];
+  int cur_rb = (int)(lo / CT);
+  issue_v(cur_rb);
+  issue_w(lo, 0);
+  cp_async_commit();
+  load_c(lo, acc);
+  for (long long u = lo; u < hi; ++u) {
+    const int buf = (int)(u - lo) & 1;
+    cp_async_wait<0>();
+    __syncthreads();  // W(u) (and V) landed for everyone; everyone is done with W(u-1)
+    const bool more = u + 1 < hi;
+    const int nrb = more ? (int)((u + 1) / CT) : cur_rb;
+    if (more && nrb == cur_rb) { issue_w(u + 1, buf ^ 1); cp_async_commit(); }
+    if (more) load_c(u + 1, nxt);
+    const double* Ws = Wsb + buf * 64 * RK_LDW;
+    const double* ap = Ws + t * RK_LDW + wc * 32 + g;  // A[m=c][k=q] = W[q][c]
+    const double* bp = Vs + t * RK_LDV + wr * 32 + g;  // B[k=q][n=r] = V[r][q]
+    for (int ks = 0; ks < kpad / 4; ++ks) {
+      double a[4], b[4];
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        a[x] = ap[ks * 4 * RK_LDW + x * 8];
+        b[x] = bp[ks * 4 * RK_LDV + x * 8];
+      }
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+    }
+    store_c(u, acc);
+    if (more) {
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) { acc[mt][nt][0] = nxt[mt][nt][0]; acc[mt][nt][1] = nxt[mt][nt][1]; }
+      if (nrb != cur_rb) {
+        __syncthreads();  // all warps finished reading the old V tile
+        cur_rb = nrb;
+        issue_v(cur_rb);
+        issue_w(u + 1, buf ^ 1);
+        cp_async_commit();
+      }
     }
   }
 }
@@ -267,20 +343,35 @@ extern "C" int qrdm_k_trailing(const qrdm_prob* p, int j_host, void* stream) {
   const int mpad = (p->m + VT_BK - 1) / VT_BK * VT_BK;
   const int nchunks = (mpad - jal) / VT_BK;
   const int ntiles = (ncmax + VT_BN - 1) / VT_BN;
-  int splits = (2 * p->sm_count + ntiles - 1) / ntiles;
-  if (splits > nchunks) splits = nchunks;
+  // row splits: k_vtc runs one CTA per SM, so pick the split count whose CTA total fills whole
+  // waves (and whose chunk ranges are balanced) — wave quantisation cost 14% at 381 CTAs / 148 SMs
   const size_t cap = p->wp_elems / ((size_t)64 * p->ldw);
-  if ((size_t)splits > cap) splits = (int)cap;
-  if (splits < 1) splits = 1;
+  int smax = (2 * p->sm_count + ntiles - 1) / ntiles;
+  if (smax < 16) smax = 16;
+  if (smax > nchunks) smax = nchunks;
+  if ((size_t)smax > cap) smax = (int)cap;
+  if (smax < 1) smax = 1;
+  int splits = 1;
+  double best = 0.0;
+  for (int sp = 1; sp <= smax; ++sp) {
+    const long ctas = (long)ntiles * sp;
+    const long waves = (ctas + p->sm_count - 1) / p->sm_count;
+    const int cps = (nchunks + sp - 1) / sp;
+    const double eff = (double)ctas / (double)(waves * p->sm_count) * (double)nchunks / ((double)cps * sp);
+    if (eff > best + 0.015) { best = eff; splits = sp; }
+  }
 
   if (p->vec16) k_vtc<true><<<dim3(ntiles, splits), 256, VT_SMEM, s>>>(*p, splits);
   else k_vtc<false><<<dim3(ntiles, splits), 256, VT_SMEM, s>>>(*p, splits);
   QRDM_LAUNCH_CHECK();
   k_wsolve<<<(ncmax + WS_THREADS - 1) / WS_THREADS, WS_THREADS, WS_SMEM, s>>>(*p, splits);
   QRDM_LAUNCH_CHECK();
-  dim3 grid((ncmax + RK_BN - 1) / RK_BN, (p->m - jal + RK_BM - 1) / RK_BM);
-  if (p->vec16) k_rankk<true><<<grid, 256, RK_SMEM, s>>>(*p);
-  else k_rankk<false><<<grid, 256, RK_SMEM, s>>>(*p);
+  {
+    const long long units = (long long)((ncmax + RK_BN - 1) / RK_BN) * ((p->m - jal + RK_BM - 1) / RK_BM);
+    const int grid = (int)(units < p->sm_count ? units : p->sm_count);
+    if (p->vec16) k_rankk<true><<<grid, 256, RK_SMEM, s>>>(*p);
+    else k_rankk<false><<<grid, 256, RK_SMEM, s>>>(*p);
+  }
   QRDM_LAUNCH_CHECK();
   return 0;
 }

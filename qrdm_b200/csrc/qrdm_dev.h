@@ -14,7 +14,7 @@ extern "C" {
 #define QRDM_MAXEX 160     /* max column exchanges planned per iteration (<= 2*KMAX, see k_pick) */
 #define QRDM_MAXPOS 320    /* max column positions touched by those exchanges */
 #define QRDM_SELCAP 1024   /* capacity of the top-k candidate list in k_select */
-#define QRDM_GRAM_MAXCTA 148
+#define QRDM_GRAM_MAXCTA 296
 #define QRDM_PANEL_MAXCTA 148
 #define QRDM_ERR_INTERNAL (-103) /* planner overflow: cannot happen for nb <= QRDM_KMAX */
 #define QRDM_ROWALIGN 32   /* row tiles of the trailing kernels start at multiples of this */
