@@ -12,20 +12,24 @@
 // CTAs take bit-identical decisions (stop test, tau) and the result is run-to-run deterministic.
 // Also emits the clean copy Vc of the reflectors (unit diagonal, zeros above, zero-padded to a
 // multiple of 8 columns) that the trailing-update kernels consume.
-#include <cooperative_groups.h>
+#include <cstdlib>
 
 #include "common.cuh"
 
-#define PANEL_THREADS 256
+#define PANEL_THREADS 512
+#define PANEL_WARPS (PANEL_THREADS / 32)
+#define PANEL_CPW ((63 + PANEL_WARPS - 1) / PANEL_WARPS)  // columns per warp in the sweep
+#define PANEL_RG (PANEL_THREADS / 64)                      // reduction groups
 
+// Grid-wide barrier on a monotonically increasing counter (reset by k_pick).  Release/acquire at
+// gpu scope instead of __threadfence(): no L1 invalidation (CCTL.IVALL) on the critical path; data
+// written by other CTAs is read with ld.global.cg (L2), see the reduction below.
 __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& target, unsigned nctas) {
   __syncthreads();
   if (threadIdx.x == 0) {
     target += nctas;
-    __threadfence();
-    atomicAdd(bar, 1u);
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(bar) : "memory");
     while (ld_acquire_u32(bar) < target) { }
-    __threadfence();
   }
   __syncthreads();
 }
@@ -33,7 +37,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& target, un
 template <bool SMEM>
 __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(qrdm_prob P, int rpc) {
   extern __shared__ __align__(16) double slab[];  // SMEM mode: [64][rpc]
-  __shared__ double sred[4][64];
+  __shared__ double sred[PANEL_RG][64];
   __shared__ double S_[64], rowv[64], wv[64];
   qrdm_ctrl* ctrl = P.ctrl;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -51,13 +55,13 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(qrdm_prob P, int rpc
 #define PX(r, c) (SMEM ? slab[(c) * lds + (r)] : Ap[(size_t)(c) * lda + (size_t)(r0 + (r))])
 
   if (SMEM) {
-    for (int c = wid; c < fjb; c += 8)
+    for (int c = wid; c < fjb; c += PANEL_WARPS)
       for (int r = lane; r < nr; r += 32) slab[c * lds + r] = Ap[(size_t)c * lda + r0 + r];
     __syncthreads();
   }
 
   // partial sums for column 0: S_j = sum_{R>0} P[R,0] P[R,j]; row 0 itself goes to rowb[0]
-  for (int jj = wid; jj < fjb; jj += 8) {
+  for (int jj = wid; jj < fjb; jj += PANEL_WARPS) {
     double acc = 0.0;
     for (int r = lane; r < nr; r += 32) {
       const int R = r0 + r;
@@ -74,17 +78,30 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(qrdm_prob P, int rpc
   int k = fjb;
   for (int i = 0; i < fjb; ++i) {
     const int cur = i & 1, nxt = cur ^ 1;
-    // ---- fixed-order reduction of the partials (identical on every CTA) ----
+    // ---- fixed-order reduction of the partials (identical on every CTA => identical decisions) ----
     {
       const int jj = tid & 63, q = tid >> 6;
       double s = 0.0;
-      if (jj >= i && jj < fjb)
-        for (int bb = q; bb < G; bb += 4) s += __ldcg(&part[((size_t)cur * QRDM_PANEL_MAXCTA + bb) * 64 + jj]);  // L2: written by other SMs
+      if (jj >= i && jj < fjb) {
+        const double* src = part + ((size_t)cur * QRDM_PANEL_MAXCTA) * 64 + jj;
+        for (int bb0 = q; bb0 < G; bb0 += 8 * PANEL_RG) {
+          double v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int bb = bb0 + u * PANEL_RG;
+            v[u] = bb < G ? __ldcg(src + (size_t)bb * 64) : 0.0;  // L2: written by other SMs
+          }
+          s += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+        }
+      }
       sred[q][jj] = s;
     }
     __syncthreads();
     if (tid < 64) {
-      S_[tid] = (sred[0][tid] + sred[1][tid]) + (sred[2][tid] + sred[3][tid]);
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < PANEL_RG; ++q) s += sred[q][tid];
+      S_[tid] = s;
       rowv[tid] = __ldcg(&rowb[cur * 64 + tid]);
     }
     __syncthreads();
@@ -107,48 +124,65 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(qrdm_prob P, int rpc
       P.tau[j + i] = tau;
       if (tau != tau && ctrl->err == 0) ctrl->err = -8;  // LAPACKE_dlarft's NaN screen of tau
     }
+    const bool last = i + 1 >= fjb;
     if (tid < 64 && tid > i && tid < fjb) wv[tid] = tau * (rowv[tid] + S_[tid] * scale);
-    // ---- phase 1: v = x * scale, diagonal = beta ----
+    const double w1 = last ? 0.0 : tau * (rowv[i + 1] + S_[i + 1] * scale);
+    // ---- phase 1: v = x * scale, diagonal = beta; column i+1 gets H_i right away ----
     for (int r = tid; r < nr; r += PANEL_THREADS) {
       const int R = r0 + r;
-      if (R > i) { if (tau != 0.0) PX(r, i) = PX(r, i) * scale; }
-      else if (R == i) PX(r, i) = beta;
-    }
-    __syncthreads();
-    if (i + 1 >= fjb) break;
-    // ---- phase 2a: column i+1 (the next reflector's column) ----
-    {
-      const double w1 = wv[i + 1];
-      for (int r = tid; r < nr; r += PANEL_THREADS) {
-        const int R = r0 + r;
-        if (R < i) continue;
-        const double v = (R == i) ? 1.0 : PX(r, i);
+      if (R < i) continue;
+      double v = 1.0;
+      if (R > i) {
+        v = PX(r, i);
+        if (tau != 0.0) { v *= scale; PX(r, i) = v; }
+      } else {
+        PX(r, i) = beta;
+      }
+      if (!last) {
         const double p = fma(-v, w1, PX(r, i + 1));
         PX(r, i + 1) = p;
         if (R == i + 1) rowb[nxt * 64 + i + 1] = p;
       }
     }
     __syncthreads();
-    // ---- phase 2b: remaining columns + the fused dot products for the next reflector ----
-    for (int jj = i + 1 + wid; jj < fjb; jj += 8) {
-      double acc = 0.0;
-      if (jj == i + 1) {
-        for (int r = lane; r < nr; r += 32)
-          if (r0 + r > i + 1) { const double x = PX(r, i + 1); acc = fma(x, x, acc); }
-      } else {
-        const double wj = wv[jj];
-        for (int r = lane; r < nr; r += 32) {
-          const int R = r0 + r;
-          if (R < i) continue;
-          const double v = (R == i) ? 1.0 : PX(r, i);
-          const double p = fma(-v, wj, PX(r, jj));
-          PX(r, jj) = p;
-          if (R > i + 1) acc = fma(PX(r, i + 1), p, acc);
-          else if (R == i + 1) rowb[nxt * 64 + jj] = p;
+    if (last) break;
+    // ---- phase 2: remaining columns + the fused dot products for the next reflector ----
+    {
+      double wreg[PANEL_CPW], acc[PANEL_CPW];
+#pragma unroll
+      for (int c = 0; c < PANEL_CPW; ++c) {
+        const int jj = i + 1 + wid + c * PANEL_WARPS;
+        wreg[c] = jj < fjb ? wv[jj] : 0.0;
+        acc[c] = 0.0;
+      }
+      for (int r = lane; r < nr; r += 32) {
+        const int R = r0 + r;
+        if (R < i) continue;
+        const double v = (R == i) ? 1.0 : PX(r, i);
+        const double x1 = PX(r, i + 1);
+        const bool below = R > i + 1;
+#pragma unroll
+        for (int c = 0; c < PANEL_CPW; ++c) {
+          const int jj = i + 1 + wid + c * PANEL_WARPS;
+          if (jj < fjb) {
+            double p;
+            if (jj == i + 1) {
+              p = x1;  // already updated in phase 1: only its squared norm is needed
+            } else {
+              p = fma(-v, wreg[c], PX(r, jj));
+              PX(r, jj) = p;
+              if (R == i + 1) rowb[nxt * 64 + jj] = p;
+            }
+            if (below) acc[c] = fma(x1, p, acc[c]);
+          }
         }
       }
-      acc = warp_sum(acc);
-      if (lane == 0) part[((size_t)nxt * QRDM_PANEL_MAXCTA + b) * 64 + jj] = acc;
+#pragma unroll
+      for (int c = 0; c < PANEL_CPW; ++c) {
+        const int jj = i + 1 + wid + c * PANEL_WARPS;
+        const double a = warp_sum(acc[c]);
+        if (lane == 0 && jj < fjb) part[((size_t)nxt * QRDM_PANEL_MAXCTA + b) * 64 + jj] = a;
+      }
     }
     grid_barrier(&ctrl->panel_bar, bar_target, G);
   }
@@ -157,11 +191,11 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(qrdm_prob P, int rpc
 
   // ---- write the slab back and emit Vc ----
   if (SMEM) {
-    for (int c = wid; c < fjb; c += 8)
+    for (int c = wid; c < fjb; c += PANEL_WARPS)
       for (int r = lane; r < nr; r += 32) Ap[(size_t)c * lda + r0 + r] = slab[c * lds + r];
   }
   const int kpad = (k + 7) & ~7;
-  for (int q = wid; q < kpad; q += 8) {
+  for (int q = wid; q < kpad; q += PANEL_WARPS) {
     double* vcol = P.vc + (size_t)q * P.ldv + j;
     for (int r = lane; r < nr; r += 32) {
       const int R = r0 + r;
@@ -179,16 +213,24 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(qrdm_prob P, int rpc
 
 extern "C" int qrdm_k_panel(const qrdm_prob* p, int j_host, void* stream) {
   static bool attr_set = false;
+  static int rows_per_cta = 128;
   const int smem_cap = 200 * 1024;
   if (!attr_set) {
     cudaFuncSetAttribute(k_panel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap);
+    const char* e = getenv("QRDM_PANEL_ROWS");
+    if (e && atoi(e) >= 32) rows_per_cta = atoi(e);
     attr_set = true;
   }
   const int rows = p->m - j_host;
   if (rows <= 0) return 0;
-  int G = (rows + 31) / 32;
+  // few, fat CTAs: the per-column cost is the grid barrier + the all-to-all read of the partials,
+  // both proportional to the CTA count; grow the grid only when the slab would not fit in smem
   const int gmax = p->sm_count < QRDM_PANEL_MAXCTA ? p->sm_count : QRDM_PANEL_MAXCTA;
+  int G = (rows + rows_per_cta - 1) / rows_per_cta;
+  const int gfit = (rows + (smem_cap / 512) - 1) / (smem_cap / 512);  // CTAs needed for smem residency
+  if (G < gfit) G = gfit;
   if (G > gmax) G = gmax;
+  if (G < 1) G = 1;
   int rpc = (rows + G - 1) / G;
   qrdm_prob prob = *p;
   void* args[] = {(void*)&prob, (void*)&rpc};

@@ -145,10 +145,18 @@ __global__ void __launch_bounds__(WS_THREADS) k_wsolve(qrdm_prob P, int splits) 
   for (int e = tid; e < 4096; e += WS_THREADS) G[e] = (e >> 6) < k ? P.gram[e] : 0.0;
   if (tid < 64) taus[tid] = tid < k ? P.tau[j + tid] : 0.0;
   if (c < nc) {
-    for (int i = 0; i < k; ++i) {
-      double w = 0.0;
-      for (int s = 0; s < splits; ++s) w += P.wp[((size_t)s * 64 + i) * P.ldw + c];
-      ys[i * WS_THREADS + tid] = w;
+    for (int i0 = 0; i0 < k; i0 += 8) {  // 8 independent load chains in flight
+      double w[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) w[u] = 0.0;
+      for (int s = 0; s < splits; ++s) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (i0 + u < k) w[u] += P.wp[((size_t)s * 64 + i0 + u) * P.ldw + c];
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (i0 + u < k) ys[(i0 + u) * WS_THREADS + tid] = w[u];
     }
   }
   __syncthreads();
@@ -220,9 +228,12 @@ __global__ void __launch_bounds__(256, 1) k_rankk(qrdm_prob P) {
   if (lo >= hi) return;
   double* Cg = P.a + (size_t)(j + fjb) * P.lda;
   const int wr = wid & 3, wc = wid >> 2;  // warp tile: rows wr*32.., cols wc*32..
+  const size_t lda = (size_t)P.lda;
+  // this lane's element (mt, nt, e): column c0 + wc*32 + mt*8 + g, rows R0 + wr*32 + nt*8 + 2t + e
+  const size_t lane_off = (size_t)(wc * 32 + g) * lda + (size_t)(wr * 32 + 2 * t);
 
-  auto issue_w = [&](long long u, int buf) {
-    const int c0 = (int)(u % CT) * RK_BN;
+  auto issue_w = [&](int ct, int buf) {
+    const int c0 = ct * RK_BN;
     double* Ws = Wsb + buf * 64 * RK_LDW;
     for (int id = tid; id < kpad * (RK_BN / 2); id += 256) {
       const int q = id / (RK_BN / 2), cp = (id % (RK_BN / 2)) * 2;
@@ -236,67 +247,74 @@ __global__ void __launch_bounds__(256, 1) k_rankk(qrdm_prob P) {
       cp_async16(Vs + q * RK_LDV + rp, P.vc + (size_t)q * P.ldv + R0 + rp, 16);  // ldv covers the tile
     }
   };
-  // element (mt, nt, e) of a unit: column c0 + wc*32 + mt*8 + g, rows R0 + wr*32 + nt*8 + 2t + e
-  auto load_c = [&](long long u, double (&dst)[4][4][2]) {
-    const int R0 = jal + (int)(u / CT) * RK_BM, c0 = (int)(u % CT) * RK_BN;
+  auto interior = [&](int rb, int ct) {
+    const int R0 = jal + rb * RK_BM, c0 = ct * RK_BN;
+    return VEC16 && R0 >= j && R0 + RK_BM <= P.m && c0 + RK_BN <= nc;
+  };
+  auto load_c = [&](int rb, int ct, double (&dst)[4][4][2]) {
+    const int R0 = jal + rb * RK_BM, c0 = ct * RK_BN;
+    const double* base = Cg + (size_t)c0 * lda + R0 + lane_off;
+    if (interior(rb, ct)) {  // the common case: 16 unconditional 16-byte loads in flight
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt) {
-      const int c = c0 + wc * 32 + mt * 8 + g;
-      const double* col = Cg + (size_t)c * P.lda;
+      for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        const int r = R0 + wr * 32 + nt * 8 + 2 * t;
-        double v0 = 0.0, v1 = 0.0;
-        if (c < nc) {
-          if (VEC16 && r >= j && r + 1 < P.m) {
-            const double2 v = *reinterpret_cast<const double2*>(col + r);
-            v0 = v.x; v1 = v.y;
-          } else {
-            if (r >= j && r < P.m) v0 = col[r];
-            if (r + 1 >= j && r + 1 < P.m) v1 = col[r + 1];
-          }
+        for (int nt = 0; nt < 4; ++nt) {
+          const double2 v = *reinterpret_cast<const double2*>(base + (size_t)(mt * 8) * lda + nt * 8);
+          dst[mt][nt][0] = v.x; dst[mt][nt][1] = v.y;
         }
-        dst[mt][nt][0] = v0; dst[mt][nt][1] = v1;
+    } else {
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) {
+        const int c = c0 + wc * 32 + mt * 8 + g;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int r = R0 + wr * 32 + nt * 8 + 2 * t;
+          const double* ptr = base + (size_t)(mt * 8) * lda + nt * 8;
+          dst[mt][nt][0] = (c < nc && r >= j && r < P.m) ? ptr[0] : 0.0;
+          dst[mt][nt][1] = (c < nc && r + 1 >= j && r + 1 < P.m) ? ptr[1] : 0.0;
+        }
       }
     }
   };
-  auto store_c = [&](long long u, const double (&src)[4][4][2]) {
-    const int R0 = jal + (int)(u / CT) * RK_BM, c0 = (int)(u % CT) * RK_BN;
+  auto store_c = [&](int rb, int ct, const double (&src)[4][4][2]) {
+    const int R0 = jal + rb * RK_BM, c0 = ct * RK_BN;
+    double* base = Cg + (size_t)c0 * lda + R0 + lane_off;
+    if (interior(rb, ct)) {
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt) {
-      const int c = c0 + wc * 32 + mt * 8 + g;
-      if (c >= nc) continue;
-      double* col = Cg + (size_t)c * P.lda;
+      for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        const int r = R0 + wr * 32 + nt * 8 + 2 * t;
-        if (VEC16 && r >= j && r + 1 < P.m) {
-          *reinterpret_cast<double2*>(col + r) = make_double2(src[mt][nt][0], src[mt][nt][1]);
-        } else {
-          if (r >= j && r < P.m) col[r] = src[mt][nt][0];
-          if (r + 1 >= j && r + 1 < P.m) col[r + 1] = src[mt][nt][1];
+        for (int nt = 0; nt < 4; ++nt)
+          *reinterpret_cast<double2*>(base + (size_t)(mt * 8) * lda + nt * 8) = make_double2(src[mt][nt][0], src[mt][nt][1]);
+    } else {
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) {
+        const int c = c0 + wc * 32 + mt * 8 + g;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int r = R0 + wr * 32 + nt * 8 + 2 * t;
+          double* ptr = base + (size_t)(mt * 8) * lda + nt * 8;
+          if (c < nc && r >= j && r < P.m) ptr[0] = src[mt][nt][0];
+          if (c < nc && r + 1 >= j && r + 1 < P.m) ptr[1] = src[mt][nt][1];
         }
       }
     }
   };
 
-  double acc[4][4][2], nxt[4][4][2];
-  int cur_rb = (int)(lo / CT);
-  issue_v(cur_rb);
-  issue_w(lo, 0);
-  cp_async_commit();
-  load_c(lo, acc);
-  for (long long u = lo; u < hi; ++u) {
-    const int buf = (int)(u - lo) & 1;
+  int rb = (int)(lo / CT), ct = (int)(lo % CT), buf = 0;
+  long long left = hi - lo;
+  // one unit: X holds C(u) (prefetched), Y receives C(u+1) while the MMAs of u run
+  auto step = [&](double (&X)[4][4][2], double (&Y)[4][4][2]) {
     cp_async_wait<0>();
     __syncthreads();  // W(u) (and V) landed for everyone; everyone is done with W(u-1)
-    const bool more = u + 1 < hi;
-    const int nrb = more ? (int)((u + 1) / CT) : cur_rb;
-    if (more && nrb == cur_rb) { issue_w(u + 1, buf ^ 1); cp_async_commit(); }
-    if (more) load_c(u + 1, nxt);
+    const bool more = left > 1;
+    int nrb = rb, nct = ct + 1;
+    if (nct == CT) { nct = 0; ++nrb; }
+    if (more && nrb == rb) { issue_w(nct, buf ^ 1); cp_async_commit(); }
+    if (more) load_c(nrb, nct, Y);
     const double* Ws = Wsb + buf * 64 * RK_LDW;
     const double* ap = Ws + t * RK_LDW + wc * 32 + g;  // A[m=c][k=q] = W[q][c]
     const double* bp = Vs + t * RK_LDV + wr * 32 + g;  // B[k=q][n=r] = V[r][q]
+#pragma unroll 2
     for (int ks = 0; ks < kpad / 4; ++ks) {
       double a[4], b[4];
 #pragma unroll
@@ -307,22 +325,26 @@ __global__ void __launch_bounds__(256, 1) k_rankk(qrdm_prob P) {
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+        for (int nt = 0; nt < 4; ++nt) dmma884(X[mt][nt][0], X[mt][nt][1], a[mt], b[nt]);
     }
-    store_c(u, acc);
-    if (more) {
-#pragma unroll
-      for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) { acc[mt][nt][0] = nxt[mt][nt][0]; acc[mt][nt][1] = nxt[mt][nt][1]; }
-      if (nrb != cur_rb) {
-        __syncthreads();  // all warps finished reading the old V tile
-        cur_rb = nrb;
-        issue_v(cur_rb);
-        issue_w(u + 1, buf ^ 1);
-        cp_async_commit();
-      }
+    store_c(rb, ct, X);
+    if (more && nrb != rb) {
+      __syncthreads();  // all warps finished reading the old V tile
+      issue_v(nrb);
+      issue_w(nct, buf ^ 1);
+      cp_async_commit();
     }
+    rb = nrb; ct = nct; buf ^= 1; --left;
+  };
+
+  double accA[4][4][2], accB[4][4][2];
+  issue_v(rb);
+  issue_w(ct, 0);
+  cp_async_commit();
+  load_c(rb, ct, accA);
+  while (left > 0) {
+    step(accA, accB);
+    if (left > 0) step(accB, accA);
   }
 }
 
