@@ -251,7 +251,6 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
     STAGE(QRDM_STAGE_PICK, qrdm_k_pick(&P, stream));
     STAGE(QRDM_STAGE_PERMUTE, qrdm_k_permute(&P, stream));
     STAGE(QRDM_STAGE_PANEL, qrdm_k_panel(&P, j, stream));
-    STAGE(QRDM_STAGE_VTV, qrdm_k_gram(&P, 1, m - j, stream));
     STAGE(QRDM_STAGE_VTC, qrdm_k_trailing(&P, j, stream));
     STAGE(QRDM_STAGE_NORM_UPDATE, qrdm_k_norm_update(&P, j, stream));
     STAGE(QRDM_STAGE_SELECT, qrdm_k_select(&P, stream)); /* next iteration's prologue + max norm */

@@ -6,9 +6,8 @@
 //
 // Three kernels:
 //   k_vtc     W_s = V_s' C_s for row split s       DMMA, K = rows, 3-stage cp.async pipeline
-//   k_wsolve  y = T' (sum_s W_s) per column by forward substitution with V'V and tau:
-//             T^-1 = striu(V'V) + diag(1/tau)  =>  y_i = tau_i (w_i - sum_{s<i} (V'V)[s,i] y_s)
-//             (tau_i = 0 gives y_i = 0 = dlarft's zero column).  Also the NaN screen of C (-13).
+//   k_tinv    T' = (I + D N)^-1 D from V'V (k_vtc's tile 0) and tau, one CTA
+//   k_wapply  W2 = -T' (sum_s W_s) per 128-column tile, DMMA; also the NaN screen of C (-13)
 //   k_rankk   C -= V y                              DMMA, K = k (<= 64) resident in smem
 // FP64 math is mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4): measured 37.0 TFLOP/s = the B200 FP64 peak,
 // vs 33.5-34 for a DFMA loop (profiles/r01_fp64_peak_microbench.txt); tcgen05/wgmma have no FP64
@@ -21,12 +20,45 @@
 #include "common.cuh"
 
 // ------------------------------------------------------------------ k_vtc
+// Persistent: one CTA per SM walks a contiguous, perfectly balanced range of (column tile,
+// 32-row chunk) units; the accumulators are flushed to a partial-W "slot" whenever the walk
+// leaves a column tile, so a tile has only 1-3 partials (vs one per row split) and there is no
+// wave quantisation.  Tile 0 is V itself: its product is V'V, which k_wsolve needs — the separate
+// Gram pass over V is gone.  k_wsolve recomputes the same unit->slot map (vt_* helpers).
 #define VT_BN 128
 #define VT_BK 32
 #define VT_LD 36  // == 4 (mod 16): conflict-free DMMA fragment loads
-#define VT_STAGES 3
+#define VT_STAGES 2  // two CTAs per SM hide each other's barrier / refill bubbles
 #define VT_STAGE_DOUBLES ((64 + VT_BN) * VT_LD)
 #define VT_SMEM (VT_STAGES * VT_STAGE_DOUBLES * 8)
+
+struct VtGeom {
+  int j, fjb, k, nc, kpad, jal, NCH, CT;  // CT counts the V'V tile (tile 0)
+  long long U;
+};
+__device__ __forceinline__ VtGeom vt_geom(const qrdm_prob& P) {
+  VtGeom g;
+  const qrdm_ctrl* ctrl = P.ctrl;
+  g.j = ctrl->j; g.fjb = ctrl->fjb; g.k = ctrl->fjb_cmp;
+  g.nc = P.n - g.j - g.fjb;
+  g.kpad = (g.k + 7) & ~7;
+  g.jal = g.j & ~(QRDM_ROWALIGN - 1);
+  const int mpad = (P.m + VT_BK - 1) / VT_BK * VT_BK;
+  g.NCH = (mpad - g.jal) / VT_BK;
+  g.CT = 1 + (g.nc > 0 ? (g.nc + VT_BN - 1) / VT_BN : 0);
+  g.U = (long long)g.CT * g.NCH;
+  return g;
+}
+__device__ __forceinline__ long long vt_lo(long long U, int G, int b) { return U * b / G; }
+// first CTA whose unit range reaches into tile T
+__device__ __forceinline__ int vt_bfirst(long long U, int G, int NCH, int T) {
+  const long long X = (long long)T * NCH;
+  int b = (int)(X * G / U);
+  if (b >= G) b = G - 1;
+  while (b > 0 && vt_lo(U, G, b) > X) --b;
+  while (b + 1 < G && vt_lo(U, G, b + 1) <= X) ++b;
+  return b;
+}
 
 template <bool VEC16>
 __device__ __forceinline__ void load_rowpair(double* dst, const double* src, int r, int m, bool col_ok) {
@@ -41,161 +73,253 @@ __device__ __forceinline__ void load_rowpair(double* dst, const double* src, int
   }
 }
 
-template <bool VEC16>
-__global__ void __launch_bounds__(256, 1) k_vtc(qrdm_prob P, int splits) {
-  extern __shared__ __align__(16) double sm[];
-  const qrdm_ctrl* ctrl = P.ctrl;
+template <bool VEC16, bool FULLK>
+__device__ __forceinline__ void vtc_body(const qrdm_prob& P, const VtGeom& ge, int wslot_stride_cols, double* sm) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
-  const int j = ctrl->j, fjb = ctrl->fjb, k = ctrl->fjb_cmp;
-  const int nc = P.n - j - fjb;
-  const int c0 = blockIdx.x * VT_BN;
-  if (c0 >= nc || k <= 0) return;
-  const int kpad = (k + 7) & ~7, MT = kpad >> 3;
-  const int jal = j & ~(QRDM_ROWALIGN - 1);
-  const int mpad = (P.m + VT_BK - 1) / VT_BK * VT_BK;
-  const int nchunks = (mpad - jal) / VT_BK;
-  const int cps = (nchunks + splits - 1) / splits;
-  const int ch_lo = blockIdx.y * cps, ch_hi = min(nchunks, ch_lo + cps);
-  const double* Cg = P.a + (size_t)(j + fjb) * P.lda;
+  const int G = gridDim.x, b = blockIdx.x;
+  const long long lo = vt_lo(ge.U, G, b), hi = vt_lo(ge.U, G, b + 1);
+  if (lo >= hi) return;
+  const int MT = FULLK ? 8 : (ge.kpad >> 3);
+  const double* Cg = P.a + (size_t)(ge.j + ge.fjb) * P.lda;
 
   double acc[8][2][2];
 #pragma unroll
   for (int a = 0; a < 8; ++a)
 #pragma unroll
-    for (int b = 0; b < 2; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    for (int c = 0; c < 2; ++c) acc[a][c][0] = acc[a][c][1] = 0.0;
 
-  auto issue = [&](int chunk, int stage) {
+  auto issue = [&](long long u, int stage) {
+    const int T = (int)(u / ge.NCH), chunk = (int)(u - (long long)T * ge.NCH);
     double* Vs = sm + (size_t)stage * VT_STAGE_DOUBLES;
     double* Cs = Vs + 64 * VT_LD;
-    const int r0 = jal + chunk * VT_BK;
-    // V: kpad columns x 16 row pairs
-    for (int id = tid; id < kpad * 16; id += 256) {
+    const int r0 = ge.jal + chunk * VT_BK;
+    for (int id = tid; id < ge.kpad * 16; id += 256) {  // V: kpad columns x 16 row pairs
       const int q = id >> 4, rp = (id & 15) * 2;
       cp_async16(Vs + q * VT_LD + rp, P.vc + (size_t)q * P.ldv + r0 + rp, 16);
     }
-    for (int id = tid; id < VT_BN * 16; id += 256) {
-      const int c = id >> 4, rp = (id & 15) * 2;
-      const bool ok = c0 + c < nc;
-      const double* src = ok ? Cg + (size_t)(c0 + c) * P.lda + r0 + rp : Cg;
-      load_rowpair<VEC16>(Cs + c * VT_LD + rp, src, r0 + rp, P.m, ok);
+    if (T == 0) {  // the "C" tile is V itself (columns >= kpad read as zero)
+      for (int id = tid; id < VT_BN * 16; id += 256) {
+        const int c = id >> 4, rp = (id & 15) * 2;
+        const bool ok = c < ge.kpad;
+        cp_async16(Cs + c * VT_LD + rp, ok ? P.vc + (size_t)c * P.ldv + r0 + rp : P.vc, ok ? 16 : 0);
+      }
+    } else {
+      const int c0 = (T - 1) * VT_BN;
+      for (int id = tid; id < VT_BN * 16; id += 256) {
+        const int c = id >> 4, rp = (id & 15) * 2;
+        const bool ok = c0 + c < ge.nc;
+        const double* src = ok ? Cg + (size_t)(c0 + c) * P.lda + r0 + rp : Cg;
+        load_rowpair<VEC16>(Cs + c * VT_LD + rp, src, r0 + rp, P.m, ok);
+      }
+    }
+  };
+  auto flush = [&](int T) {
+    const int slot = b - vt_bfirst(ge.U, G, ge.NCH, T);
+    double* W = P.wp + (size_t)slot * 64 * wslot_stride_cols + (size_t)T * VT_BN;
+#pragma unroll
+    for (int mt = 0; mt < 8; ++mt) {
+      if (mt < MT) {
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          const int q = mt * 8 + g, c = wid * 16 + nt * 8 + 2 * t;
+          *reinterpret_cast<double2*>(W + (size_t)q * wslot_stride_cols + c) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+          acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+        }
+      }
     }
   };
 
-  const int nmy = ch_hi - ch_lo;
-#pragma unroll
-  for (int s = 0; s < VT_STAGES - 1; ++s) {
-    if (s < nmy) issue(ch_lo + s, s);
-    cp_async_commit();
-  }
+  const int nmy = (int)(hi - lo);
+  issue(lo, 0);
+  cp_async_commit();
+  int curT = (int)(lo / ge.NCH);
   for (int it = 0; it < nmy; ++it) {
-    cp_async_wait<VT_STAGES - 2>();
+    const int T = (int)((lo + it) / ge.NCH);
+    if (T != curT) { flush(curT); curT = T; }
+    cp_async_wait<0>();
     __syncthreads();
-    const int nxt = it + VT_STAGES - 1;
-    if (nxt < nmy) issue(ch_lo + nxt, nxt % VT_STAGES);
+    if (it + 1 < nmy) issue(lo + it + 1, (it + 1) & 1);
     cp_async_commit();
-    const double* Vs = sm + (size_t)(it % VT_STAGES) * VT_STAGE_DOUBLES;
+    const double* Vs = sm + (size_t)(it & 1) * VT_STAGE_DOUBLES;
     const double* Cs = Vs + 64 * VT_LD;
     const double* bp0 = Cs + (wid * 16 + g) * VT_LD + t;
     const double* bp1 = bp0 + 8 * VT_LD;
     const double* ap = Vs + g * VT_LD + t;
-#pragma unroll
+    // one k4-step per trip (NOT unrolled: ptxas otherwise strings all k-steps of one accumulator
+    // into a dependent DMMA chain); 16 independent DMMAs per trip, other warps cover the LDS latency
+#pragma unroll 1
     for (int ks = 0; ks < VT_BK / 4; ++ks) {
       const double b0 = bp0[ks * 4], b1 = bp1[ks * 4];
+      double a[8];
+#pragma unroll
+      for (int mt = 0; mt < 8; ++mt)
+        if (mt < MT) a[mt] = ap[mt * 8 * VT_LD + ks * 4];
 #pragma unroll
       for (int mt = 0; mt < 8; ++mt) {
         if (mt < MT) {
-          const double a = ap[mt * 8 * VT_LD + ks * 4];
-          dmma884(acc[mt][0][0], acc[mt][0][1], a, b0);
-          dmma884(acc[mt][1][0], acc[mt][1][1], a, b1);
+          dmma884(acc[mt][0][0], acc[mt][0][1], a[mt], b0);
+          dmma884(acc[mt][1][0], acc[mt][1][1], a[mt], b1);
         }
       }
     }
   }
   cp_async_wait<0>();
-  // store the partial W (row-major [split][q][ldw]); columns >= nc are never read
-  double* W = P.wp + (size_t)blockIdx.y * 64 * P.ldw;
-#pragma unroll
-  for (int mt = 0; mt < 8; ++mt) {
-    if (mt < MT) {
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        const int q = mt * 8 + g, c = c0 + wid * 16 + nt * 8 + 2 * t;
-        if (c < nc) *reinterpret_cast<double2*>(W + (size_t)q * P.ldw + c) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
-      }
-    }
-  }
+  flush(curT);
 }
 
-// ------------------------------------------------------------------ k_wsolve
-#define WS_THREADS 128
-#define WS_SMEM ((64 * 64 + 64 + 64 * WS_THREADS) * 8)
-
-__global__ void __launch_bounds__(WS_THREADS) k_wsolve(qrdm_prob P, int splits) {
+template <bool VEC16>
+__global__ void __launch_bounds__(256, 2) k_vtc(qrdm_prob P, int wslot_stride_cols) {
   extern __shared__ __align__(16) double sm[];
-  double* G = sm;                 // V'V, [s*64 + i]
-  double* taus = sm + 4096;       // 64
-  double* ys = sm + 4096 + 64;    // [i][thread]
-  qrdm_ctrl* ctrl = P.ctrl;
+  const VtGeom ge = vt_geom(P);
+  if (ge.k <= 0 || ge.nc <= 0) return;
+  if (ge.kpad == 64) vtc_body<VEC16, true>(P, ge, wslot_stride_cols, sm);  // the common case: no predicates
+  else vtc_body<VEC16, false>(P, ge, wslot_stride_cols, sm);
+}
+
+// ------------------------------------------------------------------ k_tinv + k_wapply
+// T' W without ever forming T by dlarft's recurrence:  y = T'w satisfies
+//   y_i = tau_i (w_i - sum_{s<i} (V'V)[s,i] y_s)   <=>   (I + D N) y = D w,
+// N = strictly-lower part of V'V, D = diag(tau).  k_tinv (one CTA) sums the V'V slots and inverts
+// the unit lower-triangular I + D N by blocked substitution: M = (I + D N)^-1 D = T'.  A zero tau_i
+// simply gives a zero row/column, like dlarft.  k_wapply then computes  W2 = -M (sum_s W_s)  for
+// each 128-column tile with DMMA, fusing the slot reduction, the sign (k_rankk adds) and the NaN
+// screen of C (any NaN in C poisons its W column): LAPACKE_dlarfb_mia's -13, src/dlarfb.c:73-75.
+#define TI_THREADS 256
+#define TI_SMEM (2 * 64 * 65 * 8)
+
+__device__ __forceinline__ int vt_slot_list(const VtGeom& ge, int vt_grid, int T, int* list, int cap) {
+  // indices b - bfirst of the CTAs that wrote a partial for tile T, in fixed (ascending) order
+  const int bf = vt_bfirst(ge.U, vt_grid, ge.NCH, T);
+  const long long Tend = (long long)(T + 1) * ge.NCH;
+  int n = 0;
+  for (int b = bf; b < vt_grid && vt_lo(ge.U, vt_grid, b) < Tend && n < cap; ++b)
+    if (vt_lo(ge.U, vt_grid, b + 1) > vt_lo(ge.U, vt_grid, b)) list[n++] = b - bf;
+  return n;
+}
+
+__global__ void __launch_bounds__(TI_THREADS) k_tinv(qrdm_prob P, int vt_grid, int wslot_stride_cols) {
+  extern __shared__ __align__(16) double sm[];
+  double* B = sm;            // B[i][s] = tau_i * (V'V)[s][i] for s < i
+  double* X = sm + 64 * 65;  // X[i][p]: column p of (I + B)^-1, one thread per column
+  __shared__ double taus[64];
+  __shared__ int slots[QRDM_PANEL_MAXCTA * 2 + 8];
+  __shared__ int nslots;
   const int tid = threadIdx.x;
-  const int j = ctrl->j, fjb = ctrl->fjb, k = ctrl->fjb_cmp;
-  const int nc = P.n - j - fjb;
-  const int c = blockIdx.x * WS_THREADS + tid;
-  if (blockIdx.x * WS_THREADS >= nc || k <= 0) return;
-  const int kpad = (k + 7) & ~7;
-  for (int e = tid; e < 4096; e += WS_THREADS) G[e] = (e >> 6) < k ? P.gram[e] : 0.0;
-  if (tid < 64) taus[tid] = tid < k ? P.tau[j + tid] : 0.0;
-  if (c < nc) {
-    for (int i0 = 0; i0 < k; i0 += 8) {  // 8 independent load chains in flight
-      double w[8];
+  const VtGeom ge = vt_geom(P);
+  const int k = ge.k;
+  if (k <= 0 || ge.nc <= 0) return;
+  if (tid == 0) nslots = vt_slot_list(ge, vt_grid, 0, slots, QRDM_PANEL_MAXCTA * 2 + 8);
+  if (tid < 64) taus[tid] = tid < k ? P.tau[ge.j + tid] : 0.0;
+  __syncthreads();
+  const size_t sstride = (size_t)64 * wslot_stride_cols;
+  for (int e = tid; e < 4096; e += TI_THREADS) {
+    const int s = e >> 6, i = e & 63;  // (V'V)[s][i], needed for s < i < k
+    double g = 0.0;
+    if (s < i && i < k)
+      for (int q = 0; q < nslots; ++q) g += P.wp[(size_t)slots[q] * sstride + (size_t)s * wslot_stride_cols + i];
+    B[i * 65 + s] = taus[i] * g;
+  }
+  __syncthreads();
+  if (tid < 64) {
+    const int p = tid;  // solve (I + B) x = e_p, 16 rows at a time
+    for (int b0 = 0; b0 < 64; b0 += 16) {
+      double a[16], y[16];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) w[u] = 0.0;
-      for (int s = 0; s < splits; ++s) {
+      for (int ii = 0; ii < 16; ++ii) a[ii] = (b0 + ii == p) ? 1.0 : 0.0;
+      for (int s = 0; s < b0; ++s) {
+        const double xs = X[s * 65 + p];
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
-          if (i0 + u < k) w[u] += P.wp[((size_t)s * 64 + i0 + u) * P.ldw + c];
+        for (int ii = 0; ii < 16; ++ii) a[ii] = fma(-B[(b0 + ii) * 65 + s], xs, a[ii]);
       }
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
-        if (i0 + u < k) ys[(i0 + u) * WS_THREADS + tid] = w[u];
+      for (int ii = 0; ii < 16; ++ii) {
+        double acc = a[ii];
+#pragma unroll
+        for (int s2 = 0; s2 < ii; ++s2) acc = fma(-B[(b0 + ii) * 65 + b0 + s2], y[s2], acc);
+        y[ii] = acc;
+      }
+#pragma unroll
+      for (int ii = 0; ii < 16; ++ii) X[(b0 + ii) * 65 + p] = y[ii];
     }
   }
   __syncthreads();
-  if (c >= nc) return;
-  bool bad = false;
-  // blocked forward substitution, 16 reflectors at a time: the contributions of the earlier blocks
-  // are 16 independent FMA chains (ILP), only the 16x16 triangle is a dependent recurrence
-  for (int b0 = 0; b0 < k; b0 += 16) {
-    double a[16], y[16];
-#pragma unroll
-    for (int ii = 0; ii < 16; ++ii) a[ii] = (b0 + ii < k) ? ys[(b0 + ii) * WS_THREADS + tid] : 0.0;
-    for (int s = 0; s < b0; ++s) {
-      const double ysv = ys[s * WS_THREADS + tid];
-      const double2* grow = reinterpret_cast<const double2*>(G + s * 64 + b0);
-#pragma unroll
-      for (int ii = 0; ii < 8; ++ii) {
-        const double2 gv = grow[ii];
-        a[2 * ii] = fma(-gv.x, ysv, a[2 * ii]);
-        a[2 * ii + 1] = fma(-gv.y, ysv, a[2 * ii + 1]);
+  // M = (I + B)^-1 D  -> P.gram (row-major 64 x 64; rows/columns >= k are zero)
+  for (int e = tid; e < 4096; e += TI_THREADS) {
+    const int q = e >> 6, pp = e & 63;
+    P.gram[e] = (q < k && pp < k) ? X[q * 65 + pp] * taus[pp] : 0.0;
+  }
+}
+
+#define WA_LDM 68
+#define WA_LDW 132
+#define WA_SMEM ((64 * WA_LDM + 64 * WA_LDW) * 8)
+
+__global__ void __launch_bounds__(256) k_wapply(qrdm_prob P, int vt_grid, int wslot_stride_cols) {
+  extern __shared__ __align__(16) double sm[];
+  double* Ms = sm;                  // [q][WA_LDM]
+  double* Ws = sm + 64 * WA_LDM;    // [p][WA_LDW]
+  __shared__ int slots[QRDM_PANEL_MAXCTA * 2 + 8];
+  __shared__ int nslots;
+  qrdm_ctrl* ctrl = P.ctrl;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
+  const VtGeom ge = vt_geom(P);
+  const int c0 = blockIdx.x * VT_BN;
+  if (ge.k <= 0 || c0 >= ge.nc) return;
+  const int T = blockIdx.x + 1;
+  if (tid == 0) nslots = vt_slot_list(ge, vt_grid, T, slots, QRDM_PANEL_MAXCTA * 2 + 8);
+  for (int e = tid; e < 4096; e += 256) Ms[(e >> 6) * WA_LDM + (e & 63)] = P.gram[e];
+  __syncthreads();
+  const size_t sstride = (size_t)64 * wslot_stride_cols;
+  const int ns = nslots;
+  for (int e = tid; e < 64 * (VT_BN / 2); e += 256) {  // fixed-order slot sum, 16-byte accesses
+    const int pq = e / (VT_BN / 2), cp = (e % (VT_BN / 2)) * 2;
+    double2 sacc = make_double2(0.0, 0.0);
+    if (pq < ge.kpad) {
+      const double* src = P.wp + (size_t)pq * wslot_stride_cols + (size_t)T * VT_BN + cp;
+      for (int q = 0; q < ns; ++q) {
+        const double2 v = *reinterpret_cast<const double2*>(src + (size_t)slots[q] * sstride);
+        sacc.x += v.x; sacc.y += v.y;
       }
     }
+    *reinterpret_cast<double2*>(Ws + pq * WA_LDW + cp) = sacc;
+  }
+  __syncthreads();
+  double acc[8][2][2];
 #pragma unroll
-    for (int ii = 0; ii < 16; ++ii) {
-      double acc = a[ii];
+  for (int a = 0; a < 8; ++a)
 #pragma unroll
-      for (int s2 = 0; s2 < ii; ++s2) acc = fma(-G[(b0 + s2) * 64 + b0 + ii], y[s2], acc);
-      y[ii] = taus[(b0 + ii) & 63] * acc;
+    for (int c = 0; c < 2; ++c) acc[a][c][0] = acc[a][c][1] = 0.0;
+  const double* ap = Ms + g * WA_LDM + t;                 // A[m=q][k=p] = M[q][p]
+  const double* bp = Ws + t * WA_LDW + wid * 16 + g;      // B[k=p][n=c] = W[p][c]
+  const int ksteps = ge.kpad >> 2;
+#pragma unroll 1
+  for (int ks = 0; ks < ksteps; ++ks) {
+    const double b0 = bp[ks * 4 * WA_LDW], b1 = bp[ks * 4 * WA_LDW + 8];
+    double a[8];
+#pragma unroll
+    for (int mt = 0; mt < 8; ++mt) a[mt] = ap[mt * 8 * WA_LDM + ks * 4];
+#pragma unroll
+    for (int mt = 0; mt < 8; ++mt) {
+      dmma884(acc[mt][0][0], acc[mt][0][1], a[mt], b0);
+      dmma884(acc[mt][1][0], acc[mt][1][1], a[mt], b1);
     }
+  }
+  bool bad = false;
 #pragma unroll
-    for (int ii = 0; ii < 16; ++ii) {
-      if (b0 + ii < k) {
-        bad |= (y[ii] != y[ii]);
-        ys[(b0 + ii) * WS_THREADS + tid] = y[ii];
-        P.w2[(size_t)(b0 + ii) * P.ldw + c] = -y[ii];  // negated: k_rankk computes C + V (-T'W)
+  for (int mt = 0; mt < 8; ++mt) {
+    const int q = mt * 8 + g;
+    if (q < ge.kpad) {
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const int c = c0 + wid * 16 + nt * 8 + 2 * t;
+        const double v0 = acc[mt][nt][0], v1 = acc[mt][nt][1];
+        if (c < ge.nc) bad |= (v0 != v0);
+        if (c + 1 < ge.nc) bad |= (v1 != v1);
+        *reinterpret_cast<double2*>(P.w2 + (size_t)q * P.ldw + c) = make_double2(-v0, -v1);
       }
     }
   }
-  for (int i = k; i < kpad; ++i) P.w2[(size_t)i * P.ldw + c] = 0.0;
-  if (bad) atomicCAS(&ctrl->err, 0, -13);  // LAPACKE_dlarfb_mia: NaN in C (src/dlarfb.c:73-75)
+  if (bad) atomicCAS(&ctrl->err, 0, -13);
 }
 
 // ------------------------------------------------------------------ k_rankk
@@ -205,13 +329,13 @@ __global__ void __launch_bounds__(WS_THREADS) k_wsolve(qrdm_prob P, int splits) 
 // prefetched into registers, so HBM latency is never exposed.  k_wsolve stores -T'W, which lets
 // the accumulators be initialised with C itself: C_new = C + V (-T'W) comes straight out of DMMA.
 #define RK_BM 128  // rows
-#define RK_BN 64   // columns
+#define RK_BN 32   // columns
 #define RK_LDV (RK_BM + 4)
 #define RK_LDW (RK_BN + 4)
 #define RK_SMEM ((64 * RK_LDV + 2 * 64 * RK_LDW) * 8)
 
 template <bool VEC16>
-__global__ void __launch_bounds__(256, 1) k_rankk(qrdm_prob P) {
+__global__ void __launch_bounds__(256, 2) k_rankk(qrdm_prob P) {
   extern __shared__ __align__(16) double sm[];
   double* Vs = sm;                 // [q][RK_LDV]
   double* Wsb = sm + 64 * RK_LDV;  // 2 x [q][RK_LDW]
@@ -227,10 +351,10 @@ __global__ void __launch_bounds__(256, 1) k_rankk(qrdm_prob P) {
   const long long lo = U * blockIdx.x / gridDim.x, hi = U * (blockIdx.x + 1) / gridDim.x;
   if (lo >= hi) return;
   double* Cg = P.a + (size_t)(j + fjb) * P.lda;
-  const int wr = wid & 3, wc = wid >> 2;  // warp tile: rows wr*32.., cols wc*32..
+  const int wr = wid & 3, wc = wid >> 2;  // warp tile: rows wr*32.., cols wc*16..
   const size_t lda = (size_t)P.lda;
-  // this lane's element (mt, nt, e): column c0 + wc*32 + mt*8 + g, rows R0 + wr*32 + nt*8 + 2t + e
-  const size_t lane_off = (size_t)(wc * 32 + g) * lda + (size_t)(wr * 32 + 2 * t);
+  // this lane's element (mt, nt, e): column c0 + wc*16 + mt*8 + g, rows R0 + wr*32 + nt*8 + 2t + e
+  const size_t lane_off = (size_t)(wc * 16 + g) * lda + (size_t)(wr * 32 + 2 * t);
 
   auto issue_w = [&](int ct, int buf) {
     const int c0 = ct * RK_BN;
@@ -251,12 +375,12 @@ __global__ void __launch_bounds__(256, 1) k_rankk(qrdm_prob P) {
     const int R0 = jal + rb * RK_BM, c0 = ct * RK_BN;
     return VEC16 && R0 >= j && R0 + RK_BM <= P.m && c0 + RK_BN <= nc;
   };
-  auto load_c = [&](int rb, int ct, double (&dst)[4][4][2]) {
+  auto load_c = [&](int rb, int ct, double (&dst)[2][4][2]) {
     const int R0 = jal + rb * RK_BM, c0 = ct * RK_BN;
     const double* base = Cg + (size_t)c0 * lda + R0 + lane_off;
     if (interior(rb, ct)) {  // the common case: 16 unconditional 16-byte loads in flight
 #pragma unroll
-      for (int mt = 0; mt < 4; ++mt)
+      for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
           const double2 v = *reinterpret_cast<const double2*>(base + (size_t)(mt * 8) * lda + nt * 8);
@@ -264,8 +388,8 @@ __global__ void __launch_bounds__(256, 1) k_rankk(qrdm_prob P) {
         }
     } else {
 #pragma unroll
-      for (int mt = 0; mt < 4; ++mt) {
-        const int c = c0 + wc * 32 + mt * 8 + g;
+      for (int mt = 0; mt < 2; ++mt) {
+        const int c = c0 + wc * 16 + mt * 8 + g;
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
           const int r = R0 + wr * 32 + nt * 8 + 2 * t;
@@ -276,19 +400,19 @@ __global__ void __launch_bounds__(256, 1) k_rankk(qrdm_prob P) {
       }
     }
   };
-  auto store_c = [&](int rb, int ct, const double (&src)[4][4][2]) {
+  auto store_c = [&](int rb, int ct, const double (&src)[2][4][2]) {
     const int R0 = jal + rb * RK_BM, c0 = ct * RK_BN;
     double* base = Cg + (size_t)c0 * lda + R0 + lane_off;
     if (interior(rb, ct)) {
 #pragma unroll
-      for (int mt = 0; mt < 4; ++mt)
+      for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt)
           *reinterpret_cast<double2*>(base + (size_t)(mt * 8) * lda + nt * 8) = make_double2(src[mt][nt][0], src[mt][nt][1]);
     } else {
 #pragma unroll
-      for (int mt = 0; mt < 4; ++mt) {
-        const int c = c0 + wc * 32 + mt * 8 + g;
+      for (int mt = 0; mt < 2; ++mt) {
+        const int c = c0 + wc * 16 + mt * 8 + g;
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
           const int r = R0 + wr * 32 + nt * 8 + 2 * t;
@@ -303,7 +427,7 @@ __global__ void __launch_bounds__(256, 1) k_rankk(qrdm_prob P) {
   int rb = (int)(lo / CT), ct = (int)(lo % CT), buf = 0;
   long long left = hi - lo;
   // one unit: X holds C(u) (prefetched), Y receives C(u+1) while the MMAs of u run
-  auto step = [&](double (&X)[4][4][2], double (&Y)[4][4][2]) {
+  auto step = [&](double (&X)[2][4][2], double (&Y)[2][4][2]) {
     cp_async_wait<0>();
     __syncthreads();  // W(u) (and V) landed for everyone; everyone is done with W(u-1)
     const bool more = left > 1;
@@ -312,18 +436,17 @@ __global__ void __launch_bounds__(256, 1) k_rankk(qrdm_prob P) {
     if (more && nrb == rb) { issue_w(nct, buf ^ 1); cp_async_commit(); }
     if (more) load_c(nrb, nct, Y);
     const double* Ws = Wsb + buf * 64 * RK_LDW;
-    const double* ap = Ws + t * RK_LDW + wc * 32 + g;  // A[m=c][k=q] = W[q][c]
+    const double* ap = Ws + t * RK_LDW + wc * 16 + g;  // A[m=c][k=q] = W[q][c]
     const double* bp = Vs + t * RK_LDV + wr * 32 + g;  // B[k=q][n=r] = V[r][q]
 #pragma unroll 2
-    for (int ks = 0; ks < kpad / 4; ++ks) {
-      double a[4], b[4];
+    for (int ks = 0; ks < kpad / 4; ++ks) {  // 8 independent DMMAs per k4-step
+      double a[2], b[4];
 #pragma unroll
-      for (int x = 0; x < 4; ++x) {
-        a[x] = ap[ks * 4 * RK_LDW + x * 8];
-        b[x] = bp[ks * 4 * RK_LDV + x * 8];
-      }
+      for (int x = 0; x < 2; ++x) a[x] = ap[ks * 4 * RK_LDW + x * 8];
 #pragma unroll
-      for (int mt = 0; mt < 4; ++mt)
+      for (int x = 0; x < 4; ++x) b[x] = bp[ks * 4 * RK_LDV + x * 8];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) dmma884(X[mt][nt][0], X[mt][nt][1], a[mt], b[nt]);
     }
@@ -337,7 +460,7 @@ __global__ void __launch_bounds__(256, 1) k_rankk(qrdm_prob P) {
     rb = nrb; ct = nct; buf ^= 1; --left;
   };
 
-  double accA[4][4][2], accB[4][4][2];
+  double accA[2][4][2], accB[2][4][2];
   issue_v(rb);
   issue_w(ct, 0);
   cp_async_commit();
@@ -353,7 +476,8 @@ extern "C" int qrdm_k_trailing(const qrdm_prob* p, int j_host, void* stream) {
   if (!attr_set) {
     cudaFuncSetAttribute(k_vtc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VT_SMEM);
     cudaFuncSetAttribute(k_vtc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VT_SMEM);
-    cudaFuncSetAttribute(k_wsolve, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM);
+    cudaFuncSetAttribute(k_wapply, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_SMEM);
+    cudaFuncSetAttribute(k_tinv, cudaFuncAttributeMaxDynamicSharedMemorySize, TI_SMEM);
     cudaFuncSetAttribute(k_rankk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RK_SMEM);
     cudaFuncSetAttribute(k_rankk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RK_SMEM);
     attr_set = true;
@@ -364,33 +488,24 @@ extern "C" int qrdm_k_trailing(const qrdm_prob* p, int j_host, void* stream) {
   const int jal = j_host & ~(QRDM_ROWALIGN - 1);
   const int mpad = (p->m + VT_BK - 1) / VT_BK * VT_BK;
   const int nchunks = (mpad - jal) / VT_BK;
-  const int ntiles = (ncmax + VT_BN - 1) / VT_BN;
-  // row splits: k_vtc runs one CTA per SM, so pick the split count whose CTA total fills whole
-  // waves (and whose chunk ranges are balanced) — wave quantisation cost 14% at 381 CTAs / 148 SMs
-  const size_t cap = p->wp_elems / ((size_t)64 * p->ldw);
-  int smax = (2 * p->sm_count + ntiles - 1) / ntiles;
-  if (smax < 16) smax = 16;
-  if (smax > nchunks) smax = nchunks;
-  if ((size_t)smax > cap) smax = (int)cap;
-  if (smax < 1) smax = 1;
-  int splits = 1;
-  double best = 0.0;
-  for (int sp = 1; sp <= smax; ++sp) {
-    const long ctas = (long)ntiles * sp;
-    const long waves = (ctas + p->sm_count - 1) / p->sm_count;
-    const int cps = (nchunks + sp - 1) / sp;
-    const double eff = (double)ctas / (double)(waves * p->sm_count) * (double)nchunks / ((double)cps * sp);
-    if (eff > best + 0.015) { best = eff; splits = sp; }
-  }
-
-  if (p->vec16) k_vtc<true><<<dim3(ntiles, splits), 256, VT_SMEM, s>>>(*p, splits);
-  else k_vtc<false><<<dim3(ntiles, splits), 256, VT_SMEM, s>>>(*p, splits);
+  const int ct_ub = 1 + (ncmax + VT_BN - 1) / VT_BN;  // + the V'V tile
+  // persistent grid: one CTA per SM, never more CTAs than units (device-side nc <= ncmax keeps
+  // U >= nchunks * 2 >= grid whenever anything is left to update)
+  long long units_lb = (long long)nchunks * 2;
+  int vt_grid = 2 * p->sm_count;
+  if (vt_grid > units_lb) vt_grid = (int)units_lb;
+  // partial-W slots are laid out [slot][64][stride]; (grid/CT + 2) slots always fit (see host alloc)
+  const int stride = ct_ub * VT_BN;
+  if (p->vec16) k_vtc<true><<<vt_grid, 256, VT_SMEM, s>>>(*p, stride);
+  else k_vtc<false><<<vt_grid, 256, VT_SMEM, s>>>(*p, stride);
   QRDM_LAUNCH_CHECK();
-  k_wsolve<<<(ncmax + WS_THREADS - 1) / WS_THREADS, WS_THREADS, WS_SMEM, s>>>(*p, splits);
+  k_tinv<<<1, TI_THREADS, TI_SMEM, s>>>(*p, vt_grid, stride);
+  QRDM_LAUNCH_CHECK();
+  k_wapply<<<(ncmax + VT_BN - 1) / VT_BN, 256, WA_SMEM, s>>>(*p, vt_grid, stride);
   QRDM_LAUNCH_CHECK();
   {
     const long long units = (long long)((ncmax + RK_BN - 1) / RK_BN) * ((p->m - jal + RK_BM - 1) / RK_BM);
-    const int grid = (int)(units < p->sm_count ? units : p->sm_count);
+    const int grid = (int)(units < 2 * p->sm_count ? units : 2 * p->sm_count);
     if (p->vec16) k_rankk<true><<<grid, 256, RK_SMEM, s>>>(*p);
     else k_rankk<false><<<grid, 256, RK_SMEM, s>>>(*p);
   }

@@ -39,7 +39,7 @@ __device__ __forceinline__ void dmma16816(double* c, const double* a, const doub
 }
 
 template <int ILP>
-__global__ void __launch_bounds__(256) dmma884_kernel(double* out, int iters, double a, double b) {
+__global__ void __launch_bounds__(1024) dmma884_kernel(double* out, int iters, double a, double b) {
   double c[ILP][2];
 #pragma unroll
   for (int i = 0; i < ILP; ++i) { c[i][0] = threadIdx.x; c[i][1] = i; }
@@ -99,7 +99,7 @@ int main() {
   cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
   int sms = p.multiProcessorCount;
   printf("device %s, %d SMs, clock %d MHz\n", p.name, sms, p.clockRate / 1000);
-  double* out; CK(cudaMalloc(&out, sizeof(double) * sms * 8 * 256));
+  double* out; CK(cudaMalloc(&out, sizeof(double) * sms * 8 * 1024));
   const int iters = 20000;
   for (int bps = 1; bps <= 4; bps *= 2) {
     int grid = sms * bps;
@@ -115,6 +115,19 @@ int main() {
     { constexpr int ILP = 8;
       float ms = time_it([&] { dmma16816_kernel<ILP><<<grid, 256>>>(out, iters, 1.0000001, 1e-9); });
       printf("DMMA 16816 ILP%-2d blocks/SM %d: %8.2f TFLOP/s\n", ILP, bps, 2.0 * 2048 * ILP * iters * 8.0 * grid / ms / 1e9); }
+  }
+  // how many warps per SM sub-partition does DMMA need?  (threads per block, 1 block per SM)
+  for (int threads = 128; threads <= 1024; threads *= 2) {
+    constexpr int ILP = 8;
+    float ms = time_it([&] { dmma884_kernel<ILP><<<sms, threads>>>(out, iters, 1.0000001, 1e-9); });
+    printf("DMMA 884  ILP8 %4d threads/SM (%d warps/SMSP): %8.2f TFLOP/s\n", threads, threads / 128,
+           2.0 * 256 * ILP * iters * (threads / 32.0) * sms / ms / 1e9);
+  }
+  for (int threads = 128; threads <= 512; threads *= 2) {
+    constexpr int ILP = 16;
+    float ms = time_it([&] { dmma884_kernel<ILP><<<sms, threads>>>(out, iters, 1.0000001, 1e-9); });
+    printf("DMMA 884 ILP16 %4d threads/SM (%d warps/SMSP): %8.2f TFLOP/s\n", threads, threads / 128,
+           2.0 * 256 * ILP * iters * (threads / 32.0) * sms / ms / 1e9);
   }
   CK(cudaDeviceSynchronize());
   CK(cudaGetLastError());
