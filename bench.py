@@ -236,11 +236,19 @@ def main():
         raise SystemExit("qrdm_b200_init failed")
 
     m, n, kind, stop_mode, desc = WORKLOADS[args.workload]
+    if os.environ.get("QRDM_BENCH_SHAPE"):  # experiments only: "m,n" Gaussian
+        m, n = (int(x) for x in os.environ["QRDM_BENCH_SHAPE"].split(","))
+        kind, stop_mode, desc = "gaussian", 0, f"experiment {m}x{n} Gaussian"
     minmn = min(m, n)
     stream = torch.cuda.current_stream()
 
     # ---- synthetic input, resident in HBM; (n, m) row-major tensor == m x n column-major ----
     A0 = make_matrix_torch(torch, m, n, kind, seed=rank, device=dev)
+    lda = m + int(os.environ.get("QRDM_BENCH_LDA_PAD", "0"))  # experiment: non-power-of-two column stride
+    if lda != m:
+        A0p = torch.zeros((n, lda), dtype=torch.float64, device=dev)
+        A0p[:, :m] = A0
+        A0 = A0p
     A = torch.empty_like(A0)
     d_jpvt = torch.zeros(n, dtype=torch.int32, device=dev)
     d_tau = torch.zeros(minmn, dtype=torch.float64, device=dev)
@@ -249,7 +257,7 @@ def main():
 
     def one_step():
         A.copy_(A0)  # restore the input (D2D, 8mn bytes read + written; inside the timed region)
-        info, ncols = qrdm_b200.dgeqrdm_device(A, m, n, m, d_jpvt, d_tau, thres=THRES, nb=NB,
+        info, ncols = qrdm_b200.dgeqrdm_device(A, m, n, lda, d_jpvt, d_tau, thres=THRES, nb=NB,
                                                stop_mode=stop_mode, stream=stream.cuda_stream)
         if info != 0:
             raise SystemExit(f"dgeqrdm_dev failed: info={info}")
@@ -294,7 +302,7 @@ def main():
 
     # ---- end to end through the reference-facing C ABI with pinned host buffers ----
     hA0 = torch.empty((n, m), dtype=torch.float64, pin_memory=True)
-    hA0.copy_(A0)
+    hA0.copy_(A0[:, :m])
     hA = torch.empty((n, m), dtype=torch.float64, pin_memory=True)
     h_jpvt = np.zeros(n, dtype=np.int32)
     h_tau = np.zeros(minmn, dtype=np.float64)

@@ -230,6 +230,7 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
   P.nrm_part = w->nrm_part; P.nrm_splits = w->nrm_splits; P.flag_list = w->flag_list;
   P.sm_count = w->sm_count;
   P.vec16 = (((size_t)d_a & 15) == 0 && (lda & 1) == 0) ? 1 : 0;
+  { const char *dbg = getenv("QRDM_B200_DEBUG"); P.debug = dbg ? atoi(dbg) : 0; }
 
   memset(&g_stats, 0, sizeof(g_stats));
   g_ev_used = 0;

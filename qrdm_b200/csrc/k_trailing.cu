@@ -27,7 +27,10 @@
 // Gram pass over V is gone.  k_wsolve recomputes the same unit->slot map (vt_* helpers).
 #define VT_BN 128
 #define VT_BK 32
-#define VT_LD 36  // == 4 (mod 16): conflict-free DMMA fragment loads
+// smem tile layout: dense [column][32 rows], rows in 16-byte pairs whose index is XOR-swizzled with
+// the column parity (bit 2), so the 16-byte fragment loads of a quarter-warp hit 8 distinct banks
+#define VT_LD 32
+__device__ __forceinline__ int vt_sw(int col, int rowpair_idx) { return col * VT_LD + ((rowpair_idx ^ ((col & 1) << 2)) << 1); }
 #define VT_STAGES 2  // two CTAs per SM hide each other's barrier / refill bubbles
 #define VT_STAGE_DOUBLES ((64 + VT_BN) * VT_LD)
 #define VT_SMEM (VT_STAGES * VT_STAGE_DOUBLES * 8)
@@ -95,13 +98,13 @@ __device__ __forceinline__ void vtc_body(const qrdm_prob& P, const VtGeom& ge, i
     const int r0 = ge.jal + chunk * VT_BK;
     for (int id = tid; id < ge.kpad * 16; id += 256) {  // V: kpad columns x 16 row pairs
       const int q = id >> 4, rp = (id & 15) * 2;
-      cp_async16(Vs + q * VT_LD + rp, P.vc + (size_t)q * P.ldv + r0 + rp, 16);
+      cp_async16(Vs + vt_sw(q, rp >> 1), P.vc + (size_t)q * P.ldv + r0 + rp, 16);
     }
     if (T == 0) {  // the "C" tile is V itself (columns >= kpad read as zero)
       for (int id = tid; id < VT_BN * 16; id += 256) {
         const int c = id >> 4, rp = (id & 15) * 2;
         const bool ok = c < ge.kpad;
-        cp_async16(Cs + c * VT_LD + rp, ok ? P.vc + (size_t)c * P.ldv + r0 + rp : P.vc, ok ? 16 : 0);
+        cp_async16(Cs + vt_sw(c, rp >> 1), ok ? P.vc + (size_t)c * P.ldv + r0 + rp : P.vc, ok ? 16 : 0);
       }
     } else {
       const int c0 = (T - 1) * VT_BN;
@@ -109,7 +112,7 @@ __device__ __forceinline__ void vtc_body(const qrdm_prob& P, const VtGeom& ge, i
         const int c = id >> 4, rp = (id & 15) * 2;
         const bool ok = c0 + c < ge.nc;
         const double* src = ok ? Cg + (size_t)(c0 + c) * P.lda + r0 + rp : Cg;
-        load_rowpair<VEC16>(Cs + c * VT_LD + rp, src, r0 + rp, P.m, ok);
+        load_rowpair<VEC16>(Cs + vt_sw(c, rp >> 1), src, r0 + rp, P.m, ok);
       }
     }
   };
@@ -142,23 +145,34 @@ __device__ __forceinline__ void vtc_body(const qrdm_prob& P, const VtGeom& ge, i
     cp_async_commit();
     const double* Vs = sm + (size_t)(it & 1) * VT_STAGE_DOUBLES;
     const double* Cs = Vs + 64 * VT_LD;
-    const double* bp0 = Cs + (wid * 16 + g) * VT_LD + t;
+    // K is consumed 8 rows at a time: lane t owns rows 2t, 2t+1 of the group, so one 16-byte LDS per
+    // column feeds the fragments of two DMMA k-steps (k = {0,2,4,6} then {1,3,5,7}).  One group per
+    // trip, NOT unrolled: ptxas otherwise strings all k-steps of an accumulator into a dependent chain.
+    const int swz = (g & 1) << 2;
+    const double* bp0 = Cs + (wid * 16 + g) * VT_LD;
     const double* bp1 = bp0 + 8 * VT_LD;
-    const double* ap = Vs + g * VT_LD + t;
-    // one k4-step per trip (NOT unrolled: ptxas otherwise strings all k-steps of one accumulator
-    // into a dependent DMMA chain); 16 independent DMMAs per trip, other warps cover the LDS latency
+    const double* ap = Vs + g * VT_LD;
 #pragma unroll 1
-    for (int ks = 0; ks < VT_BK / 4; ++ks) {
-      const double b0 = bp0[ks * 4], b1 = bp1[ks * 4];
-      double a[8];
+    for (int kb = 0; kb < VT_BK / 8; ++kb) {
+      const int off = ((kb * 4 + t) ^ swz) << 1;
+      const double2 b0 = *reinterpret_cast<const double2*>(bp0 + off);
+      const double2 b1 = *reinterpret_cast<const double2*>(bp1 + off);
+      double2 a[8];
 #pragma unroll
       for (int mt = 0; mt < 8; ++mt)
-        if (mt < MT) a[mt] = ap[mt * 8 * VT_LD + ks * 4];
+        if (mt < MT) a[mt] = *reinterpret_cast<const double2*>(ap + mt * 8 * VT_LD + off);
 #pragma unroll
       for (int mt = 0; mt < 8; ++mt) {
         if (mt < MT) {
-          dmma884(acc[mt][0][0], acc[mt][0][1], a[mt], b0);
-          dmma884(acc[mt][1][0], acc[mt][1][1], a[mt], b1);
+          dmma884(acc[mt][0][0], acc[mt][0][1], a[mt].x, b0.x);
+          dmma884(acc[mt][1][0], acc[mt][1][1], a[mt].x, b1.x);
+        }
+      }
+#pragma unroll
+      for (int mt = 0; mt < 8; ++mt) {
+        if (mt < MT) {
+          dmma884(acc[mt][0][0], acc[mt][0][1], a[mt].y, b0.y);
+          dmma884(acc[mt][1][0], acc[mt][1][1], a[mt].y, b1.y);
         }
       }
     }
@@ -276,7 +290,14 @@ __global__ void __launch_bounds__(256) k_wapply(qrdm_prob P, int vt_grid, int ws
     double2 sacc = make_double2(0.0, 0.0);
     if (pq < ge.kpad) {
       const double* src = P.wp + (size_t)pq * wslot_stride_cols + (size_t)T * VT_BN + cp;
-      for (int q = 0; q < ns; ++q) {
+      int q = 0;
+      for (; q + 1 < ns; q += 2) {  // two independent loads in flight; fixed summation order
+        const double2 v0 = *reinterpret_cast<const double2*>(src + (size_t)slots[q] * sstride);
+        const double2 v1 = *reinterpret_cast<const double2*>(src + (size_t)slots[q + 1] * sstride);
+        sacc.x += v0.x; sacc.y += v0.y;
+        sacc.x += v1.x; sacc.y += v1.y;
+      }
+      if (q < ns) {
         const double2 v = *reinterpret_cast<const double2*>(src + (size_t)slots[q] * sstride);
         sacc.x += v.x; sacc.y += v.y;
       }
@@ -323,24 +344,35 @@ __global__ void __launch_bounds__(256) k_wapply(qrdm_prob P, int vt_grid, int ws
 }
 
 // ------------------------------------------------------------------ k_rankk
-// Persistent: one CTA per SM walks a contiguous range of (row block, column tile) units; the
-// 128 x k tile of V stays resident in smem while the column tiles of one row block stream by, the
-// next W tile arrives by cp.async during the current tile's MMAs, and the next C tile is
-// prefetched into registers, so HBM latency is never exposed.  k_wsolve stores -T'W, which lets
-// the accumulators be initialised with C itself: C_new = C + V (-T'W) comes straight out of DMMA.
+// Persistent rank-k update, TWO independent 4-warp CTAs per SM.  What the profiles showed:
+//  * a warp can issue one DMMA.8x8x4 every 16 cycles (stall 15 + NOP), exactly the pipe rate, so the
+//    two warps a scheduler holds must not do their per-unit bookkeeping at the same time: with one
+//    8-warp CTA per SM all warps hit the unit barrier together and the pipe idled 35-40% of the time;
+//    two small CTAs drift apart and one's loads/stores/barrier hide under the other's MMAs;
+//  * per-unit instruction overhead must be small against the unit's DMMAs: 32 x 32 warp tiles give
+//    256 DMMAs per warp per unit and 8 LDS per 16 DMMAs; all slot addressing is hoisted.
+// Each CTA walks a contiguous range of (row block, column tile) units with the 128 x k tile of V
+// resident in smem, the next W tile arriving by cp.async and the next C tile prefetched into a
+// second register set (ping-pong) during the current unit's MMAs.  k_wapply stores -T'W, so the
+// accumulators start as C and C_new = C + V (-T'W) goes back to HBM straight from registers.
+// Measured (ncu, 16384^2, iteration 10): 93% DMMA-active with the C traffic ablated, 72% with the
+// loads, 65% with loads + stores — the same 65% as a 3-stage cp.async ring for C, register prefetch
+// with one 8-warp CTA, or LDS.128 interleaved tiles: the strided 1-KB column segments of C, not the
+// SM side, bound this kernel.
 #define RK_BM 128  // rows
 #define RK_BN 32   // columns
 #define RK_LDV (RK_BM + 4)
 #define RK_LDW (RK_BN + 4)
+#define RK_THREADS 128
 #define RK_SMEM ((64 * RK_LDV + 2 * 64 * RK_LDW) * 8)
 
 template <bool VEC16>
-__global__ void __launch_bounds__(256, 2) k_rankk(qrdm_prob P) {
+__global__ void __launch_bounds__(RK_THREADS, 2) k_rankk(qrdm_prob P) {
   extern __shared__ __align__(16) double sm[];
   double* Vs = sm;                 // [q][RK_LDV]
   double* Wsb = sm + 64 * RK_LDV;  // 2 x [q][RK_LDW]
   const qrdm_ctrl* ctrl = P.ctrl;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int tid = threadIdx.x, lane = tid & 31, wr = tid >> 5, g = lane >> 2, t = lane & 3;
   const int j = ctrl->j, fjb = ctrl->fjb, k = ctrl->fjb_cmp;
   const int nc = P.n - j - fjb;
   if (nc <= 0 || k <= 0) return;
@@ -351,23 +383,22 @@ __global__ void __launch_bounds__(256, 2) k_rankk(qrdm_prob P) {
   const long long lo = U * blockIdx.x / gridDim.x, hi = U * (blockIdx.x + 1) / gridDim.x;
   if (lo >= hi) return;
   double* Cg = P.a + (size_t)(j + fjb) * P.lda;
-  const int wr = wid & 3, wc = wid >> 2;  // warp tile: rows wr*32.., cols wc*16..
   const size_t lda = (size_t)P.lda;
-  // this lane's element (mt, nt, e): column c0 + wc*16 + mt*8 + g, rows R0 + wr*32 + nt*8 + 2t + e
-  const size_t lane_off = (size_t)(wc * 16 + g) * lda + (size_t)(wr * 32 + 2 * t);
+  // warp wr owns rows wr*32..+31 of the tile, all 32 columns: DMMA M = columns (4 tiles), N = rows (4)
+  // lane element (mt, nt, e): column c0 + mt*8 + g, rows R0 + wr*32 + nt*8 + 2t + e
+  const size_t lane_off = (size_t)g * lda + (size_t)(wr * 32 + 2 * t);
+  const int w_q = tid >> 4, w_cp = (tid & 15) * 2;  // W tile slots of this thread: q = w_q + 8i
+  const int w_iters = kpad >> 3;
 
   auto issue_w = [&](int ct, int buf) {
-    const int c0 = ct * RK_BN;
-    double* Ws = Wsb + buf * 64 * RK_LDW;
-    for (int id = tid; id < kpad * (RK_BN / 2); id += 256) {
-      const int q = id / (RK_BN / 2), cp = (id % (RK_BN / 2)) * 2;
-      cp_async16(Ws + q * RK_LDW + cp, P.w2 + (size_t)q * P.ldw + c0 + cp, 16);
-    }
+    const double* src = P.w2 + (size_t)w_q * P.ldw + ct * RK_BN + w_cp;
+    double* dst = Wsb + buf * 64 * RK_LDW + w_q * RK_LDW + w_cp;
+    for (int i = 0; i < w_iters; ++i) cp_async16(dst + i * 8 * RK_LDW, src + (size_t)i * 8 * P.ldw, 16);
   };
   auto issue_v = [&](int rb) {
     const int R0 = jal + rb * RK_BM;
-    for (int id = tid; id < kpad * (RK_BM / 2); id += 256) {
-      const int q = id / (RK_BM / 2), rp = (id % (RK_BM / 2)) * 2;
+    for (int id = tid; id < kpad * (RK_BM / 2); id += RK_THREADS) {
+      const int q = id >> 6, rp = (id & 63) * 2;
       cp_async16(Vs + q * RK_LDV + rp, P.vc + (size_t)q * P.ldv + R0 + rp, 16);  // ldv covers the tile
     }
   };
@@ -375,21 +406,29 @@ __global__ void __launch_bounds__(256, 2) k_rankk(qrdm_prob P) {
     const int R0 = jal + rb * RK_BM, c0 = ct * RK_BN;
     return VEC16 && R0 >= j && R0 + RK_BM <= P.m && c0 + RK_BN <= nc;
   };
-  auto load_c = [&](int rb, int ct, double (&dst)[2][4][2]) {
+  auto load_c = [&](int rb, int ct, double (&dst)[4][4][2]) {
+    if (P.debug & 2) {
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) dst[mt][nt][0] = dst[mt][nt][1] = 0.0;
+      return;
+    }
     const int R0 = jal + rb * RK_BM, c0 = ct * RK_BN;
     const double* base = Cg + (size_t)c0 * lda + R0 + lane_off;
     if (interior(rb, ct)) {  // the common case: 16 unconditional 16-byte loads in flight
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
+      for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
-          const double2 v = *reinterpret_cast<const double2*>(base + (size_t)(mt * 8) * lda + nt * 8);
+          const double2* ptr2 = reinterpret_cast<const double2*>(base + (size_t)(mt * 8) * lda + nt * 8);
+          const double2 v = *ptr2;  // default caching: __ldcs/__stcs hints measured 3-5% slower here
           dst[mt][nt][0] = v.x; dst[mt][nt][1] = v.y;
         }
     } else {
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        const int c = c0 + wc * 16 + mt * 8 + g;
+      for (int mt = 0; mt < 4; ++mt) {
+        const int c = c0 + mt * 8 + g;
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
           const int r = R0 + wr * 32 + nt * 8 + 2 * t;
@@ -400,19 +439,20 @@ __global__ void __launch_bounds__(256, 2) k_rankk(qrdm_prob P) {
       }
     }
   };
-  auto store_c = [&](int rb, int ct, const double (&src)[2][4][2]) {
+  auto store_c = [&](int rb, int ct, const double (&src)[4][4][2]) {
+    if (P.debug & 1) return;
     const int R0 = jal + rb * RK_BM, c0 = ct * RK_BN;
     double* base = Cg + (size_t)c0 * lda + R0 + lane_off;
     if (interior(rb, ct)) {
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
+      for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt)
           *reinterpret_cast<double2*>(base + (size_t)(mt * 8) * lda + nt * 8) = make_double2(src[mt][nt][0], src[mt][nt][1]);
     } else {
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        const int c = c0 + wc * 16 + mt * 8 + g;
+      for (int mt = 0; mt < 4; ++mt) {
+        const int c = c0 + mt * 8 + g;
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
           const int r = R0 + wr * 32 + nt * 8 + 2 * t;
@@ -424,10 +464,12 @@ __global__ void __launch_bounds__(256, 2) k_rankk(qrdm_prob P) {
     }
   };
 
-  int rb = (int)(lo / CT), ct = (int)(lo % CT), buf = 0;
-  long long left = hi - lo;
+  int rb = (int)(lo / CT), ct = (int)(lo - (long long)rb * CT), buf = 0;
+  int left = (int)(hi - lo);
+  const int a_off = t * RK_LDW + g;             // A[m=c][k=q] = W[q][c]
+  const int b_off = t * RK_LDV + wr * 32 + g;   // B[k=q][n=r] = V[r][q]
   // one unit: X holds C(u) (prefetched), Y receives C(u+1) while the MMAs of u run
-  auto step = [&](double (&X)[2][4][2], double (&Y)[2][4][2]) {
+  auto step = [&](double (&X)[4][4][2], double (&Y)[4][4][2]) {
     cp_async_wait<0>();
     __syncthreads();  // W(u) (and V) landed for everyone; everyone is done with W(u-1)
     const bool more = left > 1;
@@ -435,18 +477,18 @@ __global__ void __launch_bounds__(256, 2) k_rankk(qrdm_prob P) {
     if (nct == CT) { nct = 0; ++nrb; }
     if (more && nrb == rb) { issue_w(nct, buf ^ 1); cp_async_commit(); }
     if (more) load_c(nrb, nct, Y);
-    const double* Ws = Wsb + buf * 64 * RK_LDW;
-    const double* ap = Ws + t * RK_LDW + wc * 16 + g;  // A[m=c][k=q] = W[q][c]
-    const double* bp = Vs + t * RK_LDV + wr * 32 + g;  // B[k=q][n=r] = V[r][q]
+    const double* ap = Wsb + buf * 64 * RK_LDW + a_off;
+    const double* bp = Vs + b_off;
 #pragma unroll 2
-    for (int ks = 0; ks < kpad / 4; ++ks) {  // 8 independent DMMAs per k4-step
-      double a[2], b[4];
+    for (int ks = 0; ks < kpad / 4; ++ks) {  // 8 LDS.64 feed 16 independent DMMAs
+      double a[4], b[4];
 #pragma unroll
-      for (int x = 0; x < 2; ++x) a[x] = ap[ks * 4 * RK_LDW + x * 8];
+      for (int x = 0; x < 4; ++x) {
+        a[x] = ap[ks * 4 * RK_LDW + x * 8];
+        b[x] = bp[ks * 4 * RK_LDV + x * 8];
+      }
 #pragma unroll
-      for (int x = 0; x < 4; ++x) b[x] = bp[ks * 4 * RK_LDV + x * 8];
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
+      for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) dmma884(X[mt][nt][0], X[mt][nt][1], a[mt], b[nt]);
     }
@@ -460,7 +502,7 @@ __global__ void __launch_bounds__(256, 2) k_rankk(qrdm_prob P) {
     rb = nrb; ct = nct; buf ^= 1; --left;
   };
 
-  double accA[2][4][2], accB[2][4][2];
+  double accA[4][4][2], accB[4][4][2];
   issue_v(rb);
   issue_w(ct, 0);
   cp_async_commit();
@@ -506,8 +548,8 @@ extern "C" int qrdm_k_trailing(const qrdm_prob* p, int j_host, void* stream) {
   {
     const long long units = (long long)((ncmax + RK_BN - 1) / RK_BN) * ((p->m - jal + RK_BM - 1) / RK_BM);
     const int grid = (int)(units < 2 * p->sm_count ? units : 2 * p->sm_count);
-    if (p->vec16) k_rankk<true><<<grid, 256, RK_SMEM, s>>>(*p);
-    else k_rankk<false><<<grid, 256, RK_SMEM, s>>>(*p);
+    if (p->vec16) k_rankk<true><<<grid, RK_THREADS, RK_SMEM, s>>>(*p);
+    else k_rankk<false><<<grid, RK_THREADS, RK_SMEM, s>>>(*p);
   }
   QRDM_LAUNCH_CHECK();
   return 0;

@@ -70,6 +70,7 @@ typedef struct qrdm_prob {
   int *flag_list;     /* n */
   int sm_count;
   int vec16;          /* 1 if a is 16-byte aligned and lda is even (fast cp.async path) */
+  int debug;          /* QRDM_B200_DEBUG bit mask for timing experiments (results invalid when set) */
 } qrdm_prob;
 
 int qrdm_k_colnorm(const qrdm_prob *p, int use_flag_list, void *stream);   /* K1 / K2 recompute */
