@@ -38,7 +38,16 @@ typedef struct {
   qrdm_ctrl *mailbox;
   void *ev[4];
   void *ev_stage[2];
+  void *compute_stream, *copy_stream; /* non-blocking streams of the host-pointer entry points */
 } qrdm_workspace;
+
+/* optional streaming write-back of finished columns (host-pointer entry point, pinned buffers) */
+typedef struct {
+  double *h_a;
+  int h_lda;
+  void *copy_stream;
+  int done_cols; /* columns [0, done_cols) already enqueued for D2H */
+} qrdm_writeback;
 
 static qrdm_workspace g_ws;
 static qrdm_b200_stats g_stats;
@@ -90,11 +99,15 @@ int qrdm_b200_init(int device) {
   CU(qrdm_rt_malloc((void **)&w->ctrl, sizeof(qrdm_ctrl)));
   CU(qrdm_rt_malloc((void **)&w->gram_part, sizeof(double) * 4096 * QRDM_GRAM_MAXCTA));
   CU(qrdm_rt_malloc((void **)&w->gram, sizeof(double) * 4096));
-  CU(qrdm_rt_malloc((void **)&w->panel_part, sizeof(double) * 2 * QRDM_PANEL_MAXCTA * 64));
-  CU(qrdm_rt_malloc((void **)&w->panel_row, sizeof(double) * 2 * 64));
+  CU(qrdm_rt_malloc((void **)&w->panel_part, 16 * 2 * QRDM_PANEL_MAXCTA * 64)); /* LL packets */
+  CU(qrdm_rt_memset(w->panel_part, 0, 16 * 2 * QRDM_PANEL_MAXCTA * 64, NULL));
+  CU(qrdm_rt_malloc((void **)&w->panel_row, 16 * 2 * 128));
+  CU(qrdm_rt_memset(w->panel_row, 0, 16 * 2 * 128, NULL));
   CU(qrdm_rt_host_alloc((void **)&w->mailbox, sizeof(qrdm_ctrl)));
   for (int i = 0; i < 4; ++i) CU(qrdm_rt_event_create(&w->ev[i]));
   for (int i = 0; i < 2; ++i) CU(qrdm_rt_event_create(&w->ev_stage[i]));
+  CU(qrdm_rt_stream_create(&w->compute_stream));
+  CU(qrdm_rt_stream_create(&w->copy_stream));
   w->ready = 1;
   if (g_profile < 0) {
     const char *e = getenv("QRDM_B200_PROFILE");
@@ -204,7 +217,7 @@ static int read_mailbox(const qrdm_prob *p, void *stream) {
 
 /* The factorisation proper on device-resident data. */
 static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double *d_tau, int *ncols,
-                         const double *thres, int nb, void *stream) {
+                         const double *thres, int nb, void *stream, qrdm_writeback *wb) {
   qrdm_workspace *w = &g_ws;
   const double eps = DBL_EPSILON * 0.5; /* dlamch('e'), src/dgeqrdm_work.c:528 */
   const int minmn = m < n ? m : n;
@@ -274,6 +287,15 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
     }
     g_stats.trailing_flops += 4.0 * (double)(m - j) * (double)(cols - k) * (double)k;
     j += k;
+    if (wb) {
+      /* columns [done, j) are final (later iterations only touch columns >= j, and the mailbox
+       * sync above means every kernel of this iteration has finished): stream them to the host
+       * while the next iterations compute */
+      CU(qrdm_rt_d2h_2d(wb->h_a + (size_t)wb->done_cols * wb->h_lda, sizeof(double) * wb->h_lda,
+                        d_a + (size_t)wb->done_cols * lda, sizeof(double) * lda, sizeof(double) * m,
+                        (size_t)(j - wb->done_cols), wb->copy_stream));
+      wb->done_cols = j;
+    }
     if (stop_mode && mb->maxnrm * sqrt((double)(cols - k)) <= eta) break; /* :782-785 */
   }
   CU(qrdm_rt_event_record(w->ev[1], stream));
@@ -293,7 +315,7 @@ int dgeqrdm_dev(int m, int n, double *d_a, int lda, int *d_jpvt, double *d_tau, 
                 const double *thres, int nb, void *stream) {
   int rc = check_args(QRDM_COL_MAJOR, m, n, lda, thres, nb);
   if (rc) return rc;
-  return factor_device(m, n, d_a, lda, d_jpvt, d_tau, ncols, thres, nb, stream);
+  return factor_device(m, n, d_a, lda, d_jpvt, d_tau, ncols, thres, nb, stream, NULL);
 }
 
 int dgeqrdm_work(int matrix_layout, int m, int n, double *a, int lda, int *jpvt, double *tau,
@@ -309,7 +331,7 @@ int dgeqrdm_work(int matrix_layout, int m, int n, double *a, int lda, int *jpvt,
     }
   rc = qrdm_b200_init(-1);
   if (rc) return rc;
-  void *stream = NULL;
+  void *stream = w->compute_stream;
   const int minmn = m < n ? m : n;
   const int ldd = (m + 1) & ~1; /* even leading dimension on the device: 16-byte aligned columns */
   const size_t a_bytes = sizeof(double) * (size_t)ldd * n;
@@ -337,11 +359,20 @@ int dgeqrdm_work(int matrix_layout, int m, int n, double *a, int lda, int *jpvt,
   CU(qrdm_rt_h2d_2d(w->d_a, sizeof(double) * ldd, a, sizeof(double) * lda, sizeof(double) * m, n, stream));
   CU(qrdm_rt_h2d(w->d_tau, tau, sizeof(double) * minmn, stream)); /* entries >= rank stay as given */
   CU(qrdm_rt_event_record(w->ev[3], stream));
-  int info = factor_device(m, n, w->d_a, ldd, w->d_jpvt, w->d_tau, ncols, thres, nb, stream);
+  /* pinned host buffer: overlap the D2H of finished columns with the rest of the factorisation */
+  qrdm_writeback wb = {a, lda, w->copy_stream, 0};
+  const int overlap = qrdm_rt_is_pinned(a) && !getenv("QRDM_B200_NO_OVERLAP");
+  int info = factor_device(m, n, w->d_a, ldd, w->d_jpvt, w->d_tau, ncols, thres, nb, stream, overlap ? &wb : NULL);
   if (info <= QRDM_ERR_CUDA) return info;
   const double ms_h2d = qrdm_rt_event_ms(w->ev[2], w->ev[3]);
   CU(qrdm_rt_event_record(w->ev[2], stream));
-  CU(qrdm_rt_d2h_2d(a, sizeof(double) * lda, w->d_a, sizeof(double) * ldd, sizeof(double) * m, n, stream));
+  {
+    const int done = overlap ? wb.done_cols : 0; /* the unreduced tail (early stop / error) */
+    if (done < n)
+      CU(qrdm_rt_d2h_2d(a + (size_t)done * lda, sizeof(double) * lda, w->d_a + (size_t)done * ldd,
+                        sizeof(double) * ldd, sizeof(double) * m, (size_t)(n - done), stream));
+    if (overlap) CU(qrdm_rt_sync(w->copy_stream));
+  }
   CU(qrdm_rt_d2h(jpvt, w->d_jpvt, sizeof(int) * n, stream));
   CU(qrdm_rt_d2h(tau, w->d_tau, sizeof(double) * minmn, stream));
   CU(qrdm_rt_event_record(w->ev[3], stream));

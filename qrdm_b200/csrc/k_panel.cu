@@ -12,6 +12,7 @@
 // CTAs take bit-identical decisions (stop test, tau) and the result is run-to-run deterministic.
 // Also emits the clean copy Vc of the reflectors (unit diagonal, zeros above, zero-padded to a
 // multiple of 8 columns) that the trailing-update kernels consume.
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -21,23 +22,35 @@
 #define PANEL_CPW ((63 + PANEL_WARPS - 1) / PANEL_WARPS)  // columns per warp in the sweep
 #define PANEL_RG (PANEL_THREADS / 64)                      // reduction groups
 
-// Grid-wide barrier on a monotonically increasing counter (reset by k_pick).  Release/acquire at
-// gpu scope instead of __threadfence(): no L1 invalidation (CCTL.IVALL) on the critical path; data
-// written by other CTAs is read with ld.global.cg (L2), see the reduction below.
-__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& target, unsigned nctas) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    target += nctas;
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(bar) : "memory");
-    while (ld_acquire_u32(bar) < target) { }
-  }
-  __syncthreads();
+// Cross-CTA exchange without barriers: every value travels as a 16-byte "LL" packet
+// {lo32, tag, hi32, tag} (the scheme NCCL's low-latency protocol uses): an aligned 8-byte store is
+// atomic, so a reader that sees the expected tag in both halves has the payload — no fence, no
+// counter, one L2 round trip.  tag = (panel launch epoch << 8) + step + 1 is never reused.
+// Per column the reduction is a reduce-scatter + broadcast: CTA (jj mod G) gathers the G partials of
+// column jj, sums them in a fixed order (deterministic) and publishes the total; everybody then
+// polls the 64 totals + the 64 entries of the pivot row published by the CTA that owns that row.
+// Traffic per column ~ G*64 packets instead of the G*G*64 of an all-to-all read, latency two
+// round trips, and identical inputs on every CTA => bit-identical decisions (stop test, tau).
+struct __align__(16) LLPacket { unsigned lo, tag0, hi, tag1; };
+
+__device__ __forceinline__ void ll_store(LLPacket* p, double v, unsigned tag) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "r"((unsigned)b), "r"(tag),
+               "r"((unsigned)(b >> 32)), "r"(tag)
+               : "memory");
+}
+__device__ __forceinline__ double ll_load(const LLPacket* p, unsigned tag) {
+  unsigned lo, t0, hi, t1;
+  do {
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(lo), "=r"(t0), "=r"(hi), "=r"(t1) : "l"(p) : "memory");
+  } while (t0 != tag || t1 != tag);
+  return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
 }
 
 template <bool SMEM>
-__global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(qrdm_prob P, int rpc) {
+__global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(qrdm_prob P, int rpc, unsigned epoch) {
   extern __shared__ __align__(16) double slab[];  // SMEM mode: [64][rpc]
-  __shared__ double sred[PANEL_RG][64];
+  __shared__ double sred[PANEL_WARPS];
   __shared__ double S_[64], rowv[64], wv[64];
   qrdm_ctrl* ctrl = P.ctrl;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -48,9 +61,9 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(qrdm_prob P, int rpc
   const int r0 = min(rows, b * rpc), r1 = min(rows, r0 + rpc), nr = r1 - r0;
   double* Ap = P.a + (size_t)j * lda + j;
   const int lds = rpc;
-  double* part = P.panel_part;  // [2][PANEL_MAXCTA][64]
-  double* rowb = P.panel_row;   // [2][64]
-  unsigned bar_target = 0;
+  LLPacket* part = reinterpret_cast<LLPacket*>(P.panel_part);  // [2][PANEL_MAXCTA][64]
+  LLPacket* bcast = reinterpret_cast<LLPacket*>(P.panel_row);  // [2][128]: 64 totals + 64 pivot-row entries
+  const unsigned tag_base = epoch << 8;
 
 #define PX(r, c) (SMEM ? slab[(c) * lds + (r)] : Ap[(size_t)(c) * lda + (size_t)(r0 + (r))])
 
@@ -60,51 +73,53 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(qrdm_prob P, int rpc
     __syncthreads();
   }
 
-  // partial sums for column 0: S_j = sum_{R>0} P[R,0] P[R,j]; row 0 itself goes to rowb[0]
+  // partial sums for column 0: S_j = sum_{R>0} P[R,0] P[R,j]; row 0 itself is published directly
   for (int jj = wid; jj < fjb; jj += PANEL_WARPS) {
     double acc = 0.0;
     for (int r = lane; r < nr; r += 32) {
       const int R = r0 + r;
       const double p = PX(r, jj);
       if (R > 0) acc = fma(PX(r, 0), p, acc);
-      else rowb[jj] = p;
+      else ll_store(&bcast[64 + jj], p, tag_base + 1);
     }
     acc = warp_sum(acc);
-    if (lane == 0) part[(size_t)b * 64 + jj] = acc;
+    if (lane == 0) ll_store(&part[(size_t)b * 64 + jj], acc, tag_base + 1);
   }
-  grid_barrier(&ctrl->panel_bar, bar_target, G);
 
   double thres = 5e-14;  // reference src/dgeqr2.c:40
   int k = fjb;
+  long long tph[5] = {0, 0, 0, 0, 0};  // QRDM_B200_DEBUG & 8: per-phase cycle counts of CTA 0
+  const bool timing = (P.debug & 8) && b == 0 && tid == 0;
   for (int i = 0; i < fjb; ++i) {
     const int cur = i & 1, nxt = cur ^ 1;
-    // ---- fixed-order reduction of the partials (identical on every CTA => identical decisions) ----
-    {
-      const int jj = tid & 63, q = tid >> 6;
-      double s = 0.0;
-      if (jj >= i && jj < fjb) {
-        const double* src = part + ((size_t)cur * QRDM_PANEL_MAXCTA) * 64 + jj;
-        for (int bb0 = q; bb0 < G; bb0 += 8 * PANEL_RG) {
-          double v[8];
+    const unsigned tag = tag_base + i + 1;
+    long long tq0 = timing ? clock64() : 0;
+    // ---- reduce-scatter: this CTA totals the columns jj == b (mod G) ----
+    for (int jj = i + ((b - i % G + G) % G); jj < fjb; jj += G) {
+      double v = 0.0;
+      if (tid < G) v = ll_load(&part[((size_t)cur * QRDM_PANEL_MAXCTA + tid) * 64 + jj], tag);
+      v = warp_sum(v);                       // lanes <-> CTAs: fixed association order
+      if (lane == 0) sred[wid] = v;
+      __syncthreads();
+      if (tid == 0) {
+        double tot = 0.0;
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int bb = bb0 + u * PANEL_RG;
-            v[u] = bb < G ? __ldcg(src + (size_t)bb * 64) : 0.0;  // L2: written by other SMs
-          }
-          s += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
-        }
+        for (int w = 0; w < PANEL_WARPS; ++w) tot += sred[w];
+        ll_store(&bcast[cur * 128 + jj], tot, tag);
       }
-      sred[q][jj] = s;
+      __syncthreads();
+    }
+    if (timing) { const long long tq = clock64(); tph[0] += tq - tq0; tq0 = tq; }
+    // ---- broadcast: everybody picks up the totals and the pivot row ----
+    if (tid < 128) {
+      const int jj = tid & 63;
+      if (jj >= i && jj < fjb) {
+        const double v = ll_load(&bcast[cur * 128 + tid], tag);
+        if (tid < 64) S_[jj] = v; else rowv[jj] = v;
+      }
     }
     __syncthreads();
-    if (tid < 64) {
-      double s = 0.0;
-#pragma unroll
-      for (int q = 0; q < PANEL_RG; ++q) s += sred[q][tid];
-      S_[tid] = s;
-      rowv[tid] = __ldcg(&rowb[cur * 64 + tid]);
-    }
-    __syncthreads();
+    if (timing) { const long long tq = clock64(); tph[1] += tq - tq0; tq0 = tq; }
     // ---- reflector scalars: dlarfg_mia (src/dlarfg.c:120-185), redundantly on every thread ----
     const double alpha = rowv[i];
     const int len = rows - i;
@@ -141,10 +156,11 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(qrdm_prob P, int rpc
       if (!last) {
         const double p = fma(-v, w1, PX(r, i + 1));
         PX(r, i + 1) = p;
-        if (R == i + 1) rowb[nxt * 64 + i + 1] = p;
+        if (R == i + 1) ll_store(&bcast[nxt * 128 + 64 + i + 1], p, tag + 1);
       }
     }
     __syncthreads();
+    if (timing) { const long long tq = clock64(); tph[2] += tq - tq0; tq0 = tq; }
     if (last) break;
     // ---- phase 2: remaining columns + the fused dot products for the next reflector ----
     {
@@ -171,7 +187,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(qrdm_prob P, int rpc
             } else {
               p = fma(-v, wreg[c], PX(r, jj));
               PX(r, jj) = p;
-              if (R == i + 1) rowb[nxt * 64 + jj] = p;
+              if (R == i + 1) ll_store(&bcast[nxt * 128 + 64 + jj], p, tag + 1);
             }
             if (below) acc[c] = fma(x1, p, acc[c]);
           }
@@ -181,11 +197,15 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(qrdm_prob P, int rpc
       for (int c = 0; c < PANEL_CPW; ++c) {
         const int jj = i + 1 + wid + c * PANEL_WARPS;
         const double a = warp_sum(acc[c]);
-        if (lane == 0 && jj < fjb) part[((size_t)nxt * QRDM_PANEL_MAXCTA + b) * 64 + jj] = a;
+        if (lane == 0 && jj < fjb) ll_store(&part[((size_t)nxt * QRDM_PANEL_MAXCTA + b) * 64 + jj], a, tag + 1);
       }
     }
-    grid_barrier(&ctrl->panel_bar, bar_target, G);
+    __syncthreads();  // sred / S_ / rowv / wv are rewritten by the next step
+    if (timing) { const long long tq = clock64(); tph[3] += tq - tq0; tq0 = tq; }
   }
+  if (timing && j == 640)
+    printf("panel j=%d G=%d rpc=%d fjb=%d cycles: reduce %lld bcast %lld scalars+phase1 %lld phase2 %lld\n", j, G, rpc, fjb,
+           tph[0], tph[1], tph[2], tph[3]);
   __syncthreads();
   if (b == 0 && tid == 0) ctrl->fjb_cmp = k;
 
@@ -211,6 +231,221 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(qrdm_prob P, int rpc
 #undef PX
 }
 
+// ---------------------------------------------------------------------------------------------
+// Register-resident variant for panels of <= 128 rows per CTA (m_r <= 128 * #SMs = 18944 on B200:
+// every square BASELINE config).  The cycle counters of the smem version (QRDM_B200_DEBUG=8) showed
+// the per-column time was NOT the cross-CTA exchange but the SM-local work: ~3100 cycles of sweep
+// (shared-memory bandwidth: every element read and written through smem each column) and ~3700
+// cycles of reflector scalars computed redundantly by 512 threads on the 64-lane FP64 pipe.  Here
+// each thread keeps its 16 slab entries (rows lane+32*ri, columns wid+16*c) in registers for the
+// whole panel; only the two active columns (v and the next pivot column) pass through smem, the
+// scalars are computed once per warp with a single sqrt (beta^2 = alpha^2 + ||x||^2, stop test on
+// ||x||^2 < thres^2), and the exchange stays the LL reduce-scatter + broadcast of the kernel above.
+__global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_reg(qrdm_prob P, int rpc, unsigned epoch) {
+  __shared__ double sred[PANEL_WARPS];
+  __shared__ double S_[64], rowv[64], wv[64];
+  __shared__ double vbuf[128], xbuf[128];
+  qrdm_ctrl* ctrl = P.ctrl;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int j = ctrl->j, fjb = ctrl->fjb;
+  if (fjb <= 0) return;
+  const int rows = P.m - j, lda = P.lda;
+  const int G = gridDim.x, b = blockIdx.x;
+  const int r0 = min(rows, b * rpc), r1 = min(rows, r0 + rpc), nr = r1 - r0;  // nr <= 128
+  double* Ap = P.a + (size_t)j * lda + j;
+  LLPacket* part = reinterpret_cast<LLPacket*>(P.panel_part);
+  LLPacket* bcast = reinterpret_cast<LLPacket*>(P.panel_row);
+  const unsigned tag_base = epoch << 8;
+
+  double reg[4][4];  // [ri][c]: row r0 + lane + 32*ri, column wid + 16*c
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int ri = 0; ri < 4; ++ri) {
+      const int r = lane + 32 * ri, jj = wid + 16 * c;
+      reg[ri][c] = (r < nr && jj < fjb) ? Ap[(size_t)jj * lda + r0 + r] : 0.0;
+    }
+  // column 0 through smem so that everybody can form the first dot products
+  if (wid == 0) {
+#pragma unroll
+    for (int ri = 0; ri < 4; ++ri) xbuf[lane + 32 * ri] = reg[ri][0];
+  }
+  __syncthreads();
+  {
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int ri = 0; ri < 4; ++ri) {
+      const int r = lane + 32 * ri, R = r0 + r;
+      const double x0 = xbuf[r];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int jj = wid + 16 * c;
+        if (r < nr && jj < fjb) {
+          if (R > 0) acc[c] = fma(x0, reg[ri][c], acc[c]);
+          else ll_store(&bcast[64 + jj], reg[ri][c], tag_base + 1);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int jj = wid + 16 * c;
+      const double a = warp_sum(acc[c]);
+      if (lane == 0 && jj < fjb) ll_store(&part[(size_t)b * 64 + jj], a, tag_base + 1);
+    }
+  }
+  __syncthreads();
+
+  double thres2 = 5e-14 * 5e-14;  // (reference src/dgeqr2.c:40)^2
+  int k = fjb;
+  long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // QRDM_B200_DEBUG & 8: per-phase cycle counts of one CTA
+  const bool timing = (P.debug & 8) && b == (G > 40 ? 40 : 0) && tid == 0;
+  for (int i = 0; i < fjb; ++i) {
+    const int cur = i & 1, nxt = cur ^ 1;
+    const unsigned tag = tag_base + i + 1;
+    long long tq0 = timing ? clock64() : 0;
+    // ---- reduce-scatter: this CTA totals the columns jj == b (mod G) ----
+    for (int jj = i + ((b - i % G + G) % G); jj < fjb; jj += G) {
+      double v = 0.0;
+      if (tid < G) v = ll_load(&part[((size_t)cur * QRDM_PANEL_MAXCTA + tid) * 64 + jj], tag);
+      v = warp_sum(v);
+      if (lane == 0) sred[wid] = v;
+      __syncthreads();
+      if (tid == 0) {
+        double tot = 0.0;
+#pragma unroll
+        for (int w = 0; w < PANEL_WARPS; ++w) tot += sred[w];
+        ll_store(&bcast[cur * 128 + jj], tot, tag);
+      }
+      __syncthreads();
+    }
+    if (timing) { const long long tq = clock64(); tph[0] += tq - tq0; tq0 = tq; }
+    // ---- broadcast: everybody picks up the totals and the pivot row ----
+    if (tid < 128) {
+      const int jj = tid & 63;
+      if (jj >= i && jj < fjb) {
+        const double v = ll_load(&bcast[cur * 128 + tid], tag);
+        if (tid < 64) S_[jj] = v; else rowv[jj] = v;
+      }
+    }
+    __syncthreads();
+    if (timing) { const long long tq = clock64(); tph[1] += tq - tq0; tq0 = tq; }
+    // ---- reflector scalars (dlarfg_mia, src/dlarfg.c:120-185), one sqrt, two divisions ----
+    const double alpha = rowv[i], xn2 = S_[i];
+    const int len = rows - i;
+    double tau = 0.0, beta = alpha, scale = 1.0;
+    if (len > 1) {
+      if (i > 0 && xn2 < thres2) { k = i; break; }  // DM early stop: column i left untouched
+      if (xn2 != 0.0) {
+        const double h = sqrt(fma(alpha, alpha, xn2));
+        beta = (alpha >= 0.0) ? -h : h;
+        tau = (beta - alpha) / beta;
+        scale = 1.0 / (alpha - beta);
+      }
+    }
+    if (i == 0 && fjb > 1 && P.tau_ > 0.0) { const double th = P.tau_ * fabs(beta); thres2 = th * th; }
+    if (b == 0 && tid == 0) {
+      P.tau[j + i] = tau;
+      if (tau != tau && ctrl->err == 0) ctrl->err = -8;  // LAPACKE_dlarft's NaN screen of tau
+    }
+    if (timing) { const long long tq = clock64(); tph[5] += tq - tq0; }
+    const bool last = i + 1 >= fjb;
+    const int wi = i & 15, ci = i >> 4;
+    // ---- publish v (column i, scaled) and the old next pivot column through smem ----
+    if (wid == wi) {
+#pragma unroll
+      for (int ri = 0; ri < 4; ++ri) {
+        const int r = lane + 32 * ri, R = r0 + r;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c == ci) {
+            double v = 0.0;
+            if (r < nr) {
+              if (R > i) { v = reg[ri][c]; if (tau != 0.0) { v *= scale; reg[ri][c] = v; } }
+              else if (R == i) { v = 1.0; reg[ri][c] = beta; }
+            }
+            vbuf[r] = v;
+          }
+        }
+      }
+    }
+    if (!last && wid == ((i + 1) & 15)) {
+      const int c1 = (i + 1) >> 4;
+#pragma unroll
+      for (int ri = 0; ri < 4; ++ri)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c == c1) xbuf[lane + 32 * ri] = reg[ri][c];
+    }
+    if (tid < 64 && tid > i && tid < fjb) wv[tid] = tau * (rowv[tid] + S_[tid] * scale);
+    if (timing) { const long long tq = clock64(); tph[6] += tq - tq0; }
+    __syncthreads();
+    if (timing) { const long long tq = clock64(); tph[2] += tq - tq0; tq0 = tq; }
+    if (last) break;
+    // ---- sweep: apply H_i to the remaining columns, fused dot products for the next reflector ----
+    {
+      const double w1 = wv[i + 1];
+      double wreg[4], acc[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int jj = wid + 16 * c;
+        wreg[c] = (jj > i && jj < fjb) ? wv[jj] : 0.0;
+        acc[c] = 0.0;
+      }
+#pragma unroll
+      for (int ri = 0; ri < 4; ++ri) {
+        const int r = lane + 32 * ri, R = r0 + r;
+        const double v = vbuf[r];
+        const double x1 = fma(-v, w1, xbuf[r]);  // next pivot column after H_i
+        const bool below = R > i + 1 && r < nr;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int jj = wid + 16 * c;
+          if (jj > i && jj < fjb) {
+            const double p = fma(-v, wreg[c], reg[ri][c]);
+            reg[ri][c] = p;
+            if (below) acc[c] = fma(x1, p, acc[c]);
+            else if (R == i + 1 && r < nr) ll_store(&bcast[nxt * 128 + 64 + jj], p, tag + 1);
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int jj = wid + 16 * c;
+        const double a = warp_sum(acc[c]);
+        if (lane == 0 && jj > i && jj < fjb) ll_store(&part[((size_t)nxt * QRDM_PANEL_MAXCTA + b) * 64 + jj], a, tag + 1);
+      }
+    }
+    if (timing) { const long long tq = clock64(); tph[3] += tq - tq0; tq0 = tq; }
+    __syncthreads();  // vbuf / xbuf / S_ / rowv / wv are rewritten by the next step
+    if (timing) { const long long tq = clock64(); tph[4] += tq - tq0; tq0 = tq; }
+  }
+  if (timing && j == 640)
+    printf("panel_reg j=%d G=%d rpc=%d fjb=%d cycles: reduce %lld bcast %lld scalars+publish %lld (scalars %lld, to-sync %lld) sweep %lld endsync %lld\n", j, G, rpc, fjb,
+           tph[0], tph[1], tph[2], tph[5], tph[6], tph[3], tph[4]);
+  __syncthreads();
+  if (b == 0 && tid == 0) ctrl->fjb_cmp = k;
+
+  // ---- write the slab back and emit Vc ----
+  const int kpad = (k + 7) & ~7;
+  const int jal = j & ~(QRDM_ROWALIGN - 1);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int jj = wid + 16 * c;
+#pragma unroll
+    for (int ri = 0; ri < 4; ++ri) {
+      const int r = lane + 32 * ri, R = r0 + r;
+      if (r < nr && jj < fjb) Ap[(size_t)jj * lda + R] = reg[ri][c];
+      if (r < nr && jj < kpad) {
+        double v = 0.0;
+        if (jj < k) v = (R > jj) ? reg[ri][c] : (R == jj ? 1.0 : 0.0);
+        P.vc[(size_t)jj * P.ldv + j + R] = v;
+      }
+    }
+    if (b == 0 && jj < kpad)
+      for (int g = jal + lane; g < j; g += 32) P.vc[(size_t)jj * P.ldv + g] = 0.0;
+  }
+}
+
 extern "C" int qrdm_k_panel(const qrdm_prob* p, int j_host, void* stream) {
   static bool attr_set = false;
   static int rows_per_cta = 128;
@@ -226,14 +461,26 @@ extern "C" int qrdm_k_panel(const qrdm_prob* p, int j_host, void* stream) {
   // few, fat CTAs: the per-column cost is the grid barrier + the all-to-all read of the partials,
   // both proportional to the CTA count; grow the grid only when the slab would not fit in smem
   const int gmax = p->sm_count < QRDM_PANEL_MAXCTA ? p->sm_count : QRDM_PANEL_MAXCTA;
+  if (rows <= 128 * gmax && !getenv("QRDM_PANEL_NOREG")) {  // register-resident slabs, 128 rows per CTA
+    int Gr = (rows + 127) / 128, rpcr = (rows + Gr - 1) / Gr;
+    static unsigned epoch_r = 0x400000;
+    epoch_r = epoch_r + 1 >= 0x7fffff ? 0x400000 : epoch_r + 1;
+    qrdm_prob prob_r = *p;
+    void* args_r[] = {(void*)&prob_r, (void*)&rpcr, (void*)&epoch_r};
+    cudaError_t er = cudaLaunchCooperativeKernel((void*)k_panel_reg, dim3(Gr), dim3(PANEL_THREADS), args_r, 0, (cudaStream_t)stream);
+    ++g_qrdm_launches;
+    return er == cudaSuccess ? 0 : (int)er;
+  }
   int G = (rows + rows_per_cta - 1) / rows_per_cta;
   const int gfit = (rows + (smem_cap / 512) - 1) / (smem_cap / 512);  // CTAs needed for smem residency
   if (G < gfit) G = gfit;
   if (G > gmax) G = gmax;
   if (G < 1) G = 1;
   int rpc = (rows + G - 1) / G;
+  static unsigned epoch = 0;
+  epoch = epoch + 1 >= 0x400000 ? 1 : epoch + 1;  // tags (epoch << 8) + step; the register kernel uses the upper half
   qrdm_prob prob = *p;
-  void* args[] = {(void*)&prob, (void*)&rpc};
+  void* args[] = {(void*)&prob, (void*)&rpc, (void*)&epoch};
   const size_t smem = (size_t)rpc * 64 * sizeof(double);
   cudaError_t e;
   if (smem <= (size_t)smem_cap)

@@ -57,8 +57,8 @@ typedef struct qrdm_prob {
   qrdm_ctrl *ctrl;
   double *gram_part;  /* [QRDM_GRAM_MAXCTA][64*64] partial Gram blocks */
   double *gram;       /* [64*64] reduced Gram (candidates, then V'V) */
-  double *panel_part; /* [2][QRDM_PANEL_MAXCTA][64] */
-  double *panel_row;  /* [2][64] */
+  double *panel_part; /* [2][QRDM_PANEL_MAXCTA][64] 16-byte LL packets (partial column sums) */
+  double *panel_row;  /* [2][128] LL packets: 64 column totals + 64 pivot-row entries */
   double *vc;         /* ldv x 64 clean copy of V (unit diagonal, zeros above), rows = global rows */
   int ldv;            /* multiple of QRDM_ROWALIGN, >= roundup(m, QRDM_ROWALIGN) */
   double *wp;         /* [splits][64][ldw] partial W = V'C */
@@ -93,6 +93,9 @@ int qrdm_rt_d2h(void *dst, const void *src, size_t bytes, void *stream);
 int qrdm_rt_h2d_2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height, void *stream);
 int qrdm_rt_d2h_2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height, void *stream);
 int qrdm_rt_sync(void *stream);
+int qrdm_rt_stream_create(void **stream);
+int qrdm_rt_is_pinned(const void *ptr);
+int qrdm_rt_stream_wait_event(void *stream, void *ev);
 int qrdm_rt_event_create(void **ev);
 int qrdm_rt_event_record(void *ev, void *stream);
 int qrdm_rt_event_sync(void *ev);

@@ -27,6 +27,13 @@ int qrdm_rt_h2d_2d(void* dst, size_t dpitch, const void* src, size_t spitch, siz
 int qrdm_rt_d2h_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, void* stream) {
   return (int)cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
 }
+int qrdm_rt_stream_create(void** stream) { return (int)cudaStreamCreateWithFlags((cudaStream_t*)stream, cudaStreamNonBlocking); }
+int qrdm_rt_is_pinned(const void* ptr) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return at.type == cudaMemoryTypeHost ? 1 : 0;
+}
+int qrdm_rt_stream_wait_event(void* stream, void* ev) { return (int)cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)ev, 0); }
 int qrdm_rt_sync(void* stream) { return (int)cudaStreamSynchronize((cudaStream_t)stream); }
 int qrdm_rt_event_create(void** ev) { return (int)cudaEventCreate((cudaEvent_t*)ev); }
 int qrdm_rt_event_record(void* ev, void* stream) { return (int)cudaEventRecord((cudaEvent_t)ev, (cudaStream_t)stream); }

@@ -156,6 +156,30 @@ def test_device_resident_entry_point(q, oracle_ref):
     parity.check_against(host, exp, (m, n))
 
 
+def test_pinned_host_buffer_streams_columns_back(q):
+    """With a pinned host buffer the entry point overlaps the D2H of finished columns with the rest
+    of the factorisation (second stream); results must be bit-identical to the pageable path,
+    also when the stop rule leaves an unreduced tail."""
+    import torch
+    from qrdm_b200 import _lib
+    for A, stop in ((g.gaussian(1500, 900, 14), 0), (g.graded(700, seed=6), 1)):
+        m, n = A.shape
+        ref_out = q.dgeqrdm(A, stop_mode=stop)
+        hA = torch.empty((n, m), dtype=torch.float64, pin_memory=True)      # (n, m) row-major == column-major
+        hA.copy_(torch.from_numpy(np.ascontiguousarray(A.T)))
+        jpvt = np.zeros(n, dtype=np.int32)
+        tau = np.zeros(min(m, n))
+        ncols = np.zeros(n, dtype=np.int32)
+        ncols[0] = stop
+        th = np.array([0.9, 0.15, 0.0])
+        info = _lib.lib.dgeqrdm(102, m, n, hA.data_ptr(), m, jpvt.ctypes.data, tau.ctypes.data,
+                                ncols.ctypes.data, th.ctypes.data, 64)
+        assert info == 0
+        assert np.array_equal(hA.numpy().T, ref_out["A"])
+        assert np.array_equal(jpvt, ref_out["jpvt"]) and np.array_equal(ncols, ref_out["ncols"])
+        assert np.array_equal(tau, ref_out["tau"])
+
+
 def test_bitwise_determinism(q):
     A = g.gaussian(1200, 800, 13)
     a = q.dgeqrdm(A)
