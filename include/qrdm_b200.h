@@ -55,6 +55,19 @@ int dgeqrdm_work(int matrix_layout, int m, int n, double *a, int lda, int *jpvt,
 int dgeqrdm_dev(int m, int n, double *d_a, int lda, int *d_jpvt, double *d_tau, int *ncols,
                 const double *thres, int nb, void *stream);
 
+/* Addition: 1-D block-row sharded factorisation across the GPUs of one node, one
+ * process per GPU.  Rank p passes its rows [row0, row0 + m_local) of all n columns (device memory,
+ * column-major, lda >= m_local); d_jpvt / d_tau / ncols come back replicated on every rank.  The
+ * all-reduces (column-norm partials, candidate Gram, one 128-double vector per panel column, the
+ * V'C slots) run on NCCL over NVLink on `stream`.  Set the communicator up first:
+ * rank 0 calls qrdm_b200_comm_unique_id, the 128 bytes are broadcast by the launcher
+ * (e.g. torch.distributed), every rank calls qrdm_b200_comm_init. */
+int qrdm_b200_comm_unique_id(char *out128);
+int qrdm_b200_comm_init(int rank, int nranks, const char *id128);
+void qrdm_b200_comm_destroy(void);
+int dgeqrdm_dev_sharded(int m_local, int m_global, int row0, int nranks, int n, double *d_a, int lda,
+                        int *d_jpvt, double *d_tau, int *ncols, const double *thres, int nb, void *stream);
+
 /* Addition: per-call statistics of the last dgeqrdm*() on this thread's device. */
 typedef struct qrdm_b200_stats {
   int iterations;        /* DM iterations (= number of ncols entries written) */

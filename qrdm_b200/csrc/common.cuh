@@ -14,6 +14,12 @@ extern long long g_qrdm_launches;  // kernels launched by this process (stats: g
     if (e__ != cudaSuccess) return (int)e__;  \
   } while (0)
 
+// first local row that is still active when j columns are done (row-sharded: global row j)
+__device__ __forceinline__ int qrdm_jr(const qrdm_prob& P, int j) {
+  const int x = j - P.row0;
+  return x < 0 ? 0 : (x > P.m ? P.m : x);
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -28,6 +28,8 @@ typedef struct {
   qrdm_ctrl *ctrl;
   double *vn1, *vn2, *gram_part, *gram, *panel_part, *panel_row, *vc, *wp, *w2, *nrm_part;
   int *flag_list;
+  double *mg_buf;
+  unsigned *mg_cnt;
   size_t wp_elems;
   int ldv, ldw, nrm_splits;
   /* staging for the host-pointer entry points */
@@ -40,6 +42,11 @@ typedef struct {
   void *ev_stage[2];
   void *compute_stream, *copy_stream; /* non-blocking streams of the host-pointer entry points */
 } qrdm_workspace;
+
+/* 1-D block-row sharding: this rank holds global rows [row0, row0 + m_local) */
+typedef struct {
+  int row0, m_glob, nranks;
+} qrdm_shard;
 
 /* optional streaming write-back of finished columns (host-pointer entry point, pinned buffers) */
 typedef struct {
@@ -83,7 +90,7 @@ void qrdm_b200_shutdown(void) {
   qrdm_workspace *w = &g_ws;
   if (!w->ready) return;
   ws_free_sized(w);
-  void *fixed[] = {w->ctrl, w->gram_part, w->gram, w->panel_part, w->panel_row, w->d_a, w->d_tau, w->d_jpvt};
+  void *fixed[] = {w->ctrl, w->gram_part, w->gram, w->panel_part, w->panel_row, w->d_a, w->d_tau, w->d_jpvt, w->mg_buf, w->mg_cnt};
   for (size_t i = 0; i < sizeof(fixed) / sizeof(fixed[0]); ++i)
     if (fixed[i]) qrdm_rt_free(fixed[i]);
   if (w->mailbox) qrdm_rt_host_free(w->mailbox);
@@ -103,6 +110,9 @@ int qrdm_b200_init(int device) {
   CU(qrdm_rt_memset(w->panel_part, 0, 16 * 2 * QRDM_PANEL_MAXCTA * 64, NULL));
   CU(qrdm_rt_malloc((void **)&w->panel_row, 16 * 2 * 128));
   CU(qrdm_rt_memset(w->panel_row, 0, 16 * 2 * 128, NULL));
+  CU(qrdm_rt_malloc((void **)&w->mg_buf, sizeof(double) * (512 + 128 * 2 * 160)));
+  CU(qrdm_rt_malloc((void **)&w->mg_cnt, 64));
+  CU(qrdm_rt_memset(w->mg_cnt, 0, 64, NULL));
   CU(qrdm_rt_host_alloc((void **)&w->mailbox, sizeof(qrdm_ctrl)));
   for (int i = 0; i < 4; ++i) CU(qrdm_rt_event_create(&w->ev[i]));
   for (int i = 0; i < 2; ++i) CU(qrdm_rt_event_create(&w->ev_stage[i]));
@@ -217,10 +227,14 @@ static int read_mailbox(const qrdm_prob *p, void *stream) {
 
 /* The factorisation proper on device-resident data. */
 static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double *d_tau, int *ncols,
-                         const double *thres, int nb, void *stream, qrdm_writeback *wb) {
+                         const double *thres, int nb, void *stream, qrdm_writeback *wb,
+                         const qrdm_shard *sh) {
   qrdm_workspace *w = &g_ws;
   const double eps = DBL_EPSILON * 0.5; /* dlamch('e'), src/dgeqrdm_work.c:528 */
-  const int minmn = m < n ? m : n;
+  /* row-sharded over several GPUs (QRDM_B200_FORCE_MG=1 exercises that path on a 1-rank communicator) */
+  const int mg = sh && (sh->nranks > 1 || getenv("QRDM_B200_FORCE_MG") != NULL);
+  const int m_glob = sh ? sh->m_glob : m;
+  const int minmn = m_glob < n ? m_glob : n;
   int stop_mode = 0;
   double eta = 0.0;
   if (ncols[0] == 1) { stop_mode = 1; eta = eps * n; }                    /* :531-534 */
@@ -243,6 +257,8 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
   P.nrm_part = w->nrm_part; P.nrm_splits = w->nrm_splits; P.flag_list = w->flag_list;
   P.sm_count = w->sm_count;
   P.vec16 = (((size_t)d_a & 15) == 0 && (lda & 1) == 0) ? 1 : 0;
+  P.row0 = sh ? sh->row0 : 0; P.m_glob = m_glob; P.nranks = sh ? sh->nranks : 1;
+  P.w_reduced = mg; P.mg_buf = w->mg_buf; P.mg_cnt = w->mg_cnt;
   { const char *dbg = getenv("QRDM_B200_DEBUG"); P.debug = dbg ? atoi(dbg) : 0; }
 
   memset(&g_stats, 0, sizeof(g_stats));
@@ -252,7 +268,14 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
   CU(qrdm_rt_memset(w->ctrl, 0, sizeof(qrdm_ctrl), stream));
   CU(qrdm_rt_memset(w->vc, 0, sizeof(double) * (size_t)w->ldv * 64, stream));
 
-  STAGE(QRDM_STAGE_NORM_INIT, qrdm_k_colnorm(&P, 0, stream));   /* :672-682 */
+  if (!mg) {
+    STAGE(QRDM_STAGE_NORM_INIT, qrdm_k_colnorm(&P, 0, stream));   /* :672-682 */
+  } else { /* partial sums of squares -> all-reduce -> sqrt */
+    int nsplit = 1;
+    CU(qrdm_k_colnorm_part(&P, 0, &nsplit, stream));
+    if (qrdm_rt_allreduce(P.nrm_part, (size_t)nsplit * n, stream)) return QRDM_ERR_COMM;
+    CU(qrdm_k_colnorm_fin(&P, 0, nsplit, stream));
+  }
   STAGE(QRDM_STAGE_SELECT, qrdm_k_select(&P, stream));
   rc = read_mailbox(&P, stream);
   if (rc) return rc;
@@ -261,12 +284,46 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
   int info = 0, it = 0, j = 0;
   while (j < minmn) { /* :694 */
     const int cols = n - j;
-    STAGE(QRDM_STAGE_GRAM, qrdm_k_gram(&P, 0, m - j, stream));
-    STAGE(QRDM_STAGE_PICK, qrdm_k_pick(&P, stream));
-    STAGE(QRDM_STAGE_PERMUTE, qrdm_k_permute(&P, stream));
-    STAGE(QRDM_STAGE_PANEL, qrdm_k_panel(&P, j, stream));
-    STAGE(QRDM_STAGE_VTC, qrdm_k_trailing(&P, j, stream));
-    STAGE(QRDM_STAGE_NORM_UPDATE, qrdm_k_norm_update(&P, j, stream));
+    int jr = j - P.row0;
+    jr = jr < 0 ? 0 : (jr > m ? m : jr); /* first active local row */
+    if (!mg) {
+      STAGE(QRDM_STAGE_GRAM, qrdm_k_gram(&P, 0, m - jr, stream));
+      STAGE(QRDM_STAGE_PICK, qrdm_k_pick(&P, stream));
+      STAGE(QRDM_STAGE_PERMUTE, qrdm_k_permute(&P, stream));
+      STAGE(QRDM_STAGE_PANEL, qrdm_k_panel(&P, j, stream));
+      STAGE(QRDM_STAGE_VTC, qrdm_k_trailing(&P, j, stream));
+      STAGE(QRDM_STAGE_NORM_UPDATE, qrdm_k_norm_update(&P, j, stream));
+    } else {
+      /* every row sum is computed locally, all-reduced over NVLink, and consumed by a replicated
+       * kernel: all ranks hold identical vn1/jpvt/ctrl and take identical decisions */
+      const int kmax_h = nb < n - j ? (nb < m_glob - j ? nb : m_glob - j) : (n - j < m_glob - j ? n - j : m_glob - j);
+      int vt_stride = 0, vt_grid = 0, nsplit = 1;
+      CU(qrdm_k_gram_part(&P, m - jr > 0 ? m - jr : 1, stream));
+      if (qrdm_rt_allreduce(P.gram, 4096, stream)) return QRDM_ERR_COMM;
+      CU(qrdm_k_pick(&P, stream));
+      CU(qrdm_k_permute(&P, stream));
+      CU(qrdm_k_panel_mg_init(&P, j, stream));
+      if (qrdm_rt_allreduce(P.mg_buf, 128, stream)) return QRDM_ERR_COMM;
+      for (int i = 0; i < kmax_h; ++i) {
+        CU(qrdm_k_panel_mg_step(&P, j, i, stream));
+        if (i + 1 < kmax_h && qrdm_rt_allreduce(P.mg_buf + ((i + 1) & 1) * 128, 128, stream)) return QRDM_ERR_COMM;
+      }
+      CU(qrdm_k_panel_mg_finish(&P, j, stream));
+      CU(qrdm_k_vtc_only(&P, j, &vt_stride, &vt_grid, stream));
+      if (vt_stride > 0) {
+        CU(qrdm_k_wreduce(&P, j, vt_grid, vt_stride, stream));
+        if (qrdm_rt_allreduce(P.wp, (size_t)64 * vt_stride, stream)) return QRDM_ERR_COMM;
+        CU(qrdm_k_trailing_finish(&P, j, vt_grid, vt_stride, stream));
+      }
+      if (n - j - 1 > 0) {
+        CU(qrdm_k_norm_dpart(&P, j, stream));
+        if (qrdm_rt_allreduce(P.nrm_part, (size_t)n, stream)) return QRDM_ERR_COMM;
+        CU(qrdm_k_norm_apply(&P, j, stream));
+        CU(qrdm_k_colnorm_part(&P, 2, &nsplit, stream));
+        if (qrdm_rt_allreduce(P.nrm_part, (size_t)nsplit * n, stream)) return QRDM_ERR_COMM;
+        CU(qrdm_k_colnorm_fin(&P, 2, nsplit, stream));
+      }
+    }
     STAGE(QRDM_STAGE_SELECT, qrdm_k_select(&P, stream)); /* next iteration's prologue + max norm */
     {
       long long lb = qrdm_rt_launch_count();
@@ -285,7 +342,7 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
       info = QRDM_ERR_INTERNAL;
       break;
     }
-    g_stats.trailing_flops += 4.0 * (double)(m - j) * (double)(cols - k) * (double)k;
+    g_stats.trailing_flops += 4.0 * (double)(m - jr) * (double)(cols - k) * (double)k;
     j += k;
     if (wb) {
       /* columns [done, j) are final (later iterations only touch columns >= j, and the mailbox
@@ -315,7 +372,7 @@ int dgeqrdm_dev(int m, int n, double *d_a, int lda, int *d_jpvt, double *d_tau, 
                 const double *thres, int nb, void *stream) {
   int rc = check_args(QRDM_COL_MAJOR, m, n, lda, thres, nb);
   if (rc) return rc;
-  return factor_device(m, n, d_a, lda, d_jpvt, d_tau, ncols, thres, nb, stream, NULL);
+  return factor_device(m, n, d_a, lda, d_jpvt, d_tau, ncols, thres, nb, stream, NULL, NULL);
 }
 
 int dgeqrdm_work(int matrix_layout, int m, int n, double *a, int lda, int *jpvt, double *tau,
@@ -362,7 +419,7 @@ int dgeqrdm_work(int matrix_layout, int m, int n, double *a, int lda, int *jpvt,
   /* pinned host buffer: overlap the D2H of finished columns with the rest of the factorisation */
   qrdm_writeback wb = {a, lda, w->copy_stream, 0};
   const int overlap = qrdm_rt_is_pinned(a) && !getenv("QRDM_B200_NO_OVERLAP");
-  int info = factor_device(m, n, w->d_a, ldd, w->d_jpvt, w->d_tau, ncols, thres, nb, stream, overlap ? &wb : NULL);
+  int info = factor_device(m, n, w->d_a, ldd, w->d_jpvt, w->d_tau, ncols, thres, nb, stream, overlap ? &wb : NULL, NULL);
   if (info <= QRDM_ERR_CUDA) return info;
   const double ms_h2d = qrdm_rt_event_ms(w->ev[2], w->ev[3]);
   CU(qrdm_rt_event_record(w->ev[2], stream));
@@ -385,4 +442,24 @@ int dgeqrdm_work(int matrix_layout, int m, int n, double *a, int lda, int *jpvt,
 int dgeqrdm(int matrix_layout, int m, int n, double *a, int lda, int *jpvt, double *tau, int *ncols,
             double *thres, int nb) {
   return dgeqrdm_work(matrix_layout, m, n, a, lda, jpvt, tau, ncols, thres, nb);
+}
+
+/* ---- 1-D block-row sharded entry point (one process per GPU; NCCL communicator set up through
+ * qrdm_b200_comm_unique_id / qrdm_b200_comm_init, e.g. with the id broadcast by torch.distributed) ---- */
+int qrdm_b200_comm_unique_id(char *out128) { return qrdm_rt_comm_unique_id(out128) ? QRDM_ERR_COMM : 0; }
+int qrdm_b200_comm_init(int rank, int nranks, const char *id128) {
+  int rc = qrdm_b200_init(-1);
+  if (rc) return rc;
+  return qrdm_rt_comm_init(rank, nranks, id128) ? QRDM_ERR_COMM : 0;
+}
+void qrdm_b200_comm_destroy(void) { qrdm_rt_comm_destroy(); }
+
+int dgeqrdm_dev_sharded(int m_local, int m_global, int row0, int nranks, int n, double *d_a, int lda,
+                        int *d_jpvt, double *d_tau, int *ncols, const double *thres, int nb, void *stream) {
+  if (m_local < 0 || row0 < 0 || row0 + m_local > m_global || nranks < 1) return bad_argument(2);
+  int rc = check_args(QRDM_COL_MAJOR, m_global, n, lda > m_global ? lda : m_global, thres, nb);
+  if (rc) return rc;
+  if (lda < (m_local > 1 ? m_local : 1)) return bad_argument(5);
+  qrdm_shard sh = {row0, m_global, nranks};
+  return factor_device(m_local, n, d_a, lda, d_jpvt, d_tau, ncols, thres, nb, stream, NULL, &sh);
 }

@@ -25,13 +25,13 @@ __global__ void __launch_bounds__(256) k_gram_partial(qrdm_prob P, int of_v) {
   if (of_v) {
     nc = (ctrl->fjb_cmp + 7) & ~7;
     base = P.vc; ld = P.ldv;
-    r_lo = j; r_hi = P.m;
+    r_lo = qrdm_jr(P, j); r_hi = P.m;
     if (tid < 64) scol[tid] = tid;
   } else {
     nc = ctrl->nc;
     if (nc <= 1) return;  // a single candidate is always taken, no cosines needed
     base = P.a + (size_t)j * P.lda; ld = P.lda;
-    r_lo = j; r_hi = P.m;
+    r_lo = qrdm_jr(P, j); r_hi = P.m;
     if (tid < 64) scol[tid] = tid < nc ? ctrl->cand[tid] : 0;
   }
   __syncthreads();
@@ -114,3 +114,6 @@ extern "C" int qrdm_k_gram(const qrdm_prob* p, int of_v, int rows_hint, void* st
   QRDM_LAUNCH_CHECK();
   return 0;
 }
+
+// row-sharded: partial + local reduce into p->gram; the caller all-reduces p->gram (4096 doubles)
+extern "C" int qrdm_k_gram_part(const qrdm_prob* p, int rows_hint, void* stream) { return qrdm_k_gram(p, 0, rows_hint, stream); }

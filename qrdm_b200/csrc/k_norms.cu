@@ -14,9 +14,28 @@ __global__ void __launch_bounds__(256) k_colnorm_partial(qrdm_prob P, int use_li
   __shared__ double scratch[32];
   const qrdm_ctrl* ctrl = P.ctrl;
   int r0, c0, count;
+  if (use_list == 2) {  // row-sharded recompute: flag array over the active columns
+    const int cfirst = ctrl->j + ctrl->fjb_cmp;
+    r0 = qrdm_jr(P, cfirst);
+    const int len2 = P.m - r0, nsplit2 = gridDim.y, split2 = blockIdx.y;
+    int seg2 = (len2 + nsplit2 - 1) / nsplit2;
+    seg2 = (seg2 + 1) & ~1;
+    const int lo2 = min(len2, split2 * seg2), hi2 = min(len2, lo2 + seg2);
+    for (int c = cfirst + blockIdx.x; c < P.n; c += gridDim.x) {
+      double t = 0.0;
+      if (ctrl->nflag > 0 && P.flag_list[c]) {
+        const double* col = P.a + (size_t)c * P.lda + r0;
+        double s0 = 0.0;
+        for (int q = lo2 + threadIdx.x; q < hi2; q += blockDim.x) s0 = fma(col[q], col[q], s0);
+        t = block_sum(s0, scratch);
+      }
+      if (threadIdx.x == 0) P.nrm_part[(size_t)split2 * P.n + c] = t;
+    }
+    return;
+  }
   if (use_list) {
     count = ctrl->nflag;
-    r0 = ctrl->j + ctrl->fjb_cmp;  // rows below the block just factored
+    r0 = qrdm_jr(P, ctrl->j + ctrl->fjb_cmp);  // (local) rows below the block just factored
     c0 = 0;
   } else {
     count = P.n;
@@ -50,8 +69,18 @@ __global__ void __launch_bounds__(256) k_colnorm_partial(qrdm_prob P, int use_li
 }
 
 __global__ void __launch_bounds__(256) k_colnorm_finalize(qrdm_prob P, int use_list, int nsplit) {
-  const int count = use_list ? P.ctrl->nflag : P.n;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (use_list == 2) {  // row-sharded recompute: nrm_part[q*n + c] holds the all-reduced partials of flagged columns
+    const int c = P.ctrl->j + P.ctrl->fjb_cmp + idx;
+    if (c >= P.n || P.ctrl->nflag == 0 || !P.flag_list[c]) return;
+    double s2 = 0.0;
+    for (int q = 0; q < nsplit; ++q) s2 += P.nrm_part[(size_t)q * P.n + c];
+    const double v2 = sqrt(s2);
+    P.vn1[c] = v2;
+    P.vn2[c] = v2;
+    return;
+  }
+  const int count = use_list ? P.ctrl->nflag : P.n;
   if (idx >= count) return;
   double s = 0.0;
   for (int q = 0; q < nsplit; ++q) s += P.nrm_part[(size_t)q * P.n + idx];
@@ -60,6 +89,29 @@ __global__ void __launch_bounds__(256) k_colnorm_finalize(qrdm_prob P, int use_l
   P.vn1[c] = v;
   P.vn2[c] = v;
   if (!use_list) P.jpvt[c] = c + 1;  // src/dgeqrdm_work.c:596-609 with every column free
+}
+
+static int colnorm_nsplit(const qrdm_prob* p, int* gx_out) {
+  const int len = p->m;
+  int nsplit = 1;
+  const long target = 4L * p->sm_count;
+  if (p->n < target) nsplit = (int)min((long)p->nrm_splits, max(1L, min(target / max(1, p->n), (long)(len / 4096))));
+  if (nsplit < 1 || p->nranks > 1) nsplit = 1;  // row-sharded: the all-reduce length must agree on all ranks
+  *gx_out = (int)min((long)p->n, max(1L, target / nsplit));
+  return nsplit;
+}
+extern "C" int qrdm_k_colnorm_part(const qrdm_prob* p, int use_list, int* nsplit_out, void* stream) {
+  int gx;
+  const int nsplit = colnorm_nsplit(p, &gx);
+  k_colnorm_partial<<<dim3(gx, nsplit), 256, 0, (cudaStream_t)stream>>>(*p, use_list);
+  QRDM_LAUNCH_CHECK();
+  *nsplit_out = nsplit;
+  return 0;
+}
+extern "C" int qrdm_k_colnorm_fin(const qrdm_prob* p, int use_list, int nsplit, void* stream) {
+  k_colnorm_finalize<<<(p->n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*p, use_list, nsplit);
+  QRDM_LAUNCH_CHECK();
+  return 0;
 }
 
 extern "C" int qrdm_k_colnorm(const qrdm_prob* p, int use_list, void* stream) {
@@ -81,6 +133,8 @@ extern "C" int qrdm_k_colnorm(const qrdm_prob* p, int use_list, void* stream) {
 // K2: one warp per active column c >= j + k.  d = sum of squares of the k new R rows of that
 // column; t = max(0,(1+d/vn1)(1-d/vn1)); if t*(vn1/vn2)^2 <= sqrt(eps) the column goes on the
 // exact-recompute list, else vn1 *= sqrt(t)  (reference src/dgeqrdm_work.c:81-108).
+// MODE 0: fused (single GPU); 1: partial sums only; 2: apply the guard to all-reduced sums
+template <int MODE>
 __global__ void __launch_bounds__(256) k_norm_update(qrdm_prob P, double tol3z) {
   qrdm_ctrl* ctrl = P.ctrl;
   const int j = ctrl->j, k = ctrl->fjb_cmp;
@@ -88,21 +142,32 @@ __global__ void __launch_bounds__(256) k_norm_update(qrdm_prob P, double tol3z) 
   const int c = j + k + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= P.n) return;
   const double v1 = P.vn1[c];
-  if (v1 == 0.0) return;
-  const double* col = P.a + (size_t)c * P.lda + j;
+  if (v1 == 0.0) { if (MODE == 1 && lane == 0) P.nrm_part[c] = 0.0; return; }
   double d = 0.0;
-  for (int r = lane; r < k; r += 32) d = fma(col[r], col[r], d);
-  d = warp_sum(d);
+  if (MODE != 2) {  // sum of squares of the (local part of the) k new R rows of this column
+    const int rlo = qrdm_jr(P, j), rhi = qrdm_jr(P, j + k);
+    const double* col = P.a + (size_t)c * P.lda;
+    for (int r = rlo + lane; r < rhi; r += 32) d = fma(col[r], col[r], d);
+    d = warp_sum(d);
+    if (MODE == 1) {  // row-sharded, part 1: publish the partial; the all-reduce follows
+      if (lane == 0) P.nrm_part[c] = d;
+      return;
+    }
+  } else {
+    d = P.nrm_part[c];  // row-sharded, part 2: all-reduced sum
+  }
   if (lane == 0) {
     double t = sqrt(fabs(d)) / v1;
     t = (t + 1.0) * (1.0 - t);
     t = (0.0 >= t) ? 0.0 : t;
     const double q = v1 / P.vn2[c];
     const double t2 = t * (q * q);
+    if (MODE == 2) P.flag_list[c] = 0;  // row-sharded: flag_list is a per-column flag ARRAY so that every
+                                        // rank recomputes the same columns in the same slots
     if (t2 <= tol3z) {
-      if (P.m - (j + k) > 0) {
-        const int slot = atomicAdd(&ctrl->nflag, 1);
-        P.flag_list[slot] = c;
+      if (P.m_glob - (j + k) > 0) {
+        if (MODE == 2) { P.flag_list[c] = 1; atomicAdd(&ctrl->nflag, 1); }
+        else { const int slot = atomicAdd(&ctrl->nflag, 1); P.flag_list[slot] = c; }
       } else {
         P.vn1[c] = 0.0;
         P.vn2[c] = 0.0;
@@ -117,7 +182,22 @@ extern "C" int qrdm_k_norm_update(const qrdm_prob* p, int j_host, void* stream) 
   cudaStream_t s = (cudaStream_t)stream;
   const int maxcols = p->n - j_host - 1;  // k >= 1
   if (maxcols <= 0) return 0;
-  k_norm_update<<<(maxcols + 7) / 8, 256, 0, s>>>(*p, 1.0536712127723509e-08 /* tol3z = sqrt(dlamch('e')) = sqrt(2^-53), src/dgeqrdm_work.c:528-529 */);
+  k_norm_update<0><<<(maxcols + 7) / 8, 256, 0, s>>>(*p, 1.0536712127723509e-08 /* tol3z = sqrt(dlamch('e')) = sqrt(2^-53), src/dgeqrdm_work.c:528-529 */);
   QRDM_LAUNCH_CHECK();
   return qrdm_k_colnorm(p, 1, stream);
+}
+
+extern "C" int qrdm_k_norm_dpart(const qrdm_prob* p, int j_host, void* stream) {
+  const int maxcols = p->n - j_host - 1;
+  if (maxcols <= 0) return 0;
+  k_norm_update<1><<<(maxcols + 7) / 8, 256, 0, (cudaStream_t)stream>>>(*p, 0.0);
+  QRDM_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int qrdm_k_norm_apply(const qrdm_prob* p, int j_host, void* stream) {
+  const int maxcols = p->n - j_host - 1;
+  if (maxcols <= 0) return 0;
+  k_norm_update<2><<<(maxcols + 7) / 8, 256, 0, (cudaStream_t)stream>>>(*p, 1.0536712127723509e-08);
+  QRDM_LAUNCH_CHECK();
+  return 0;
 }

@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(qrdm_prob P) {
   if (tid == 0) {
     const int k = ctrl->fjb_cmp;
     const int j = ctrl->j + k;
-    const int rows = P.m - j, cols = P.n - j;
+    const int rows = P.m_glob - j, cols = P.n - j;
     int kmax = min(P.nb, min(rows, cols));
     if (kmax < 0) kmax = 0;
     S.j = j; S.cols = cols; S.kmax = kmax;

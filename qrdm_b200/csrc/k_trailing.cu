@@ -36,7 +36,7 @@ __device__ __forceinline__ int vt_sw(int col, int rowpair_idx) { return col * VT
 #define VT_SMEM (VT_STAGES * VT_STAGE_DOUBLES * 8)
 
 struct VtGeom {
-  int j, fjb, k, nc, kpad, jal, NCH, CT;  // CT counts the V'V tile (tile 0)
+  int j, jr, fjb, k, nc, kpad, jal, NCH, CT;  // j: columns done; jr: first active LOCAL row; CT counts the V'V tile
   long long U;
 };
 __device__ __forceinline__ VtGeom vt_geom(const qrdm_prob& P) {
@@ -45,7 +45,8 @@ __device__ __forceinline__ VtGeom vt_geom(const qrdm_prob& P) {
   g.j = ctrl->j; g.fjb = ctrl->fjb; g.k = ctrl->fjb_cmp;
   g.nc = P.n - g.j - g.fjb;
   g.kpad = (g.k + 7) & ~7;
-  g.jal = g.j & ~(QRDM_ROWALIGN - 1);
+  g.jr = qrdm_jr(P, g.j);
+  g.jal = g.jr & ~(QRDM_ROWALIGN - 1);
   const int mpad = (P.m + VT_BK - 1) / VT_BK * VT_BK;
   g.NCH = (mpad - g.jal) / VT_BK;
   g.CT = 1 + (g.nc > 0 ? (g.nc + VT_BN - 1) / VT_BN : 0);
@@ -185,7 +186,7 @@ template <bool VEC16>
 __global__ void __launch_bounds__(256, 2) k_vtc(qrdm_prob P, int wslot_stride_cols) {
   extern __shared__ __align__(16) double sm[];
   const VtGeom ge = vt_geom(P);
-  if (ge.k <= 0 || ge.nc <= 0) return;
+  if (ge.k <= 0 || ge.nc <= 0 || ge.jr >= P.m) return;
   if (ge.kpad == 64) vtc_body<VEC16, true>(P, ge, wslot_stride_cols, sm);  // the common case: no predicates
   else vtc_body<VEC16, false>(P, ge, wslot_stride_cols, sm);
 }
@@ -206,6 +207,7 @@ __device__ __forceinline__ int vt_slot_list(const VtGeom& ge, int vt_grid, int T
   const int bf = vt_bfirst(ge.U, vt_grid, ge.NCH, T);
   const long long Tend = (long long)(T + 1) * ge.NCH;
   int n = 0;
+  (void)cap;
   for (int b = bf; b < vt_grid && vt_lo(ge.U, vt_grid, b) < Tend && n < cap; ++b)
     if (vt_lo(ge.U, vt_grid, b + 1) > vt_lo(ge.U, vt_grid, b)) list[n++] = b - bf;
   return n;
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(TI_THREADS) k_tinv(qrdm_prob P, int vt_grid, i
   const VtGeom ge = vt_geom(P);
   const int k = ge.k;
   if (k <= 0 || ge.nc <= 0) return;
-  if (tid == 0) nslots = vt_slot_list(ge, vt_grid, 0, slots, QRDM_PANEL_MAXCTA * 2 + 8);
+  if (tid == 0) { if (P.w_reduced) { slots[0] = 0; nslots = 1; } else nslots = vt_slot_list(ge, vt_grid, 0, slots, QRDM_PANEL_MAXCTA * 2 + 8); }
   if (tid < 64) taus[tid] = tid < k ? P.tau[ge.j + tid] : 0.0;
   __syncthreads();
   const size_t sstride = (size_t)64 * wslot_stride_cols;
@@ -280,7 +282,7 @@ __global__ void __launch_bounds__(256) k_wapply(qrdm_prob P, int vt_grid, int ws
   const int c0 = blockIdx.x * VT_BN;
   if (ge.k <= 0 || c0 >= ge.nc) return;
   const int T = blockIdx.x + 1;
-  if (tid == 0) nslots = vt_slot_list(ge, vt_grid, T, slots, QRDM_PANEL_MAXCTA * 2 + 8);
+  if (tid == 0) { if (P.w_reduced) { slots[0] = 0; nslots = 1; } else nslots = vt_slot_list(ge, vt_grid, T, slots, QRDM_PANEL_MAXCTA * 2 + 8); }
   for (int e = tid; e < 4096; e += 256) Ms[(e >> 6) * WA_LDM + (e & 63)] = P.gram[e];
   __syncthreads();
   const size_t sstride = (size_t)64 * wslot_stride_cols;
@@ -373,16 +375,18 @@ __global__ void __launch_bounds__(RK_THREADS, 2) k_rankk(qrdm_prob P) {
   double* Wsb = sm + 64 * RK_LDV;  // 2 x [q][RK_LDW]
   const qrdm_ctrl* ctrl = P.ctrl;
   const int tid = threadIdx.x, lane = tid & 31, wr = tid >> 5, g = lane >> 2, t = lane & 3;
-  const int j = ctrl->j, fjb = ctrl->fjb, k = ctrl->fjb_cmp;
-  const int nc = P.n - j - fjb;
+  const int jc = ctrl->j, fjb = ctrl->fjb, k = ctrl->fjb_cmp;
+  const int nc = P.n - jc - fjb;
   if (nc <= 0 || k <= 0) return;
+  const int j = qrdm_jr(P, jc);  // first active local row (== jc on a single GPU)
+  if (j >= P.m) return;          // row-sharded: this rank has no rows left
   const int kpad = (k + 7) & ~7;
   const int jal = j & ~(QRDM_ROWALIGN - 1);
   const int RB = (P.m - jal + RK_BM - 1) / RK_BM, CT = (nc + RK_BN - 1) / RK_BN;
   const long long U = (long long)RB * CT;
   const long long lo = U * blockIdx.x / gridDim.x, hi = U * (blockIdx.x + 1) / gridDim.x;
   if (lo >= hi) return;
-  double* Cg = P.a + (size_t)(j + fjb) * P.lda;
+  double* Cg = P.a + (size_t)(jc + fjb) * P.lda;
   const size_t lda = (size_t)P.lda;
   // warp wr owns rows wr*32..+31 of the tile, all 32 columns: DMMA M = columns (4 tiles), N = rows (4)
   // lane element (mt, nt, e): column c0 + mt*8 + g, rows R0 + wr*32 + nt*8 + 2t + e
@@ -513,44 +517,104 @@ __global__ void __launch_bounds__(RK_THREADS, 2) k_rankk(qrdm_prob P) {
   }
 }
 
-extern "C" int qrdm_k_trailing(const qrdm_prob* p, int j_host, void* stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_vtc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VT_SMEM);
-    cudaFuncSetAttribute(k_vtc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VT_SMEM);
-    cudaFuncSetAttribute(k_wapply, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_SMEM);
-    cudaFuncSetAttribute(k_tinv, cudaFuncAttributeMaxDynamicSharedMemorySize, TI_SMEM);
-    cudaFuncSetAttribute(k_rankk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RK_SMEM);
-    cudaFuncSetAttribute(k_rankk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RK_SMEM);
-    attr_set = true;
+// Row-sharded build: fold the partial-W slots of every tile into slot 0 (fixed order) so that ONE
+// contiguous [64][stride] block can be all-reduced over NVLink; ranks that have no rows left
+// contribute zeros.  k_tinv / k_wapply then read slot 0 only (P.w_reduced).
+__global__ void __launch_bounds__(256) k_wreduce(qrdm_prob P, int vt_grid, int wslot_stride_cols) {
+  __shared__ int slots[QRDM_PANEL_MAXCTA * 2 + 8];
+  __shared__ int nslots;
+  const VtGeom ge = vt_geom(P);
+  const int T = blockIdx.x;
+  if (ge.k <= 0 || T >= ge.CT) return;
+  const bool have_rows = ge.jr < P.m && ge.nc > 0;
+  if (threadIdx.x == 0) nslots = have_rows ? vt_slot_list(ge, vt_grid, T, slots, QRDM_PANEL_MAXCTA * 2 + 8) : 0;
+  __syncthreads();
+  const size_t sstride = (size_t)64 * wslot_stride_cols;
+  const int ns = nslots;
+  for (int e = threadIdx.x; e < 64 * VT_BN; e += 256) {
+    const int q = e / VT_BN, c = e % VT_BN;
+    double* dst = P.wp + (size_t)q * wslot_stride_cols + (size_t)T * VT_BN + c;
+    double s2 = 0.0;
+    if (q < ge.kpad)
+      for (int i = 0; i < ns; ++i) s2 += dst[(size_t)slots[i] * sstride];
+    dst[0] = s2;
   }
+}
+
+static void trailing_attrs() {
+  static bool attr_set = false;
+  if (attr_set) return;
+  cudaFuncSetAttribute(k_vtc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VT_SMEM);
+  cudaFuncSetAttribute(k_vtc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VT_SMEM);
+  cudaFuncSetAttribute(k_wapply, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_SMEM);
+  cudaFuncSetAttribute(k_tinv, cudaFuncAttributeMaxDynamicSharedMemorySize, TI_SMEM);
+  cudaFuncSetAttribute(k_rankk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RK_SMEM);
+  cudaFuncSetAttribute(k_rankk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RK_SMEM);
+  attr_set = true;
+}
+static int host_jr(const qrdm_prob* p, int j) {
+  const int x = j - p->row0;
+  return x < 0 ? 0 : (x > p->m ? p->m : x);
+}
+
+// pass 1: W slots (and V'V in tile 0)
+extern "C" int qrdm_k_vtc_only(const qrdm_prob* p, int j_host, int* stride_out, int* grid_out, void* stream) {
+  trailing_attrs();
   cudaStream_t s = (cudaStream_t)stream;
   const int ncmax = p->n - j_host - 1;  // fjb >= 1
+  *stride_out = 0; *grid_out = 0;
   if (ncmax <= 0) return 0;
-  const int jal = j_host & ~(QRDM_ROWALIGN - 1);
+  const int jal = host_jr(p, j_host) & ~(QRDM_ROWALIGN - 1);
   const int mpad = (p->m + VT_BK - 1) / VT_BK * VT_BK;
   const int nchunks = (mpad - jal) / VT_BK;
   const int ct_ub = 1 + (ncmax + VT_BN - 1) / VT_BN;  // + the V'V tile
-  // persistent grid: one CTA per SM, never more CTAs than units (device-side nc <= ncmax keeps
+  // persistent grid: two CTAs per SM, never more CTAs than units (device-side nc <= ncmax keeps
   // U >= nchunks * 2 >= grid whenever anything is left to update)
   long long units_lb = (long long)nchunks * 2;
   int vt_grid = 2 * p->sm_count;
   if (vt_grid > units_lb) vt_grid = (int)units_lb;
+  if (vt_grid < 1) vt_grid = 1;
   // partial-W slots are laid out [slot][64][stride]; (grid/CT + 2) slots always fit (see host alloc)
   const int stride = ct_ub * VT_BN;
+  *stride_out = stride; *grid_out = vt_grid;
+  if (nchunks <= 0) return 0;  // row-sharded: no local rows left
   if (p->vec16) k_vtc<true><<<vt_grid, 256, VT_SMEM, s>>>(*p, stride);
   else k_vtc<false><<<vt_grid, 256, VT_SMEM, s>>>(*p, stride);
   QRDM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int qrdm_k_wreduce(const qrdm_prob* p, int j_host, int vt_grid, int stride, void* stream) {
+  if (stride <= 0) return 0;
+  k_wreduce<<<stride / VT_BN, 256, 0, (cudaStream_t)stream>>>(*p, vt_grid, stride);
+  QRDM_LAUNCH_CHECK();
+  return 0;
+}
+
+// T', W2 = -T' W, and pass 2
+extern "C" int qrdm_k_trailing_finish(const qrdm_prob* p, int j_host, int vt_grid, int stride, void* stream) {
+  trailing_attrs();
+  cudaStream_t s = (cudaStream_t)stream;
+  const int ncmax = p->n - j_host - 1;
+  if (ncmax <= 0 || stride <= 0) return 0;
+  const int jal = host_jr(p, j_host) & ~(QRDM_ROWALIGN - 1);
   k_tinv<<<1, TI_THREADS, TI_SMEM, s>>>(*p, vt_grid, stride);
   QRDM_LAUNCH_CHECK();
   k_wapply<<<(ncmax + VT_BN - 1) / VT_BN, 256, WA_SMEM, s>>>(*p, vt_grid, stride);
   QRDM_LAUNCH_CHECK();
-  {
+  if (p->m - jal > 0) {
     const long long units = (long long)((ncmax + RK_BN - 1) / RK_BN) * ((p->m - jal + RK_BM - 1) / RK_BM);
     const int grid = (int)(units < 2 * p->sm_count ? units : 2 * p->sm_count);
     if (p->vec16) k_rankk<true><<<grid, RK_THREADS, RK_SMEM, s>>>(*p);
     else k_rankk<false><<<grid, RK_THREADS, RK_SMEM, s>>>(*p);
+    QRDM_LAUNCH_CHECK();
   }
-  QRDM_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int qrdm_k_trailing(const qrdm_prob* p, int j_host, void* stream) {
+  int stride = 0, grid = 0;
+  int rc = qrdm_k_vtc_only(p, j_host, &stride, &grid, stream);
+  if (rc) return rc;
+  return qrdm_k_trailing_finish(p, j_host, grid, stride, stream);
 }

@@ -36,8 +36,10 @@ typedef struct qrdm_ctrl {
   double maxnrm; /* max partial column norm of the active columns (stop rule) */
   double pad2_;
   /* ---- device-only part ---- */
-  unsigned int panel_bar; /* grid barrier counter of k_panel */
-  int pad3_[3];
+  unsigned int panel_bar; /* (unused since the LL exchange) */
+  int mg_k;               /* row-sharded panel: column at which the early stop fired, or -1 */
+  int pad3_[2];
+  double mg_thres2;       /* row-sharded panel: squared stop threshold carried across step kernels */
   int cand[QRDM_KMAX];        /* candidate column offsets (relative to j), by norm descending */
   double candnrm[QRDM_KMAX];  /* their partial norms */
   int sel[QRDM_KMAX];         /* accepted offsets, acceptance order */
@@ -71,6 +73,12 @@ typedef struct qrdm_prob {
   int sm_count;
   int vec16;          /* 1 if a is 16-byte aligned and lda is even (fast cp.async path) */
   int debug;          /* QRDM_B200_DEBUG bit mask for timing experiments (results invalid when set) */
+  /* 1-D block-row sharding: this rank holds global rows [row0, row0 + m) of all n
+   * columns; m_glob = total rows.  Single GPU: row0 = 0, m_glob = m, nranks = 1. */
+  int row0, m_glob, nranks;
+  int w_reduced;      /* 1: partial-W slot 0 already holds the (all-reduced) sum over all slots */
+  double *mg_buf;     /* sharded panel: [2][128] send/recv vectors + [G][128] per-CTA partials */
+  unsigned *mg_cnt;   /* sharded panel: arrival counter of the last-CTA reduction */
 } qrdm_prob;
 
 int qrdm_k_colnorm(const qrdm_prob *p, int use_flag_list, void *stream);   /* K1 / K2 recompute */
@@ -81,6 +89,23 @@ int qrdm_k_permute(const qrdm_prob *p, void *stream);                       /* K
 int qrdm_k_panel(const qrdm_prob *p, int j_host, void *stream);             /* K4 */
 int qrdm_k_trailing(const qrdm_prob *p, int j_host, void *stream);          /* K6: vtc, wsolve, rankk */
 int qrdm_k_norm_update(const qrdm_prob *p, int j_host, void *stream);       /* K2 */
+/* row-sharded variants: each stage is split at the point where the all-reduce sits */
+int qrdm_k_colnorm_part(const qrdm_prob *p, int use_flag_list, int *nsplit_out, void *stream);
+int qrdm_k_colnorm_fin(const qrdm_prob *p, int use_flag_list, int nsplit, void *stream);
+int qrdm_k_gram_part(const qrdm_prob *p, int rows_hint, void *stream); /* partial + local reduce -> p->gram */
+int qrdm_k_norm_dpart(const qrdm_prob *p, int j_host, void *stream);   /* d[c] partial -> nrm_part[0..n) */
+int qrdm_k_norm_apply(const qrdm_prob *p, int j_host, void *stream);
+int qrdm_k_vtc_only(const qrdm_prob *p, int j_host, int *stride_out, int *grid_out, void *stream);
+int qrdm_k_wreduce(const qrdm_prob *p, int j_host, int vt_grid, int stride, void *stream);
+int qrdm_k_trailing_finish(const qrdm_prob *p, int j_host, int vt_grid, int stride, void *stream);
+int qrdm_k_panel_mg_init(const qrdm_prob *p, int j_host, void *stream);
+int qrdm_k_panel_mg_step(const qrdm_prob *p, int j_host, int step, void *stream);
+int qrdm_k_panel_mg_finish(const qrdm_prob *p, int j_host, void *stream);
+/* NCCL (dlopen'ed libnccl.so.2): in-place sum all-reduce of doubles on the stream */
+int qrdm_rt_comm_unique_id(char *out128);
+int qrdm_rt_comm_init(int rank, int nranks, const char *id128);
+int qrdm_rt_comm_destroy(void);
+int qrdm_rt_allreduce(double *buf, size_t count, void *stream);
 
 /* runtime helpers so that the host driver stays plain C */
 int qrdm_rt_malloc(void **ptr, size_t bytes);

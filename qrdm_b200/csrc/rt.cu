@@ -1,6 +1,9 @@
 // rt.cu — CUDA runtime wrappers with C linkage so the host driver (dgeqrdm_host.c) stays plain C,
 // plus the FP64 peak micro-benchmark bench.py uses as the roofline denominator of K6.
 #include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include "common.cuh"
 
@@ -114,3 +117,73 @@ extern "C" double qrdm_rt_fp64_peak(int use_dmma, void* stream) {
                                 : 2.0 * 16 * (double)iters * 256.0 * grid;
   return flops / (best * 1e-3) / 1e12;
 }
+
+// ---- NCCL, bound at run time (dlopen) so that libqrdm_b200.so has no link-time dependency and a
+// process that already loaded torch's bundled libnccl.so.2 shares that copy ----
+namespace {
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  ncclComm_t comm = nullptr;
+  int nranks = 1;
+} g_nccl;
+
+bool nccl_load() {
+  if (g_nccl.handle) return true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    g_nccl.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.handle) break;
+  }
+  if (!g_nccl.handle) { fprintf(stderr, "qrdm_b200: cannot dlopen libnccl.so.2: %s\n", dlerror()); return false; }
+  g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(g_nccl.handle, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(g_nccl.handle, "ncclCommInitRank");
+  g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(g_nccl.handle, "ncclCommDestroy");
+  g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(g_nccl.handle, "ncclAllReduce");
+  g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(g_nccl.handle, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce) {
+    fprintf(stderr, "qrdm_b200: libnccl.so.2 lacks the expected symbols\n");
+    return false;
+  }
+  return true;
+}
+int nccl_check(ncclResult_t r, const char* what) {
+  if (r == ncclSuccess) return 0;
+  fprintf(stderr, "qrdm_b200: NCCL error in %s: %s\n", what, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  return -1;
+}
+}  // namespace
+
+extern "C" {
+int qrdm_rt_comm_unique_id(char* out128) {
+  if (!nccl_load()) return -1;
+  ncclUniqueId id;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  if (nccl_check(g_nccl.GetUniqueId(&id), "ncclGetUniqueId")) return -1;
+  memcpy(out128, &id, 128);
+  return 0;
+}
+int qrdm_rt_comm_init(int rank, int nranks, const char* id128) {
+  if (!nccl_load()) return -1;
+  if (g_nccl.comm) { g_nccl.CommDestroy(g_nccl.comm); g_nccl.comm = nullptr; }
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  if (nccl_check(g_nccl.CommInitRank(&g_nccl.comm, nranks, id, rank), "ncclCommInitRank")) return -1;
+  g_nccl.nranks = nranks;
+  return 0;
+}
+int qrdm_rt_comm_destroy(void) {
+  if (g_nccl.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(g_nccl.comm);
+  g_nccl.comm = nullptr;
+  g_nccl.nranks = 1;
+  return 0;
+}
+int qrdm_rt_allreduce(double* buf, size_t count, void* stream) {
+  if (!g_nccl.comm) { fprintf(stderr, "qrdm_b200: all-reduce without a communicator (call qrdm_b200_comm_init)\n"); return -1; }
+  return nccl_check(g_nccl.AllReduce(buf, buf, count, ncclDouble, ncclSum, g_nccl.comm, (cudaStream_t)stream), "ncclAllReduce");
+}
+}  // extern "C"

@@ -1,0 +1,75 @@
+"""1-D block-row sharded dgeqrdm across the GPUs of one node, one process per GPU.
+
+`torch.distributed` is only the launcher-side plumbing (rendezvous, broadcasting the NCCL unique
+id); the data-path collectives are `ncclAllReduce` calls issued by the C host driver on the
+compute stream (`dgeqrdm_dev_sharded` in include/qrdm_b200.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+
+def row_partition(m: int, world: int) -> list[tuple[int, int]]:
+    """Contiguous row blocks [row0, row0 + rows) per rank, multiples of 32 rows except the last
+    (row tiles of the trailing kernels start at multiples of 32)."""
+    if world < 1 or m < 0:
+        raise ValueError("bad partition request")
+    per = -(-m // world)
+    per = -(-per // 32) * 32
+    out = []
+    for r in range(world):
+        lo = min(m, r * per)
+        hi = min(m, lo + per)
+        out.append((lo, hi - lo))
+    return out
+
+
+def broadcast_unique_id(make_id, rank: int, group=None, device=None) -> bytes:
+    """Rank 0 produces the 128-byte NCCL unique id (`make_id()`), everybody receives it through
+    torch.distributed (works with the gloo and the nccl backend)."""
+    import torch
+    import torch.distributed as dist
+    buf = torch.zeros(128, dtype=torch.uint8, device=device)
+    if rank == 0:
+        raw = make_id()
+        if len(raw) != 128:
+            raise ValueError("NCCL unique id must be 128 bytes")
+        buf.copy_(torch.frombuffer(bytearray(raw), dtype=torch.uint8))
+    dist.broadcast(buf, src=0, group=group)
+    return bytes(buf.cpu().numpy().tobytes())
+
+
+def init_comm(rank: int, world: int, group=None, device=None) -> None:
+    """Create the library's NCCL communicator for this process (idempotent per process)."""
+    from . import _lib
+
+    def make_id():
+        raw = C.create_string_buffer(128)
+        if _lib.lib.qrdm_b200_comm_unique_id(raw) != 0:
+            raise RuntimeError("qrdm_b200_comm_unique_id failed (libnccl.so.2 not loadable?)")
+        return raw.raw
+
+    uid = broadcast_unique_id(make_id, rank, group=group, device=device)
+    if _lib.lib.qrdm_b200_comm_init(int(rank), int(world), uid) != 0:
+        raise RuntimeError("qrdm_b200_comm_init failed")
+
+
+def dgeqrdm_sharded(dA_local, m_local, m_global, row0, world, n, lda, d_jpvt, d_tau,
+                    thres=(0.9, 0.15), nb=64, stop_mode=0, stream=None):
+    """Factor the row-sharded matrix in place; returns (info, ncols).  `dA_local` is this rank's
+    (n, lda) row-major float64 CUDA tensor = its m_local x n column-major row block."""
+    from . import _lib
+    import torch
+    ncols = np.zeros(max(n, 1), dtype=np.int32)
+    ncols[0] = stop_mode
+    th = np.zeros(3, dtype=np.float64)
+    th[: len(thres)] = thres
+    if stream is None:
+        stream = torch.cuda.current_stream().cuda_stream
+    info = _lib.lib.dgeqrdm_dev_sharded(int(m_local), int(m_global), int(row0), int(world), int(n),
+                                        C.c_void_p(int(dA_local.data_ptr())), int(lda),
+                                        C.c_void_p(int(d_jpvt.data_ptr())), C.c_void_p(int(d_tau.data_ptr())),
+                                        ncols.ctypes.data, th.ctypes.data, int(nb), C.c_void_p(int(stream)))
+    return int(info), ncols
