@@ -198,6 +198,59 @@ def cpu_baseline(args, m, n, kind, stop_mode, desc):
             "seconds": dt, "sample": f"scalar C port (oracle/qrdm_port.c) on a {sm_}x{sn_} Gaussian sample"}
 
 
+def run_row_sharded(torch, dist, qrdm_b200, rank, world, dev, m, n, steps, warmup):
+    """BASELINE config C4: tall-skinny m x n Gaussian, 1-D block-row sharded over `world` GPUs with
+    NCCL all-reduces in the data path (strong scaling: the matrix is fixed, each rank holds m/world
+    rows).  world == 1 runs the ordinary single-GPU path on the whole matrix."""
+    from qrdm_b200 import sharded
+    row0, ml = sharded.row_partition(m, world)[rank]
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(4321 + rank)
+    A0 = torch.randn((n, ml), dtype=torch.float64, device=dev, generator=gen)
+    A = torch.empty_like(A0)
+    d_jpvt = torch.zeros(n, dtype=torch.int32, device=dev)
+    d_tau = torch.zeros(min(m, n), dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream()
+    if world > 1:
+        sharded.init_comm(rank, world, device=dev)
+
+    def step():
+        A.copy_(A0)
+        if world > 1:
+            info, ncols = sharded.dgeqrdm_sharded(A, ml, m, row0, world, n, ml, d_jpvt, d_tau, thres=THRES, nb=NB,
+                                                  stream=stream.cuda_stream)
+        else:
+            info, ncols = qrdm_b200.dgeqrdm_device(A, m, n, m, d_jpvt, d_tau, thres=THRES, nb=NB,
+                                                   stream=stream.cuda_stream)
+        if info != 0:
+            raise SystemExit(f"row-sharded dgeqrdm failed: info={info}")
+        return ncols
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        ncols = step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    rk = int(ncols.sum())
+    del A0, A
+    torch.cuda.empty_cache()
+    return {"workload": f"tall-skinny {m}x{n} Gaussian, row-sharded over {world} GPU(s) (configs[3])",
+            "n_gpus": world, "scaling": "strong", "ms_per_step": ms / steps, "seconds": ms / steps / 1e3,
+            "value": steps * flops(m, n, rk) / (ms * 1e-3) / 1e9, "unit": "GFLOP/s", "revealed_rank": rk,
+            "rows_per_gpu": ml, "collectives": "ncclAllReduce (f64 sum) on the compute stream" if world > 1 else "none"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -208,6 +261,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=6144, help="edge of the CPU-baseline sample block")
     ap.add_argument("--ref-sample", type=int, default=6144, help="edge of the --impl reference sample block")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-row-sharded", action="store_true", help="skip the configs[3] row-sharded leg")
+    ap.add_argument("--sharded-rows", type=int, default=2_000_000)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = max(args.warmup, 1)  # contract says W >= 3; honour smaller only for ncu captures
@@ -335,6 +390,19 @@ def main():
     e2e_val = world * e2e_steps * flops(m, n, e2e_rank) / e2e_t / 1e9
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- configs[3]: the row-sharded tall-skinny case (every rank takes part) ----
+    row_sharded = None
+    if not args.no_row_sharded and not os.environ.get("QRDM_BENCH_SHAPE"):
+        del A0, A, hA0, hA
+        torch.cuda.empty_cache()
+        try:
+            row_sharded = run_row_sharded(torch, dist, qrdm_b200, rank, world, dev, args.sharded_rows, 512,
+                                          steps=2, warmup=1)
+        except SystemExit:
+            raise
+        except Exception as exc:  # never sink the headline measurement
+            row_sharded = {"error": str(exc)[:300]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -373,6 +441,8 @@ def main():
                      "traffic": None},
         "stages": {"panel_ms_per_step": panel_ms / args.steps, "trailing_ms_per_step": trailing_ms / args.steps},
     }
+    if row_sharded is not None:
+        line["row_sharded"] = row_sharded
     if world == 1 and not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = cpu_baseline(args, m, n, kind, stop_mode, desc)
