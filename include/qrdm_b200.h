@@ -55,6 +55,12 @@ int dgeqrdm_work(int matrix_layout, int m, int n, double *a, int lda, int *jpvt,
 int dgeqrdm_dev(int m, int n, double *d_a, int lda, int *d_jpvt, double *d_tau, int *ncols,
                 const double *thres, int nb, void *stream);
 
+/* Addition: batched mode — `batch` independent m x n HOST matrices, matrix b
+ * at a + b*stride_a; jpvt (b*n), tau (b*min(m,n)), ncols (b*n) laid out per matrix; infos[b] per
+ * matrix (may be NULL).  Returns 0 or the first non-zero info.  Across GPUs each rank passes its share. */
+int dgeqrdm_batched(int batch, int m, int n, double *a, int lda, long long stride_a, int *jpvt, double *tau,
+                    int *ncols, double *thres, int nb, int *infos);
+
 /* Addition: 1-D block-row sharded factorisation across the GPUs of one node, one
  * process per GPU.  Rank p passes its rows [row0, row0 + m_local) of all n columns (device memory,
  * column-major, lda >= m_local); d_jpvt / d_tau / ncols come back replicated on every rank.  The

@@ -23,7 +23,7 @@ STAGES = ["norm_init", "select", "gram", "pick", "permute", "panel", "vtv", "tra
           "rankk", "norm_update", "sync"]
 
 # every symbol include/qrdm_b200.h declares (checked by tests/test_abi.py)
-EXPORTS = ["dgeqrdm", "dgeqrdm_work", "dgeqrdm_dev", "dgeqrdm_dev_sharded", "qrdm_b200_get_stats",
+EXPORTS = ["dgeqrdm", "dgeqrdm_work", "dgeqrdm_dev", "dgeqrdm_dev_sharded", "dgeqrdm_batched", "qrdm_b200_get_stats",
            "qrdm_b200_set_profile", "qrdm_b200_init", "qrdm_b200_shutdown", "qrdm_b200_measure_fp64_peak",
            "qrdm_b200_version", "qrdm_b200_comm_unique_id", "qrdm_b200_comm_init", "qrdm_b200_comm_destroy"]
 
@@ -57,6 +57,9 @@ def _load():
     lib.qrdm_b200_comm_init.restype = C.c_int
     lib.qrdm_b200_comm_init.argtypes = [C.c_int, C.c_int, C.c_char_p]
     lib.qrdm_b200_comm_destroy.restype = None
+    lib.dgeqrdm_batched.restype = C.c_int
+    lib.dgeqrdm_batched.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.dgeqrdm_dev_sharded.restype = C.c_int
     lib.dgeqrdm_dev_sharded.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]

@@ -46,6 +46,25 @@ def dgeqrdm_device(dA, m, n, lda, d_jpvt, d_tau, thres=(0.9, 0.15), nb=64, stop_
     return int(info), ncols
 
 
+def dgeqrdm_batched(As, thres=(0.9, 0.15), nb=64, stop_mode=0):
+    """Factor a batch of equally-shaped host matrices (``As``: array-like (batch, m, n)) through
+    ``dgeqrdm_batched``.  Returns dict(info, infos, A (batch, m, n), jpvt, tau, ncols)."""
+    As = np.asarray(As, dtype=np.float64)
+    batch, m, n = As.shape
+    buf = np.empty((batch, n, m), dtype=np.float64)          # each [b] is column-major m x n
+    buf[...] = As.transpose(0, 2, 1)
+    jpvt = np.zeros((batch, n), dtype=np.int32)
+    tau = np.zeros((batch, min(m, n)), dtype=np.float64)
+    ncols = np.zeros((batch, n), dtype=np.int32)
+    ncols[:, 0] = stop_mode
+    infos = np.zeros(batch, dtype=np.int32)
+    th = np.zeros(3, dtype=np.float64)
+    th[: len(thres)] = thres
+    info = _lib.lib.dgeqrdm_batched(batch, m, n, buf.ctypes.data, m, m * n, jpvt.ctypes.data, tau.ctypes.data,
+                                    ncols.ctypes.data, th.ctypes.data, int(nb), infos.ctypes.data)
+    return dict(info=int(info), infos=infos, A=buf.transpose(0, 2, 1), jpvt=jpvt, tau=tau, ncols=ncols)
+
+
 def stats():
     return _lib.stats()
 

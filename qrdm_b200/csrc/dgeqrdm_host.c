@@ -463,3 +463,55 @@ int dgeqrdm_dev_sharded(int m_local, int m_global, int row0, int nranks, int n, 
   qrdm_shard sh = {row0, m_global, nranks};
   return factor_device(m_local, n, d_a, lda, d_jpvt, d_tau, ncols, thres, nb, stream, NULL, &sh);
 }
+
+/* ---- batched mode: `batch` independent m x n matrices, matrix b at
+ * a + b*stride_a (column-major, lda), outputs at jpvt + b*n, tau + b*min(m,n), ncols + b*n.
+ * Round 1: the whole batch is made device-resident with one H2D, then factored one matrix after
+ * the other by the single-matrix driver (launch-latency bound for small matrices — the planned
+ * replacement is one persistent CTA-cluster per matrix); multi-GPU = each rank passes its share. ---- */
+int dgeqrdm_batched(int batch, int m, int n, double *a, int lda, long long stride_a, int *jpvt, double *tau,
+                    int *ncols, double *thres, int nb, int *infos) {
+  qrdm_workspace *w = &g_ws;
+  if (batch <= 0 || stride_a < (long long)lda * n) return bad_argument(1);
+  int rc = check_args(QRDM_COL_MAJOR, m, n, lda, thres, nb);
+  if (rc) return rc;
+  rc = qrdm_b200_init(-1);
+  if (rc) return rc;
+  void *stream = w->compute_stream;
+  const int minmn = m < n ? m : n;
+  const int ldd = (m + 1) & ~1;
+  double *d_all = NULL, *d_tau = NULL;
+  int *d_jpvt = NULL;
+  const size_t per = (size_t)ldd * n;
+  CU(qrdm_rt_malloc((void **)&d_all, sizeof(double) * per * batch));
+  CU(qrdm_rt_malloc((void **)&d_tau, sizeof(double) * (size_t)minmn * batch));
+  CU(qrdm_rt_malloc((void **)&d_jpvt, sizeof(int) * (size_t)n * batch));
+  for (int b = 0; b < batch; ++b)
+    CU(qrdm_rt_h2d_2d(d_all + per * b, sizeof(double) * ldd, a + (size_t)stride_a * b, sizeof(double) * lda,
+                      sizeof(double) * m, n, stream));
+  CU(qrdm_rt_h2d(d_tau, tau, sizeof(double) * (size_t)minmn * batch, stream));
+  int worst = 0;
+  double ms = 0.0;
+  long long launches = 0;
+  for (int b = 0; b < batch; ++b) {
+    int info = factor_device(m, n, d_all + per * b, ldd, d_jpvt + (size_t)n * b, d_tau + (size_t)minmn * b,
+                             ncols + (size_t)n * b, thres, nb, stream, NULL, NULL);
+    if (infos) infos[b] = info;
+    if (info <= QRDM_ERR_CUDA) { worst = info; break; }
+    if (info != 0 && worst == 0) worst = info;
+    ms += g_stats.ms_total;
+    launches += g_stats.launches;
+  }
+  for (int b = 0; b < batch; ++b)
+    CU(qrdm_rt_d2h_2d(a + (size_t)stride_a * b, sizeof(double) * lda, d_all + per * b, sizeof(double) * ldd,
+                      sizeof(double) * m, n, stream));
+  CU(qrdm_rt_d2h(jpvt, d_jpvt, sizeof(int) * (size_t)n * batch, stream));
+  CU(qrdm_rt_d2h(tau, d_tau, sizeof(double) * (size_t)minmn * batch, stream));
+  CU(qrdm_rt_sync(stream));
+  g_stats.ms_total = ms;
+  g_stats.launches = launches;
+  qrdm_rt_free(d_all);
+  qrdm_rt_free(d_tau);
+  qrdm_rt_free(d_jpvt);
+  return worst;
+}

@@ -303,20 +303,14 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_reg(qrdm_prob P, int
     const int cur = i & 1, nxt = cur ^ 1;
     const unsigned tag = tag_base + i + 1;
     long long tq0 = timing ? clock64() : 0;
-    // ---- reduce-scatter: this CTA totals the columns jj == b (mod G) ----
-    for (int jj = i + ((b - i % G + G) % G); jj < fjb; jj += G) {
+    // ---- reduce-scatter: column jj is totalled by warp (jj - i - off) / G of CTA jj mod G, so a small
+    // grid (few rows) spreads its columns over the warps instead of looping over them; lanes <-> CTAs,
+    // fixed association order, no block barrier ----
+    for (int jj = i + ((b - i % G + G) % G) + wid * G; jj < fjb; jj += PANEL_WARPS * G) {
       double v = 0.0;
-      if (tid < G) v = ll_load(&part[((size_t)cur * QRDM_PANEL_MAXCTA + tid) * 64 + jj], tag);
+      for (int c = lane; c < G; c += 32) v += ll_load(&part[((size_t)cur * QRDM_PANEL_MAXCTA + c) * 64 + jj], tag);
       v = warp_sum(v);
-      if (lane == 0) sred[wid] = v;
-      __syncthreads();
-      if (tid == 0) {
-        double tot = 0.0;
-#pragma unroll
-        for (int w = 0; w < PANEL_WARPS; ++w) tot += sred[w];
-        ll_store(&bcast[cur * 128 + jj], tot, tag);
-      }
-      __syncthreads();
+      if (lane == 0) ll_store(&bcast[cur * 128 + jj], v, tag);
     }
     if (timing) { const long long tq = clock64(); tph[0] += tq - tq0; tq0 = tq; }
     // ---- broadcast: everybody picks up the totals and the pivot row ----

@@ -180,6 +180,19 @@ def test_pinned_host_buffer_streams_columns_back(q):
         assert np.array_equal(tau, ref_out["tau"])
 
 
+def test_batched_kahan(q, oracle_ref):
+    """BASELINE config C5 unit: a batch of Kahan-type matrices (per-matrix theta, seeded diagonal
+    perturbation), every matrix against the unmodified reference."""
+    n, batch = 96, 6
+    As = np.stack([g.kahan(n, theta=1.1 + 0.04 * b, perturb=1e3, seed=b) for b in range(batch)])
+    out = q.dgeqrdm_batched(As)
+    assert out["info"] == 0 and not out["infos"].any()
+    for b in range(batch):
+        exp = oracle_ref.ref_dgeqrdm(As[b])
+        got = dict(info=0, A=out["A"][b], jpvt=out["jpvt"][b], tau=out["tau"][b], ncols=out["ncols"][b])
+        parity.check_against(got, exp, (n, n), exact=True)
+
+
 def test_bitwise_determinism(q):
     A = g.gaussian(1200, 800, 13)
     a = q.dgeqrdm(A)
