@@ -55,19 +55,24 @@ __global__ void __launch_bounds__(256) k_pick(qrdm_prob P) {
 
   if (wid == 0) {
     // ---- greedy pick (lock-step warp, scalars warp-uniform), src/dgeqrdm_work.c:382-403 ----
+    // lane l tracks, for candidates l and l+32, the largest |cos| against the columns accepted so
+    // far; candidate t is accepted iff that running maximum is < delta (one shuffle per candidate,
+    // one pair of smem reads per acceptance)
     int fjb = 1;
     if (lane == 0) S.selpos[0] = 0;
-    __syncwarp();
+    double m0 = (nc > 1 && lane < nc) ? fmax(0.0, fabs(S.cosm[lane])) : 0.0;  // vs candidate 0 (a NaN cosine is ignored,
+    double m1 = (nc > 1 && lane + 32 < nc) ? fmax(0.0, fabs(S.cosm[lane + 32])) : 0.0;  // like the reference's `maxval < fabs()`)
     for (int t = 1; t < nc; ++t) {
-      double mx = 0.0;
-      for (int s = lane; s < fjb; s += 32) mx = fmax(mx, fabs(S.cosm[S.selpos[s] * 65 + t]));
-      mx = warp_max(mx);
+      const double mine = (t & 32) ? m1 : m0;
+      const double mx = __shfl_sync(0xffffffffu, mine, t & 31);
       if (mx < P.delta && fjb < kmax) {
         if (lane == 0) S.selpos[fjb] = t;
         ++fjb;
+        if (lane < nc) m0 = fmax(m0, fabs(S.cosm[t * 65 + lane]));
+        if (lane + 32 < nc) m1 = fmax(m1, fabs(S.cosm[t * 65 + lane + 32]));
       }
-      __syncwarp();
     }
+    __syncwarp();
     for (int s = lane; s < fjb; s += 32) {
       const int c = S.cand[S.selpos[s]];
       S.sel[s] = c;

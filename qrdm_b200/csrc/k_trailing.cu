@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(256, 2) k_vtc(qrdm_prob P, int wslot_stride_co
 // simply gives a zero row/column, like dlarft.  k_wapply then computes  W2 = -M (sum_s W_s)  for
 // each 128-column tile with DMMA, fusing the slot reduction, the sign (k_rankk adds) and the NaN
 // screen of C (any NaN in C poisons its W column): LAPACKE_dlarfb_mia's -13, src/dlarfb.c:73-75.
-#define TI_THREADS 256
+#define TI_THREADS 1024
 #define TI_SMEM (2 * 64 * 65 * 8)
 
 __device__ __forceinline__ int vt_slot_list(const VtGeom& ge, int vt_grid, int T, int* list, int cap) {
@@ -231,8 +231,15 @@ __global__ void __launch_bounds__(TI_THREADS) k_tinv(qrdm_prob P, int vt_grid, i
   for (int e = tid; e < 4096; e += TI_THREADS) {
     const int s = e >> 6, i = e & 63;  // (V'V)[s][i], needed for s < i < k
     double g = 0.0;
-    if (s < i && i < k)
-      for (int q = 0; q < nslots; ++q) g += P.wp[(size_t)slots[q] * sstride + (size_t)s * wslot_stride_cols + i];
+    if (s < i && i < k) {
+      const double* src = P.wp + (size_t)s * wslot_stride_cols + i;
+      for (int q = 0; q < nslots; q += 4) {  // up to 4 slot loads in flight; fixed summation order
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = (q + u < nslots) ? src[(size_t)slots[q + u] * sstride] : 0.0;
+        g += v[0]; g += v[1]; g += v[2]; g += v[3];
+      }
+    }
     B[i * 65 + s] = taus[i] * g;
   }
   __syncthreads();
@@ -292,16 +299,13 @@ __global__ void __launch_bounds__(256) k_wapply(qrdm_prob P, int vt_grid, int ws
     double2 sacc = make_double2(0.0, 0.0);
     if (pq < ge.kpad) {
       const double* src = P.wp + (size_t)pq * wslot_stride_cols + (size_t)T * VT_BN + cp;
-      int q = 0;
-      for (; q + 1 < ns; q += 2) {  // two independent loads in flight; fixed summation order
-        const double2 v0 = *reinterpret_cast<const double2*>(src + (size_t)slots[q] * sstride);
-        const double2 v1 = *reinterpret_cast<const double2*>(src + (size_t)slots[q + 1] * sstride);
-        sacc.x += v0.x; sacc.y += v0.y;
-        sacc.x += v1.x; sacc.y += v1.y;
-      }
-      if (q < ns) {
-        const double2 v = *reinterpret_cast<const double2*>(src + (size_t)slots[q] * sstride);
-        sacc.x += v.x; sacc.y += v.y;
+      for (int q = 0; q < ns; q += 4) {  // up to 4 slot loads in flight; fixed summation order
+        double2 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          v[u] = (q + u < ns) ? *reinterpret_cast<const double2*>(src + (size_t)slots[q + u] * sstride) : make_double2(0.0, 0.0);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { sacc.x += v[u].x; sacc.y += v[u].y; }
       }
     }
     *reinterpret_cast<double2*>(Ws + pq * WA_LDW + cp) = sacc;
