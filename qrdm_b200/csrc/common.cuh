@@ -20,6 +20,33 @@ __device__ __forceinline__ int qrdm_jr(const qrdm_prob& P, int j) {
   return x < 0 ? 0 : (x > P.m ? P.m : x);
 }
 
+// Geometry the kernels work on: normally the iteration's panel (j, fjb, fjb_cmp) with the trailing
+// matrix to its right; in the blocked tall-panel mode (P.sub = s + 1) the 8-column sub-panel that
+// starts at panel column s, whose "trailing matrix" is the rest of the panel.
+struct QrdmGeom {
+  int j;      // first column (= first global row) of the block being applied
+  int fjb;    // columns of that block (the update starts right after them)
+  int k;      // reflectors in the block
+  int n_end;  // one past the last column the update touches
+  int voff;   // column of Vc that holds reflector 0 of the block
+};
+__device__ __forceinline__ QrdmGeom qrdm_geom(const qrdm_prob& P) {
+  const qrdm_ctrl* c = P.ctrl;
+  QrdmGeom g;
+  if (P.sub == 0) {
+    g.j = c->j; g.fjb = c->fjb; g.k = c->fjb_cmp; g.n_end = P.n; g.voff = 0;
+  } else {
+    const int s = P.sub - 1;
+    const bool dead = s >= c->fjb || (s > 0 && c->tall_done);
+    g.j = c->j + s;
+    g.fjb = dead ? 0 : min(QRDM_TALL_B, c->fjb - s);
+    g.k = dead ? 0 : c->sub_k;
+    g.n_end = c->j + c->fjb;
+    g.voff = s;
+  }
+  return g;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -146,6 +146,11 @@ static int ws_ensure(int m, int n) {
   CU(qrdm_rt_malloc((void **)&w->w2, sizeof(double) * (size_t)w->ldw * 64));
   CU(qrdm_rt_malloc((void **)&w->nrm_part, sizeof(double) * (size_t)cn * w->nrm_splits));
   CU(qrdm_rt_malloc((void **)&w->flag_list, sizeof(int) * (size_t)cn));
+  if ((size_t)(cm / 2048 + 2) * 512 > (size_t)4096 * QRDM_GRAM_MAXCTA) { /* skinny-update partials of very tall matrices */
+    if (w->gram_part) qrdm_rt_free(w->gram_part);
+    w->gram_part = NULL;
+    CU(qrdm_rt_malloc((void **)&w->gram_part, sizeof(double) * (size_t)(cm / 2048 + 2) * 512));
+  }
   w->cap_m = cm;
   w->cap_n = cn;
   return 0;

@@ -54,7 +54,11 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(qrdm_prob P, int rpc
   __shared__ double S_[64], rowv[64], wv[64];
   qrdm_ctrl* ctrl = P.ctrl;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int j = ctrl->j, fjb = ctrl->fjb;
+  // blocked tall-panel mode (P.sub = s + 1): this launch factors the 8-column sub-panel that starts
+  // at panel column s; stop threshold / counters are carried in ctrl (see qrdm_geom)
+  const QrdmGeom qg = qrdm_geom(P);
+  const int j = qg.j, fjb = qg.fjb, sub_s = P.sub ? P.sub - 1 : 0;
+  const int jmain = ctrl->j, fjb_main = ctrl->fjb;
   if (fjb <= 0) return;
   const int rows = P.m - j, lda = P.lda;
   const int G = gridDim.x, b = blockIdx.x;
@@ -86,7 +90,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(qrdm_prob P, int rpc
     if (lane == 0) ll_store(&part[(size_t)b * 64 + jj], acc, tag_base + 1);
   }
 
-  double thres = 5e-14;  // reference src/dgeqr2.c:40
+  double thres = (sub_s == 0) ? 5e-14 : ctrl->tall_thres;  // reference src/dgeqr2.c:40
   int k = fjb;
   long long tph[5] = {0, 0, 0, 0, 0};  // QRDM_B200_DEBUG & 8: per-phase cycle counts of CTA 0
   const bool timing = (P.debug & 8) && b == 0 && tid == 0;
@@ -126,7 +130,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(qrdm_prob P, int rpc
     double tau = 0.0, beta = alpha, scale = 1.0;
     if (len > 1) {
       const double xnorm = sqrt(S_[i]);
-      if (i > 0 && xnorm < thres) { k = i; break; }  // DM early stop: column i left untouched
+      if (sub_s + i > 0 && xnorm < thres) { k = i; break; }  // DM early stop: column i left untouched
       if (xnorm != 0.0) {
         const double h = hypot(alpha, xnorm);
         beta = (alpha >= 0.0) ? -h : h;
@@ -134,7 +138,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(qrdm_prob P, int rpc
         scale = 1.0 / (alpha - beta);
       }
     }
-    if (i == 0 && fjb > 1 && P.tau_ > 0.0) thres = P.tau_ * fabs(beta);  // src/dgeqr2.c:176-177
+    if (sub_s + i == 0 && fjb_main > 1 && P.tau_ > 0.0) thres = P.tau_ * fabs(beta);  // src/dgeqr2.c:176-177
     if (b == 0 && tid == 0) {
       P.tau[j + i] = tau;
       if (tau != tau && ctrl->err == 0) ctrl->err = -8;  // LAPACKE_dlarft's NaN screen of tau
@@ -207,16 +211,27 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(qrdm_prob P, int rpc
     printf("panel j=%d G=%d rpc=%d fjb=%d cycles: reduce %lld bcast %lld scalars+phase1 %lld phase2 %lld\n", j, G, rpc, fjb,
            tph[0], tph[1], tph[2], tph[3]);
   __syncthreads();
-  if (b == 0 && tid == 0) ctrl->fjb_cmp = k;
+  if (b == 0 && tid == 0) {
+    if (P.sub) {
+      const int tk = (sub_s == 0 ? 0 : ctrl->tall_k) + k;
+      ctrl->sub_k = k;
+      ctrl->tall_k = tk;
+      ctrl->tall_done = (k < fjb) ? 1 : 0;  // dead sub-panels never get here, so 0 is right after a full one
+      ctrl->tall_thres = thres;
+      ctrl->fjb_cmp = tk;
+    } else {
+      ctrl->fjb_cmp = k;
+    }
+  }
 
   // ---- write the slab back and emit Vc ----
   if (SMEM) {
     for (int c = wid; c < fjb; c += PANEL_WARPS)
       for (int r = lane; r < nr; r += 32) Ap[(size_t)c * lda + r0 + r] = slab[c * lds + r];
   }
-  const int kpad = (k + 7) & ~7;
+  const int kpad = P.sub ? min(QRDM_TALL_B, 64 - qg.voff) : ((k + 7) & ~7);
   for (int q = wid; q < kpad; q += PANEL_WARPS) {
-    double* vcol = P.vc + (size_t)q * P.ldv + j;
+    double* vcol = P.vc + (size_t)(qg.voff + q) * P.ldv + j;
     for (int r = lane; r < nr; r += 32) {
       const int R = r0 + r;
       double v = 0.0;
@@ -224,8 +239,8 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(qrdm_prob P, int rpc
       vcol[R] = v;
     }
     if (b == 0) {  // rows between the aligned tile start and j must read as zero
-      const int jal = j & ~(QRDM_ROWALIGN - 1);
-      for (int g = jal + lane; g < j; g += 32) P.vc[(size_t)q * P.ldv + g] = 0.0;
+      const int jal = jmain & ~(QRDM_ROWALIGN - 1);
+      for (int g = jal + lane; g < j; g += 32) P.vc[(size_t)(qg.voff + q) * P.ldv + g] = 0.0;
     }
   }
 #undef PX
@@ -241,10 +256,12 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(qrdm_prob P, int rpc
 // whole panel; only the two active columns (v and the next pivot column) pass through smem, the
 // scalars are computed once per warp with a single sqrt (beta^2 = alpha^2 + ||x||^2, stop test on
 // ||x||^2 < thres^2), and the exchange stays the LL reduce-scatter + broadcast of the kernel above.
+// RI = rows per lane: 4 (<= 128 rows per CTA) or 8 (<= 256 rows per CTA, twice the registers)
+template <int RI>
 __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_reg(qrdm_prob P, int rpc, unsigned epoch) {
   __shared__ double sred[PANEL_WARPS];
   __shared__ double S_[64], rowv[64], wv[64];
-  __shared__ double vbuf[128], xbuf[128];
+  __shared__ double vbuf[32 * RI], xbuf[32 * RI];
   qrdm_ctrl* ctrl = P.ctrl;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int j = ctrl->j, fjb = ctrl->fjb;
@@ -257,24 +274,24 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_reg(qrdm_prob P, int
   LLPacket* bcast = reinterpret_cast<LLPacket*>(P.panel_row);
   const unsigned tag_base = epoch << 8;
 
-  double reg[4][4];  // [ri][c]: row r0 + lane + 32*ri, column wid + 16*c
+  double reg[RI][4];  // [ri][c]: row r0 + lane + 32*ri, column wid + 16*c
 #pragma unroll
   for (int c = 0; c < 4; ++c)
 #pragma unroll
-    for (int ri = 0; ri < 4; ++ri) {
+    for (int ri = 0; ri < RI; ++ri) {
       const int r = lane + 32 * ri, jj = wid + 16 * c;
       reg[ri][c] = (r < nr && jj < fjb) ? Ap[(size_t)jj * lda + r0 + r] : 0.0;
     }
   // column 0 through smem so that everybody can form the first dot products
   if (wid == 0) {
 #pragma unroll
-    for (int ri = 0; ri < 4; ++ri) xbuf[lane + 32 * ri] = reg[ri][0];
+    for (int ri = 0; ri < RI; ++ri) xbuf[lane + 32 * ri] = reg[ri][0];
   }
   __syncthreads();
   {
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int ri = 0; ri < 4; ++ri) {
+    for (int ri = 0; ri < RI; ++ri) {
       const int r = lane + 32 * ri, R = r0 + r;
       const double x0 = xbuf[r];
 #pragma unroll
@@ -347,7 +364,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_reg(qrdm_prob P, int
     // ---- publish v (column i, scaled) and the old next pivot column through smem ----
     if (wid == wi) {
 #pragma unroll
-      for (int ri = 0; ri < 4; ++ri) {
+      for (int ri = 0; ri < RI; ++ri) {
         const int r = lane + 32 * ri, R = r0 + r;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -365,7 +382,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_reg(qrdm_prob P, int
     if (!last && wid == ((i + 1) & 15)) {
       const int c1 = (i + 1) >> 4;
 #pragma unroll
-      for (int ri = 0; ri < 4; ++ri)
+      for (int ri = 0; ri < RI; ++ri)
 #pragma unroll
         for (int c = 0; c < 4; ++c)
           if (c == c1) xbuf[lane + 32 * ri] = reg[ri][c];
@@ -386,7 +403,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_reg(qrdm_prob P, int
         acc[c] = 0.0;
       }
 #pragma unroll
-      for (int ri = 0; ri < 4; ++ri) {
+      for (int ri = 0; ri < RI; ++ri) {
         const int r = lane + 32 * ri, R = r0 + r;
         const double v = vbuf[r];
         const double x1 = fma(-v, w1, xbuf[r]);  // next pivot column after H_i
@@ -426,7 +443,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_reg(qrdm_prob P, int
   for (int c = 0; c < 4; ++c) {
     const int jj = wid + 16 * c;
 #pragma unroll
-    for (int ri = 0; ri < 4; ++ri) {
+    for (int ri = 0; ri < RI; ++ri) {
       const int r = lane + 32 * ri, R = r0 + r;
       if (r < nr && jj < fjb) Ap[(size_t)jj * lda + R] = reg[ri][c];
       if (r < nr && jj < kpad) {
@@ -437,6 +454,171 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_reg(qrdm_prob P, int
     }
     if (b == 0 && jj < kpad)
       for (int g = jal + lane; g < j; g += 32) P.vc[(size_t)jj * P.ldv + g] = 0.0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sub-panel kernel of the blocked tall panel: QRDM_TALL_B (= 8) columns, slab in global memory.
+// With so few columns the row dimension is what has to be parallel: threads <-> rows (coalesced,
+// several independent rows in flight per thread), the <= 8 column values of a row live in registers
+// for the whole sweep, and the per-column sums are reduced block-wide once per step.  The cross-CTA
+// exchange is a single hop: every CTA reads all G partials of the <= 8 columns (G*8 LL packets).
+#define TALL_B QRDM_TALL_B
+__global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_tall(qrdm_prob P, int rpc, unsigned epoch) {
+  __shared__ double S_[TALL_B], rowv[TALL_B];
+  __shared__ double sacc[PANEL_WARPS][TALL_B];
+  qrdm_ctrl* ctrl = P.ctrl;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const QrdmGeom qg = qrdm_geom(P);
+  const int j = qg.j, fjb = qg.fjb, sub_s = P.sub - 1;
+  const int jmain = ctrl->j, fjb_main = ctrl->fjb;
+  if (fjb <= 0) return;
+  const int rows = P.m - j, lda = P.lda;
+  const int G = gridDim.x, b = blockIdx.x;
+  const int r0 = min(rows, b * rpc), r1 = min(rows, r0 + rpc), nr = r1 - r0;
+  double* Ap = P.a + (size_t)j * lda + j + r0;  // local row r, sub-panel column c: Ap[c*lda + r]
+  LLPacket* part = reinterpret_cast<LLPacket*>(P.panel_part);  // [2][PANEL_MAXCTA][64]
+  LLPacket* bcast = reinterpret_cast<LLPacket*>(P.panel_row);  // [2][128]
+  const unsigned tag_base = epoch << 8;
+
+  // block-wide sums of acc[0..TALL_B) -> LL packets part[buf][b][jj] for jj in [lo, fjb)
+  auto publish = [&](double (&acc)[TALL_B], int buf, int lo, unsigned tag) {
+#pragma unroll
+    for (int c = 0; c < TALL_B; ++c) acc[c] = warp_sum(acc[c]);
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < TALL_B; ++c) sacc[wid][c] = acc[c];
+    }
+    __syncthreads();
+    if (tid < TALL_B && tid >= lo && tid < fjb) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < PANEL_WARPS; ++w) t += sacc[w][tid];
+      ll_store(&part[((size_t)buf * QRDM_PANEL_MAXCTA + b) * 64 + tid], t, tag);
+    }
+    __syncthreads();
+  };
+
+  {  // dot products of column 0 with every column (rows below the diagonal); row 0 is the pivot row
+    double acc[TALL_B];
+#pragma unroll
+    for (int c = 0; c < TALL_B; ++c) acc[c] = 0.0;
+    for (int r = tid; r < nr; r += PANEL_THREADS) {
+      const int R = r0 + r;
+      double v[TALL_B];
+#pragma unroll
+      for (int c = 0; c < TALL_B; ++c) v[c] = c < fjb ? Ap[(size_t)c * lda + r] : 0.0;
+      if (R > 0) {
+#pragma unroll
+        for (int c = 0; c < TALL_B; ++c) acc[c] = fma(v[0], v[c], acc[c]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < TALL_B; ++c)
+          if (c < fjb) ll_store(&bcast[64 + c], v[c], tag_base + 1);
+      }
+    }
+    publish(acc, 0, 0, tag_base + 1);
+  }
+
+  double thres = (sub_s == 0) ? 5e-14 : ctrl->tall_thres;
+  int k = fjb;
+  for (int i = 0; i < fjb; ++i) {
+    const int cur = i & 1, nxt = cur ^ 1;
+    const unsigned tag = tag_base + i + 1;
+    // ---- gather: warp jj totals column jj over all CTAs (lanes <-> CTAs, fixed order); pivot row ----
+    if (wid < TALL_B && wid >= i && wid < fjb) {
+      double v = 0.0;
+      for (int c = lane; c < G; c += 32) v += ll_load(&part[((size_t)cur * QRDM_PANEL_MAXCTA + c) * 64 + wid], tag);
+      v = warp_sum(v);
+      if (lane == 0) { S_[wid] = v; rowv[wid] = ll_load(&bcast[cur * 128 + 64 + wid], tag); }
+    }
+    __syncthreads();
+    // ---- reflector scalars (dlarfg_mia) ----
+    const double alpha = rowv[i];
+    const int len = rows - i;
+    double tau = 0.0, beta = alpha, scale = 1.0;
+    if (len > 1) {
+      const double xnorm = sqrt(S_[i]);
+      if (sub_s + i > 0 && xnorm < thres) { k = i; break; }  // DM early stop
+      if (xnorm != 0.0) {
+        const double h = hypot(alpha, xnorm);
+        beta = (alpha >= 0.0) ? -h : h;
+        tau = (beta - alpha) / beta;
+        scale = 1.0 / (alpha - beta);
+      }
+    }
+    if (sub_s + i == 0 && fjb_main > 1 && P.tau_ > 0.0) thres = P.tau_ * fabs(beta);
+    if (b == 0 && tid == 0) {
+      P.tau[j + i] = tau;
+      if (tau != tau && ctrl->err == 0) ctrl->err = -8;
+    }
+    double w[TALL_B];
+#pragma unroll
+    for (int c = 0; c < TALL_B; ++c) w[c] = (c > i && c < fjb) ? tau * (rowv[c] + S_[c] * scale) : 0.0;
+    const bool last = i + 1 >= fjb;
+    // ---- sweep: one pass over the rows, all remaining columns of a row in registers ----
+    double acc[TALL_B];
+#pragma unroll
+    for (int c = 0; c < TALL_B; ++c) acc[c] = 0.0;
+    for (int r = tid; r < nr; r += PANEL_THREADS) {
+      const int R = r0 + r;
+      if (R < i) continue;
+      double v = 1.0;
+      if (R > i) {
+        v = Ap[(size_t)i * lda + r];
+        if (tau != 0.0) { v *= scale; Ap[(size_t)i * lda + r] = v; }
+      } else {
+        Ap[(size_t)i * lda + r] = beta;
+      }
+      if (last) continue;
+      double pv[TALL_B];
+#pragma unroll
+      for (int c = 0; c < TALL_B; ++c)
+        if (c > i && c < fjb) pv[c] = Ap[(size_t)c * lda + r];
+      double x1 = 0.0;
+#pragma unroll
+      for (int c = 0; c < TALL_B; ++c) {
+        if (c > i && c < fjb) {
+          pv[c] = fma(-v, w[c], pv[c]);
+          Ap[(size_t)c * lda + r] = pv[c];
+          if (c == i + 1) x1 = pv[c];
+        }
+      }
+      if (R > i + 1) {
+#pragma unroll
+        for (int c = 0; c < TALL_B; ++c)
+          if (c > i && c < fjb) acc[c] = fma(x1, pv[c], acc[c]);
+      } else if (R == i + 1) {
+#pragma unroll
+        for (int c = 0; c < TALL_B; ++c)
+          if (c > i && c < fjb) ll_store(&bcast[nxt * 128 + 64 + c], pv[c], tag + 1);
+      }
+    }
+    if (last) break;
+    publish(acc, nxt, i + 1, tag + 1);
+  }
+  __syncthreads();
+  if (b == 0 && tid == 0) {
+    const int tk = (sub_s == 0 ? 0 : ctrl->tall_k) + k;
+    ctrl->sub_k = k;
+    ctrl->tall_k = tk;
+    ctrl->tall_done = (k < fjb) ? 1 : 0;
+    ctrl->tall_thres = thres;
+    ctrl->fjb_cmp = tk;
+  }
+  // ---- clean copy of the sub-panel's reflectors into Vc columns voff .. voff + 7 ----
+  const int kpad = min(TALL_B, 64 - qg.voff);
+  const int jal = jmain & ~(QRDM_ROWALIGN - 1);
+  for (int q = 0; q < kpad; ++q) {
+    double* vcol = P.vc + (size_t)(qg.voff + q) * P.ldv + j + r0;
+    for (int r = tid; r < nr; r += PANEL_THREADS) {
+      const int R = r0 + r;
+      double v = 0.0;
+      if (q < k) v = (R > q) ? Ap[(size_t)q * lda + r] : (R == q ? 1.0 : 0.0);
+      vcol[r] = v;
+    }
+    if (b == 0)
+      for (int g = jal + tid; g < j; g += PANEL_THREADS) P.vc[(size_t)(qg.voff + q) * P.ldv + g] = 0.0;
   }
 }
 
@@ -455,15 +637,51 @@ extern "C" int qrdm_k_panel(const qrdm_prob* p, int j_host, void* stream) {
   // few, fat CTAs: the per-column cost is the grid barrier + the all-to-all read of the partials,
   // both proportional to the CTA count; grow the grid only when the slab would not fit in smem
   const int gmax = p->sm_count < QRDM_PANEL_MAXCTA ? p->sm_count : QRDM_PANEL_MAXCTA;
-  if (rows <= 128 * gmax && !getenv("QRDM_PANEL_NOREG")) {  // register-resident slabs, 128 rows per CTA
-    int Gr = (rows + 127) / 128, rpcr = (rows + Gr - 1) / Gr;
+  if (rows <= 256 * gmax && !getenv("QRDM_PANEL_NOREG")) {  // register-resident slabs, 128 (or 256) rows per CTA
+    const int per = rows <= 128 * gmax ? 128 : 256;
+    int Gr = (rows + per - 1) / per, rpcr = (rows + Gr - 1) / Gr;
     static unsigned epoch_r = 0x400000;
     epoch_r = epoch_r + 1 >= 0x7fffff ? 0x400000 : epoch_r + 1;
     qrdm_prob prob_r = *p;
     void* args_r[] = {(void*)&prob_r, (void*)&rpcr, (void*)&epoch_r};
-    cudaError_t er = cudaLaunchCooperativeKernel((void*)k_panel_reg, dim3(Gr), dim3(PANEL_THREADS), args_r, 0, (cudaStream_t)stream);
+    cudaError_t er = per == 128
+        ? cudaLaunchCooperativeKernel((void*)k_panel_reg<4>, dim3(Gr), dim3(PANEL_THREADS), args_r, 0, (cudaStream_t)stream)
+        : cudaLaunchCooperativeKernel((void*)k_panel_reg<8>, dim3(Gr), dim3(PANEL_THREADS), args_r, 0, (cudaStream_t)stream);
     ++g_qrdm_launches;
     return er == cudaSuccess ? 0 : (int)er;
+  }
+  if (!getenv("QRDM_PANEL_NOBLOCK")) {
+    // Tall panel (the slab does not fit in the register file of the whole chip): blocked Householder.
+    // 8-column sub-panels are factored by the LL kernel above on 8 columns only, and each sub-panel's
+    // block reflector is applied to the rest of the panel with the trailing-update kernels (K6) — the
+    // unblocked sweep streamed all remaining panel columns through HBM for every single column
+    // (371 of 439 ms on 2,000,000 x 512).  The DM early stop is unchanged: the stop test runs inside
+    // the sub-panel kernel with the threshold carried in ctrl, and the reflectors produced before a
+    // stop are still applied to the rest of the panel, as the unblocked reference does.
+    int kmax_h = p->nb;
+    if (kmax_h > p->n - j_host) kmax_h = p->n - j_host;
+    if (kmax_h > p->m_glob - j_host) kmax_h = p->m_glob - j_host;
+    static unsigned epoch_t = 0;
+    for (int sb = 0; sb < kmax_h; sb += QRDM_TALL_B) {
+      const int rows_s = rows - sb;
+      if (rows_s <= 0) break;
+      int Gs = (rows_s + 1023) / 1024;  // >= 2 rows per thread; every SM streams its share of the rows
+      if (Gs > gmax) Gs = gmax;
+      if (Gs < 1) Gs = 1;
+      int rpcs = (rows_s + Gs - 1) / Gs;
+      epoch_t = epoch_t + 1 >= 0x200000 ? 1 : epoch_t + 1;
+      qrdm_prob prob_s = *p;
+      prob_s.sub = sb + 1;
+      void* args_s[] = {(void*)&prob_s, (void*)&rpcs, (void*)&epoch_t};
+      cudaError_t es = cudaLaunchCooperativeKernel((void*)k_panel_tall, dim3(Gs), dim3(PANEL_THREADS), args_s, 0, (cudaStream_t)stream);
+      ++g_qrdm_launches;
+      if (es != cudaSuccess) return (int)es;
+      if (sb + QRDM_TALL_B < kmax_h) {  // apply the sub-panel's reflectors to the rest of the panel
+        const int rc = qrdm_k_skinny_update(&prob_s, rows_s, stream);
+        if (rc) return rc;
+      }
+    }
+    return 0;
   }
   int G = (rows + rows_per_cta - 1) / rows_per_cta;
   const int gfit = (rows + (smem_cap / 512) - 1) / (smem_cap / 512);  // CTAs needed for smem residency
@@ -471,8 +689,8 @@ extern "C" int qrdm_k_panel(const qrdm_prob* p, int j_host, void* stream) {
   if (G > gmax) G = gmax;
   if (G < 1) G = 1;
   int rpc = (rows + G - 1) / G;
-  static unsigned epoch = 0;
-  epoch = epoch + 1 >= 0x400000 ? 1 : epoch + 1;  // tags (epoch << 8) + step; the register kernel uses the upper half
+  static unsigned epoch = 0x200000;
+  epoch = epoch + 1 >= 0x400000 ? 0x200000 : epoch + 1;  // tags (epoch << 8) + step: [1,2^21) blocked, [2^21,2^22) unblocked, upper half register kernel
   qrdm_prob prob = *p;
   void* args[] = {(void*)&prob, (void*)&rpc, (void*)&epoch};
   const size_t smem = (size_t)rpc * 64 * sizeof(double);

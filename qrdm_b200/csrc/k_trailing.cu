@@ -36,14 +36,14 @@ __device__ __forceinline__ int vt_sw(int col, int rowpair_idx) { return col * VT
 #define VT_SMEM (VT_STAGES * VT_STAGE_DOUBLES * 8)
 
 struct VtGeom {
-  int j, jr, fjb, k, nc, kpad, jal, NCH, CT;  // j: columns done; jr: first active LOCAL row; CT counts the V'V tile
+  int j, jr, fjb, k, nc, kpad, jal, NCH, CT, voff;  // j: columns done; jr: first active LOCAL row; CT counts the V'V tile
   long long U;
 };
 __device__ __forceinline__ VtGeom vt_geom(const qrdm_prob& P) {
   VtGeom g;
-  const qrdm_ctrl* ctrl = P.ctrl;
-  g.j = ctrl->j; g.fjb = ctrl->fjb; g.k = ctrl->fjb_cmp;
-  g.nc = P.n - g.j - g.fjb;
+  const QrdmGeom q = qrdm_geom(P);
+  g.j = q.j; g.fjb = q.fjb; g.k = q.k; g.voff = q.voff;
+  g.nc = q.n_end - g.j - g.fjb;
   g.kpad = (g.k + 7) & ~7;
   g.jr = qrdm_jr(P, g.j);
   g.jal = g.jr & ~(QRDM_ROWALIGN - 1);
@@ -99,13 +99,13 @@ __device__ __forceinline__ void vtc_body(const qrdm_prob& P, const VtGeom& ge, i
     const int r0 = ge.jal + chunk * VT_BK;
     for (int id = tid; id < ge.kpad * 16; id += 256) {  // V: kpad columns x 16 row pairs
       const int q = id >> 4, rp = (id & 15) * 2;
-      cp_async16(Vs + vt_sw(q, rp >> 1), P.vc + (size_t)q * P.ldv + r0 + rp, 16);
+      cp_async16(Vs + vt_sw(q, rp >> 1), P.vc + (size_t)(ge.voff + q) * P.ldv + r0 + rp, 16);
     }
     if (T == 0) {  // the "C" tile is V itself (columns >= kpad read as zero)
       for (int id = tid; id < VT_BN * 16; id += 256) {
         const int c = id >> 4, rp = (id & 15) * 2;
         const bool ok = c < ge.kpad;
-        cp_async16(Cs + vt_sw(c, rp >> 1), ok ? P.vc + (size_t)c * P.ldv + r0 + rp : P.vc, ok ? 16 : 0);
+        cp_async16(Cs + vt_sw(c, rp >> 1), ok ? P.vc + (size_t)(ge.voff + c) * P.ldv + r0 + rp : P.vc, ok ? 16 : 0);
       }
     } else {
       const int c0 = (T - 1) * VT_BN;
@@ -379,9 +379,11 @@ __global__ void __launch_bounds__(RK_THREADS, 2) k_rankk(qrdm_prob P) {
   double* Wsb = sm + 64 * RK_LDV;  // 2 x [q][RK_LDW]
   const qrdm_ctrl* ctrl = P.ctrl;
   const int tid = threadIdx.x, lane = tid & 31, wr = tid >> 5, g = lane >> 2, t = lane & 3;
-  const int jc = ctrl->j, fjb = ctrl->fjb, k = ctrl->fjb_cmp;
-  const int nc = P.n - jc - fjb;
+  const QrdmGeom qg = qrdm_geom(P);
+  const int jc = qg.j, fjb = qg.fjb, k = qg.k;
+  const int nc = qg.n_end - jc - fjb;
   if (nc <= 0 || k <= 0) return;
+  (void)ctrl;
   const int j = qrdm_jr(P, jc);  // first active local row (== jc on a single GPU)
   if (j >= P.m) return;          // row-sharded: this rank has no rows left
   const int kpad = (k + 7) & ~7;
@@ -407,7 +409,7 @@ __global__ void __launch_bounds__(RK_THREADS, 2) k_rankk(qrdm_prob P) {
     const int R0 = jal + rb * RK_BM;
     for (int id = tid; id < kpad * (RK_BM / 2); id += RK_THREADS) {
       const int q = id >> 6, rp = (id & 63) * 2;
-      cp_async16(Vs + q * RK_LDV + rp, P.vc + (size_t)q * P.ldv + R0 + rp, 16);  // ldv covers the tile
+      cp_async16(Vs + q * RK_LDV + rp, P.vc + (size_t)(qg.voff + q) * P.ldv + R0 + rp, 16);  // ldv covers the tile
     }
   };
   auto interior = [&](int rb, int ct) {

@@ -17,6 +17,7 @@ extern "C" {
 #define QRDM_GRAM_MAXCTA 296
 #define QRDM_PANEL_MAXCTA 148
 #define QRDM_ERR_INTERNAL (-103) /* planner overflow: cannot happen for nb <= QRDM_KMAX */
+#define QRDM_TALL_B 8     /* sub-panel width of the blocked panel used when the slab does not fit on chip */
 #define QRDM_ROWALIGN 32   /* row tiles of the trailing kernels start at multiples of this */
 
 /* Device-resident control block.  The first QRDM_MAILBOX_BYTES are mirrored into a pinned host
@@ -40,6 +41,12 @@ typedef struct qrdm_ctrl {
   int mg_k;               /* row-sharded panel: column at which the early stop fired, or -1 */
   int pad3_[2];
   double mg_thres2;       /* row-sharded panel: squared stop threshold carried across step kernels */
+  /* tall (blocked) panel: state carried across the 8-column sub-panels */
+  int sub_k;              /* reflectors produced by the current sub-panel */
+  int tall_k;             /* reflectors produced so far by this panel */
+  int tall_done;          /* 1 once the early stop fired: later sub-panels are no-ops */
+  int pad4_;
+  double tall_thres;      /* stop threshold (set by the panel's first column) */
   int cand[QRDM_KMAX];        /* candidate column offsets (relative to j), by norm descending */
   double candnrm[QRDM_KMAX];  /* their partial norms */
   int sel[QRDM_KMAX];         /* accepted offsets, acceptance order */
@@ -77,6 +84,8 @@ typedef struct qrdm_prob {
    * columns; m_glob = total rows.  Single GPU: row0 = 0, m_glob = m, nranks = 1. */
   int row0, m_glob, nranks;
   int w_reduced;      /* 1: partial-W slot 0 already holds the (all-reduced) sum over all slots */
+  int sub;            /* tall blocked panel: s + 1 when the kernels work on the sub-panel starting at panel
+                         column s (geometry from qrdm_sub_geom), 0 otherwise */
   double *mg_buf;     /* sharded panel: [2][128] send/recv vectors + [G][128] per-CTA partials */
   unsigned *mg_cnt;   /* sharded panel: arrival counter of the last-CTA reduction */
 } qrdm_prob;
@@ -98,6 +107,7 @@ int qrdm_k_norm_apply(const qrdm_prob *p, int j_host, void *stream);
 int qrdm_k_vtc_only(const qrdm_prob *p, int j_host, int *stride_out, int *grid_out, void *stream);
 int qrdm_k_wreduce(const qrdm_prob *p, int j_host, int vt_grid, int stride, void *stream);
 int qrdm_k_trailing_finish(const qrdm_prob *p, int j_host, int vt_grid, int stride, void *stream);
+int qrdm_k_skinny_update(const qrdm_prob *p, int rows_hint, void *stream); /* tall panel: sub-panel -> rest of panel */
 int qrdm_k_panel_mg_init(const qrdm_prob *p, int j_host, void *stream);
 int qrdm_k_panel_mg_step(const qrdm_prob *p, int j_host, int step, void *stream);
 int qrdm_k_panel_mg_finish(const qrdm_prob *p, int j_host, void *stream);
