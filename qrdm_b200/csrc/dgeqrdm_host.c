@@ -307,13 +307,40 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
       if (qrdm_rt_allreduce(P.gram, 4096, stream)) return QRDM_ERR_COMM;
       CU(qrdm_k_pick(&P, stream));
       CU(qrdm_k_permute(&P, stream));
-      CU(qrdm_k_panel_mg_init(&P, j, stream));
-      if (qrdm_rt_allreduce(P.mg_buf, 128, stream)) return QRDM_ERR_COMM;
-      for (int i = 0; i < kmax_h; ++i) {
-        CU(qrdm_k_panel_mg_step(&P, j, i, stream));
-        if (i + 1 < kmax_h && qrdm_rt_allreduce(P.mg_buf + ((i + 1) & 1) * 128, 128, stream)) return QRDM_ERR_COMM;
+      if ((m_glob - j) / P.nranks <= 16384) {
+        /* one kernel + one 128-double all-reduce per panel column */
+        CU(qrdm_k_panel_mg_init(&P, j, stream));
+        if (qrdm_rt_allreduce(P.mg_buf, 128, stream)) return QRDM_ERR_COMM;
+        for (int i = 0; i < kmax_h; ++i) {
+          CU(qrdm_k_panel_mg_step(&P, j, i, stream));
+          if (i + 1 < kmax_h && qrdm_rt_allreduce(P.mg_buf + ((i + 1) & 1) * 128, 128, stream)) return QRDM_ERR_COMM;
+        }
+        CU(qrdm_k_panel_mg_finish(&P, j, stream));
+      } else {
+        /* tall local slabs: blocked panel — 8-column sub-panels (per-column kernel + all-reduce on 8
+         * columns only), each followed by the skinny update of the rest of the panel, whose 8 x 64
+         * product V'[V | C_p] is all-reduced (512 doubles).  The choice depends on global sizes
+         * only, so every rank issues the same sequence of collectives. */
+        for (int sb = 0; sb < kmax_h; sb += QRDM_TALL_B) {
+          qrdm_prob Ps = P;
+          Ps.sub = sb + 1;
+          const int wsub = kmax_h - sb < QRDM_TALL_B ? kmax_h - sb : QRDM_TALL_B;
+          int jrs = j + sb - P.row0;
+          jrs = jrs < 0 ? 0 : (jrs > m ? m : jrs);
+          CU(qrdm_k_panel_mg_init(&Ps, j, stream));
+          if (qrdm_rt_allreduce(P.mg_buf, 128, stream)) return QRDM_ERR_COMM;
+          for (int i = 0; i < wsub; ++i) {
+            CU(qrdm_k_panel_mg_step(&Ps, j, i, stream));
+            if (i + 1 < wsub && qrdm_rt_allreduce(P.mg_buf + ((i + 1) & 1) * 128, 128, stream)) return QRDM_ERR_COMM;
+          }
+          CU(qrdm_k_panel_mg_finish(&Ps, j, stream));
+          if (sb + QRDM_TALL_B < kmax_h) {
+            CU(qrdm_k_skinny_part(&Ps, m - jrs > 0 ? m - jrs : 1, stream));
+            if (qrdm_rt_allreduce(P.gram_part, 512, stream)) return QRDM_ERR_COMM;
+            CU(qrdm_k_skinny_finish(&Ps, m - jrs > 0 ? m - jrs : 1, stream));
+          }
+        }
       }
-      CU(qrdm_k_panel_mg_finish(&P, j, stream));
       CU(qrdm_k_vtc_only(&P, j, &vt_stride, &vt_grid, stream));
       if (vt_stride > 0) {
         CU(qrdm_k_wreduce(&P, j, vt_grid, vt_stride, stream));

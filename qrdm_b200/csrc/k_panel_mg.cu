@@ -17,10 +17,14 @@
 
 struct MgGeom {
   int j, jr, fjb, rows, pr0, rpc, r0, nr;  // pr0: panel-relative global index of local row jr
+  int sub_s, voff, jmain, fjb_main;        // blocked tall-panel mode: sub-panel at panel column sub_s
 };
 __device__ __forceinline__ MgGeom mg_geom(const qrdm_prob& P) {
   MgGeom g;
-  g.j = P.ctrl->j; g.fjb = P.ctrl->fjb;
+  const QrdmGeom q = qrdm_geom(P);
+  g.j = q.j; g.fjb = q.fjb; g.voff = q.voff;
+  g.sub_s = P.sub ? P.sub - 1 : 0;
+  g.jmain = P.ctrl->j; g.fjb_main = P.ctrl->fjb;
   g.jr = qrdm_jr(P, g.j);
   g.rows = P.m - g.jr;                 // local active rows
   g.pr0 = P.row0 + g.jr - g.j;         // >= 0
@@ -59,7 +63,7 @@ __global__ void __launch_bounds__(MG_THREADS) k_panel_mg_init(qrdm_prob P) {
   const MgGeom g = mg_geom(P);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, lda = P.lda;
   if (g.fjb <= 0) return;
-  if (blockIdx.x == 0 && tid == 0) { P.ctrl->mg_k = -1; P.ctrl->mg_thres2 = 5e-14 * 5e-14; }
+  if (blockIdx.x == 0 && tid == 0) { P.ctrl->mg_k = -1; if (g.sub_s == 0) P.ctrl->mg_thres2 = 5e-14 * 5e-14; }
   double* Ap = P.a + (size_t)g.j * lda + g.jr;
   double* mine = P.mg_buf + 512 + (size_t)blockIdx.x * 128;
   for (int e = tid; e < 128; e += MG_THREADS) mine[e] = 0.0;
@@ -93,7 +97,7 @@ __global__ void __launch_bounds__(MG_THREADS) k_panel_mg_step(qrdm_prob P, int i
   double thres2 = ctrl->mg_thres2;
   double tau = 0.0, beta = alpha, scale = 1.0;
   if (len > 1) {
-    if (i > 0 && xn2 < thres2) {  // DM early stop: column i left untouched (every rank, every CTA alike)
+    if (g.sub_s + i > 0 && xn2 < thres2) {  // DM early stop: column i left untouched (every rank, every CTA alike)
       if (blockIdx.x == 0 && tid == 0) ctrl->mg_k = i;
       return;
     }
@@ -105,7 +109,7 @@ __global__ void __launch_bounds__(MG_THREADS) k_panel_mg_step(qrdm_prob P, int i
     }
   }
   if (blockIdx.x == 0 && tid == 0) {
-    if (i == 0 && g.fjb > 1 && P.tau_ > 0.0) { const double th = P.tau_ * fabs(beta); ctrl->mg_thres2 = th * th; }
+    if (g.sub_s + i == 0 && g.fjb_main > 1 && P.tau_ > 0.0) { const double th = P.tau_ * fabs(beta); ctrl->mg_thres2 = th * th; }
     P.tau[g.j + i] = tau;
     if (tau != tau && ctrl->err == 0) ctrl->err = -8;
   }
@@ -163,12 +167,22 @@ __global__ void __launch_bounds__(MG_THREADS) k_panel_mg_finish(qrdm_prob P) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, lda = P.lda;
   if (g.fjb <= 0) return;
   const int k = ctrl->mg_k >= 0 ? ctrl->mg_k : g.fjb;
-  if (blockIdx.x == 0 && tid == 0) ctrl->fjb_cmp = k;  // read by later kernels only
+  if (blockIdx.x == 0 && tid == 0) {  // read by later kernels only
+    if (P.sub) {
+      const int tk = (g.sub_s == 0 ? 0 : ctrl->tall_k) + k;
+      ctrl->sub_k = k;
+      ctrl->tall_k = tk;
+      ctrl->tall_done = (k < g.fjb) ? 1 : 0;
+      ctrl->fjb_cmp = tk;
+    } else {
+      ctrl->fjb_cmp = k;
+    }
+  }
   const double* Ap = P.a + (size_t)g.j * lda + g.jr;
-  const int kpad = (k + 7) & ~7;
-  const int jal = g.jr & ~(QRDM_ROWALIGN - 1);
+  const int kpad = P.sub ? min(QRDM_TALL_B, 64 - g.voff) : ((k + 7) & ~7);
+  const int jal = qrdm_jr(P, g.jmain) & ~(QRDM_ROWALIGN - 1);
   for (int q = wid; q < kpad; q += MG_WARPS) {
-    double* vcol = P.vc + (size_t)q * P.ldv + g.jr;
+    double* vcol = P.vc + (size_t)(g.voff + q) * P.ldv + g.jr;
     for (int r = lane; r < g.nr; r += 32) {
       const int R = g.pr0 + g.r0 + r;
       double v = 0.0;
@@ -176,12 +190,13 @@ __global__ void __launch_bounds__(MG_THREADS) k_panel_mg_finish(qrdm_prob P) {
       vcol[g.r0 + r] = v;
     }
     if (blockIdx.x == 0)
-      for (int gg = jal + lane; gg < g.jr; gg += 32) P.vc[(size_t)q * P.ldv + gg] = 0.0;
+      for (int gg = jal + lane; gg < g.jr; gg += 32) P.vc[(size_t)(g.voff + q) * P.ldv + gg] = 0.0;
   }
 }
 #undef PA
 
 static int mg_grid(const qrdm_prob* p, int j_host) {
+  if (p->sub) j_host += p->sub - 1;
   int jr = j_host - p->row0;
   jr = jr < 0 ? 0 : (jr > p->m ? p->m : jr);
   const int rows = p->m - jr;

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(512) k_sub_w2(qrdm_prob P, int nchunks_max) {
   const SkGeom g = sk_geom(P);
   if (g.k <= 0 || g.ncp <= 0) return;
   const int tid = threadIdx.x;
-  const int nchunks = min(nchunks_max, (g.rows + SK_RC - 1) / SK_RC);
+  const int nchunks = P.w_reduced ? 1 : min(nchunks_max, (g.rows + SK_RC - 1) / SK_RC);  // w_reduced: chunk 0 = all-reduced sum
   const int ngroups = 1 + (g.ncp + 7) / 8;
   if (tid < ngroups * 64) {
     double s = 0.0;
@@ -158,6 +158,17 @@ __global__ void __launch_bounds__(SK_THREADS, 1) k_sub_apply(qrdm_prob P) {
   }
 }
 
+// row-sharded build: fold the chunk partials into chunk 0 (fixed order) so that 512 doubles can be
+// all-reduced; a rank without rows contributes zeros
+__global__ void __launch_bounds__(512) k_sub_wred(qrdm_prob P, int nchunks_max) {
+  const SkGeom g = sk_geom(P);
+  if (g.k <= 0 || g.ncp <= 0) return;
+  const int nchunks = min(nchunks_max, g.rows > 0 ? (g.rows + SK_RC - 1) / SK_RC : 0);
+  double s = 0.0;
+  for (int b = 0; b < nchunks; ++b) s += P.gram_part[(size_t)b * 512 + threadIdx.x];
+  P.gram_part[threadIdx.x] = s;
+}
+
 // rows_hint: host-side upper bound of the rows of the sub-panel
 extern "C" int qrdm_k_skinny_update(const qrdm_prob* p, int rows_hint, void* stream) {
   static bool attr_set = false;
@@ -172,6 +183,34 @@ extern "C" int qrdm_k_skinny_update(const qrdm_prob* p, int rows_hint, void* str
   k_sub_w<<<nch, SK_THREADS, SK_SMEM, s>>>(*p);
   QRDM_LAUNCH_CHECK();
   k_sub_w2<<<1, 512, 0, s>>>(*p, nch);
+  QRDM_LAUNCH_CHECK();
+  k_sub_apply<<<nch, SK_THREADS, SK_SMEM, s>>>(*p);
+  QRDM_LAUNCH_CHECK();
+  return 0;
+}
+
+// row-sharded variant, split at the all-reduce: part 1 = partials folded into gram_part[0..512)
+extern "C" int qrdm_k_skinny_part(const qrdm_prob* p, int rows_hint, void* stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_sub_w, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM);
+    cudaFuncSetAttribute(k_sub_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM);
+    attr_set = true;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  int nch = (rows_hint + SK_RC - 1) / SK_RC;
+  if (nch < 1) nch = 1;
+  k_sub_w<<<nch, SK_THREADS, SK_SMEM, s>>>(*p);
+  QRDM_LAUNCH_CHECK();
+  k_sub_wred<<<1, 512, 0, s>>>(*p, nch);
+  QRDM_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int qrdm_k_skinny_finish(const qrdm_prob* p, int rows_hint, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  int nch = (rows_hint + SK_RC - 1) / SK_RC;
+  if (nch < 1) nch = 1;
+  k_sub_w2<<<1, 512, 0, s>>>(*p, 1);
   QRDM_LAUNCH_CHECK();
   k_sub_apply<<<nch, SK_THREADS, SK_SMEM, s>>>(*p);
   QRDM_LAUNCH_CHECK();

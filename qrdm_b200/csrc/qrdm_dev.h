@@ -108,6 +108,8 @@ int qrdm_k_vtc_only(const qrdm_prob *p, int j_host, int *stride_out, int *grid_o
 int qrdm_k_wreduce(const qrdm_prob *p, int j_host, int vt_grid, int stride, void *stream);
 int qrdm_k_trailing_finish(const qrdm_prob *p, int j_host, int vt_grid, int stride, void *stream);
 int qrdm_k_skinny_update(const qrdm_prob *p, int rows_hint, void *stream); /* tall panel: sub-panel -> rest of panel */
+int qrdm_k_skinny_part(const qrdm_prob *p, int rows_hint, void *stream);   /* row-sharded: before the all-reduce */
+int qrdm_k_skinny_finish(const qrdm_prob *p, int rows_hint, void *stream); /* row-sharded: after it */
 int qrdm_k_panel_mg_init(const qrdm_prob *p, int j_host, void *stream);
 int qrdm_k_panel_mg_step(const qrdm_prob *p, int j_host, int step, void *stream);
 int qrdm_k_panel_mg_finish(const qrdm_prob *p, int j_host, void *stream);

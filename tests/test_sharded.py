@@ -91,7 +91,8 @@ def test_sharded_code_path_on_one_gpu(oracle_ref, monkeypatch):
     monkeypatch.setenv("QRDM_B200_FORCE_MG", "1")
     try:
         for A, kw in [(g.gaussian(700, 300, 21), {}), (g.gaussian(300, 450, 22), {}),
-                      (g.kahan(130), {}), (g.gaussian(5000, 160, 23), dict(nb=32, thres=(0.7, 0.3)))]:
+                      (g.kahan(130), {}), (g.gaussian(5000, 160, 23), dict(nb=32, thres=(0.7, 0.3))),
+                      (g.gaussian(40000, 100, 24), {})]:   # > 16384 rows per rank: blocked sharded panel
             m, n = A.shape
             lda = m + (m & 1)
             loc = torch.zeros((n, lda), dtype=torch.float64, device="cuda")
