@@ -10,8 +10,8 @@
 #include "common.cuh"
 
 #define SK_RC 2048           // rows per CTA chunk
-#define SK_THREADS 512       // thread = (column c = tid >> 6, row lane rl = tid & 63)
-#define SK_SMEM (SK_RC * 8 * 8)
+#define SK_THREADS 256       // thread <-> rows tid, tid+256, ... of the chunk (coalesced per column)
+#define SK_RPT (SK_RC / SK_THREADS)
 
 struct SkGeom { int j, jr, k, ncp, rows, c0, voff; };
 __device__ __forceinline__ SkGeom sk_geom(const qrdm_prob& P) {
@@ -25,57 +25,59 @@ __device__ __forceinline__ SkGeom sk_geom(const qrdm_prob& P) {
   if (q.fjb <= 0) g.k = 0;
   return g;
 }
-__device__ __forceinline__ void sk_load_v(const qrdm_prob& P, const SkGeom& g, double* Vs, int row0, int nrc) {
-  for (int e = threadIdx.x; e < SK_RC * 8; e += SK_THREADS) {
-    const int q = e / SK_RC, r = e - q * SK_RC;  // consecutive threads -> consecutive rows (coalesced)
-    Vs[r * 8 + q] = (r < nrc && q < g.k) ? P.vc[(size_t)(g.voff + q) * P.ldv + g.jr + row0 + r] : 0.0;
-  }
-}
 
+// W_ext partial of one 2048-row chunk.  Each thread keeps the 8 reflector entries of its row in
+// registers and, per group of 8 columns, issues 8 independent loads and 64 FMAs into an 8x8
+// register tile; the tiles are reduced block-wide once per group (fixed order).
 __global__ void __launch_bounds__(SK_THREADS, 1) k_sub_w(qrdm_prob P) {
-  extern __shared__ __align__(16) double Vs[];  // [row][8]
-  __shared__ double red[SK_THREADS / 32][8];
+  __shared__ double red[SK_THREADS / 32][64];
   const SkGeom g = sk_geom(P);
   if (g.k <= 0 || g.ncp <= 0) return;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, c = tid >> 6, rl = tid & 63;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int row0 = blockIdx.x * SK_RC;
   if (row0 >= g.rows) return;
   const int nrc = min(SK_RC, g.rows - row0);
-  sk_load_v(P, g, Vs, row0, nrc);
-  __syncthreads();
   const int ngroups = 1 + (g.ncp + 7) / 8;
   double* out = P.gram_part + (size_t)blockIdx.x * 512;  // [group][q][c]: 8 groups x 64
+  const double* vbase = P.vc + (size_t)g.voff * P.ldv + g.jr + row0;
+  const double* abase = P.a + (size_t)g.c0 * P.lda + g.jr + row0;
   for (int gi = 0; gi < ngroups; ++gi) {
-    double acc[8];
+    double acc[8][8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) acc[q] = 0.0;
-    const int col = (gi - 1) * 8 + c;
-    const bool ok = gi == 0 || col < g.ncp;
-    const double* src = P.a + (size_t)(g.c0 + (gi == 0 ? 0 : col)) * P.lda + g.jr + row0;
-#pragma unroll 4
-    for (int r = rl; r < nrc; r += 64) {
-      const double x = gi == 0 ? Vs[r * 8 + c] : (ok ? src[r] : 0.0);
-      const double2 v01 = *reinterpret_cast<const double2*>(Vs + r * 8);
-      const double2 v23 = *reinterpret_cast<const double2*>(Vs + r * 8 + 2);
-      const double2 v45 = *reinterpret_cast<const double2*>(Vs + r * 8 + 4);
-      const double2 v67 = *reinterpret_cast<const double2*>(Vs + r * 8 + 6);
-      acc[0] = fma(v01.x, x, acc[0]); acc[1] = fma(v01.y, x, acc[1]);
-      acc[2] = fma(v23.x, x, acc[2]); acc[3] = fma(v23.y, x, acc[3]);
-      acc[4] = fma(v45.x, x, acc[4]); acc[5] = fma(v45.y, x, acc[5]);
-      acc[6] = fma(v67.x, x, acc[6]); acc[7] = fma(v67.y, x, acc[7]);
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[q][c] = 0.0;
+    for (int it = 0; it < SK_RPT; ++it) {
+      const int r = tid + it * SK_THREADS;
+      if (r >= nrc) break;
+      double v[8], x[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = q < g.k ? vbase[(size_t)q * P.ldv + r] : 0.0;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int col = (gi - 1) * 8 + c;
+        x[c] = gi == 0 ? v[c] : (col < g.ncp ? abase[(size_t)col * P.lda + r] : 0.0);
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[q][c] = fma(v[q], x[c], acc[q][c]);
     }
 #pragma unroll
-    for (int q = 0; q < 8; ++q) acc[q] = warp_sum(acc[q]);
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const double t = warp_sum(acc[q][c]);
+        if (lane == 0) red[wid][q * 8 + c] = t;
+      }
     __syncthreads();
-    if (lane == 0) {
+    if (tid < 64) {
+      double t = 0.0;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) red[wid][q] = acc[q];
+      for (int w = 0; w < SK_THREADS / 32; ++w) t += red[w][tid];
+      out[gi * 64 + tid] = t;
     }
     __syncthreads();
-    if (tid < 64) {  // (q, cc): the two warps of column cc
-      const int q = tid >> 3, cc = tid & 7;
-      out[gi * 64 + q * 8 + cc] = red[2 * cc][q] + red[2 * cc + 1][q];
-    }
   }
 }
 
@@ -88,9 +90,16 @@ __global__ void __launch_bounds__(512) k_sub_w2(qrdm_prob P, int nchunks_max) {
   const int nchunks = P.w_reduced ? 1 : min(nchunks_max, (g.rows + SK_RC - 1) / SK_RC);  // w_reduced: chunk 0 = all-reduced sum
   const int ngroups = 1 + (g.ncp + 7) / 8;
   if (tid < ngroups * 64) {
-    double s = 0.0;
-    for (int b = 0; b < nchunks; ++b) s += P.gram_part[(size_t)b * 512 + tid];  // fixed order
-    W[tid] = s;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int b = 0;
+    for (; b + 3 < nchunks; b += 4) {  // fixed association order
+      s0 += P.gram_part[(size_t)b * 512 + tid];
+      s1 += P.gram_part[(size_t)(b + 1) * 512 + tid];
+      s2 += P.gram_part[(size_t)(b + 2) * 512 + tid];
+      s3 += P.gram_part[(size_t)(b + 3) * 512 + tid];
+    }
+    for (; b < nchunks; ++b) s0 += P.gram_part[(size_t)b * 512 + tid];
+    W[tid] = (s0 + s1) + (s2 + s3);
   }
   __syncthreads();
   if (tid < 8) {  // column p = tid of X = (I + D N)^-1, N = strictly-lower V'V, D = diag(tau); T' = X D
@@ -121,39 +130,46 @@ __global__ void __launch_bounds__(512) k_sub_w2(qrdm_prob P, int nchunks_max) {
   }
 }
 
-__global__ void __launch_bounds__(SK_THREADS, 1) k_sub_apply(qrdm_prob P) {
-  extern __shared__ __align__(16) double Vs[];  // [row][8]
+// C_p += V W2: per group of 8 columns the 8x8 block of W2 sits in registers; every row needs 8
+// independent loads, 64 FMAs and 8 stores.
+__global__ void __launch_bounds__(SK_THREADS, 2) k_sub_apply(qrdm_prob P) {
   __shared__ double W2s[8 * 64];
   const SkGeom g = sk_geom(P);
   if (g.k <= 0 || g.ncp <= 0) return;
-  const int tid = threadIdx.x, c = tid >> 6, rl = tid & 63;
+  const int tid = threadIdx.x;
   const int row0 = blockIdx.x * SK_RC;
   if (row0 >= g.rows) return;
   const int nrc = min(SK_RC, g.rows - row0);
-  sk_load_v(P, g, Vs, row0, nrc);
   for (int e = tid; e < 8 * 64; e += SK_THREADS) {
     const int q = e >> 6, col = e & 63;
     W2s[e] = col < g.ncp ? P.w2[(size_t)q * P.ldw + col] : 0.0;
   }
   __syncthreads();
+  const double* vbase = P.vc + (size_t)g.voff * P.ldv + g.jr + row0;
+  double* abase = P.a + (size_t)g.c0 * P.lda + g.jr + row0;
   const int ngroups = (g.ncp + 7) / 8;
-  for (int gi = 0; gi < ngroups; ++gi) {
-    const int col = gi * 8 + c;
-    if (col >= g.ncp) continue;
-    double w[8];
+  for (int it = 0; it < SK_RPT; ++it) {
+    const int r = tid + it * SK_THREADS;
+    if (r >= nrc) break;
+    double v[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) w[q] = W2s[q * 64 + col];
-    double* dst = P.a + (size_t)(g.c0 + col) * P.lda + g.jr + row0;
-#pragma unroll 4
-    for (int r = rl; r < nrc; r += 64) {
-      const double2 v01 = *reinterpret_cast<const double2*>(Vs + r * 8);
-      const double2 v23 = *reinterpret_cast<const double2*>(Vs + r * 8 + 2);
-      const double2 v45 = *reinterpret_cast<const double2*>(Vs + r * 8 + 4);
-      const double2 v67 = *reinterpret_cast<const double2*>(Vs + r * 8 + 6);
-      double x = dst[r];
-      x = fma(v01.x, w[0], x); x = fma(v01.y, w[1], x); x = fma(v23.x, w[2], x); x = fma(v23.y, w[3], x);
-      x = fma(v45.x, w[4], x); x = fma(v45.y, w[5], x); x = fma(v67.x, w[6], x); x = fma(v67.y, w[7], x);
-      dst[r] = x;
+    for (int q = 0; q < 8; ++q) v[q] = q < g.k ? vbase[(size_t)q * P.ldv + r] : 0.0;
+    for (int gi = 0; gi < ngroups; ++gi) {
+      double x[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int col = gi * 8 + c;
+        x[c] = col < g.ncp ? abase[(size_t)col * P.lda + r] : 0.0;
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) x[c] = fma(v[q], W2s[q * 64 + gi * 8 + c], x[c]);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int col = gi * 8 + c;
+        if (col < g.ncp) abase[(size_t)col * P.lda + r] = x[c];
+      }
     }
   }
 }
@@ -164,43 +180,38 @@ __global__ void __launch_bounds__(512) k_sub_wred(qrdm_prob P, int nchunks_max) 
   const SkGeom g = sk_geom(P);
   if (g.k <= 0 || g.ncp <= 0) return;
   const int nchunks = min(nchunks_max, g.rows > 0 ? (g.rows + SK_RC - 1) / SK_RC : 0);
-  double s = 0.0;
-  for (int b = 0; b < nchunks; ++b) s += P.gram_part[(size_t)b * 512 + threadIdx.x];
-  P.gram_part[threadIdx.x] = s;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int b = 0;
+  for (; b + 3 < nchunks; b += 4) {
+    s0 += P.gram_part[(size_t)b * 512 + threadIdx.x];
+    s1 += P.gram_part[(size_t)(b + 1) * 512 + threadIdx.x];
+    s2 += P.gram_part[(size_t)(b + 2) * 512 + threadIdx.x];
+    s3 += P.gram_part[(size_t)(b + 3) * 512 + threadIdx.x];
+  }
+  for (; b < nchunks; ++b) s0 += P.gram_part[(size_t)b * 512 + threadIdx.x];
+  P.gram_part[threadIdx.x] = (s0 + s1) + (s2 + s3);
 }
 
 // rows_hint: host-side upper bound of the rows of the sub-panel
 extern "C" int qrdm_k_skinny_update(const qrdm_prob* p, int rows_hint, void* stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_sub_w, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM);
-    cudaFuncSetAttribute(k_sub_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM);
-    attr_set = true;
-  }
   cudaStream_t s = (cudaStream_t)stream;
   int nch = (rows_hint + SK_RC - 1) / SK_RC;
   if (nch < 1) nch = 1;
-  k_sub_w<<<nch, SK_THREADS, SK_SMEM, s>>>(*p);
+  k_sub_w<<<nch, SK_THREADS, 0, s>>>(*p);
   QRDM_LAUNCH_CHECK();
   k_sub_w2<<<1, 512, 0, s>>>(*p, nch);
   QRDM_LAUNCH_CHECK();
-  k_sub_apply<<<nch, SK_THREADS, SK_SMEM, s>>>(*p);
+  k_sub_apply<<<nch, SK_THREADS, 0, s>>>(*p);
   QRDM_LAUNCH_CHECK();
   return 0;
 }
 
 // row-sharded variant, split at the all-reduce: part 1 = partials folded into gram_part[0..512)
 extern "C" int qrdm_k_skinny_part(const qrdm_prob* p, int rows_hint, void* stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_sub_w, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM);
-    cudaFuncSetAttribute(k_sub_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM);
-    attr_set = true;
-  }
   cudaStream_t s = (cudaStream_t)stream;
   int nch = (rows_hint + SK_RC - 1) / SK_RC;
   if (nch < 1) nch = 1;
-  k_sub_w<<<nch, SK_THREADS, SK_SMEM, s>>>(*p);
+  k_sub_w<<<nch, SK_THREADS, 0, s>>>(*p);
   QRDM_LAUNCH_CHECK();
   k_sub_wred<<<1, 512, 0, s>>>(*p, nch);
   QRDM_LAUNCH_CHECK();
@@ -212,7 +223,7 @@ extern "C" int qrdm_k_skinny_finish(const qrdm_prob* p, int rows_hint, void* str
   if (nch < 1) nch = 1;
   k_sub_w2<<<1, 512, 0, s>>>(*p, 1);
   QRDM_LAUNCH_CHECK();
-  k_sub_apply<<<nch, SK_THREADS, SK_SMEM, s>>>(*p);
+  k_sub_apply<<<nch, SK_THREADS, 0, s>>>(*p);
   QRDM_LAUNCH_CHECK();
   return 0;
 }
