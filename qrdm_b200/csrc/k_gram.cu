@@ -11,7 +11,7 @@
 // HBM/L2-bound: algorithmic bytes 8 * rows * nc.
 #include "common.cuh"
 
-#define GR_ROWS 32
+#define GR_ROWS 64
 #define GR_LD 66  // doubles per smem row: 64 columns + 2 pad (keeps 16B alignment of float4 reads)
 
 __global__ void __launch_bounds__(256) k_gram_partial(qrdm_prob P, int of_v) {
@@ -49,18 +49,22 @@ __global__ void __launch_bounds__(256) k_gram_partial(qrdm_prob P, int of_v) {
 
   // software pipeline: the global loads of sub-chunk i+1 are in flight while sub-chunk i is
   // multiplied out of shared memory (warps over columns, lanes along rows: coalesced)
-  double pre[8];
+  double pre[2][8];  // 16 independent loads in flight per thread
   auto fetch = [&](int r0) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int c = wid + 8 * q, r = r0 + lane;
-      pre[q] = (c < nc && r < my_hi) ? base[(size_t)scol[c] * ld + r] : 0.0;
-    }
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int c = wid + 8 * q, r = r0 + lane + 32 * h;
+        pre[h][q] = (c < nc && r < my_hi) ? base[(size_t)scol[c] * ld + r] : 0.0;
+      }
   };
   if (my_lo < my_hi) fetch(my_lo);
   for (int r0 = my_lo; r0 < my_hi; r0 += GR_ROWS) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) tile[lane * GR_LD + wid + 8 * q] = pre[q];
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) tile[(lane + 32 * h) * GR_LD + wid + 8 * q] = pre[h][q];
     __syncthreads();
     if (r0 + GR_ROWS < my_hi) fetch(r0 + GR_ROWS);
 #pragma unroll 4

@@ -156,6 +156,24 @@ def test_device_resident_entry_point(q, oracle_ref):
     parity.check_against(host, exp, (m, n))
 
 
+def test_device_entry_point_odd_lda(q, oracle_ref):
+    """Odd leading dimension on the device: columns are only 8-byte aligned, every kernel takes its
+    non-vectorised path (8-byte cp.async, scalar loads/stores)."""
+    import torch
+    for (m, n, lda) in [(300, 210, 301), (1100, 700, 1103)]:
+        A = g.gaussian(m, n, 30 + m)
+        buf = torch.full((n, lda), 3.25, dtype=torch.float64, device="cuda")
+        buf[:, :m] = torch.from_numpy(np.ascontiguousarray(A.T)).cuda()
+        d_jpvt = torch.zeros(n, dtype=torch.int32, device="cuda")
+        d_tau = torch.zeros(min(m, n), dtype=torch.float64, device="cuda")
+        info, ncols = q.dgeqrdm_device(buf, m, n, lda, d_jpvt, d_tau)
+        assert info == 0
+        out = buf.cpu().numpy()
+        assert np.all(out[:, m:] == 3.25)                      # padding rows untouched
+        got = dict(info=info, A=out[:, :m].T, jpvt=d_jpvt.cpu().numpy(), tau=d_tau.cpu().numpy(), ncols=ncols)
+        parity.check_against(got, oracle_ref.ref_dgeqrdm(A), (m, n))
+
+
 def test_pinned_host_buffer_streams_columns_back(q):
     """With a pinned host buffer the entry point overlaps the D2H of finished columns with the rest
     of the factorisation (second stream); results must be bit-identical to the pageable path,
