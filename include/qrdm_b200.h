@@ -56,10 +56,20 @@ int dgeqrdm_dev(int m, int n, double *d_a, int lda, int *d_jpvt, double *d_tau, 
                 const double *thres, int nb, void *stream);
 
 /* Addition: batched mode — `batch` independent m x n HOST matrices, matrix b
- * at a + b*stride_a; jpvt (b*n), tau (b*min(m,n)), ncols (b*n) laid out per matrix; infos[b] per
- * matrix (may be NULL).  Returns 0 or the first non-zero info.  Across GPUs each rank passes its share. */
+ * at a + b*stride_a; jpvt (b*n), tau (b*min(m,n)), ncols (b*n, [b*n] = stop-rule mode on entry) laid out
+ * per matrix; infos[b] per matrix (may be NULL).  Returns 0 or the first non-zero info.  Matrices with
+ * m, n <= 1024 are factored by ONE kernel launch per chunk of 592 matrices, one CTA per matrix, with the
+ * upload of the next chunk and the download of the previous one overlapped; larger ones run one after the
+ * other through the one-matrix path.  Across GPUs each rank passes its share (independent units). */
 int dgeqrdm_batched(int batch, int m, int n, double *a, int lda, long long stride_a, int *jpvt, double *tau,
                     int *ncols, double *thres, int nb, int *infos);
+
+/* Device-resident batched variant (m, n <= 1024, else QRDM_ERR_UNSUPPORTED): every array is a DEVICE
+ * pointer except thres; d_ncols is [batch][n] with the stop-rule mode in [b][0] on entry and the block
+ * sizes on exit; d_infos [batch] (may be NULL) receives the per-matrix info.  One launch; returns after
+ * it has completed on the stream. */
+int dgeqrdm_batched_dev(int batch, int m, int n, double *d_a, int lda, long long stride_a, int *d_jpvt,
+                        double *d_tau, int *d_ncols, int *d_infos, const double *thres, int nb, void *stream);
 
 /* Addition: 1-D block-row sharded factorisation across the GPUs of one node, one
  * process per GPU.  Rank p passes its rows [row0, row0 + m_local) of all n columns (device memory,

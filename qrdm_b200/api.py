@@ -65,6 +65,18 @@ def dgeqrdm_batched(As, thres=(0.9, 0.15), nb=64, stop_mode=0):
     return dict(info=int(info), infos=infos, A=buf.transpose(0, 2, 1), jpvt=jpvt, tau=tau, ncols=ncols)
 
 
+def dgeqrdm_batched_device(batch, m, n, d_a, lda, stride_a, d_jpvt, d_tau, d_ncols, d_infos=0, thres=(0.9, 0.15), nb=64,
+                           stream=0):
+    """Device-resident batch (raw device pointers as ints, e.g. ``tensor.data_ptr()``): one launch of the
+    one-CTA-per-matrix kernel.  ``d_ncols`` is [batch][n] int32 with the stop mode in [b][0] on entry."""
+    th = np.zeros(3, dtype=np.float64)
+    th[: len(thres)] = thres
+    return int(_lib.lib.dgeqrdm_batched_dev(int(batch), int(m), int(n), C.c_void_p(int(d_a)), int(lda), int(stride_a),
+                                            C.c_void_p(int(d_jpvt)), C.c_void_p(int(d_tau)), C.c_void_p(int(d_ncols)),
+                                            C.c_void_p(int(d_infos)) if d_infos else None, th.ctypes.data, int(nb),
+                                            C.c_void_p(int(stream)) if stream else None))
+
+
 def stats():
     return _lib.stats()
 

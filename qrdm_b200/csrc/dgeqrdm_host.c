@@ -41,6 +41,7 @@ typedef struct {
   void *ev[4];
   void *ev_stage[2];
   void *compute_stream, *copy_stream; /* non-blocking streams of the host-pointer entry points */
+  void *h2d_stream;                   /* third stream of the batched pipeline (created on first use) */
 } qrdm_workspace;
 
 /* 1-D block-row sharding: this rank holds global rows [row0, row0 + m_local) */
@@ -501,6 +502,34 @@ int dgeqrdm_dev_sharded(int m_local, int m_global, int row0, int nranks, int n, 
  * Round 1: the whole batch is made device-resident with one H2D, then factored one matrix after
  * the other by the single-matrix driver (launch-latency bound for small matrices — the planned
  * replacement is one persistent CTA-cluster per matrix); multi-GPU = each rank passes its share. ---- */
+/* Batched mode (BASELINE configs[4]): matrices with m, n <= 1024 run as ONE launch with one
+ * CTA per matrix (k_small.cu); larger ones fall back to a loop over the one-matrix path. */
+int dgeqrdm_batched_dev(int batch, int m, int n, double *d_a, int lda, long long stride_a, int *d_jpvt,
+                        double *d_tau, int *d_ncols, int *d_infos, const double *thres, int nb, void *stream) {
+  if (batch <= 0 || stride_a < (long long)lda * n) return bad_argument(1);
+  int rc = check_args(QRDM_COL_MAJOR, m, n, lda, thres, nb);
+  if (rc) return rc;
+  rc = qrdm_b200_init(-1);
+  if (rc) return rc;
+  if (!qrdm_k_small_supported(m, n)) return QRDM_ERR_UNSUPPORTED;
+  qrdm_workspace *w = &g_ws;
+  memset(&g_stats, 0, sizeof(g_stats));
+  const long long launches0 = qrdm_rt_launch_count();
+  CU(qrdm_rt_event_record(w->ev[0], stream));
+  CU(qrdm_k_small(batch, m, n, d_a, lda, stride_a, d_jpvt, d_tau, d_ncols, d_infos, thres[0], thres[1], thres[2], nb,
+                  stream));
+  CU(qrdm_rt_event_record(w->ev[1], stream));
+  CU(qrdm_rt_event_sync(w->ev[1]));
+  g_stats.ms_total = qrdm_rt_event_ms(w->ev[0], w->ev[1]);
+  g_stats.launches = qrdm_rt_launch_count() - launches0;
+  return 0;
+}
+
+static int batched_loop(int batch, int m, int n, double *a, int lda, long long stride_a, int *jpvt, double *tau,
+                        int *ncols, double *thres, int nb, int *infos);
+
+#define QRDM_BATCH_CHUNK 592 /* matrices per pipeline stage: 4 waves of 148 CTAs */
+
 int dgeqrdm_batched(int batch, int m, int n, double *a, int lda, long long stride_a, int *jpvt, double *tau,
                     int *ncols, double *thres, int nb, int *infos) {
   qrdm_workspace *w = &g_ws;
@@ -509,6 +538,92 @@ int dgeqrdm_batched(int batch, int m, int n, double *a, int lda, long long strid
   if (rc) return rc;
   rc = qrdm_b200_init(-1);
   if (rc) return rc;
+  if (!qrdm_k_small_supported(m, n) || getenv("QRDM_B200_BATCH_LOOP"))
+    return batched_loop(batch, m, n, a, lda, stride_a, jpvt, tau, ncols, thres, nb, infos);
+  /* three streams: chunk c+1 is uploaded and chunk c-1 downloaded while chunk c is factored */
+  if (!w->h2d_stream) CU(qrdm_rt_stream_create(&w->h2d_stream));
+  void *s_up = w->h2d_stream, *s_k = w->compute_stream, *s_down = w->copy_stream;
+  const int minmn = m < n ? m : n;
+  const int ldd = (m + 1) & ~1;
+  const size_t per = (size_t)ldd * n;
+  const int chunk = batch < QRDM_BATCH_CHUNK ? batch : QRDM_BATCH_CHUNK;
+  const int nbuf = batch > chunk ? 3 : 1; /* ring of device chunks */
+  double *d_all = NULL, *d_tau = NULL;
+  int *d_jpvt = NULL, *d_ncols = NULL, *d_infos = NULL;
+  void *ev_up[3] = {0}, *ev_k[3] = {0}, *ev_down[3] = {0};
+  CU(qrdm_rt_malloc((void **)&d_all, sizeof(double) * per * chunk * nbuf));
+  CU(qrdm_rt_malloc((void **)&d_tau, sizeof(double) * (size_t)minmn * chunk * nbuf));
+  CU(qrdm_rt_malloc((void **)&d_jpvt, sizeof(int) * (size_t)n * chunk * nbuf));
+  CU(qrdm_rt_malloc((void **)&d_ncols, sizeof(int) * (size_t)n * chunk * nbuf));
+  CU(qrdm_rt_malloc((void **)&d_infos, sizeof(int) * (size_t)chunk * nbuf));
+  for (int q = 0; q < nbuf; ++q) {
+    CU(qrdm_rt_event_create(&ev_up[q]));
+    CU(qrdm_rt_event_create(&ev_k[q]));
+    CU(qrdm_rt_event_create(&ev_down[q]));
+  }
+  int *h_infos = (int *)malloc(sizeof(int) * (size_t)batch);
+  if (!h_infos) return QRDM_ERR_CUDA;
+  memset(&g_stats, 0, sizeof(g_stats));
+  const long long launches0 = qrdm_rt_launch_count();
+  CU(qrdm_rt_event_record(w->ev[0], s_k));
+  int nchunks = (batch + chunk - 1) / chunk;
+  for (int c = 0; c < nchunks; ++c) {
+    const int q = c % nbuf, b0 = c * chunk, cnt = batch - b0 < chunk ? batch - b0 : chunk;
+    double *da = d_all + per * chunk * q;
+    double *dt = d_tau + (size_t)minmn * chunk * q;
+    int *dj = d_jpvt + (size_t)n * chunk * q, *dn = d_ncols + (size_t)n * chunk * q, *di = d_infos + (size_t)chunk * q;
+    if (c >= nbuf) CU(qrdm_rt_stream_wait_event(s_up, ev_down[q])); /* ring slot free again */
+    if (lda == m && ldd == m && stride_a == (long long)m * n) {
+      CU(qrdm_rt_h2d(da, a + (size_t)stride_a * b0, sizeof(double) * per * cnt, s_up));
+    } else {
+      for (int b = 0; b < cnt; ++b)
+        CU(qrdm_rt_h2d_2d(da + per * b, sizeof(double) * ldd, a + (size_t)stride_a * (b0 + b), sizeof(double) * lda,
+                          sizeof(double) * m, n, s_up));
+    }
+    CU(qrdm_rt_h2d(dt, tau + (size_t)minmn * b0, sizeof(double) * (size_t)minmn * cnt, s_up));
+    CU(qrdm_rt_h2d(dn, ncols + (size_t)n * b0, sizeof(int) * (size_t)n * cnt, s_up));
+    CU(qrdm_rt_event_record(ev_up[q], s_up));
+    CU(qrdm_rt_stream_wait_event(s_k, ev_up[q]));
+    CU(qrdm_k_small(cnt, m, n, da, ldd, (long long)per, dj, dt, dn, di, thres[0], thres[1], thres[2], nb, s_k));
+    CU(qrdm_rt_event_record(ev_k[q], s_k));
+    CU(qrdm_rt_stream_wait_event(s_down, ev_k[q]));
+    if (lda == m && ldd == m && stride_a == (long long)m * n) {
+      CU(qrdm_rt_d2h(a + (size_t)stride_a * b0, da, sizeof(double) * per * cnt, s_down));
+    } else {
+      for (int b = 0; b < cnt; ++b)
+        CU(qrdm_rt_d2h_2d(a + (size_t)stride_a * (b0 + b), sizeof(double) * lda, da + per * b, sizeof(double) * ldd,
+                          sizeof(double) * m, n, s_down));
+    }
+    CU(qrdm_rt_d2h(jpvt + (size_t)n * b0, dj, sizeof(int) * (size_t)n * cnt, s_down));
+    CU(qrdm_rt_d2h(tau + (size_t)minmn * b0, dt, sizeof(double) * (size_t)minmn * cnt, s_down));
+    CU(qrdm_rt_d2h(ncols + (size_t)n * b0, dn, sizeof(int) * (size_t)n * cnt, s_down));
+    CU(qrdm_rt_d2h(h_infos + b0, di, sizeof(int) * (size_t)cnt, s_down));
+    CU(qrdm_rt_event_record(ev_down[q], s_down));
+  }
+  CU(qrdm_rt_event_record(w->ev[1], s_k));
+  CU(qrdm_rt_sync(s_down));
+  CU(qrdm_rt_sync(s_k));
+  g_stats.ms_total = qrdm_rt_event_ms(w->ev[0], w->ev[1]);
+  g_stats.launches = qrdm_rt_launch_count() - launches0;
+  int worst = 0;
+  for (int b = 0; b < batch; ++b) {
+    if (infos) infos[b] = h_infos[b];
+    if (h_infos[b] != 0 && worst == 0) worst = h_infos[b];
+  }
+  free(h_infos);
+  for (int q = 0; q < nbuf; ++q) { qrdm_rt_event_destroy(ev_up[q]); qrdm_rt_event_destroy(ev_k[q]); qrdm_rt_event_destroy(ev_down[q]); }
+  qrdm_rt_free(d_all);
+  qrdm_rt_free(d_tau);
+  qrdm_rt_free(d_jpvt);
+  qrdm_rt_free(d_ncols);
+  qrdm_rt_free(d_infos);
+  return worst;
+}
+
+/* matrices too large for the one-CTA kernel: one after the other through the one-matrix path */
+static int batched_loop(int batch, int m, int n, double *a, int lda, long long stride_a, int *jpvt, double *tau,
+                        int *ncols, double *thres, int nb, int *infos) {
+  qrdm_workspace *w = &g_ws;
   void *stream = w->compute_stream;
   const int minmn = m < n ? m : n;
   const int ldd = (m + 1) & ~1;

@@ -1,0 +1,615 @@
+// k_small.cu — batched mode (BASELINE.json configs[4]: 8192 Kahan-type 512 x 512 matrices): one CTA
+// factors one small matrix from the first norm to the last block, so a batch runs as `batch`
+// independent CTAs with no host round trips and no inter-CTA traffic ("independent
+// units").  The matrix stays in global memory (2 MB at 512^2: L2-resident while it is being worked
+// on); the control block, the partial norms, the Gram/T' matrices and all staging tiles live in
+// shared memory, reached through generic pointers so that the selection logic is literally the
+// same code as the one-kernel-per-stage path (select_body.cuh, pick_body.cuh).
+//
+// Per matrix this is the whole loop of reference src/dgeqrdm_work.c:640-787:
+//   norms (:672-682) -> [ DM_perm (:280-418) -> permute_marked (:149-262) -> dgeqr2_mia panel
+//   (src/dgeqr2.c:148-191) -> dlarft + dlarfb (:751-767) -> norm_update (:36-122) -> stop rule
+//   (:782-785) ]*
+// Differences in HOW (never in what is decided):
+//   * the candidates' cosines are evaluated lazily: first only against candidate 0 (always
+//     accepted); candidates that already fail the delta test there can never be accepted and are
+//     dropped before the full Gram matrix of the survivors is formed — for Kahan-type matrices that
+//     removes the 64 x 64 x rows Gram product from every one of the 511 iterations;
+//   * blocks of <= 8 reflectors are applied one trailing column per warp with the column held in
+//     registers (C read once, written once); wider blocks go through 64-column tiles
+//     (W = V'C, W2 = -T'W, C += V W2) on the FP64 FMA pipe.
+#include <cstdio>
+#include "pick_body.cuh"
+#include "select_body.cuh"
+
+#define SM_NT 512
+#define SM_NW (SM_NT / 32)
+#define SM_MAXDIM 1024  // m, n <= 1024 (the column-in-registers path holds 32 rows per lane)
+#define SM_KSMALL 8
+#define SM_LD 66        // doubles per row of the [row][column] staging tiles
+#define SM_RK_ROWS 128  // rows per chunk of the rank-k update
+
+struct SmallArgs {
+  int batch, m, n, lda, nb;
+  long long stride_a;
+  double delta, tau_, eps, eta3;
+  double* a;
+  int* jpvt;
+  double* tau;
+  int* ncols;  // [batch][n]; [b][0] holds the stop-rule mode on entry
+  int* infos;  // [batch] or NULL
+};
+
+struct SmallShared {
+  qrdm_ctrl ctrl;
+  alignas(16) double vn1[SM_MAXDIM];
+  double vn2[SM_MAXDIM];
+  alignas(16) double gram[4096];  // candidates' Gram matrix, later M = T'
+  alignas(16) double wbuf[4096];  // V'V, later W = V'C of the current column tile
+  alignas(16) double w2buf[4096]; // -T'W
+  double S_[64], rowv[64], wv[64], taus[64];
+  int xcol[64], xdiag[64], ycol[64], ydiag[64];
+  int flag[SM_MAXDIM];
+  double eta;
+  int stop_mode, it, bad, keep[64];
+  union alignas(16) {
+    SelShared sel;
+    PickShared pick;
+    struct { double tx[64 * SM_LD], ty[64 * SM_LD]; } xty;
+    struct { double B[64 * 65], X[64 * 65]; } tinv;
+    struct { double v[SM_KSMALL][SM_MAXDIM]; } sk;
+    struct { double vch[64][SM_RK_ROWS]; } rk;
+    struct { double vbuf[SM_MAXDIM], xold[SM_MAXDIM]; } pan;
+  } u;
+};
+
+// out[s][t] = sum over rows r_lo <= r < r_hi of X[r][s] * Y[r][t]  (64 x 64, row-major, smem).
+// Column q of X is column xcol[q] of A; if xdiag[q] >= 0 it is a Householder vector stored in place:
+// implicit 1 at row xdiag[q], zeros above.  `same`: Y == X, only the upper block triangle is
+// computed and mirrored.  Two row groups of 256 threads, 4 x 4 accumulators per thread, the next
+// 64-row chunk is in flight (registers) while the current one is multiplied out of shared memory.
+__device__ __noinline__ void small_xty(const double* __restrict__ a, int lda, int r_lo, int r_hi, const int* xcol, const int* xdiag,
+                                       int nx, const int* ycol, const int* ydiag, int ny, bool same, double* out, double* tx,
+                                       double* ty) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int grp = tid >> 8, t256 = tid & 255, ty4 = (t256 >> 4) * 4, tx4 = (t256 & 15) * 4;
+  const bool active = ty4 < nx && tx4 < ny && !(same && tx4 < ty4);
+  double acc[4][4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[p][q] = 0.0;
+  double preX[8], preY[8];
+  auto fetch = [&](int r0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = wid + SM_NW * q, r = r0 + lane + 32 * h;
+        double vx = 0.0, vy = 0.0;
+        if (r < r_hi) {
+          if (c < nx) { const int d = xdiag[c]; vx = r < d ? 0.0 : (r == d ? 1.0 : a[(size_t)xcol[c] * lda + r]); }
+          if (!same && c < ny) { const int d = ydiag[c]; vy = r < d ? 0.0 : (r == d ? 1.0 : a[(size_t)ycol[c] * lda + r]); }
+        }
+        preX[q * 2 + h] = vx;
+        preY[q * 2 + h] = vy;
+      }
+  };
+  const double* tyy = same ? tx : ty;
+  if (r_lo < r_hi) fetch(r_lo);
+  for (int r0 = r_lo; r0 < r_hi; r0 += 64) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        tx[(lane + 32 * h) * SM_LD + wid + SM_NW * q] = preX[q * 2 + h];
+        if (!same) ty[(lane + 32 * h) * SM_LD + wid + SM_NW * q] = preY[q * 2 + h];
+      }
+    __syncthreads();
+    if (r0 + 64 < r_hi) fetch(r0 + 64);
+    if (active) {
+#pragma unroll 4
+      for (int rr = 0; rr < 32; ++rr) {
+        const int r = grp * 32 + rr;
+        const double2 a01 = *reinterpret_cast<const double2*>(&tx[r * SM_LD + ty4]);
+        const double2 a23 = *reinterpret_cast<const double2*>(&tx[r * SM_LD + ty4 + 2]);
+        const double2 b01 = *reinterpret_cast<const double2*>(&tyy[r * SM_LD + tx4]);
+        const double2 b23 = *reinterpret_cast<const double2*>(&tyy[r * SM_LD + tx4 + 2]);
+        const double av[4] = {a01.x, a01.y, a23.x, a23.y};
+        const double bv[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[p][q] = fma(av[p], bv[q], acc[p][q]);
+      }
+    }
+    __syncthreads();
+  }
+  // combine the two row groups in fixed order (tx doubles as scratch: 64*66 >= 4096)
+  if (grp == 1) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) tx[(ty4 + p) * 64 + tx4 + q] = acc[p][q];
+  }
+  __syncthreads();
+  if (grp == 0) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) out[(ty4 + p) * 64 + tx4 + q] = acc[p][q] + tx[(ty4 + p) * 64 + tx4 + q];
+  }
+  __syncthreads();
+  if (same) {
+    for (int e = tid; e < 4096; e += SM_NT) {
+      const int s = e >> 6, t = e & 63;
+      if ((t >> 2) < (s >> 2)) out[e] = out[t * 64 + s];
+    }
+    __syncthreads();
+  }
+}
+
+// ---- cosines: lazy evaluation of DM_perm's Gram matrix (src/dgeqrdm_work.c:365-403) ----
+__device__ __forceinline__ void small_cosines(const qrdm_prob& P, SmallShared& S) {
+  qrdm_ctrl* ctrl = P.ctrl;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int j = ctrl->j, nc = ctrl->nc;
+  if (nc <= 1) return;
+  // (1) dots of candidate 0 with every candidate: warp per candidate
+  const double* c0 = P.a + (size_t)(j + ctrl->cand[0]) * P.lda;
+  for (int t = wid; t < nc; t += SM_NW) {
+    const double* ct = P.a + (size_t)(j + ctrl->cand[t]) * P.lda;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int r = j + lane;
+    for (; r + 96 < P.m; r += 128) {
+      s0 = fma(c0[r], ct[r], s0);
+      s1 = fma(c0[r + 32], ct[r + 32], s1);
+      s2 = fma(c0[r + 64], ct[r + 64], s2);
+      s3 = fma(c0[r + 96], ct[r + 96], s3);
+    }
+    for (; r < P.m; r += 32) s0 = fma(c0[r], ct[r], s0);
+    const double d = warp_sum((s0 + s1) + (s2 + s3));
+    if (lane == 0) S.S_[t] = d;
+  }
+  __syncthreads();
+  // (2) keep candidate 0 and those whose |cos| against it is < delta (same expression as the pick:
+  // G * (1/n_s) * (1/n_t); a NaN cosine is ignored there, so it is kept here)
+  if (tid == 0) {
+    const double i0 = 1.0 / ctrl->candnrm[0];
+    int cnt = 1;
+    S.keep[0] = 0;
+    for (int t = 1; t < nc; ++t) {
+      const double cs = fabs(S.S_[t] * i0 * (1.0 / ctrl->candnrm[t]));
+      if (!(cs >= P.delta)) S.keep[cnt++] = t;
+    }
+    for (int q = 1; q < cnt; ++q) {  // compact in place (keep[q] >= q)
+      ctrl->cand[q] = ctrl->cand[S.keep[q]];
+      ctrl->candnrm[q] = ctrl->candnrm[S.keep[q]];
+    }
+    ctrl->nc = cnt;
+  }
+  __syncthreads();
+  const int nc2 = ctrl->nc;
+  if (nc2 <= 1) return;
+  if (tid < 64) { S.xcol[tid] = tid < nc2 ? j + ctrl->cand[tid] : 0; S.xdiag[tid] = -1; }
+  __syncthreads();
+  small_xty(P.a, P.lda, j, P.m, S.xcol, S.xdiag, nc2, S.xcol, S.xdiag, nc2, true, S.gram, S.u.xty.tx, S.u.xty.ty);
+}
+
+// ---- K3d: rotate the columns along the planned cycles (all rows, all cycles in parallel) ----
+__device__ __forceinline__ void small_permute(const qrdm_prob& P) {
+  const qrdm_ctrl* ctrl = P.ctrl;
+  const int ncyc = ctrl->ncyc, j = ctrl->j;
+  const int total = ncyc * P.m;
+  for (int e = threadIdx.x; e < total; e += SM_NT) {
+    const int cyc = e / P.m, r = e - cyc * P.m;
+    const int b = ctrl->cyc_start[cyc], en = ctrl->cyc_start[cyc + 1];
+    double* a = P.a + (size_t)j * P.lda + r;
+    const double first = a[(size_t)ctrl->cyc_pos[b] * P.lda];
+    for (int q = b; q < en - 1; ++q) a[(size_t)ctrl->cyc_pos[q] * P.lda] = a[(size_t)ctrl->cyc_pos[q + 1] * P.lda];
+    a[(size_t)ctrl->cyc_pos[en - 1] * P.lda] = first;
+  }
+}
+
+// ---- K4: Householder panel with the DM early stop (src/dgeqr2.c:148-191, src/dlarfg.c:120-185,
+// src/dlarf.c:133-185), in place.  One fused sweep per column: apply H_i to the remaining panel
+// columns and accumulate, in the same pass, the dot products the next reflector needs
+// (S_[jj] = x_{i+1}' x_jj below the next pivot row, rowv[jj] = the next pivot row). ----
+__device__ __forceinline__ void small_panel(const qrdm_prob& P, SmallShared& S) {
+  qrdm_ctrl* ctrl = P.ctrl;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int j = ctrl->j, fjb = ctrl->fjb, lda = P.lda;
+  const int rows = P.m - j;
+  double* Ap = P.a + (size_t)j * lda + j;
+  double* vbuf = S.u.pan.vbuf;
+  double* xold = S.u.pan.xold;
+  // dots of column 0 with every panel column (rows >= 1), pivot row 0
+  for (int jj = wid; jj < fjb; jj += SM_NW) {
+    const double* cj = Ap + (size_t)jj * lda;
+    double s0 = 0.0, s1 = 0.0;
+    int r = 1 + lane;
+    for (; r + 32 < rows; r += 64) { s0 = fma(Ap[r], cj[r], s0); s1 = fma(Ap[r + 32], cj[r + 32], s1); }
+    if (r < rows) s0 = fma(Ap[r], cj[r], s0);
+    const double d = warp_sum(s0 + s1);
+    if (lane == 0) { S.S_[jj] = d; S.rowv[jj] = cj[0]; }
+  }
+  __syncthreads();
+  double thres2 = 5e-14 * 5e-14;  // (src/dgeqr2.c:40)^2
+  int k = fjb;
+  for (int i = 0; i < fjb; ++i) {
+    const double alpha = S.rowv[i], xn2 = S.S_[i];
+    const int len = rows - i;
+    double tau = 0.0, beta = alpha, scale = 1.0;
+#ifdef SM_DEBUG
+    if (tid == 0 && blockIdx.x == 0) printf("j=%d i=%d fjb=%d rows=%d alpha=%.3e xn2=%.3e thres2=%.3e\n", j, i, fjb, rows, alpha, xn2, thres2);
+#endif
+    if (len > 1) {
+      if (i > 0 && xn2 < thres2) { k = i; break; }  // DM early stop: column i left untouched
+      if (xn2 != 0.0) {
+        const double h = sqrt(fma(alpha, alpha, xn2));
+        beta = (alpha >= 0.0) ? -h : h;
+        tau = (beta - alpha) / beta;
+        scale = 1.0 / (alpha - beta);
+      }
+    }
+    if (i == 0 && fjb > 1 && P.tau_ > 0.0) { const double th = P.tau_ * fabs(beta); thres2 = th * th; }
+    const bool last = i + 1 >= fjb;
+    if (tid == 0) {
+      P.tau[j + i] = tau;
+      if (tau != tau && ctrl->err == 0) ctrl->err = -8;  // LAPACKE_dlarft's NaN screen of tau
+    }
+    // publish v (scaled column i, unit diagonal) and a snapshot of column i+1 before H_i
+    double* ci = Ap + (size_t)i * lda;
+    const double* cn = Ap + (size_t)(i + 1) * lda;
+    for (int r = tid; r < rows; r += SM_NT) {
+      double v = 0.0;
+      if (r > i) { v = ci[r]; if (tau != 0.0) { v *= scale; ci[r] = v; } }
+      else if (r == i) { v = 1.0; ci[r] = beta; }
+      vbuf[r] = v;
+      if (!last) xold[r] = cn[r];
+    }
+    if (tid < 64 && tid > i && tid < fjb) S.wv[tid] = tau * (S.rowv[tid] + S.S_[tid] * scale);
+    __syncthreads();
+    if (last) break;
+    const double w1 = S.wv[i + 1];
+    for (int jj = i + 1 + wid; jj < fjb; jj += SM_NW) {
+      double* cj = Ap + (size_t)jj * lda;
+      const double wj = S.wv[jj];
+      double s0 = 0.0, s1 = 0.0, prow = 0.0;
+      int r = i + lane;
+      for (; r + 32 < rows; r += 64) {
+        const double p0 = fma(-vbuf[r], wj, cj[r]);
+        const double p1 = fma(-vbuf[r + 32], wj, cj[r + 32]);
+        cj[r] = p0;
+        cj[r + 32] = p1;
+        const double x0 = fma(-vbuf[r], w1, xold[r]), x1 = fma(-vbuf[r + 32], w1, xold[r + 32]);
+        if (r > i + 1) s0 = fma(x0, p0, s0); else if (r == i + 1) prow = p0;
+        s1 = fma(x1, p1, s1);  // r + 32 > i + 1 always
+      }
+      if (r < rows) {
+        const double p0 = fma(-vbuf[r], wj, cj[r]);
+        cj[r] = p0;
+        const double x0 = fma(-vbuf[r], w1, xold[r]);
+        if (r > i + 1) s0 = fma(x0, p0, s0); else if (r == i + 1) prow = p0;
+      }
+      const double d = warp_sum(s0 + s1);
+      prow = __shfl_sync(0xffffffffu, prow, 1);  // row i+1 is lane 1's first element
+      if (lane == 0) { S.S_[jj] = d; S.rowv[jj] = prow; }
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (tid == 0) ctrl->fjb_cmp = k;
+}
+
+// ---- T' = (I + D N)^-1 D from V'V (S.wbuf) and tau -> S.gram  (replaces LAPACKE_dlarft) ----
+__device__ __forceinline__ void small_tinv(const qrdm_prob& P, SmallShared& S, int j, int k) {
+  const int tid = threadIdx.x;
+  double* B = S.u.tinv.B;
+  double* X = S.u.tinv.X;
+  if (tid < 64) S.taus[tid] = tid < k ? P.tau[j + tid] : 0.0;
+  __syncthreads();
+  for (int e = tid; e < 4096; e += SM_NT) {
+    const int s = e >> 6, i = e & 63;
+    B[i * 65 + s] = (s < i && i < k) ? S.taus[i] * S.wbuf[s * 64 + i] : 0.0;
+  }
+  __syncthreads();
+  if (tid < 64) {
+    const int p = tid;  // column p of (I + B)^-1 by forward substitution
+    for (int i = 0; i < k; ++i) {
+      double acc = (i == p) ? 1.0 : 0.0;
+      for (int s = 0; s < i; ++s) acc = fma(-B[i * 65 + s], X[s * 65 + p], acc);
+      X[i * 65 + p] = acc;
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < 4096; e += SM_NT) {
+    const int q = e >> 6, pp = e & 63;
+    S.gram[e] = (q < k && pp < k) ? X[q * 65 + pp] * S.taus[pp] : 0.0;
+  }
+  __syncthreads();
+}
+
+// ---- K6 for narrow blocks: one trailing column per warp, held in registers ----
+__device__ __forceinline__ void small_trailing_narrow(const qrdm_prob& P, SmallShared& S, int j, int fjb, int k) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int rows = P.m - j, lda = P.lda;
+  for (int e = tid; e < k * rows; e += SM_NT) {  // V with unit diagonal / zeros above, [p][r]
+    const int p = e / rows, r = e - p * rows;
+    S.u.sk.v[p][r] = r < p ? 0.0 : (r == p ? 1.0 : P.a[(size_t)(j + p) * lda + j + r]);
+  }
+  __syncthreads();
+  const int nblk = (rows + 31) >> 5;
+  bool bad = false;
+  for (int c = j + fjb + wid; c < P.n; c += SM_NW) {
+    double* col = P.a + (size_t)c * lda + j;
+    double x[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int r = lane + 32 * i;
+      x[i] = (i < nblk && r < rows) ? col[r] : 0.0;
+    }
+    double w[SM_KSMALL];
+    for (int p = 0; p < k; ++p) {
+      const double* vp = S.u.sk.v[p];
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        if (i < nblk) {
+          const int r = lane + 32 * i;
+          s0 = fma(r < rows ? vp[r] : 0.0, x[i], s0);
+          s1 = fma(r + 32 < rows ? vp[r + 32] : 0.0, x[i + 1], s1);
+        }
+      }
+      const double d = warp_sum(s0 + s1);
+      bad |= d != d;
+#pragma unroll
+      for (int q = 0; q < SM_KSMALL; ++q)
+        if (q == p) w[q] = d;
+    }
+    // y = T' w (lower triangular), then x -= V y
+    for (int q = 0; q < k; ++q) {
+      double y = 0.0;
+#pragma unroll
+      for (int p = 0; p < SM_KSMALL; ++p)
+        if (p <= q && p < k) y = fma(S.gram[q * 64 + p], w[p], y);
+      const double* vq = S.u.sk.v[q];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (i < nblk) {
+          const int r = lane + 32 * i;
+          if (r < rows) x[i] = fma(-vq[r], y, x[i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int r = lane + 32 * i;
+      if (i < nblk && r < rows) col[r] = x[i];
+    }
+  }
+  if (bad) S.bad = 1;
+}
+
+// ---- K6 for wide blocks: 64-column tiles, W = V'C, W2 = -T'W, C += V W2 ----
+__device__ __forceinline__ void small_trailing_wide(const qrdm_prob& P, SmallShared& S, int j, int fjb, int k) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int rows = P.m - j, lda = P.lda;
+  const int nct = P.n - j - fjb;
+  for (int c0 = 0; c0 < nct; c0 += 64) {
+    const int ny = min(64, nct - c0);
+    if (tid < 64) {
+      S.xcol[tid] = j + (tid < k ? tid : 0); S.xdiag[tid] = j + (tid < k ? tid : 0);
+      S.ycol[tid] = j + fjb + c0 + (tid < ny ? tid : 0); S.ydiag[tid] = -1;
+    }
+    __syncthreads();
+    small_xty(P.a, lda, j, P.m, S.xcol, S.xdiag, k, S.ycol, S.ydiag, ny, false, S.wbuf, S.u.xty.tx, S.u.xty.ty);
+    // W2[q][t] = -sum_p M[q][p] W[p][t]; NaN screen of C (LAPACKE_dlarfb_mia's -13)
+    {
+      const int q = tid >> 3, t0 = (tid & 7) * 8;
+      double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      bool bad = false;
+      if (q < k) {
+        for (int p = 0; p <= q; ++p) {  // T' is lower triangular
+          const double mqp = S.gram[q * 64 + p];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) acc[u] = fma(mqp, S.wbuf[p * 64 + t0 + u], acc[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) bad |= (t0 + u < ny) && (S.wbuf[q * 64 + t0 + u] != S.wbuf[q * 64 + t0 + u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) S.w2buf[q * 64 + t0 + u] = (t0 + u < ny) ? -acc[u] : 0.0;
+      if (bad) S.bad = 1;
+    }
+    __syncthreads();
+    // rank-k update: lanes along rows (4 each), warps along columns (4 each)
+    for (int r0 = 0; r0 < rows; r0 += SM_RK_ROWS) {
+      for (int e = tid; e < k * SM_RK_ROWS; e += SM_NT) {
+        const int p = e / SM_RK_ROWS, rr = e - p * SM_RK_ROWS, r = r0 + rr;
+        S.u.rk.vch[p][rr] = (r >= rows || r < p) ? 0.0 : (r == p ? 1.0 : P.a[(size_t)(j + p) * lda + j + r]);
+      }
+      double cv[4][4];
+      const int rb = r0 + 4 * lane;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const int c = 4 * wid + cc;
+        const double* col = P.a + (size_t)(j + fjb + c0 + c) * lda + j;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) cv[cc][u] = (c < ny && rb + u < rows) ? col[rb + u] : 0.0;
+      }
+      __syncthreads();
+      for (int p = 0; p < k; ++p) {
+        const double2 v01 = *reinterpret_cast<const double2*>(&S.u.rk.vch[p][4 * lane]);
+        const double2 v23 = *reinterpret_cast<const double2*>(&S.u.rk.vch[p][4 * lane + 2]);
+        const double2 w01 = *reinterpret_cast<const double2*>(&S.w2buf[p * 64 + 4 * wid]);
+        const double2 w23 = *reinterpret_cast<const double2*>(&S.w2buf[p * 64 + 4 * wid + 2]);
+        const double vv[4] = {v01.x, v01.y, v23.x, v23.y};
+        const double ww[4] = {w01.x, w01.y, w23.x, w23.y};
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+          for (int u = 0; u < 4; ++u) cv[cc][u] = fma(vv[u], ww[cc], cv[cc][u]);
+      }
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const int c = 4 * wid + cc;
+        double* col = P.a + (size_t)(j + fjb + c0 + c) * lda + j;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (c < ny && rb + u < rows) col[rb + u] = cv[cc][u];
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ---- K2: partial-norm downdate with the recompute guard (src/dgeqrdm_work.c:36-122) ----
+__device__ __forceinline__ void small_norm_update(const qrdm_prob& P, SmallShared& S, double tol3z) {
+  qrdm_ctrl* ctrl = P.ctrl;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int j = ctrl->j, k = ctrl->fjb_cmp;
+  for (int c = j + k + tid; c < P.n; c += SM_NT) {
+    const double v1 = S.vn1[c];
+    if (v1 == 0.0) continue;
+    const double* col = P.a + (size_t)c * P.lda;
+    double d0 = 0.0, d1 = 0.0;
+    int r = j;
+    for (; r + 1 < j + k; r += 2) { d0 = fma(col[r], col[r], d0); d1 = fma(col[r + 1], col[r + 1], d1); }
+    if (r < j + k) d0 = fma(col[r], col[r], d0);
+    const double d = d0 + d1;
+    double t = sqrt(fabs(d)) / v1;
+    t = (t + 1.0) * (1.0 - t);
+    t = (0.0 >= t) ? 0.0 : t;
+    const double q = v1 / S.vn2[c];
+    const double t2 = t * (q * q);
+    if (t2 <= tol3z) {
+      if (P.m - (j + k) > 0) S.flag[atomicAdd(&ctrl->nflag, 1)] = c;
+      else { S.vn1[c] = 0.0; S.vn2[c] = 0.0; }
+    } else {
+      S.vn1[c] = v1 * sqrt(t);
+    }
+  }
+  __syncthreads();
+  const int nflag = ctrl->nflag;
+  for (int f = wid; f < nflag; f += SM_NW) {  // exact recompute, warp per flagged column
+    const int c = S.flag[f];
+    const double* col = P.a + (size_t)c * P.lda;
+    double s0 = 0.0, s1 = 0.0;
+    int r = j + k + lane;
+    for (; r + 32 < P.m; r += 64) { s0 = fma(col[r], col[r], s0); s1 = fma(col[r + 32], col[r + 32], s1); }
+    if (r < P.m) s0 = fma(col[r], col[r], s0);
+    const double v = sqrt(warp_sum(s0 + s1));
+    if (lane == 0) { S.vn1[c] = v; S.vn2[c] = v; }
+  }
+}
+
+__global__ void __launch_bounds__(SM_NT, 1) k_small(SmallArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmallShared& S = *reinterpret_cast<SmallShared*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int b = blockIdx.x;
+  if (b >= A.batch) return;
+
+  qrdm_prob P = {};
+  P.m = A.m; P.n = A.n; P.lda = A.lda; P.nb = A.nb;
+  P.delta = A.delta; P.tau_ = A.tau_;
+  P.a = A.a + (size_t)A.stride_a * b;
+  P.jpvt = A.jpvt + (size_t)A.n * b;
+  P.tau = A.tau + (size_t)min(A.m, A.n) * b;
+  P.vn1 = S.vn1; P.vn2 = S.vn2; P.ctrl = &S.ctrl; P.gram = S.gram;
+  P.row0 = 0; P.m_glob = A.m; P.nranks = 1; P.sub = 0; P.debug = 0;
+  int* ncols = A.ncols + (size_t)A.n * b;
+  const int minmn = min(A.m, A.n);
+
+  for (int i = tid; i < (int)(sizeof(qrdm_ctrl) / sizeof(int)); i += SM_NT) reinterpret_cast<int*>(&S.ctrl)[i] = 0;
+  if (tid == 0) {
+    const int mode = ncols[0];  // src/dgeqrdm_work.c:531-543
+    S.stop_mode = (mode >= 1 && mode <= 3) ? mode : 0;
+    S.eta = mode == 1 ? A.eps * A.n : (mode == 2 ? A.eps * sqrt((double)A.n) : (mode == 3 ? A.eta3 : 0.0));
+    S.it = 0;
+    S.bad = 0;
+  }
+  // initial norms (src/dgeqrdm_work.c:672-682), jpvt = identity (:596-609 with every column free)
+  for (int c = wid; c < A.n; c += SM_NW) {
+    const double* col = P.a + (size_t)c * A.lda;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int r = lane;
+    for (; r + 96 < A.m; r += 128) {
+      s0 = fma(col[r], col[r], s0);
+      s1 = fma(col[r + 32], col[r + 32], s1);
+      s2 = fma(col[r + 64], col[r + 64], s2);
+      s3 = fma(col[r + 96], col[r + 96], s3);
+    }
+    for (; r < A.m; r += 32) s0 = fma(col[r], col[r], s0);
+    const double v = sqrt(warp_sum((s0 + s1) + (s2 + s3)));
+    if (lane == 0) { S.vn1[c] = v; S.vn2[c] = v; P.jpvt[c] = c + 1; }
+  }
+  __syncthreads();
+  qrdm_select_body<SM_NT>(P, S.u.sel);
+  __syncthreads();
+  if (tid == 0) S.eta *= S.ctrl.maxnrm;  // :684
+  __syncthreads();
+
+  while (true) {
+    const int j = S.ctrl.j;
+    if (j >= minmn) break;
+    const int cols = A.n - j;
+    small_cosines(P, S);
+    __syncthreads();
+    qrdm_pick_body(P, S.u.pick);
+    __syncthreads();
+    small_permute(P);
+    __syncthreads();
+    small_panel(P, S);
+    __syncthreads();
+    const int fjb = S.ctrl.fjb, k = S.ctrl.fjb_cmp;
+    if (k > 0 && A.n - j - fjb > 0) {
+      if (k == 1) {
+        if (tid == 0) S.gram[0] = P.tau[j];
+        __syncthreads();
+      } else {
+        if (tid < 64) { S.xcol[tid] = j + (tid < k ? tid : 0); S.xdiag[tid] = j + (tid < k ? tid : 0); }
+        __syncthreads();
+        small_xty(P.a, A.lda, j, A.m, S.xcol, S.xdiag, k, S.xcol, S.xdiag, k, true, S.wbuf, S.u.xty.tx, S.u.xty.ty);
+        small_tinv(P, S, j, k);
+      }
+      if (k <= SM_KSMALL) small_trailing_narrow(P, S, j, fjb, k);
+      else small_trailing_wide(P, S, j, fjb, k);
+      __syncthreads();
+      if (tid == 0 && S.bad && S.ctrl.err == 0) S.ctrl.err = -13;
+    }
+    __syncthreads();
+    small_norm_update(P, S, 1.0536712127723509e-08 /* sqrt(dlamch('e')), src/dgeqrdm_work.c:528-529 */);
+    __syncthreads();
+    qrdm_select_body<SM_NT>(P, S.u.sel);  // next iteration's prologue: j += k, max norm, candidates
+    __syncthreads();
+    const int kk = S.ctrl.last_k;
+    if (tid == 0) ncols[S.it++] = kk;  // :740
+    if (S.ctrl.err != 0) break;
+    if (kk <= 0) { if (tid == 0) S.ctrl.err = QRDM_ERR_INTERNAL; break; }
+    if (S.stop_mode && S.ctrl.maxnrm * sqrt((double)(cols - kk)) <= S.eta) break;  // :782-785
+  }
+  __syncthreads();
+  if (tid == 0 && A.infos) A.infos[b] = S.ctrl.err;
+}
+
+extern "C" int qrdm_k_small_supported(int m, int n) { return m <= SM_MAXDIM && n <= SM_MAXDIM; }
+
+extern "C" int qrdm_k_small(int batch, int m, int n, double* d_a, int lda, long long stride_a, int* d_jpvt, double* d_tau,
+                            int* d_ncols, int* d_infos, double delta, double tau_, double eta3, int nb, void* stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallShared));
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  SmallArgs A;
+  A.batch = batch; A.m = m; A.n = n; A.lda = lda; A.nb = nb;
+  A.stride_a = stride_a;
+  A.delta = delta; A.tau_ = tau_; A.eps = 1.1102230246251565e-16 /* dlamch('e') */; A.eta3 = eta3;
+  A.a = d_a; A.jpvt = d_jpvt; A.tau = d_tau; A.ncols = d_ncols; A.infos = d_infos;
+  k_small<<<batch, SM_NT, sizeof(SmallShared), (cudaStream_t)stream>>>(A);
+  QRDM_LAUNCH_CHECK();
+  return 0;
+}

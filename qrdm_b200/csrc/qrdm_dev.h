@@ -113,6 +113,11 @@ int qrdm_k_skinny_finish(const qrdm_prob *p, int rows_hint, void *stream); /* ro
 int qrdm_k_panel_mg_init(const qrdm_prob *p, int j_host, void *stream);
 int qrdm_k_panel_mg_step(const qrdm_prob *p, int j_host, int step, void *stream);
 int qrdm_k_panel_mg_finish(const qrdm_prob *p, int j_host, void *stream);
+/* batched mode: one CTA per matrix, the whole factorisation in one launch (k_small.cu).  d_ncols is
+ * [batch][n] with the stop-rule mode in [b][0] on entry; d_infos [batch] or NULL. */
+int qrdm_k_small_supported(int m, int n);
+int qrdm_k_small(int batch, int m, int n, double *d_a, int lda, long long stride_a, int *d_jpvt, double *d_tau,
+                 int *d_ncols, int *d_infos, double delta, double tau_, double eta3, int nb, void *stream);
 /* NCCL (dlopen'ed libnccl.so.2): in-place sum all-reduce of doubles on the stream */
 int qrdm_rt_comm_unique_id(char *out128);
 int qrdm_rt_comm_init(int rank, int nranks, const char *id128);
@@ -134,6 +139,7 @@ int qrdm_rt_stream_create(void **stream);
 int qrdm_rt_is_pinned(const void *ptr);
 int qrdm_rt_stream_wait_event(void *stream, void *ev);
 int qrdm_rt_event_create(void **ev);
+int qrdm_rt_event_destroy(void *ev);
 int qrdm_rt_event_record(void *ev, void *stream);
 int qrdm_rt_event_sync(void *ev);
 double qrdm_rt_event_ms(void *ev0, void *ev1);

@@ -39,6 +39,7 @@ int qrdm_rt_is_pinned(const void* ptr) {
 int qrdm_rt_stream_wait_event(void* stream, void* ev) { return (int)cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)ev, 0); }
 int qrdm_rt_sync(void* stream) { return (int)cudaStreamSynchronize((cudaStream_t)stream); }
 int qrdm_rt_event_create(void** ev) { return (int)cudaEventCreate((cudaEvent_t*)ev); }
+int qrdm_rt_event_destroy(void* ev) { return ev ? (int)cudaEventDestroy((cudaEvent_t)ev) : 0; }
 int qrdm_rt_event_record(void* ev, void* stream) { return (int)cudaEventRecord((cudaEvent_t)ev, (cudaStream_t)stream); }
 int qrdm_rt_event_sync(void* ev) { return (int)cudaEventSynchronize((cudaEvent_t)ev); }
 double qrdm_rt_event_ms(void* ev0, void* ev1) {
