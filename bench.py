@@ -251,6 +251,81 @@ def run_row_sharded(torch, dist, qrdm_b200, rank, world, dev, m, n, steps, warmu
             "rows_per_gpu": ml, "collectives": "ncclAllReduce (f64 sum) on the compute stream" if world > 1 else "none"}
 
 
+def run_batched(torch, dist, qrdm_b200, rank, world, dev, total, n, steps, warmup, with_cpu):
+    """BASELINE config C5: `total` Kahan-type n x n matrices (per-matrix theta in [1.1, 1.3], seeded diagonal
+    perturbation 1e3*eps*(n..1)), split evenly over `world` GPUs as independent units (no collective); every
+    rank factors its share with ONE launch of the one-CTA-per-matrix kernel (dgeqrdm_batched_dev)."""
+    from qrdm_b200 import generators as g
+    from qrdm_b200 import sharded
+    per = sharded.batch_partition(total, world)[rank][1]
+    distinct = 37
+    base = np.stack([np.ascontiguousarray(g.kahan(n, theta=1.1 + 0.2 * b / distinct, perturb=1e3, seed=1000 * rank + b).T)
+                     for b in range(distinct)])
+    d_base = torch.from_numpy(base).to(dev)
+    idx = torch.arange(per, device=dev) % distinct
+    d_a = torch.empty((per, n, n), dtype=torch.float64, device=dev)
+    d_jpvt = torch.zeros((per, n), dtype=torch.int32, device=dev)
+    d_tau = torch.zeros((per, n), dtype=torch.float64, device=dev)
+    d_ncols = torch.zeros((per, n), dtype=torch.int32, device=dev)
+    d_infos = torch.zeros((per,), dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step():
+        torch.index_select(d_base, 0, idx, out=d_a)
+        d_ncols.zero_()
+        rc = qrdm_b200.api.dgeqrdm_batched_device(per, n, n, d_a.data_ptr(), n, n * n, d_jpvt.data_ptr(), d_tau.data_ptr(),
+                                                  d_ncols.data_ptr(), d_infos.data_ptr(), thres=THRES, nb=NB,
+                                                  stream=stream.cuda_stream)
+        if rc != 0:
+            raise SystemExit(f"dgeqrdm_batched_dev failed: {rc}")
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    bad = int((d_infos != 0).sum())
+    ranks_ = d_ncols[:distinct].sum(dim=1).tolist()
+    fl = sum(flops(n, n, int(r)) for r in ranks_) / distinct * per
+    iters = float((d_ncols[:distinct] > 0).sum(dim=1).float().mean())
+    agg = torch.tensor([ms, fl, bad], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = agg.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+        ms, fl, bad = float(mx[0]), float(agg[1]), int(agg[2])
+    out = {"workload": f"{total} Kahan-type {n}x{n} matrices split over {world} GPU(s), independent units (configs[4])",
+           "n_gpus": world, "scaling": "strong", "matrices_per_gpu": per, "ms_per_step": ms / steps,
+           "matrices_per_s": total * steps / (ms * 1e-3), "value": steps * fl / (ms * 1e-3) / 1e9, "unit": "GFLOP/s",
+           "mean_iterations_per_matrix": iters, "nonzero_infos": bad, "gpu_launches_per_step": 1,
+           "timed_region": "K x (device-side restore of the batch + one k_small launch), CUDA events, max over ranks"}
+    if with_cpu and rank == 0:
+        try:
+            from oracle import ref as oracle
+            oracle.set_ref_threads(1)
+            t0 = time.perf_counter()
+            cnt = 6
+            for b in range(cnt):
+                oracle.ref_dgeqrdm(np.asfortranarray(base[b].T), thres=THRES, nb=NB)
+            dt = (time.perf_counter() - t0) / cnt
+            cores = len(os.sched_getaffinity(0))
+            out["cpu_reference"] = {"ms_per_matrix_1_thread": dt * 1e3, "cores": cores,
+                                    "matrices_per_s_all_cores_extrapolated": cores / dt,
+                                    "sample": f"{cnt} of the matrices, unmodified reference, 1 BLAS thread each"}
+        except Exception as exc:
+            out["cpu_reference"] = {"error": str(exc)[:200]}
+    del d_a, d_base
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -264,6 +339,8 @@ def main():
     ap.add_argument("--no-row-sharded", action="store_true", help="skip the configs[3] row-sharded leg")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the C1/C2 context timings")
     ap.add_argument("--sharded-rows", type=int, default=2_000_000)
+    ap.add_argument("--no-batched", action="store_true", help="skip the configs[4] batched leg")
+    ap.add_argument("--batch-total", type=int, default=8192)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = max(args.warmup, 1)  # contract says W >= 3; honour smaller only for ncu captures
@@ -404,6 +481,16 @@ def main():
         except Exception as exc:  # never sink the headline measurement
             row_sharded = {"error": str(exc)[:300]}
 
+    batched = None
+    if not args.no_batched and not os.environ.get("QRDM_BENCH_SHAPE"):
+        try:
+            batched = run_batched(torch, dist, qrdm_b200, rank, world, dev, args.batch_total, 512, steps=2, warmup=1,
+                                  with_cpu=(world == 1 and not args.no_cpu_baseline))
+        except SystemExit:
+            raise
+        except Exception as exc:
+            batched = {"error": str(exc)[:300]}
+
     # ---- the other single-GPU BASELINE configs (parity-test cases, reported for context) ----
     other = {}
     if world == 1 and not args.no_other_configs and not os.environ.get("QRDM_BENCH_SHAPE"):
@@ -473,6 +560,8 @@ def main():
     }
     if row_sharded is not None:
         line["row_sharded"] = row_sharded
+    if batched is not None:
+        line["batched"] = batched
     if other:
         line["other_configs"] = other
     if world == 1 and not args.no_cpu_baseline:

@@ -15,8 +15,9 @@
 //     accepted); candidates that already fail the delta test there can never be accepted and are
 //     dropped before the full Gram matrix of the survivors is formed — for Kahan-type matrices that
 //     removes the 64 x 64 x rows Gram product from every one of the 511 iterations;
-//   * blocks of <= 8 reflectors are applied one trailing column per warp with the column held in
-//     registers (C read once, written once); wider blocks go through 64-column tiles
+//   * the panel is blocked in 8-column sub-panels held in registers; blocks of <= 8 reflectors are
+//     applied to the trailing matrix in order, one column per warp with the column held in registers
+//     (C read once, written once, no T factor); wider blocks go through 64-column tiles
 //     (W = V'C, W2 = -T'W, C += V W2) on the FP64 FMA pipe.
 #include <cstdio>
 #include "pick_body.cuh"
@@ -26,8 +27,26 @@
 #define SM_NW (SM_NT / 32)
 #define SM_MAXDIM 1024  // m, n <= 1024 (the column-in-registers path holds 32 rows per lane)
 #define SM_KSMALL 8
+#define SM_VPAD 96     // zero rows after V[p][0..1024): r_lo + 32 * NB may overshoot by < 64 + 32
 #define SM_LD 66        // doubles per row of the [row][column] staging tiles
 #define SM_RK_ROWS 128  // rows per chunk of the rank-k update
+
+#ifdef SM_DEBUG  // per-phase cycle counts of CTA 0 (development aid)
+__device__ long long g_pt[12];
+#define SM_PS(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long t_ = clock64(); g_pt[i] += t_ - S.ptq2; S.ptq2 = t_; } } while (0)
+#define SM_PS0 do { if (threadIdx.x == 0 && blockIdx.x == 0) S.ptq2 = clock64(); } while (0)
+#define SM_PT(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long t_ = clock64(); if ((i) > 0) g_pt[i] += t_ - S.ptq; S.ptq = t_; } } while (0)
+#define SM_TDECL long long tph_[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, tq_ = 0
+#define SM_T(i) do { const long long t_ = clock64(); if ((i) > 0) tph_[i] += t_ - tq_; tq_ = t_; } while (0)
+#define SM_TPRINT do { if (tid == 0 && blockIdx.x == 0) printf("cycles: cosines %lld pick %lld permute %lld panel %lld tfactor %lld trailing %lld normupd %lld select %lld\n", tph_[1], tph_[2], tph_[3], tph_[4], tph_[5], tph_[6], tph_[7], tph_[8]); printf("panel: load+dots %lld steps %lld writeback %lld blockupd %lld\n", g_pt[1], g_pt[2], g_pt[3], g_pt[4]); printf("step: scalars %lld update+dots %lld sync1 %lld reduce %lld sync2 %lld\n", g_pt[5], g_pt[6], g_pt[7], g_pt[8], g_pt[9]); } while (0)
+#else
+#define SM_PT(i)
+#define SM_PS(i)
+#define SM_PS0
+#define SM_TDECL
+#define SM_T(i)
+#define SM_TPRINT
+#endif
 
 struct SmallArgs {
   int batch, m, n, lda, nb;
@@ -48,16 +67,18 @@ struct SmallShared {
   alignas(16) double wbuf[4096];  // V'V, later W = V'C of the current column tile
   alignas(16) double w2buf[4096]; // -T'W
   double S_[64], rowv[64], wv[64], taus[64];
+  double sc[2][4];  // panel: {tau, beta, scale, stop} of the current / next column
   int xcol[64], xdiag[64], ycol[64], ydiag[64];
   int flag[SM_MAXDIM];
   double eta;
+  long long ptq, ptq2;
   int stop_mode, it, bad, keep[64];
   union alignas(16) {
     SelShared sel;
     PickShared pick;
     struct { double tx[64 * SM_LD], ty[64 * SM_LD]; } xty;
     struct { double B[64 * 65], X[64 * 65]; } tinv;
-    struct { double v[SM_KSMALL][SM_MAXDIM]; } sk;
+    struct { double v[SM_KSMALL][SM_MAXDIM + SM_VPAD]; } sk;  // reflectors of the current sub-panel, zero outside their rows
     struct { double vch[64][SM_RK_ROWS]; } rk;
     struct { double vbuf[SM_MAXDIM], xold[SM_MAXDIM]; } pan;
   } u;
@@ -211,94 +232,252 @@ __device__ __forceinline__ void small_permute(const qrdm_prob& P) {
   }
 }
 
+// Apply `nref` Householder reflectors, in order, to columns [c_lo, c_hi) of the block whose origin
+// (row j, column j) is A0: y <- (I - tau_p v_p v_p') y for p = 0..nref-1, which is what the reference's
+// unblocked loop (src/dlarf.c) and, mathematically, its dlarfb call do.  One warp holds NC whole columns in
+// registers (rows r_lo + lane + 32 q, q < NB), so every column is read once and written once; V[p][r]
+// lives in shared memory and is zero outside the reflector's rows (no row predicates in the inner loops).
+// Returns true if a dot product came out NaN (the -13 screen of LAPACKE_dlarfb_mia, src/dlarfb.c:73-75).
+template <int NB, int NC>
+__device__ __noinline__ bool small_apply_seq(double* A0, int lda, int c_lo, int c_hi, int r_lo, int rows,
+                                             const double (*V)[SM_MAXDIM + SM_VPAD], const double* taus, int nref) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  bool bad = false;
+  for (int c = c_lo + wid * NC; c < c_hi; c += SM_NW * NC) {
+    double y[NC][NB];
+#pragma unroll
+    for (int u = 0; u < NC; ++u)
+#pragma unroll
+      for (int q = 0; q < NB; ++q) {
+        const int r = r_lo + lane + 32 * q;
+        y[u][q] = (c + u < c_hi && r < rows) ? A0[(size_t)(c + u) * lda + r] : 0.0;
+      }
+    for (int p = 0; p < nref; ++p) {
+      const double* vp = V[p] + r_lo + lane;
+      double d[NC][2];
+#pragma unroll
+      for (int u = 0; u < NC; ++u) d[u][0] = d[u][1] = 0.0;
+#pragma unroll
+      for (int q = 0; q < NB; ++q) {
+        const double vv = vp[32 * q];
+#pragma unroll
+        for (int u = 0; u < NC; ++u) d[u][q & 1] = fma(vv, y[u][q], d[u][q & 1]);
+      }
+      const double tp = taus[p];
+      double f[NC];
+#pragma unroll
+      for (int u = 0; u < NC; ++u) {
+        const double t = warp_sum(d[u][0] + d[u][1]);
+        bad |= t != t;
+        f[u] = tp * t;
+      }
+#pragma unroll
+      for (int q = 0; q < NB; ++q) {
+        const double vv = vp[32 * q];
+#pragma unroll
+        for (int u = 0; u < NC; ++u) y[u][q] = fma(-vv, f[u], y[u][q]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < NC; ++u)
+#pragma unroll
+      for (int q = 0; q < NB; ++q) {
+        const int r = r_lo + lane + 32 * q;
+        if (c + u < c_hi && r < rows) A0[(size_t)(c + u) * lda + r] = y[u][q];
+      }
+  }
+  return bad;
+}
+__device__ __forceinline__ bool small_apply(double* A0, int lda, int c_lo, int c_hi, int r_lo, int rows,
+                                            const double (*V)[SM_MAXDIM + SM_VPAD], const double* taus, int nref) {
+  const int nblk = (rows - r_lo + 31) >> 5;
+  if (nblk <= 4) return small_apply_seq<4, 2>(A0, lda, c_lo, c_hi, r_lo, rows, V, taus, nref);
+  if (nblk <= 8) return small_apply_seq<8, 2>(A0, lda, c_lo, c_hi, r_lo, rows, V, taus, nref);
+  if (nblk <= 16) return small_apply_seq<16, 2>(A0, lda, c_lo, c_hi, r_lo, rows, V, taus, nref);
+  return small_apply_seq<32, 1>(A0, lda, c_lo, c_hi, r_lo, rows, V, taus, nref);
+}
+
 // ---- K4: Householder panel with the DM early stop (src/dgeqr2.c:148-191, src/dlarfg.c:120-185,
-// src/dlarf.c:133-185), in place.  One fused sweep per column: apply H_i to the remaining panel
-// columns and accumulate, in the same pass, the dot products the next reflector needs
-// (S_[jj] = x_{i+1}' x_jj below the next pivot row, rowv[jj] = the next pivot row). ----
+// src/dlarf.c:133-185).  Blocked so that the column-by-column part never waits on global memory:
+//   * the panel is processed in sub-panels of 8 columns held in REGISTERS (thread t owns rows t and
+//     t + 512 of all 8 columns); per column one block-wide reduction delivers, fused, the squared
+//     norm of the next pivot column and its dot products with the columns to its right
+//     (S_[c] = x_{i+1}' x_c below the next pivot row; rowv[c] = the next pivot row);
+//   * the 8 reflectors are then applied to the rest of the panel one column per warp, the column in
+//     registers (read once, written once), so later sub-panels start from fully updated columns —
+//     exactly the values the reference's unblocked loop would see, hence the same early stop.
+// dlarfg_mia's scalars for one column (src/dlarfg.c:120-185) + the DM stop test (:129-133), computed by ONE
+// thread and broadcast through shared memory: FP64 sqrt/div on every thread would saturate the FP64 pipe.
+__device__ __forceinline__ void small_hh_scalars(double alpha, double xn2, int len, bool can_stop, double thres2, double* out) {
+  double tau = 0.0, beta = alpha, scale = 1.0, stop = 0.0;
+  if (len > 1 && can_stop && xn2 < thres2) {
+    stop = 1.0;
+  } else if (len > 1 && xn2 != 0.0) {
+    const double hy = sqrt(fma(alpha, alpha, xn2));
+    beta = (alpha >= 0.0) ? -hy : hy;
+    tau = (beta - alpha) / beta;
+    scale = 1.0 / (alpha - beta);
+  }
+  out[0] = tau; out[1] = beta; out[2] = scale; out[3] = stop;
+}
+#define SM_PB 8
 __device__ __forceinline__ void small_panel(const qrdm_prob& P, SmallShared& S) {
   qrdm_ctrl* ctrl = P.ctrl;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int j = ctrl->j, fjb = ctrl->fjb, lda = P.lda;
   const int rows = P.m - j;
   double* Ap = P.a + (size_t)j * lda + j;
-  double* vbuf = S.u.pan.vbuf;
-  double* xold = S.u.pan.xold;
-  // dots of column 0 with every panel column (rows >= 1), pivot row 0
-  for (int jj = wid; jj < fjb; jj += SM_NW) {
-    const double* cj = Ap + (size_t)jj * lda;
-    double s0 = 0.0, s1 = 0.0;
-    int r = 1 + lane;
-    for (; r + 32 < rows; r += 64) { s0 = fma(Ap[r], cj[r], s0); s1 = fma(Ap[r + 32], cj[r + 32], s1); }
-    if (r < rows) s0 = fma(Ap[r], cj[r], s0);
-    const double d = warp_sum(s0 + s1);
-    if (lane == 0) { S.S_[jj] = d; S.rowv[jj] = cj[0]; }
-  }
-  __syncthreads();
+  double(*red)[SM_PB] = reinterpret_cast<double(*)[SM_PB]>(S.wbuf);  // [SM_NW][8] warp partials (first column)
+  double* part = S.w2buf;  // [8][512] per-thread partial dots
+  double* Sd = S.S_;    // [2][8] reduced dots, double-buffered by column parity
+  double* Rv = S.rowv;  // [2][8] pivot-row entries
   double thres2 = 5e-14 * 5e-14;  // (src/dgeqr2.c:40)^2
   int k = fjb;
-  for (int i = 0; i < fjb; ++i) {
-    const double alpha = S.rowv[i], xn2 = S.S_[i];
-    const int len = rows - i;
-    double tau = 0.0, beta = alpha, scale = 1.0;
-#ifdef SM_DEBUG
-    if (tid == 0 && blockIdx.x == 0) printf("j=%d i=%d fjb=%d rows=%d alpha=%.3e xn2=%.3e thres2=%.3e\n", j, i, fjb, rows, alpha, xn2, thres2);
-#endif
-    if (len > 1) {
-      if (i > 0 && xn2 < thres2) { k = i; break; }  // DM early stop: column i left untouched
-      if (xn2 != 0.0) {
-        const double h = sqrt(fma(alpha, alpha, xn2));
-        beta = (alpha >= 0.0) ? -h : h;
-        tau = (beta - alpha) / beta;
-        scale = 1.0 / (alpha - beta);
+  bool stopped = false;
+  SM_PT(0);
+  for (int s0 = 0; s0 < fjb && !stopped; s0 += SM_PB) {
+    const int w = min(SM_PB, fjb - s0);
+    SM_PT(0);
+    for (int e = tid; e < SM_PB * SM_VPAD; e += SM_NT) S.u.sk.v[e / SM_VPAD][SM_MAXDIM + e % SM_VPAD] = 0.0;
+    double x[2][SM_PB];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int c = 0; c < SM_PB; ++c) {
+        const int r = tid + SM_NT * h;
+        x[h][c] = (c < w && r >= s0 && r < rows) ? Ap[(size_t)(s0 + c) * lda + r] : 0.0;
+      }
+    // dots of the sub-panel's first column with all of its columns (rows below the pivot row s0)
+    {
+      double acc[SM_PB];
+#pragma unroll
+      double xm[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int r = tid + SM_NT * h;
+        xm[h] = r > s0 ? x[h][0] : 0.0;
+        if (r == s0) {
+#pragma unroll
+          for (int c = 0; c < SM_PB; ++c) Rv[c] = x[h][c];
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < SM_PB; ++c) acc[c] = warp_sum(fma(xm[0], x[0][c], xm[1] * x[1][c]));
+      if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < SM_PB; ++c) red[wid][c] = acc[c];
+      }
+      __syncthreads();
+      if (tid < SM_PB) {
+        double t = 0.0;
+        for (int q = 0; q < SM_NW; ++q) t += red[q][tid];
+        Sd[tid] = t;
+        if (tid == 0) small_hh_scalars(Rv[0], t, rows - s0, s0 > 0, thres2, S.sc[0]);
+      }
+      __syncthreads();
+    }
+    SM_PT(1);
+    int nref = w;  // reflectors this sub-panel ends up producing
+#pragma unroll
+    for (int i = 0; i < SM_PB; ++i) {
+      if (i < w && !stopped) {
+        const int gi = s0 + i, cur = (i & 1) * SM_PB, nxt = ((i + 1) & 1) * SM_PB;
+        SM_PS0;
+        const double tau = S.sc[i & 1][0], beta = S.sc[i & 1][1], scale = S.sc[i & 1][2];
+        if (S.sc[i & 1][3] != 0.0) {  // DM early stop: column gi left untouched
+          k = gi; nref = i; stopped = true;
+        } else {
+          if (gi == 0 && fjb > 1 && P.tau_ > 0.0) { const double th = P.tau_ * fabs(beta); thres2 = th * th; }
+          if (tid == 0) {
+            P.tau[j + gi] = tau;
+            S.taus[i] = tau;
+            if (tau != tau && ctrl->err == 0) ctrl->err = -8;  // LAPACKE_dlarft's NaN screen of tau
+          }
+          SM_PS(5);
+          double v[2], wc[SM_PB];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int r = tid + SM_NT * h;
+            v[h] = 0.0;
+            if (r < rows) {
+              if (r > gi) { v[h] = x[h][i]; if (tau != 0.0) { v[h] *= scale; x[h][i] = v[h]; } }
+              else if (r == gi) { v[h] = 1.0; x[h][i] = beta; }
+            }
+            S.u.sk.v[i][r] = v[h];  // zero above the pivot row and below the matrix
+          }
+#pragma unroll
+          for (int c = 0; c < SM_PB; ++c) wc[c] = (c > i && c < w) ? tau * (Rv[cur + c] + Sd[cur + c] * scale) : 0.0;
+          if (i + 1 < w) {
+            double acc[SM_PB];
+#pragma unroll
+            for (int c = 0; c < SM_PB; ++c) {
+              acc[c] = 0.0;
+              if (c > i) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  const int r = tid + SM_NT * h;
+                  x[h][c] = fma(-v[h], wc[c], x[h][c]);  // H_gi applied (rows < gi have v = 0)
+                }
+              }
+            }
+            // branch-free: the multiplicand is zeroed for rows at or above the next pivot row
+            double xm[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int r = tid + SM_NT * h;
+              xm[h] = r > gi + 1 ? x[h][i + 1 < SM_PB ? i + 1 : i] : 0.0;
+              if (r == gi + 1) {  // one thread: the next pivot row
+#pragma unroll
+                for (int c = 0; c < SM_PB; ++c)
+                  if (c > i) Rv[nxt + c] = x[h][c];
+              }
+            }
+#pragma unroll
+            for (int c = 0; c < SM_PB; ++c) {
+              if (c > i) {
+                acc[c] = fma(xm[0], x[0][c], xm[1] * x[1][c]);
+                part[c * SM_NT + tid] = acc[c];
+              }
+            }
+            SM_PS(6);
+            __syncthreads();
+            SM_PS(7);
+            if (wid > i && wid < w) {  // warp c totals the 512 partials of column c (fixed order)
+              const double* pc = part + wid * SM_NT + lane;
+              double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+#pragma unroll
+              for (int q = 0; q < SM_NW; q += 4) {
+                t0 += pc[32 * q]; t1 += pc[32 * (q + 1)]; t2 += pc[32 * (q + 2)]; t3 += pc[32 * (q + 3)];
+              }
+              const double t = warp_sum((t0 + t1) + (t2 + t3));
+              if (lane == 0) {
+                Sd[nxt + wid] = t;
+                if (wid == i + 1) small_hh_scalars(Rv[nxt + wid], t, rows - (gi + 1), true, thres2, S.sc[(i + 1) & 1]);
+              }
+            }
+            SM_PS(8);
+            __syncthreads();
+            SM_PS(9);
+          }
+        }
       }
     }
-    if (i == 0 && fjb > 1 && P.tau_ > 0.0) { const double th = P.tau_ * fabs(beta); thres2 = th * th; }
-    const bool last = i + 1 >= fjb;
-    if (tid == 0) {
-      P.tau[j + i] = tau;
-      if (tau != tau && ctrl->err == 0) ctrl->err = -8;  // LAPACKE_dlarft's NaN screen of tau
-    }
-    // publish v (scaled column i, unit diagonal) and a snapshot of column i+1 before H_i
-    double* ci = Ap + (size_t)i * lda;
-    const double* cn = Ap + (size_t)(i + 1) * lda;
-    for (int r = tid; r < rows; r += SM_NT) {
-      double v = 0.0;
-      if (r > i) { v = ci[r]; if (tau != 0.0) { v *= scale; ci[r] = v; } }
-      else if (r == i) { v = 1.0; ci[r] = beta; }
-      vbuf[r] = v;
-      if (!last) xold[r] = cn[r];
-    }
-    if (tid < 64 && tid > i && tid < fjb) S.wv[tid] = tau * (S.rowv[tid] + S.S_[tid] * scale);
+    SM_PT(2);
+    // sub-panel back to global memory (rows >= s0; rows above hold R entries of earlier blocks)
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int c = 0; c < SM_PB; ++c) {
+        const int r = tid + SM_NT * h;
+        if (c < w && r >= s0 && r < rows) Ap[(size_t)(s0 + c) * lda + r] = x[h][c];
+      }
+    __syncthreads();  // v[][] and taus[] of this sub-panel complete
+    SM_PT(3);
+    // apply its nref reflectors to the rest of the panel (columns in registers, read once, written once)
+    if (nref > 0 && s0 + w < fjb) small_apply(Ap, lda, s0 + w, fjb, s0, rows, S.u.sk.v, S.taus, nref);
     __syncthreads();
-    if (last) break;
-    const double w1 = S.wv[i + 1];
-    for (int jj = i + 1 + wid; jj < fjb; jj += SM_NW) {
-      double* cj = Ap + (size_t)jj * lda;
-      const double wj = S.wv[jj];
-      double s0 = 0.0, s1 = 0.0, prow = 0.0;
-      int r = i + lane;
-      for (; r + 32 < rows; r += 64) {
-        const double p0 = fma(-vbuf[r], wj, cj[r]);
-        const double p1 = fma(-vbuf[r + 32], wj, cj[r + 32]);
-        cj[r] = p0;
-        cj[r + 32] = p1;
-        const double x0 = fma(-vbuf[r], w1, xold[r]), x1 = fma(-vbuf[r + 32], w1, xold[r + 32]);
-        if (r > i + 1) s0 = fma(x0, p0, s0); else if (r == i + 1) prow = p0;
-        s1 = fma(x1, p1, s1);  // r + 32 > i + 1 always
-      }
-      if (r < rows) {
-        const double p0 = fma(-vbuf[r], wj, cj[r]);
-        cj[r] = p0;
-        const double x0 = fma(-vbuf[r], w1, xold[r]);
-        if (r > i + 1) s0 = fma(x0, p0, s0); else if (r == i + 1) prow = p0;
-      }
-      const double d = warp_sum(s0 + s1);
-      prow = __shfl_sync(0xffffffffu, prow, 1);  // row i+1 is lane 1's first element
-      if (lane == 0) { S.S_[jj] = d; S.rowv[jj] = prow; }
-    }
-    __syncthreads();
+    SM_PT(4);
   }
-  __syncthreads();
   if (tid == 0) ctrl->fjb_cmp = k;
 }
 
@@ -328,67 +507,6 @@ __device__ __forceinline__ void small_tinv(const qrdm_prob& P, SmallShared& S, i
     S.gram[e] = (q < k && pp < k) ? X[q * 65 + pp] * S.taus[pp] : 0.0;
   }
   __syncthreads();
-}
-
-// ---- K6 for narrow blocks: one trailing column per warp, held in registers ----
-__device__ __forceinline__ void small_trailing_narrow(const qrdm_prob& P, SmallShared& S, int j, int fjb, int k) {
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int rows = P.m - j, lda = P.lda;
-  for (int e = tid; e < k * rows; e += SM_NT) {  // V with unit diagonal / zeros above, [p][r]
-    const int p = e / rows, r = e - p * rows;
-    S.u.sk.v[p][r] = r < p ? 0.0 : (r == p ? 1.0 : P.a[(size_t)(j + p) * lda + j + r]);
-  }
-  __syncthreads();
-  const int nblk = (rows + 31) >> 5;
-  bool bad = false;
-  for (int c = j + fjb + wid; c < P.n; c += SM_NW) {
-    double* col = P.a + (size_t)c * lda + j;
-    double x[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int r = lane + 32 * i;
-      x[i] = (i < nblk && r < rows) ? col[r] : 0.0;
-    }
-    double w[SM_KSMALL];
-    for (int p = 0; p < k; ++p) {
-      const double* vp = S.u.sk.v[p];
-      double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        if (i < nblk) {
-          const int r = lane + 32 * i;
-          s0 = fma(r < rows ? vp[r] : 0.0, x[i], s0);
-          s1 = fma(r + 32 < rows ? vp[r + 32] : 0.0, x[i + 1], s1);
-        }
-      }
-      const double d = warp_sum(s0 + s1);
-      bad |= d != d;
-#pragma unroll
-      for (int q = 0; q < SM_KSMALL; ++q)
-        if (q == p) w[q] = d;
-    }
-    // y = T' w (lower triangular), then x -= V y
-    for (int q = 0; q < k; ++q) {
-      double y = 0.0;
-#pragma unroll
-      for (int p = 0; p < SM_KSMALL; ++p)
-        if (p <= q && p < k) y = fma(S.gram[q * 64 + p], w[p], y);
-      const double* vq = S.u.sk.v[q];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        if (i < nblk) {
-          const int r = lane + 32 * i;
-          if (r < rows) x[i] = fma(-vq[r], y, x[i]);
-        }
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int r = lane + 32 * i;
-      if (i < nblk && r < rows) col[r] = x[i];
-    }
-  }
-  if (bad) S.bad = 1;
 }
 
 // ---- K6 for wide blocks: 64-column tiles, W = V'C, W2 = -T'W, C += V W2 ----
@@ -551,39 +669,49 @@ __global__ void __launch_bounds__(SM_NT, 1) k_small(SmallArgs A) {
   if (tid == 0) S.eta *= S.ctrl.maxnrm;  // :684
   __syncthreads();
 
+  SM_TDECL;
   while (true) {
     const int j = S.ctrl.j;
     if (j >= minmn) break;
     const int cols = A.n - j;
-    small_cosines(P, S);
+    SM_T(0); small_cosines(P, S);
     __syncthreads();
+    SM_T(1);
     qrdm_pick_body(P, S.u.pick);
     __syncthreads();
+    SM_T(2);
     small_permute(P);
     __syncthreads();
+    SM_T(3);
     small_panel(P, S);
     __syncthreads();
+    SM_T(4);
     const int fjb = S.ctrl.fjb, k = S.ctrl.fjb_cmp;
     if (k > 0 && A.n - j - fjb > 0) {
-      if (k == 1) {
-        if (tid == 0) S.gram[0] = P.tau[j];
-        __syncthreads();
+      if (k <= SM_KSMALL) {
+        // narrow block: its reflectors are still in shared memory (sub-panel 0 of the panel) -> apply them
+        // in order, one trailing column per warp in registers; no T factor needed
+        if (small_apply(P.a + (size_t)j * A.lda + j, A.lda, fjb, A.n - j, 0, A.m - j, S.u.sk.v, S.taus, k)) S.bad = 1;
+        SM_T(5);
       } else {
         if (tid < 64) { S.xcol[tid] = j + (tid < k ? tid : 0); S.xdiag[tid] = j + (tid < k ? tid : 0); }
         __syncthreads();
         small_xty(P.a, A.lda, j, A.m, S.xcol, S.xdiag, k, S.xcol, S.xdiag, k, true, S.wbuf, S.u.xty.tx, S.u.xty.ty);
         small_tinv(P, S, j, k);
+        SM_T(5);
+        small_trailing_wide(P, S, j, fjb, k);
       }
-      if (k <= SM_KSMALL) small_trailing_narrow(P, S, j, fjb, k);
-      else small_trailing_wide(P, S, j, fjb, k);
       __syncthreads();
       if (tid == 0 && S.bad && S.ctrl.err == 0) S.ctrl.err = -13;
     }
     __syncthreads();
+    SM_T(6);
     small_norm_update(P, S, 1.0536712127723509e-08 /* sqrt(dlamch('e')), src/dgeqrdm_work.c:528-529 */);
     __syncthreads();
+    SM_T(7);
     qrdm_select_body<SM_NT>(P, S.u.sel);  // next iteration's prologue: j += k, max norm, candidates
     __syncthreads();
+    SM_T(8);
     const int kk = S.ctrl.last_k;
     if (tid == 0) ncols[S.it++] = kk;  // :740
     if (S.ctrl.err != 0) break;
@@ -591,6 +719,7 @@ __global__ void __launch_bounds__(SM_NT, 1) k_small(SmallArgs A) {
     if (S.stop_mode && S.ctrl.maxnrm * sqrt((double)(cols - kk)) <= S.eta) break;  // :782-785
   }
   __syncthreads();
+  SM_TPRINT;
   if (tid == 0 && A.infos) A.infos[b] = S.ctrl.err;
 }
 

@@ -26,6 +26,20 @@ def row_partition(m: int, world: int) -> list[tuple[int, int]]:
     return out
 
 
+def batch_partition(batch: int, world: int) -> list[tuple[int, int]]:
+    """Batched mode (independent units, no collective): matrices [first, first + count) per rank; the
+    first ``batch % world`` ranks take one extra matrix."""
+    if world < 1 or batch < 0:
+        raise ValueError("bad partition request")
+    base, extra = divmod(batch, world)
+    out, first = [], 0
+    for r in range(world):
+        cnt = base + (1 if r < extra else 0)
+        out.append((first, cnt))
+        first += cnt
+    return out
+
+
 def broadcast_unique_id(make_id, rank: int, group=None, device=None) -> bytes:
     """Rank 0 produces the 128-byte NCCL unique id (`make_id()`), everybody receives it through
     torch.distributed (works with the gloo and the nccl backend)."""

@@ -16,6 +16,17 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def test_batch_partition_covers_all_matrices():
+    from qrdm_b200.sharded import batch_partition
+    for batch, w in [(8192, 8), (8192, 1), (10, 3), (2, 4), (0, 2), (1184, 5)]:
+        parts = batch_partition(batch, w)
+        assert len(parts) == w and sum(c for _, c in parts) == batch
+        assert all(parts[i][0] + parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+        assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
+    with pytest.raises(ValueError):
+        batch_partition(4, 0)
+
+
 def test_row_partition_covers_all_rows():
     from qrdm_b200.sharded import row_partition
     for m, w in [(2_000_000, 8), (2_000_000, 4), (100, 8), (31, 2), (0, 3), (4096, 1), (257, 2)]:
