@@ -15,10 +15,11 @@
 //     accepted); candidates that already fail the delta test there can never be accepted and are
 //     dropped before the full Gram matrix of the survivors is formed — for Kahan-type matrices that
 //     removes the 64 x 64 x rows Gram product from every one of the 511 iterations;
-//   * the panel is blocked in 8-column sub-panels held in registers; blocks of <= 8 reflectors are
-//     applied to the trailing matrix in order, one column per warp with the column held in registers
-//     (C read once, written once, no T factor); wider blocks go through 64-column tiles
-//     (W = V'C, W2 = -T'W, C += V W2) on the FP64 FMA pipe.
+//   * the panel is blocked in 8-column sub-panels held in registers;
+//   * the trailing update applies the block's reflectors in order (H_k ... H_1 C, the product the
+//     compact-WY form of dlarfb evaluates) with each trailing column held in the registers of one warp:
+//     C is read once and written once, no T factor is formed; for blocks of more than 8 reflectors the
+//     reflectors stream through shared memory in double-buffered groups of 4.
 #include <cstdio>
 #include "pick_body.cuh"
 #include "select_body.cuh"
@@ -29,7 +30,6 @@
 #define SM_KSMALL 8
 #define SM_VPAD 96     // zero rows after V[p][0..1024): r_lo + 32 * NB may overshoot by < 64 + 32
 #define SM_LD 66        // doubles per row of the [row][column] staging tiles
-#define SM_RK_ROWS 128  // rows per chunk of the rank-k update
 
 #ifdef SM_DEBUG  // per-phase cycle counts of CTA 0 (development aid)
 __device__ long long g_pt[12];
@@ -63,9 +63,9 @@ struct SmallShared {
   qrdm_ctrl ctrl;
   alignas(16) double vn1[SM_MAXDIM];
   double vn2[SM_MAXDIM];
-  alignas(16) double gram[4096];  // candidates' Gram matrix, later M = T'
-  alignas(16) double wbuf[4096];  // V'V, later W = V'C of the current column tile
-  alignas(16) double w2buf[4096]; // -T'W
+  alignas(16) double gram[4096];  // candidates' Gram matrix
+  alignas(16) double red[SM_NW * 8];   // panel: warp partials of a sub-panel's first reduction
+  alignas(16) double part[8 * SM_NT];  // panel: per-thread partial dots, [column][thread]
   double S_[64], rowv[64], wv[64], taus[64];
   double sc[2][4];  // panel: {tau, beta, scale, stop} of the current / next column
   int xcol[64], xdiag[64], ycol[64], ydiag[64];
@@ -77,9 +77,7 @@ struct SmallShared {
     SelShared sel;
     PickShared pick;
     struct { double tx[64 * SM_LD], ty[64 * SM_LD]; } xty;
-    struct { double B[64 * 65], X[64 * 65]; } tinv;
     struct { double v[SM_KSMALL][SM_MAXDIM + SM_VPAD]; } sk;  // reflectors of the current sub-panel, zero outside their rows
-    struct { double vch[64][SM_RK_ROWS]; } rk;
     struct { double vbuf[SM_MAXDIM], xold[SM_MAXDIM]; } pan;
   } u;
 };
@@ -306,6 +304,98 @@ __device__ __forceinline__ bool small_apply(double* A0, int lda, int c_lo, int c
 //   * the 8 reflectors are then applied to the rest of the panel one column per warp, the column in
 //     registers (read once, written once), so later sub-panels start from fully updated columns —
 //     exactly the values the reference's unblocked loop would see, hence the same early stop.
+// The same for a block of k > 8 reflectors (the trailing update of a wide block): the columns stay in
+// registers while the reflectors stream through shared memory in groups of 4, double-buffered — group
+// g+1 is fetched from the panel (global/L2) into registers while group g is applied, then stored to the
+// other buffer.  FLOPs are the 4*rows*cols*k of the compact-WY form, no T factor, no second pass over C.
+template <int NB, int NC>
+__device__ __noinline__ bool small_apply_blocked(double* A0, int lda, int c_lo, int c_hi, int rows, int k,
+                                                 double (*Vb)[SM_MAXDIM + SM_VPAD], const double* taus) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  constexpr int SPAN = NB * 32;               // rows covered by the register tile (>= rows)
+  constexpr int EPT = (4 * SPAN) / SM_NT;     // staged elements per thread and group
+  const int ng = (k + 3) >> 2;
+  bool bad = false;
+  double pre[EPT];
+  auto fetch = [&](int g) {
+#pragma unroll
+    for (int t = 0; t < EPT; ++t) {
+      const int e = tid + SM_NT * t, p = e / SPAN, r = e % SPAN, gp = 4 * g + p;
+      pre[t] = (gp < k && r < rows) ? (r < gp ? 0.0 : (r == gp ? 1.0 : A0[(size_t)gp * lda + r])) : 0.0;
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int t = 0; t < EPT; ++t) {
+      const int e = tid + SM_NT * t, p = e / SPAN, r = e % SPAN;
+      Vb[buf * 4 + p][r] = pre[t];
+    }
+  };
+  for (int cb = c_lo; cb < c_hi; cb += SM_NW * NC) {
+    const int c = cb + wid * NC;
+    double y[NC][NB];
+#pragma unroll
+    for (int u = 0; u < NC; ++u)
+#pragma unroll
+      for (int q = 0; q < NB; ++q) {
+        const int r = lane + 32 * q;
+        y[u][q] = (c + u < c_hi && r < rows) ? A0[(size_t)(c + u) * lda + r] : 0.0;
+      }
+    fetch(0);
+    __syncthreads();
+    stash(0);
+    __syncthreads();
+    for (int g = 0; g < ng; ++g) {
+      if (g + 1 < ng) fetch(g + 1);
+      const int np = min(4, k - 4 * g);
+      for (int p = 0; p < np; ++p) {
+        const double* vp = Vb[(g & 1) * 4 + p] + lane;
+        double d[NC][2];
+#pragma unroll
+        for (int u = 0; u < NC; ++u) d[u][0] = d[u][1] = 0.0;
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+          const double vv = vp[32 * q];
+#pragma unroll
+          for (int u = 0; u < NC; ++u) d[u][q & 1] = fma(vv, y[u][q], d[u][q & 1]);
+        }
+        const double tp = taus[4 * g + p];
+        double f[NC];
+#pragma unroll
+        for (int u = 0; u < NC; ++u) {
+          const double t = warp_sum(d[u][0] + d[u][1]);
+          bad |= t != t;
+          f[u] = tp * t;
+        }
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+          const double vv = vp[32 * q];
+#pragma unroll
+          for (int u = 0; u < NC; ++u) y[u][q] = fma(-vv, f[u], y[u][q]);
+        }
+      }
+      if (g + 1 < ng) stash((g + 1) & 1);
+      __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < NC; ++u)
+#pragma unroll
+      for (int q = 0; q < NB; ++q) {
+        const int r = lane + 32 * q;
+        if (c + u < c_hi && r < rows) A0[(size_t)(c + u) * lda + r] = y[u][q];
+      }
+  }
+  return bad;
+}
+__device__ __forceinline__ bool small_apply_wide(double* A0, int lda, int c_lo, int c_hi, int rows, int k,
+                                                 double (*Vb)[SM_MAXDIM + SM_VPAD], const double* taus) {
+  const int nblk = (rows + 31) >> 5;
+  if (nblk <= 4) return small_apply_blocked<4, 2>(A0, lda, c_lo, c_hi, rows, k, Vb, taus);
+  if (nblk <= 8) return small_apply_blocked<8, 2>(A0, lda, c_lo, c_hi, rows, k, Vb, taus);
+  if (nblk <= 16) return small_apply_blocked<16, 2>(A0, lda, c_lo, c_hi, rows, k, Vb, taus);
+  return small_apply_blocked<32, 1>(A0, lda, c_lo, c_hi, rows, k, Vb, taus);
+}
+
 // dlarfg_mia's scalars for one column (src/dlarfg.c:120-185) + the DM stop test (:129-133), computed by ONE
 // thread and broadcast through shared memory: FP64 sqrt/div on every thread would saturate the FP64 pipe.
 __device__ __forceinline__ void small_hh_scalars(double alpha, double xn2, int len, bool can_stop, double thres2, double* out) {
@@ -327,8 +417,8 @@ __device__ __forceinline__ void small_panel(const qrdm_prob& P, SmallShared& S) 
   const int j = ctrl->j, fjb = ctrl->fjb, lda = P.lda;
   const int rows = P.m - j;
   double* Ap = P.a + (size_t)j * lda + j;
-  double(*red)[SM_PB] = reinterpret_cast<double(*)[SM_PB]>(S.wbuf);  // [SM_NW][8] warp partials (first column)
-  double* part = S.w2buf;  // [8][512] per-thread partial dots
+  double(*red)[SM_PB] = reinterpret_cast<double(*)[SM_PB]>(S.red);
+  double* part = S.part;
   double* Sd = S.S_;    // [2][8] reduced dots, double-buffered by column parity
   double* Rv = S.rowv;  // [2][8] pivot-row entries
   double thres2 = 5e-14 * 5e-14;  // (src/dgeqr2.c:40)^2
@@ -481,107 +571,6 @@ __device__ __forceinline__ void small_panel(const qrdm_prob& P, SmallShared& S) 
   if (tid == 0) ctrl->fjb_cmp = k;
 }
 
-// ---- T' = (I + D N)^-1 D from V'V (S.wbuf) and tau -> S.gram  (replaces LAPACKE_dlarft) ----
-__device__ __forceinline__ void small_tinv(const qrdm_prob& P, SmallShared& S, int j, int k) {
-  const int tid = threadIdx.x;
-  double* B = S.u.tinv.B;
-  double* X = S.u.tinv.X;
-  if (tid < 64) S.taus[tid] = tid < k ? P.tau[j + tid] : 0.0;
-  __syncthreads();
-  for (int e = tid; e < 4096; e += SM_NT) {
-    const int s = e >> 6, i = e & 63;
-    B[i * 65 + s] = (s < i && i < k) ? S.taus[i] * S.wbuf[s * 64 + i] : 0.0;
-  }
-  __syncthreads();
-  if (tid < 64) {
-    const int p = tid;  // column p of (I + B)^-1 by forward substitution
-    for (int i = 0; i < k; ++i) {
-      double acc = (i == p) ? 1.0 : 0.0;
-      for (int s = 0; s < i; ++s) acc = fma(-B[i * 65 + s], X[s * 65 + p], acc);
-      X[i * 65 + p] = acc;
-    }
-  }
-  __syncthreads();
-  for (int e = tid; e < 4096; e += SM_NT) {
-    const int q = e >> 6, pp = e & 63;
-    S.gram[e] = (q < k && pp < k) ? X[q * 65 + pp] * S.taus[pp] : 0.0;
-  }
-  __syncthreads();
-}
-
-// ---- K6 for wide blocks: 64-column tiles, W = V'C, W2 = -T'W, C += V W2 ----
-__device__ __forceinline__ void small_trailing_wide(const qrdm_prob& P, SmallShared& S, int j, int fjb, int k) {
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int rows = P.m - j, lda = P.lda;
-  const int nct = P.n - j - fjb;
-  for (int c0 = 0; c0 < nct; c0 += 64) {
-    const int ny = min(64, nct - c0);
-    if (tid < 64) {
-      S.xcol[tid] = j + (tid < k ? tid : 0); S.xdiag[tid] = j + (tid < k ? tid : 0);
-      S.ycol[tid] = j + fjb + c0 + (tid < ny ? tid : 0); S.ydiag[tid] = -1;
-    }
-    __syncthreads();
-    small_xty(P.a, lda, j, P.m, S.xcol, S.xdiag, k, S.ycol, S.ydiag, ny, false, S.wbuf, S.u.xty.tx, S.u.xty.ty);
-    // W2[q][t] = -sum_p M[q][p] W[p][t]; NaN screen of C (LAPACKE_dlarfb_mia's -13)
-    {
-      const int q = tid >> 3, t0 = (tid & 7) * 8;
-      double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      bool bad = false;
-      if (q < k) {
-        for (int p = 0; p <= q; ++p) {  // T' is lower triangular
-          const double mqp = S.gram[q * 64 + p];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) acc[u] = fma(mqp, S.wbuf[p * 64 + t0 + u], acc[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) bad |= (t0 + u < ny) && (S.wbuf[q * 64 + t0 + u] != S.wbuf[q * 64 + t0 + u]);
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) S.w2buf[q * 64 + t0 + u] = (t0 + u < ny) ? -acc[u] : 0.0;
-      if (bad) S.bad = 1;
-    }
-    __syncthreads();
-    // rank-k update: lanes along rows (4 each), warps along columns (4 each)
-    for (int r0 = 0; r0 < rows; r0 += SM_RK_ROWS) {
-      for (int e = tid; e < k * SM_RK_ROWS; e += SM_NT) {
-        const int p = e / SM_RK_ROWS, rr = e - p * SM_RK_ROWS, r = r0 + rr;
-        S.u.rk.vch[p][rr] = (r >= rows || r < p) ? 0.0 : (r == p ? 1.0 : P.a[(size_t)(j + p) * lda + j + r]);
-      }
-      double cv[4][4];
-      const int rb = r0 + 4 * lane;
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        const int c = 4 * wid + cc;
-        const double* col = P.a + (size_t)(j + fjb + c0 + c) * lda + j;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) cv[cc][u] = (c < ny && rb + u < rows) ? col[rb + u] : 0.0;
-      }
-      __syncthreads();
-      for (int p = 0; p < k; ++p) {
-        const double2 v01 = *reinterpret_cast<const double2*>(&S.u.rk.vch[p][4 * lane]);
-        const double2 v23 = *reinterpret_cast<const double2*>(&S.u.rk.vch[p][4 * lane + 2]);
-        const double2 w01 = *reinterpret_cast<const double2*>(&S.w2buf[p * 64 + 4 * wid]);
-        const double2 w23 = *reinterpret_cast<const double2*>(&S.w2buf[p * 64 + 4 * wid + 2]);
-        const double vv[4] = {v01.x, v01.y, v23.x, v23.y};
-        const double ww[4] = {w01.x, w01.y, w23.x, w23.y};
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc)
-#pragma unroll
-          for (int u = 0; u < 4; ++u) cv[cc][u] = fma(vv[u], ww[cc], cv[cc][u]);
-      }
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        const int c = 4 * wid + cc;
-        double* col = P.a + (size_t)(j + fjb + c0 + c) * lda + j;
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (c < ny && rb + u < rows) col[rb + u] = cv[cc][u];
-      }
-      __syncthreads();
-    }
-  }
-}
-
 // ---- K2: partial-norm downdate with the recompute guard (src/dgeqrdm_work.c:36-122) ----
 __device__ __forceinline__ void small_norm_update(const qrdm_prob& P, SmallShared& S, double tol3z) {
   qrdm_ctrl* ctrl = P.ctrl;
@@ -694,12 +683,11 @@ __global__ void __launch_bounds__(SM_NT, 1) k_small(SmallArgs A) {
         if (small_apply(P.a + (size_t)j * A.lda + j, A.lda, fjb, A.n - j, 0, A.m - j, S.u.sk.v, S.taus, k)) S.bad = 1;
         SM_T(5);
       } else {
-        if (tid < 64) { S.xcol[tid] = j + (tid < k ? tid : 0); S.xdiag[tid] = j + (tid < k ? tid : 0); }
+        // wide block: all k taus, then the reflectors stream through shared memory in groups of 4
+        if (tid < 64) S.taus[tid] = tid < k ? P.tau[j + tid] : 0.0;
         __syncthreads();
-        small_xty(P.a, A.lda, j, A.m, S.xcol, S.xdiag, k, S.xcol, S.xdiag, k, true, S.wbuf, S.u.xty.tx, S.u.xty.ty);
-        small_tinv(P, S, j, k);
         SM_T(5);
-        small_trailing_wide(P, S, j, fjb, k);
+        if (small_apply_wide(P.a + (size_t)j * A.lda + j, A.lda, fjb, A.n - j, A.m - j, k, S.u.sk.v, S.taus)) S.bad = 1;
       }
       __syncthreads();
       if (tid == 0 && S.bad && S.ctrl.err == 0) S.ctrl.err = -13;
