@@ -198,17 +198,23 @@ def test_pinned_host_buffer_streams_columns_back(q):
         assert np.array_equal(tau, ref_out["tau"])
 
 
-def test_batched_kahan(q, oracle_ref):
+def test_batched_kahan(q, oracle_ref, oracle_port):
     """BASELINE config C5 unit: a batch of Kahan-type matrices (per-matrix theta, seeded diagonal
-    perturbation), every matrix against the unmodified reference."""
+    perturbation), every matrix against the unmodified reference.  The noise tail of these matrices has
+    exactly tied column norms (ORDER margin 0 in the port), so the 1e-12 margin rule applies: blocks are
+    compared on the trusted prefix, the rest by the invariants."""
     n, batch = 96, 6
     As = np.stack([g.kahan(n, theta=1.1 + 0.04 * b, perturb=1e3, seed=b) for b in range(batch)])
     out = q.dgeqrdm_batched(As)
     assert out["info"] == 0 and not out["infos"].any()
     for b in range(batch):
         exp = oracle_ref.ref_dgeqrdm(As[b])
+        margins = oracle_port.port_dgeqrdm(As[b])["margins"]
         got = dict(info=0, A=out["A"][b], jpvt=out["jpvt"][b], tau=out["tau"][b], ncols=out["ncols"][b])
-        parity.check_against(got, exp, (n, n), exact=True)
+        parity.check_against(got, exp, (n, n), margins=margins)
+        res, orth = parity.qr_invariants(As[b], got)
+        tol = parity.invariant_tol((n, n))
+        assert res <= tol and orth <= tol, (res, orth, tol)
 
 
 def test_bitwise_determinism(q):
