@@ -33,7 +33,9 @@ struct QrdmGeom {
 __device__ __forceinline__ QrdmGeom qrdm_geom(const qrdm_prob& P) {
   const qrdm_ctrl* c = P.ctrl;
   QrdmGeom g;
-  if (P.sub == 0) {
+  if (P.pend) {  // flush of a deferred block: rows >= pend_r0 of the columns >= pend_c0
+    g.j = c->pend_r0; g.fjb = c->pend_c0 - c->pend_r0; g.k = c->pend_k; g.n_end = P.n; g.voff = 0;
+  } else if (P.sub == 0) {
     g.j = c->j; g.fjb = c->fjb; g.k = c->fjb_cmp; g.n_end = P.n; g.voff = 0;
   } else {
     const int s = P.sub - 1;

@@ -27,7 +27,7 @@ typedef struct {
   /* device buffers */
   qrdm_ctrl *ctrl;
   double *vn1, *vn2, *gram_part, *gram, *panel_part, *panel_row, *vc, *wp, *w2, *nrm_part;
-  int *flag_list;
+  int *flag_list, *upd_marks; /* upd_marks: [2][cap_n] stamps of the deferred trailing update */
   double *mg_buf;
   unsigned *mg_cnt;
   size_t wp_elems;
@@ -79,11 +79,12 @@ void qrdm_b200_set_profile(int mode) { g_profile = mode < 0 ? 0 : (mode > 2 ? 2 
 double qrdm_b200_measure_fp64_peak(int use_dmma, void *stream) { return qrdm_rt_fp64_peak(use_dmma, stream); }
 
 static void ws_free_sized(qrdm_workspace *w) {
-  void *bufs[] = {w->vn1, w->vn2, w->vc, w->wp, w->w2, w->nrm_part, w->flag_list};
+  void *bufs[] = {w->vn1, w->vn2, w->vc, w->wp, w->w2, w->nrm_part, w->flag_list, w->upd_marks};
   for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); ++i)
     if (bufs[i]) qrdm_rt_free(bufs[i]);
   w->vn1 = w->vn2 = w->vc = w->wp = w->w2 = w->nrm_part = NULL;
   w->flag_list = NULL;
+  w->upd_marks = NULL;
   w->cap_m = w->cap_n = 0;
 }
 
@@ -142,11 +143,12 @@ static int ws_ensure(int m, int n) {
   w->wp_elems = (size_t)64 * w->ldw * 16 + (size_t)64 * 256 * (2 * (size_t)w->sm_count + 2);
   CU(qrdm_rt_malloc((void **)&w->vn1, sizeof(double) * cn));
   CU(qrdm_rt_malloc((void **)&w->vn2, sizeof(double) * cn));
-  CU(qrdm_rt_malloc((void **)&w->vc, sizeof(double) * (size_t)w->ldv * 64));
+  CU(qrdm_rt_malloc((void **)&w->vc, sizeof(double) * (size_t)w->ldv * 64 * 2)); /* two buffers: current / pending block */
   CU(qrdm_rt_malloc((void **)&w->wp, sizeof(double) * w->wp_elems));
   CU(qrdm_rt_malloc((void **)&w->w2, sizeof(double) * (size_t)w->ldw * 64));
   CU(qrdm_rt_malloc((void **)&w->nrm_part, sizeof(double) * (size_t)cn * w->nrm_splits));
   CU(qrdm_rt_malloc((void **)&w->flag_list, sizeof(int) * (size_t)cn));
+  CU(qrdm_rt_malloc((void **)&w->upd_marks, sizeof(int) * (size_t)cn * 2));
   if ((size_t)(cm / 2048 + 2) * 512 > (size_t)4096 * QRDM_GRAM_MAXCTA) { /* skinny-update partials of very tall matrices */
     if (w->gram_part) qrdm_rt_free(w->gram_part);
     w->gram_part = NULL;
@@ -266,13 +268,25 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
   P.row0 = sh ? sh->row0 : 0; P.m_glob = m_glob; P.nranks = sh ? sh->nranks : 1;
   P.w_reduced = mg; P.mg_buf = w->mg_buf; P.mg_cnt = w->mg_cnt;
   { const char *dbg = getenv("QRDM_B200_DEBUG"); P.debug = dbg ? atoi(dbg) : 0; }
+  P.vc_prev = w->vc + (size_t)w->ldv * 64;
+  P.upd_flag = w->upd_marks; P.upd_eager = w->upd_marks + w->cap_n;
+  /* Deferred ("lazy") trailing update, single GPU: pass 2 of a block is postponed and fused into pass 1
+   * of the next block (k_fused) while both the trailing width and height are >= lazy_min; the columns
+   * the next selection touches are completed eagerly.  QRDM_B200_LAZY=0 disables it,
+   * QRDM_B200_LAZY_MIN overrides the threshold (tests force it on tiny matrices). */
+  int lazy_min = 1536;
+  { const char *e = getenv("QRDM_B200_LAZY_MIN"); if (e) lazy_min = atoi(e); if (lazy_min < 1) lazy_min = 1; }
+  const int lazy_on = !mg && getenv("QRDM_B200_LAZY") && atoi(getenv("QRDM_B200_LAZY")) != 0; /* opt-in until validated on the GPU */
+  int pending = 0, pend_j = 0, stamp = 0;
+  double *vcbuf[2] = {w->vc, w->vc + (size_t)w->ldv * 64};
 
   memset(&g_stats, 0, sizeof(g_stats));
   g_ev_used = 0;
   const long long launches0 = qrdm_rt_launch_count();
   CU(qrdm_rt_event_record(w->ev[0], stream));
   CU(qrdm_rt_memset(w->ctrl, 0, sizeof(qrdm_ctrl), stream));
-  CU(qrdm_rt_memset(w->vc, 0, sizeof(double) * (size_t)w->ldv * 64, stream));
+  CU(qrdm_rt_memset(w->vc, 0, sizeof(double) * (size_t)w->ldv * 64 * 2, stream));
+  CU(qrdm_rt_memset(w->upd_marks, 0, sizeof(int) * (size_t)w->cap_n * 2, stream));
 
   if (!mg) {
     STAGE(QRDM_STAGE_NORM_INIT, qrdm_k_colnorm(&P, 0, stream));   /* :672-682 */
@@ -292,13 +306,36 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
     const int cols = n - j;
     int jr = j - P.row0;
     jr = jr < 0 ? 0 : (jr > m ? m : jr); /* first active local row */
+    int lazy = 0;
     if (!mg) {
+      P.vc = vcbuf[it & 1];          /* V of this block; the pending block's V sits in the other buffer */
+      P.vc_prev = vcbuf[(it & 1) ^ 1];
       STAGE(QRDM_STAGE_GRAM, qrdm_k_gram(&P, 0, m - jr, stream));
       STAGE(QRDM_STAGE_PICK, qrdm_k_pick(&P, stream));
       STAGE(QRDM_STAGE_PERMUTE, qrdm_k_permute(&P, stream));
       STAGE(QRDM_STAGE_PANEL, qrdm_k_panel(&P, j, stream));
-      STAGE(QRDM_STAGE_VTC, qrdm_k_trailing(&P, j, stream));
-      STAGE(QRDM_STAGE_NORM_UPDATE, qrdm_k_norm_update(&P, j, stream));
+      lazy = lazy_on && n - j - QRDM_KMAX >= lazy_min && m - j - QRDM_KMAX >= lazy_min;
+      if (!pending && !lazy) {
+        STAGE(QRDM_STAGE_VTC, qrdm_k_trailing(&P, j, stream));
+      } else {
+        int vt_stride = 0, vt_grid = 0;
+        long long lb = qrdm_rt_launch_count();
+        CU(stage_begin(QRDM_STAGE_VTC, stream));
+        const int bn = pending ? 64 : 128; /* tile width of the partial-W slots */
+        if (pending) CU(qrdm_k_fused(&P, j, &vt_stride, &vt_grid, stream)); /* pass 2 of block it-1 + pass 1 of block it */
+        else CU(qrdm_k_vtc_only(&P, j, &vt_stride, &vt_grid, stream));
+        pending = 0;
+        if (vt_stride > 0) CU(qrdm_k_w2(&P, j, vt_grid, vt_stride, bn, stream));
+        if (lazy) CU(qrdm_k_rowupd(&P, j, stream));   /* the k new R rows now, the rest with the next block */
+        else CU(qrdm_k_rankk(&P, j, stream));
+        CU(stage_end(QRDM_STAGE_VTC, lb, stream));
+      }
+      if (lazy) {
+        P.stamp = ++stamp;
+        STAGE(QRDM_STAGE_NORM_UPDATE, qrdm_k_norm_update_lazy(&P, j, stream));
+      } else {
+        STAGE(QRDM_STAGE_NORM_UPDATE, qrdm_k_norm_update(&P, j, stream));
+      }
     } else {
       /* every row sum is computed locally, all-reduced over NVLink, and consumed by a replicated
        * kernel: all ranks hold identical vn1/jpvt/ctrl and take identical decisions */
@@ -358,6 +395,11 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
       }
     }
     STAGE(QRDM_STAGE_SELECT, qrdm_k_select(&P, stream)); /* next iteration's prologue + max norm */
+    if (lazy) { /* complete the update on everything the next Gram / pick / permutation / panel touches */
+      STAGE(QRDM_STAGE_VTC, qrdm_k_colupd(&P, 0, j, stream));
+      pending = 1;
+      pend_j = j;
+    }
     {
       long long lb = qrdm_rt_launch_count();
       CU(stage_begin(QRDM_STAGE_SYNC, stream));
@@ -387,6 +429,10 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
       wb->done_cols = j;
     }
     if (stop_mode && mb->maxnrm * sqrt((double)(cols - k)) <= eta) break; /* :782-785 */
+  }
+  if (pending) { /* early exit (stop rule / error) with a block still deferred: finish it */
+    P.vc_prev = vcbuf[(it - 1) & 1];
+    STAGE(QRDM_STAGE_VTC, qrdm_k_flush(&P, pend_j, stream));
   }
   CU(qrdm_rt_event_record(w->ev[1], stream));
   CU(qrdm_rt_event_sync(w->ev[1]));

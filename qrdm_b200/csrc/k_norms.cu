@@ -187,6 +187,18 @@ extern "C" int qrdm_k_norm_update(const qrdm_prob* p, int j_host, void* stream) 
   return qrdm_k_colnorm(p, 1, stream);
 }
 
+// deferred trailing update: the flagged columns are brought up to date before their exact recompute
+extern "C" int qrdm_k_norm_update_lazy(const qrdm_prob* p, int j_host, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  const int maxcols = p->n - j_host - 1;
+  if (maxcols <= 0) return 0;
+  k_norm_update<0><<<(maxcols + 7) / 8, 256, 0, s>>>(*p, 1.0536712127723509e-08);
+  QRDM_LAUNCH_CHECK();
+  const int rc = qrdm_k_colupd(p, 1, j_host, stream);
+  if (rc) return rc;
+  return qrdm_k_colnorm(p, 1, stream);
+}
+
 extern "C" int qrdm_k_norm_dpart(const qrdm_prob* p, int j_host, void* stream) {
   const int maxcols = p->n - j_host - 1;
   if (maxcols <= 0) return 0;

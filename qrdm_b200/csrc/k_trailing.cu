@@ -39,7 +39,7 @@ struct VtGeom {
   int j, jr, fjb, k, nc, kpad, jal, NCH, CT, voff;  // j: columns done; jr: first active LOCAL row; CT counts the V'V tile
   long long U;
 };
-__device__ __forceinline__ VtGeom vt_geom(const qrdm_prob& P) {
+__device__ __forceinline__ VtGeom vt_geom(const qrdm_prob& P, int bn = VT_BN) {
   VtGeom g;
   const QrdmGeom q = qrdm_geom(P);
   g.j = q.j; g.fjb = q.fjb; g.k = q.k; g.voff = q.voff;
@@ -49,7 +49,7 @@ __device__ __forceinline__ VtGeom vt_geom(const qrdm_prob& P) {
   g.jal = g.jr & ~(QRDM_ROWALIGN - 1);
   const int mpad = (P.m + VT_BK - 1) / VT_BK * VT_BK;
   g.NCH = (mpad - g.jal) / VT_BK;
-  g.CT = 1 + (g.nc > 0 ? (g.nc + VT_BN - 1) / VT_BN : 0);
+  g.CT = 1 + (g.nc > 0 ? (g.nc + bn - 1) / bn : 0);
   g.U = (long long)g.CT * g.NCH;
   return g;
 }
@@ -213,7 +213,7 @@ __device__ __forceinline__ int vt_slot_list(const VtGeom& ge, int vt_grid, int T
   return n;
 }
 
-__global__ void __launch_bounds__(TI_THREADS) k_tinv(qrdm_prob P, int vt_grid, int wslot_stride_cols) {
+__global__ void __launch_bounds__(TI_THREADS) k_tinv(qrdm_prob P, int vt_grid, int wslot_stride_cols, int bn) {
   extern __shared__ __align__(16) double sm[];
   double* B = sm;            // B[i][s] = tau_i * (V'V)[s][i] for s < i
   double* X = sm + 64 * 65;  // X[i][p]: column p of (I + B)^-1, one thread per column
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(TI_THREADS) k_tinv(qrdm_prob P, int vt_grid, i
   __shared__ int slots[QRDM_PANEL_MAXCTA * 2 + 8];
   __shared__ int nslots;
   const int tid = threadIdx.x;
-  const VtGeom ge = vt_geom(P);
+  const VtGeom ge = vt_geom(P, bn);
   const int k = ge.k;
   if (k <= 0 || ge.nc <= 0) return;
   if (tid == 0) { if (P.w_reduced) { slots[0] = 0; nslots = 1; } else nslots = vt_slot_list(ge, vt_grid, 0, slots, QRDM_PANEL_MAXCTA * 2 + 8); }
@@ -274,31 +274,34 @@ __global__ void __launch_bounds__(TI_THREADS) k_tinv(qrdm_prob P, int vt_grid, i
 }
 
 #define WA_LDM 68
-#define WA_LDW 132
-#define WA_SMEM ((64 * WA_LDM + 64 * WA_LDW) * 8)
+#define WA_SMEM_BN(BN) ((64 * WA_LDM + 64 * ((BN) + 4)) * 8)
+#define WA_SMEM WA_SMEM_BN(VT_BN)
 
-__global__ void __launch_bounds__(256) k_wapply(qrdm_prob P, int vt_grid, int wslot_stride_cols) {
+// BN = width of the column tiles the partial-W slots were produced with (128: k_vtc, 64: k_fused)
+template <int BN>
+__global__ void __launch_bounds__(2 * BN) k_wapply(qrdm_prob P, int vt_grid, int wslot_stride_cols) {
+  constexpr int NT = 2 * BN, LDW = BN + 4;
   extern __shared__ __align__(16) double sm[];
   double* Ms = sm;                  // [q][WA_LDM]
-  double* Ws = sm + 64 * WA_LDM;    // [p][WA_LDW]
+  double* Ws = sm + 64 * WA_LDM;    // [p][LDW]
   __shared__ int slots[QRDM_PANEL_MAXCTA * 2 + 8];
   __shared__ int nslots;
   qrdm_ctrl* ctrl = P.ctrl;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
-  const VtGeom ge = vt_geom(P);
-  const int c0 = blockIdx.x * VT_BN;
+  const VtGeom ge = vt_geom(P, BN);
+  const int c0 = blockIdx.x * BN;
   if (ge.k <= 0 || c0 >= ge.nc) return;
   const int T = blockIdx.x + 1;
   if (tid == 0) { if (P.w_reduced) { slots[0] = 0; nslots = 1; } else nslots = vt_slot_list(ge, vt_grid, T, slots, QRDM_PANEL_MAXCTA * 2 + 8); }
-  for (int e = tid; e < 4096; e += 256) Ms[(e >> 6) * WA_LDM + (e & 63)] = P.gram[e];
+  for (int e = tid; e < 4096; e += NT) Ms[(e >> 6) * WA_LDM + (e & 63)] = P.gram[e];
   __syncthreads();
   const size_t sstride = (size_t)64 * wslot_stride_cols;
   const int ns = nslots;
-  for (int e = tid; e < 64 * (VT_BN / 2); e += 256) {  // fixed-order slot sum, 16-byte accesses
-    const int pq = e / (VT_BN / 2), cp = (e % (VT_BN / 2)) * 2;
+  for (int e = tid; e < 64 * (BN / 2); e += NT) {  // fixed-order slot sum, 16-byte accesses
+    const int pq = e / (BN / 2), cp = (e % (BN / 2)) * 2;
     double2 sacc = make_double2(0.0, 0.0);
     if (pq < ge.kpad) {
-      const double* src = P.wp + (size_t)pq * wslot_stride_cols + (size_t)T * VT_BN + cp;
+      const double* src = P.wp + (size_t)pq * wslot_stride_cols + (size_t)T * BN + cp;
       for (int q = 0; q < ns; q += 4) {  // up to 4 slot loads in flight; fixed summation order
         double2 v[4];
 #pragma unroll
@@ -308,7 +311,7 @@ __global__ void __launch_bounds__(256) k_wapply(qrdm_prob P, int vt_grid, int ws
         for (int u = 0; u < 4; ++u) { sacc.x += v[u].x; sacc.y += v[u].y; }
       }
     }
-    *reinterpret_cast<double2*>(Ws + pq * WA_LDW + cp) = sacc;
+    *reinterpret_cast<double2*>(Ws + pq * LDW + cp) = sacc;
   }
   __syncthreads();
   double acc[8][2][2];
@@ -316,12 +319,12 @@ __global__ void __launch_bounds__(256) k_wapply(qrdm_prob P, int vt_grid, int ws
   for (int a = 0; a < 8; ++a)
 #pragma unroll
     for (int c = 0; c < 2; ++c) acc[a][c][0] = acc[a][c][1] = 0.0;
-  const double* ap = Ms + g * WA_LDM + t;                 // A[m=q][k=p] = M[q][p]
-  const double* bp = Ws + t * WA_LDW + wid * 16 + g;      // B[k=p][n=c] = W[p][c]
+  const double* ap = Ms + g * WA_LDM + t;             // A[m=q][k=p] = M[q][p]
+  const double* bp = Ws + t * LDW + wid * 16 + g;      // B[k=p][n=c] = W[p][c]
   const int ksteps = ge.kpad >> 2;
 #pragma unroll 1
   for (int ks = 0; ks < ksteps; ++ks) {
-    const double b0 = bp[ks * 4 * WA_LDW], b1 = bp[ks * 4 * WA_LDW + 8];
+    const double b0 = bp[ks * 4 * LDW], b1 = bp[ks * 4 * LDW + 8];
     double a[8];
 #pragma unroll
     for (int mt = 0; mt < 8; ++mt) a[mt] = ap[mt * 8 * WA_LDM + ks * 4];
@@ -547,13 +550,389 @@ __global__ void __launch_bounds__(256) k_wreduce(qrdm_prob P, int vt_grid, int w
   }
 }
 
+// ------------------------------------------------------------------ k_fused (deferred update)
+// Pass 2 of the PENDING block (iteration i-1) fused into pass 1 of the CURRENT block (iteration i):
+//     C_new = C + V_prev W2_prev        (what k_rankk would have done an iteration earlier)
+//     W_cur += V_cur' C_new             (what k_vtc does)
+// so every element of the trailing matrix is read once and written once per iteration (16 B per
+// 4k FLOPs = 16 flop/B at k = 64, against 8 flop/B for k_rankk alone, whose mixed read+write
+// stream bound it at 65% DMMA-active).  The columns the next selection touches (leading 64
+// positions, the candidates, columns whose norm is recomputed exactly) were brought up to date
+// eagerly by k_colupd and carry the block's stamp in upd_eager / upd_flag: their W2 column reads
+// as zero here.  The k new R rows were finished by k_rowupd; rows < j are never stored.
+//
+// Two 4-warp CTAs per SM; a unit is a 32-row chunk of a 64-column tile; warp w owns columns
+// 16w..16w+15 of the tile.  C goes global -> registers in DMMA fragment layout (prefetched one unit
+// ahead, like k_rankk); with M = columns, N = rows in phase A the accumulator fragment of lane
+// (g, t) holds rows 2t, 2t+1 of column g, which is exactly the B-operand fragment phase B needs
+// when its k-steps take the rows {2t+e}: C_new never leaves the registers between the two MMAs.
+// V_prev / V_cur chunks arrive by cp.async (2-stage ring), the W2 tile stays in smem for the whole
+// walk down a column tile; partial W goes to the same slot structure as k_vtc (tile width 64).
+#define FU_BN 64
+#define FU_BK 32
+#define FU_LDP 36  // V_prev chunk [q][36]: phase-A B operand, lanes g -> consecutive rows, t -> q stride
+#define FU_LDN 40  // V_cur  chunk [q][40]: phase-B A operand, 16-byte row pairs per lane
+#define FU_LDW 68  // W2 tile [q][68]
+#define FU_THREADS 128
+#define FU_STAGE_DOUBLES (64 * FU_LDP + 64 * FU_LDN)
+#define FU_SMEM ((64 * FU_LDW + 2 * FU_STAGE_DOUBLES) * 8)
+
+template <bool VEC16, bool FULLK>
+__device__ __forceinline__ void fused_body(const qrdm_prob& P, const VtGeom& ge, int wslot_stride_cols, double* sm) {
+  double* W2s = sm;                  // [q][FU_LDW]
+  double* stage0 = sm + 64 * FU_LDW;
+  const qrdm_ctrl* ctrl = P.ctrl;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int G = gridDim.x, b = blockIdx.x;
+  const long long lo = vt_lo(ge.U, G, b), hi = vt_lo(ge.U, G, b + 1);
+  if (lo >= hi) return;
+  const int kp_prev = (ctrl->pend_k + 7) & ~7, pend_c0 = ctrl->pend_c0;
+  const int ccol0 = ge.j + ge.fjb;  // first trailing column
+  const int jrow = ge.jr;           // first active row
+  const size_t lda = (size_t)P.lda;
+  double* Cg = P.a + (size_t)ccol0 * lda;
+  const double* Vn_g = P.vc + (size_t)ge.voff * P.ldv;
+  const int MT = FULLK ? 8 : (ge.kpad >> 3);
+
+  double acc[8][2][2];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) acc[a][c][0] = acc[a][c][1] = 0.0;
+
+  auto issue = [&](long long u, int stage) {
+    const int T = (int)(u / ge.NCH), chunk = (int)(u - (long long)T * ge.NCH);
+    double* Vp = stage0 + (size_t)stage * FU_STAGE_DOUBLES;
+    double* Vn = Vp + 64 * FU_LDP;
+    const int r0 = ge.jal + chunk * FU_BK;
+    for (int id = tid; id < ge.kpad * 16; id += FU_THREADS) {
+      const int q = id >> 4, rp = (id & 15) * 2;
+      cp_async16(Vn + q * FU_LDN + rp, Vn_g + (size_t)q * P.ldv + r0 + rp, 16);
+    }
+    if (T > 0)
+      for (int id = tid; id < kp_prev * 16; id += FU_THREADS) {
+        const int q = id >> 4, rp = (id & 15) * 2;
+        cp_async16(Vp + q * FU_LDP + rp, P.vc_prev + (size_t)q * P.ldv + r0 + rp, 16);
+      }
+  };
+  auto load_w2 = [&](int T) {  // W2 tile of the pending block; zero where the column is already up to date
+    const int c0 = (T - 1) * FU_BN;
+    for (int e = tid; e < kp_prev * FU_BN; e += FU_THREADS) {
+      const int q = e >> 6, c = e & 63;
+      const int col = ccol0 + c0 + c, idx = col - pend_c0;
+      double v = 0.0;
+      if (idx >= 0 && col < P.n && P.upd_eager[col] != P.stamp && P.upd_flag[col] != P.stamp) v = P.w2[(size_t)q * P.ldw + idx];
+      W2s[q * FU_LDW + c] = v;
+    }
+  };
+  auto interior = [&](int T, int chunk) {
+    const int R0 = ge.jal + chunk * FU_BK, c0 = (T - 1) * FU_BN;
+    return VEC16 && T > 0 && R0 >= jrow && R0 + FU_BK <= P.m && c0 + FU_BN <= ge.nc;
+  };
+  auto load_c = [&](long long u, double (&dst)[2][4][2]) {
+    const int T = (int)(u / ge.NCH), chunk = (int)(u - (long long)T * ge.NCH);
+    const int R0 = ge.jal + chunk * FU_BK;
+    if (T == 0) {  // the "C" tile is V_cur itself: its product is V'V (k_tinv)
+#pragma unroll
+      for (int ct = 0; ct < 2; ++ct) {
+        const int c = wid * 16 + ct * 8 + g;
+        const double* base = Vn_g + (size_t)c * P.ldv + R0 + 2 * t;
+#pragma unroll
+        for (int rt = 0; rt < 4; ++rt) {
+          double2 v = make_double2(0.0, 0.0);
+          if (c < ge.kpad) v = *reinterpret_cast<const double2*>(base + rt * 8);
+          dst[ct][rt][0] = v.x; dst[ct][rt][1] = v.y;
+        }
+      }
+      return;
+    }
+    const int c0 = (T - 1) * FU_BN;
+    const double* base = Cg + (size_t)(c0 + wid * 16 + g) * lda + R0 + 2 * t;
+    if (interior(T, chunk)) {
+#pragma unroll
+      for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+        for (int rt = 0; rt < 4; ++rt) {
+          const double2 v = *reinterpret_cast<const double2*>(base + (size_t)(ct * 8) * lda + rt * 8);
+          dst[ct][rt][0] = v.x; dst[ct][rt][1] = v.y;
+        }
+    } else {
+#pragma unroll
+      for (int ct = 0; ct < 2; ++ct) {
+        const int c = c0 + wid * 16 + ct * 8 + g;
+#pragma unroll
+        for (int rt = 0; rt < 4; ++rt) {
+          const int r = R0 + rt * 8 + 2 * t;
+          const double* ptr = base + (size_t)(ct * 8) * lda + rt * 8;
+          dst[ct][rt][0] = (c < ge.nc && r >= jrow && r < P.m) ? ptr[0] : 0.0;
+          dst[ct][rt][1] = (c < ge.nc && r + 1 >= jrow && r + 1 < P.m) ? ptr[1] : 0.0;
+        }
+      }
+    }
+  };
+  auto store_c = [&](int T, int chunk, const double (&src)[2][4][2]) {
+    const int R0 = ge.jal + chunk * FU_BK, c0 = (T - 1) * FU_BN;
+    double* base = Cg + (size_t)(c0 + wid * 16 + g) * lda + R0 + 2 * t;
+    if (interior(T, chunk)) {
+#pragma unroll
+      for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+        for (int rt = 0; rt < 4; ++rt)
+          *reinterpret_cast<double2*>(base + (size_t)(ct * 8) * lda + rt * 8) = make_double2(src[ct][rt][0], src[ct][rt][1]);
+    } else {
+#pragma unroll
+      for (int ct = 0; ct < 2; ++ct) {
+        const int c = c0 + wid * 16 + ct * 8 + g;
+#pragma unroll
+        for (int rt = 0; rt < 4; ++rt) {
+          const int r = R0 + rt * 8 + 2 * t;
+          double* ptr = base + (size_t)(ct * 8) * lda + rt * 8;
+          if (c < ge.nc && r >= jrow && r < P.m) ptr[0] = src[ct][rt][0];
+          if (c < ge.nc && r + 1 >= jrow && r + 1 < P.m) ptr[1] = src[ct][rt][1];
+        }
+      }
+    }
+  };
+  auto flush = [&](int T) {
+    const int slot = b - vt_bfirst(ge.U, G, ge.NCH, T);
+    double* W = P.wp + (size_t)slot * 64 * wslot_stride_cols + (size_t)T * FU_BN;
+#pragma unroll
+    for (int mt = 0; mt < 8; ++mt) {
+      if (mt < MT) {
+#pragma unroll
+        for (int ct = 0; ct < 2; ++ct) {
+          const int q = mt * 8 + g, c = wid * 16 + ct * 8 + 2 * t;
+          *reinterpret_cast<double2*>(W + (size_t)q * wslot_stride_cols + c) = make_double2(acc[mt][ct][0], acc[mt][ct][1]);
+          acc[mt][ct][0] = acc[mt][ct][1] = 0.0;
+        }
+      }
+    }
+  };
+
+  long long u = lo;
+  int left = (int)(hi - lo), st = 0;
+  int curT = (int)(lo / ge.NCH);
+  if (curT > 0) load_w2(curT);
+  issue(lo, 0);
+  cp_async_commit();
+
+  // one unit: X holds C(u) (prefetched), Y receives C(u+1) while the MMAs of u run
+  auto step = [&](double (&X)[2][4][2], double (&Y)[2][4][2]) {
+    cp_async_wait<0>();
+    __syncthreads();  // V chunks of u (and the W2 tile) landed; everyone is done with unit u-1
+    const int T = (int)(u / ge.NCH), chunk = (int)(u - (long long)T * ge.NCH);
+    if (T != curT) {
+      flush(curT);
+      curT = T;
+      load_w2(T);
+      __syncthreads();
+    }
+    if (left > 1) {
+      issue(u + 1, st ^ 1);
+      cp_async_commit();
+      load_c(u + 1, Y);
+    }
+    const double* Vp = stage0 + (size_t)st * FU_STAGE_DOUBLES;
+    const double* Vn = Vp + 64 * FU_LDP;
+    if (T > 0) {
+      // phase A: X[c][r] += sum_q W2[q][c] V_prev[r][q]   (M = columns, N = rows, K = q)
+      const double* ap = W2s + t * FU_LDW + wid * 16 + g;
+      const double* bp = Vp + t * FU_LDP + g;
+#pragma unroll 2
+      for (int ks = 0; ks < kp_prev / 4; ++ks) {
+        double a[2], bb[4];
+#pragma unroll
+        for (int x = 0; x < 2; ++x) a[x] = ap[ks * 4 * FU_LDW + x * 8];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) bb[x] = bp[ks * 4 * FU_LDP + x * 8];
+#pragma unroll
+        for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+          for (int rt = 0; rt < 4; ++rt) dmma884(X[ct][rt][0], X[ct][rt][1], a[ct], bb[rt]);
+      }
+      store_c(T, chunk, X);
+    }
+    // phase B: acc[q][c] += sum_r V_cur[r][q] X[c][r]     (M = q, N = columns, K = rows {2t+e})
+    {
+      const double* ap = Vn + g * FU_LDN + 2 * t;
+#pragma unroll
+      for (int rt = 0; rt < 4; ++rt) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {  // 4 q-tiles at a time: 16 operand registers live, dependent DMMAs 8 apart
+          double2 a[4];
+#pragma unroll
+          for (int x = 0; x < 4; ++x)
+            if (h * 4 + x < MT) a[x] = *reinterpret_cast<const double2*>(ap + (h * 4 + x) * 8 * FU_LDN + rt * 8);
+#pragma unroll
+          for (int x = 0; x < 4; ++x) {
+            if (h * 4 + x < MT) {
+              dmma884(acc[h * 4 + x][0][0], acc[h * 4 + x][0][1], a[x].x, X[0][rt][0]);
+              dmma884(acc[h * 4 + x][1][0], acc[h * 4 + x][1][1], a[x].x, X[1][rt][0]);
+            }
+          }
+#pragma unroll
+          for (int x = 0; x < 4; ++x) {
+            if (h * 4 + x < MT) {
+              dmma884(acc[h * 4 + x][0][0], acc[h * 4 + x][0][1], a[x].y, X[0][rt][1]);
+              dmma884(acc[h * 4 + x][1][0], acc[h * 4 + x][1][1], a[x].y, X[1][rt][1]);
+            }
+          }
+        }
+      }
+    }
+    ++u; st ^= 1; --left;
+  };
+
+  double XA[2][4][2], XB[2][4][2];
+  load_c(lo, XA);
+  while (left > 0) {
+    step(XA, XB);
+    if (left > 0) step(XB, XA);
+  }
+  flush(curT);
+}
+
+template <bool VEC16>
+__global__ void __launch_bounds__(FU_THREADS, 2) k_fused(qrdm_prob P, int wslot_stride_cols) {
+  extern __shared__ __align__(16) double sm[];
+  const VtGeom ge = vt_geom(P, FU_BN);
+  if (ge.k <= 0 || ge.nc <= 0 || ge.jr >= P.m) return;
+  if (ge.kpad == 64) fused_body<VEC16, true>(P, ge, wslot_stride_cols, sm);  // the common case: no predicates
+  else fused_body<VEC16, false>(P, ge, wslot_stride_cols, sm);
+}
+
+// The k new R rows of the trailing columns, finished right after W2 is known (the norm downdate
+// needs them before the next selection):  C[j:j+k, c] += V[j:j+k, :] W2[:, c].  Also records the
+// pending block in ctrl.  16 columns per CTA, thread <-> (row, 4 columns).
+__global__ void __launch_bounds__(256) k_rowupd(qrdm_prob P) {
+  __shared__ double Vt[64 * 65];  // [q][r]
+  __shared__ double Ws[64 * 17];  // [q][c]
+  qrdm_ctrl* ctrl = P.ctrl;
+  const int j = ctrl->j, fjb = ctrl->fjb, k = ctrl->fjb_cmp;
+  const int nc = P.n - j - fjb, tid = threadIdx.x;
+  if (blockIdx.x == 0 && tid == 0) { ctrl->pend_k = k; ctrl->pend_c0 = j + fjb; ctrl->pend_r0 = j + k; }
+  const int cb = blockIdx.x * 16;
+  if (k <= 0 || cb >= nc) return;
+  for (int e = tid; e < 64 * 64; e += 256) {
+    const int q = e >> 6, r = e & 63;
+    Vt[q * 65 + r] = (q < k && r < k && j + r < P.m) ? P.vc[(size_t)q * P.ldv + j + r] : 0.0;
+  }
+  for (int e = tid; e < 64 * 16; e += 256) {
+    const int q = e >> 4, c = e & 15;
+    Ws[q * 17 + c] = (q < k && cb + c < nc) ? P.w2[(size_t)q * P.ldw + cb + c] : 0.0;
+  }
+  __syncthreads();
+  const int r = tid & 63, cg = tid >> 6;
+  if (r >= k || j + r >= P.m) return;
+  double acc[4];
+#pragma unroll
+  for (int x = 0; x < 4; ++x) acc[x] = 0.0;
+  for (int q = 0; q < k; ++q) {
+    const double v = Vt[q * 65 + r];
+#pragma unroll
+    for (int x = 0; x < 4; ++x) acc[x] = fma(v, Ws[q * 17 + cg + 4 * x], acc[x]);
+  }
+#pragma unroll
+  for (int x = 0; x < 4; ++x) {
+    const int c = cb + cg + 4 * x;
+    if (c < nc) P.a[(size_t)(j + fjb + c) * P.lda + j + r] += acc[x];
+  }
+}
+
+// Eager completion of the pending update on a short list of columns (rows >= pend_r0), plain FMA:
+//   MODE 0  the leading min(64, cols) positions of the new trailing matrix + the candidates chosen
+//           by k_select (everything the Gram / pick / permutation / panel of the next iteration touches)
+//   MODE 1  the columns whose partial norm is about to be recomputed exactly (flag_list)
+// A finished column gets the block's stamp (upd_eager / upd_flag) so that nobody applies it twice.
+// Thread <-> row (its row of V_prev in registers), 8 list entries per CTA column group.
+#define CU_ROWS 128
+#define CU_GROUP 8
+template <int MODE>
+__global__ void __launch_bounds__(CU_ROWS) k_colupd(qrdm_prob P) {
+  __shared__ double Wc[CU_GROUP][64];
+  __shared__ int colof[CU_GROUP];
+  const qrdm_ctrl* ctrl = P.ctrl;
+  const int tid = threadIdx.x;
+  const int kprev = ctrl->pend_k, c0p = ctrl->pend_c0, r0p = ctrl->pend_r0;
+  if (kprev <= 0) return;
+  const int jn = ctrl->j;  // MODE 0 runs after k_select: the new first column
+  const int cols = P.n - jn;
+  const int nlist = MODE == 0 ? 64 + ctrl->nc : ctrl->nflag;
+  const int ngroups = (nlist + CU_GROUP - 1) / CU_GROUP;
+  const int r = r0p + blockIdx.x * CU_ROWS + tid;
+  const bool rok = r < P.m;
+  double v[64];
+  bool vloaded = false;
+  for (int gi = blockIdx.y; gi < ngroups; gi += gridDim.y) {
+    __syncthreads();
+    if (tid < CU_GROUP) {
+      const int e = gi * CU_GROUP + tid;
+      int col = -1;
+      if (e < nlist) {
+        if (MODE == 1) col = P.flag_list[e];
+        else if (e < 64) col = e < cols ? jn + e : -1;
+        else { const int off = ctrl->cand[e - 64]; col = off >= 64 ? jn + off : -1; }
+      }
+      if (col >= 0) {
+        if (MODE == 0) {
+          if (blockIdx.x == 0) P.upd_eager[col] = P.stamp;
+          if (P.upd_flag[col] == P.stamp) col = -1;  // already done by the MODE 1 launch of this block
+        } else if (blockIdx.x == 0) {
+          P.upd_flag[col] = P.stamp;
+        }
+      }
+      if (col >= 0 && col - c0p < 0) col = -1;  // leftover panel column: nothing pending
+      colof[tid] = col;
+    }
+    __syncthreads();
+    for (int e = tid; e < CU_GROUP * 64; e += CU_ROWS) {
+      const int x = e >> 6, q = e & 63;
+      const int col = colof[x];
+      Wc[x][q] = (col >= 0 && q < kprev) ? P.w2[(size_t)q * P.ldw + (col - c0p)] : 0.0;
+    }
+    __syncthreads();
+    if (!rok) continue;
+    if (!vloaded) {
+#pragma unroll
+      for (int q = 0; q < 64; ++q) v[q] = q < kprev ? P.vc_prev[(size_t)q * P.ldv + r] : 0.0;
+      vloaded = true;
+    }
+#pragma unroll
+    for (int x = 0; x < CU_GROUP; ++x) {
+      const int col = colof[x];
+      if (col < 0) continue;
+      double* ptr = P.a + (size_t)col * P.lda + r;
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int q = 0; q < 64; q += 2) {
+        s0 = fma(v[q], Wc[x][q], s0);
+        s1 = fma(v[q + 1], Wc[x][q + 1], s1);
+      }
+      *ptr += s0 + s1;
+    }
+  }
+}
+
+// flush helper: zero the W2 columns that carry the stamp, so that the plain k_rankk can finish the block
+__global__ void __launch_bounds__(256) k_w2mask(qrdm_prob P) {
+  const qrdm_ctrl* ctrl = P.ctrl;
+  const int c0p = ctrl->pend_c0;
+  const int col = c0p + blockIdx.x * 256 + threadIdx.x;
+  if (col >= P.n) return;
+  if (P.upd_eager[col] == P.stamp || P.upd_flag[col] == P.stamp)
+    for (int q = 0; q < 64; ++q) P.w2[(size_t)q * P.ldw + (col - c0p)] = 0.0;
+}
+
 static void trailing_attrs() {
   static bool attr_set = false;
   if (attr_set) return;
   cudaFuncSetAttribute(k_vtc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VT_SMEM);
   cudaFuncSetAttribute(k_vtc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VT_SMEM);
-  cudaFuncSetAttribute(k_wapply, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_SMEM);
+  cudaFuncSetAttribute(k_wapply<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_SMEM_BN(128));
+  cudaFuncSetAttribute(k_wapply<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_SMEM_BN(64));
   cudaFuncSetAttribute(k_tinv, cudaFuncAttributeMaxDynamicSharedMemorySize, TI_SMEM);
+  cudaFuncSetAttribute(k_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FU_SMEM);
+  cudaFuncSetAttribute(k_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FU_SMEM);
   cudaFuncSetAttribute(k_rankk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RK_SMEM);
   cudaFuncSetAttribute(k_rankk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RK_SMEM);
   attr_set = true;
@@ -597,17 +976,27 @@ extern "C" int qrdm_k_wreduce(const qrdm_prob* p, int j_host, int vt_grid, int s
   return 0;
 }
 
-// T', W2 = -T' W, and pass 2
-extern "C" int qrdm_k_trailing_finish(const qrdm_prob* p, int j_host, int vt_grid, int stride, void* stream) {
+// T' and W2 = -T' W from the partial-W slots of k_vtc (bn = 128) or k_fused (bn = 64)
+extern "C" int qrdm_k_w2(const qrdm_prob* p, int j_host, int vt_grid, int stride, int bn, void* stream) {
   trailing_attrs();
   cudaStream_t s = (cudaStream_t)stream;
   const int ncmax = p->n - j_host - 1;
   if (ncmax <= 0 || stride <= 0) return 0;
+  k_tinv<<<1, TI_THREADS, TI_SMEM, s>>>(*p, vt_grid, stride, bn);
+  QRDM_LAUNCH_CHECK();
+  if (bn == 64) k_wapply<64><<<(ncmax + 63) / 64, 128, WA_SMEM_BN(64), s>>>(*p, vt_grid, stride);
+  else k_wapply<128><<<(ncmax + 127) / 128, 256, WA_SMEM_BN(128), s>>>(*p, vt_grid, stride);
+  QRDM_LAUNCH_CHECK();
+  return 0;
+}
+
+// pass 2 alone: C += V W2 on rows >= j (or, with p->pend, the deferred block on rows >= pend_r0)
+extern "C" int qrdm_k_rankk(const qrdm_prob* p, int j_host, void* stream) {
+  trailing_attrs();
+  cudaStream_t s = (cudaStream_t)stream;
+  const int ncmax = p->n - j_host - 1;
+  if (ncmax <= 0) return 0;
   const int jal = host_jr(p, j_host) & ~(QRDM_ROWALIGN - 1);
-  k_tinv<<<1, TI_THREADS, TI_SMEM, s>>>(*p, vt_grid, stride);
-  QRDM_LAUNCH_CHECK();
-  k_wapply<<<(ncmax + VT_BN - 1) / VT_BN, 256, WA_SMEM, s>>>(*p, vt_grid, stride);
-  QRDM_LAUNCH_CHECK();
   if (p->m - jal > 0) {
     const long long units = (long long)((ncmax + RK_BN - 1) / RK_BN) * ((p->m - jal + RK_BM - 1) / RK_BM);
     const int grid = (int)(units < 2 * p->sm_count ? units : 2 * p->sm_count);
@@ -618,9 +1007,73 @@ extern "C" int qrdm_k_trailing_finish(const qrdm_prob* p, int j_host, int vt_gri
   return 0;
 }
 
+// T', W2 = -T' W, and pass 2
+extern "C" int qrdm_k_trailing_finish(const qrdm_prob* p, int j_host, int vt_grid, int stride, void* stream) {
+  const int ncmax = p->n - j_host - 1;
+  if (ncmax <= 0 || stride <= 0) return 0;
+  const int rc = qrdm_k_w2(p, j_host, vt_grid, stride, VT_BN, stream);
+  if (rc) return rc;
+  return qrdm_k_rankk(p, j_host, stream);
+}
+
 extern "C" int qrdm_k_trailing(const qrdm_prob* p, int j_host, void* stream) {
   int stride = 0, grid = 0;
   int rc = qrdm_k_vtc_only(p, j_host, &stride, &grid, stream);
   if (rc) return rc;
   return qrdm_k_trailing_finish(p, j_host, grid, stride, stream);
+}
+
+// ---- deferred-update launchers ----
+extern "C" int qrdm_k_fused(const qrdm_prob* p, int j_host, int* stride_out, int* grid_out, void* stream) {
+  trailing_attrs();
+  cudaStream_t s = (cudaStream_t)stream;
+  const int ncmax = p->n - j_host - 1;
+  *stride_out = 0; *grid_out = 0;
+  if (ncmax <= 0) return 0;
+  const int jal = host_jr(p, j_host) & ~(QRDM_ROWALIGN - 1);
+  const int mpad = (p->m + FU_BK - 1) / FU_BK * FU_BK;
+  const int nchunks = (mpad - jal) / FU_BK;
+  const int ct_ub = 1 + (ncmax + FU_BN - 1) / FU_BN;
+  long long units_lb = (long long)nchunks * 2;
+  int grid = 2 * p->sm_count;
+  if (grid > units_lb) grid = (int)units_lb;
+  if (grid < 1) grid = 1;
+  const int stride = ct_ub * FU_BN;
+  *stride_out = stride; *grid_out = grid;
+  if (nchunks <= 0) return 0;
+  if (p->vec16) k_fused<true><<<grid, FU_THREADS, FU_SMEM, s>>>(*p, stride);
+  else k_fused<false><<<grid, FU_THREADS, FU_SMEM, s>>>(*p, stride);
+  QRDM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int qrdm_k_rowupd(const qrdm_prob* p, int j_host, void* stream) {
+  const int ncmax = p->n - j_host - 1;
+  k_rowupd<<<ncmax > 0 ? (ncmax + 15) / 16 : 1, 256, 0, (cudaStream_t)stream>>>(*p);
+  QRDM_LAUNCH_CHECK();
+  return 0;
+}
+
+// j_host: first column of the iteration that created the pending block (rows >= j_host + 1 may be active)
+extern "C" int qrdm_k_colupd(const qrdm_prob* p, int mode, int j_host, void* stream) {
+  const int rows = p->m - j_host - 1;
+  if (rows <= 0) return 0;
+  const int gx = (rows + CU_ROWS - 1) / CU_ROWS;
+  qrdm_prob q = *p;
+  q.vc_prev = p->vc;  // called in the iteration that created the pending block: its V is still "current"
+  if (mode == 0) k_colupd<0><<<dim3(gx, 16), CU_ROWS, 0, (cudaStream_t)stream>>>(q);
+  else k_colupd<1><<<dim3(gx, gx >= 64 ? 4 : 16), CU_ROWS, 0, (cudaStream_t)stream>>>(q);
+  QRDM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int qrdm_k_flush(const qrdm_prob* p, int j_host, void* stream) {
+  const int ncmax = p->n - j_host - 1;
+  if (ncmax <= 0) return 0;
+  k_w2mask<<<(ncmax + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*p);
+  QRDM_LAUNCH_CHECK();
+  qrdm_prob q = *p;
+  q.pend = 1;
+  q.vc = p->vc_prev;
+  return qrdm_k_rankk(&q, j_host, stream);
 }

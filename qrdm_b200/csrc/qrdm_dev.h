@@ -52,6 +52,12 @@ typedef struct qrdm_ctrl {
   int sel[QRDM_KMAX];         /* accepted offsets, acceptance order */
   int cyc_start[QRDM_MAXPOS + 1];
   int cyc_pos[QRDM_MAXPOS];   /* cycle c: new[p_k] = old[p_{k+1}], new[p_last] = old[p_0] */
+  /* deferred ("lazy") trailing update: block reflector whose pass 2 has not been applied to the bulk
+   * of the trailing matrix yet (written by k_rowupd, read by k_fused / k_colupd / the flush) */
+  int pend_k;   /* reflectors of the pending block */
+  int pend_c0;  /* first column the pending update applies to (= j + fjb of its iteration) */
+  int pend_r0;  /* first row still to be updated (= j + k of its iteration: the k new R rows are done) */
+  int pad5_;
 } qrdm_ctrl;
 #define QRDM_MAILBOX_BYTES 64
 
@@ -88,6 +94,12 @@ typedef struct qrdm_prob {
                          column s (geometry from qrdm_sub_geom), 0 otherwise */
   double *mg_buf;     /* sharded panel: [2][128] send/recv vectors + [G][128] per-CTA partials */
   unsigned *mg_cnt;   /* sharded panel: arrival counter of the last-CTA reduction */
+  /* deferred trailing update (k_fused): vc / vc_prev alternate between two ldv x 64 buffers */
+  double *vc_prev;    /* clean V of the pending block */
+  int *upd_flag;      /* [n] == stamp: column already brought up to date by k_colupd (flagged-norm list) */
+  int *upd_eager;     /* [n] == stamp: likewise for the eager set (leading 64 positions + candidates) */
+  int stamp;          /* id of the pending block (> 0) */
+  int pend;           /* 1: kernels take their geometry from ctrl->pend_* (flush of a pending block) */
 } qrdm_prob;
 
 int qrdm_k_colnorm(const qrdm_prob *p, int use_flag_list, void *stream);   /* K1 / K2 recompute */
@@ -107,6 +119,14 @@ int qrdm_k_norm_apply(const qrdm_prob *p, int j_host, void *stream);
 int qrdm_k_vtc_only(const qrdm_prob *p, int j_host, int *stride_out, int *grid_out, void *stream);
 int qrdm_k_wreduce(const qrdm_prob *p, int j_host, int vt_grid, int stride, void *stream);
 int qrdm_k_trailing_finish(const qrdm_prob *p, int j_host, int vt_grid, int stride, void *stream);
+/* deferred trailing update: pass 2 of the pending block fused into pass 1 of the current one */
+int qrdm_k_fused(const qrdm_prob *p, int j_host, int *stride_out, int *grid_out, void *stream);
+int qrdm_k_w2(const qrdm_prob *p, int j_host, int vt_grid, int stride, int bn, void *stream); /* T', W2 = -T'W */
+int qrdm_k_rankk(const qrdm_prob *p, int j_host, void *stream);    /* pass 2 alone */
+int qrdm_k_rowupd(const qrdm_prob *p, int j_host, void *stream);   /* the k new R rows of the trailing columns */
+int qrdm_k_colupd(const qrdm_prob *p, int mode, int j_host, void *stream); /* 0: eager set, 1: flagged-norm list */
+int qrdm_k_norm_update_lazy(const qrdm_prob *p, int j_host, void *stream);
+int qrdm_k_flush(const qrdm_prob *p, int j_host, void *stream);    /* apply a pending block to the whole trailing matrix */
 int qrdm_k_skinny_update(const qrdm_prob *p, int rows_hint, void *stream); /* tall panel: sub-panel -> rest of panel */
 int qrdm_k_skinny_part(const qrdm_prob *p, int rows_hint, void *stream);   /* row-sharded: before the all-reduce */
 int qrdm_k_skinny_finish(const qrdm_prob *p, int rows_hint, void *stream); /* row-sharded: after it */
