@@ -271,12 +271,14 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
   P.vc_prev = w->vc + (size_t)w->ldv * 64;
   P.upd_flag = w->upd_marks; P.upd_eager = w->upd_marks + w->cap_n;
   /* Deferred ("lazy") trailing update, single GPU: pass 2 of a block is postponed and fused into pass 1
-   * of the next block (k_fused) while both the trailing width and height are >= lazy_min; the columns
+   * of the next block (k_fused) while the trailing matrix has at least lazy_min^2 elements; the columns
    * the next selection touches are completed eagerly.  QRDM_B200_LAZY=0 disables it,
    * QRDM_B200_LAZY_MIN overrides the threshold (tests force it on tiny matrices). */
-  int lazy_min = 1536;
+  /* measured on B200 (16384^2): the fused kernel saves ~0.5 ms x (size/16384)^2 per iteration against
+   * k_vtc + k_rankk, the eager completion costs ~0.09 ms: break-even near a 7000 x 7000 trailing matrix */
+  int lazy_min = 7168;
   { const char *e = getenv("QRDM_B200_LAZY_MIN"); if (e) lazy_min = atoi(e); if (lazy_min < 1) lazy_min = 1; }
-  const int lazy_on = !mg && getenv("QRDM_B200_LAZY") && atoi(getenv("QRDM_B200_LAZY")) != 0; /* opt-in until validated on the GPU */
+  const int lazy_on = !mg && !(getenv("QRDM_B200_LAZY") && atoi(getenv("QRDM_B200_LAZY")) == 0);
   int pending = 0, pend_j = 0, stamp = 0;
   double *vcbuf[2] = {w->vc, w->vc + (size_t)w->ldv * 64};
 
@@ -314,7 +316,8 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
       STAGE(QRDM_STAGE_PICK, qrdm_k_pick(&P, stream));
       STAGE(QRDM_STAGE_PERMUTE, qrdm_k_permute(&P, stream));
       STAGE(QRDM_STAGE_PANEL, qrdm_k_panel(&P, j, stream));
-      lazy = lazy_on && n - j - QRDM_KMAX >= lazy_min && m - j - QRDM_KMAX >= lazy_min;
+      lazy = lazy_on && n - j - QRDM_KMAX >= 1 && m - j - QRDM_KMAX >= 1 &&
+             (double)(n - j - QRDM_KMAX) * (double)(m - j - QRDM_KMAX) >= (double)lazy_min * (double)lazy_min;
       if (!pending && !lazy) {
         STAGE(QRDM_STAGE_VTC, qrdm_k_trailing(&P, j, stream));
       } else {
@@ -325,9 +328,9 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
         if (pending) CU(qrdm_k_fused(&P, j, &vt_stride, &vt_grid, stream)); /* pass 2 of block it-1 + pass 1 of block it */
         else CU(qrdm_k_vtc_only(&P, j, &vt_stride, &vt_grid, stream));
         pending = 0;
-        if (vt_stride > 0) CU(qrdm_k_w2(&P, j, vt_grid, vt_stride, bn, stream));
-        if (lazy) CU(qrdm_k_rowupd(&P, j, stream));   /* the k new R rows now, the rest with the next block */
-        else CU(qrdm_k_rankk(&P, j, stream));
+        /* lazy: k_wapply also finishes the k new R rows; everything below them waits for the next k_fused */
+        if (vt_stride > 0) CU(qrdm_k_w2(&P, j, vt_grid, vt_stride, bn | (lazy ? 1 : 0), stream));
+        if (!lazy) CU(qrdm_k_rankk(&P, j, stream));
         CU(stage_end(QRDM_STAGE_VTC, lb, stream));
       }
       if (lazy) {

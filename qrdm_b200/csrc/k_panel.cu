@@ -346,7 +346,10 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_reg(qrdm_prob P, int
     double tau = 0.0, beta = alpha, scale = 1.0;
     if (len > 1) {
       if (i > 0 && xn2 < thres2) { k = i; break; }  // DM early stop: column i left untouched
-      if (xn2 != 0.0) {
+      // Only the warps that consume the scalars compute them: warps 0-1 (wv, tau), the owner of column i
+      // (scale, beta) and, in column 0, everybody (thres2 needs beta).  512 threads doing an FP64 sqrt and
+      // two divisions each cost 3500 cycles per column on the FP64 pipe (QRDM_B200_DEBUG=8 phase counts).
+      if (xn2 != 0.0 && (i == 0 || wid < 2 || wid == (i & 15))) {
         const double h = sqrt(fma(alpha, alpha, xn2));
         beta = (alpha >= 0.0) ? -h : h;
         tau = (beta - alpha) / beta;

@@ -274,26 +274,36 @@ __global__ void __launch_bounds__(TI_THREADS) k_tinv(qrdm_prob P, int vt_grid, i
 }
 
 #define WA_LDM 68
-#define WA_SMEM_BN(BN) ((64 * WA_LDM + 64 * ((BN) + 4)) * 8)
+#define WA_SMEM_BN(BN) ((2 * 64 * WA_LDM + 64 * ((BN) + 4)) * 8)
 #define WA_SMEM WA_SMEM_BN(VT_BN)
 
 // BN = width of the column tiles the partial-W slots were produced with (128: k_vtc, 64: k_fused)
+// rows_mode (deferred update): the tile's part of the k new R rows is finished here as well,
+//   C[j:j+k, tile] += V[j:j+k, :] W2[:, tile]   (the norm downdate needs them before the next selection;
+// everything below row j+k waits for k_fused), and the pending block is recorded in ctrl.
 template <int BN>
-__global__ void __launch_bounds__(2 * BN) k_wapply(qrdm_prob P, int vt_grid, int wslot_stride_cols) {
+__global__ void __launch_bounds__(2 * BN) k_wapply(qrdm_prob P, int vt_grid, int wslot_stride_cols, int rows_mode) {
   constexpr int NT = 2 * BN, LDW = BN + 4;
   extern __shared__ __align__(16) double sm[];
   double* Ms = sm;                  // [q][WA_LDM]
-  double* Ws = sm + 64 * WA_LDM;    // [p][LDW]
+  double* Vt = sm + 64 * WA_LDM;    // [r][WA_LDM]: rows j..j+63 of V (rows_mode)
+  double* Ws = sm + 2 * 64 * WA_LDM;  // [p][LDW]
   __shared__ int slots[QRDM_PANEL_MAXCTA * 2 + 8];
   __shared__ int nslots;
   qrdm_ctrl* ctrl = P.ctrl;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
   const VtGeom ge = vt_geom(P, BN);
   const int c0 = blockIdx.x * BN;
+  if (rows_mode && blockIdx.x == 0 && tid == 0) { ctrl->pend_k = ge.k; ctrl->pend_c0 = ge.j + ge.fjb; ctrl->pend_r0 = ge.j + ge.k; }
   if (ge.k <= 0 || c0 >= ge.nc) return;
   const int T = blockIdx.x + 1;
   if (tid == 0) { if (P.w_reduced) { slots[0] = 0; nslots = 1; } else nslots = vt_slot_list(ge, vt_grid, T, slots, QRDM_PANEL_MAXCTA * 2 + 8); }
   for (int e = tid; e < 4096; e += NT) Ms[(e >> 6) * WA_LDM + (e & 63)] = P.gram[e];
+  if (rows_mode)
+    for (int e = tid; e < 4096; e += NT) {
+      const int q = e >> 6, r = e & 63;  // consecutive threads -> consecutive rows of one column of V
+      Vt[r * WA_LDM + q] = (q < ge.k && r < ge.k && ge.j + r < P.m) ? P.vc[(size_t)(ge.voff + q) * P.ldv + ge.j + r] : 0.0;
+    }
   __syncthreads();
   const size_t sstride = (size_t)64 * wslot_stride_cols;
   const int ns = nslots;
@@ -350,6 +360,46 @@ __global__ void __launch_bounds__(2 * BN) k_wapply(qrdm_prob P, int vt_grid, int
     }
   }
   if (bad) atomicCAS(&ctrl->err, 0, -13);
+  if (!rows_mode) return;
+  // ---- the k new R rows of this tile.  Each warp keeps to its own 16 columns of Ws (the ones it read
+  // above), so overwriting them with W2 needs no block barrier ----
+  __syncwarp();
+#pragma unroll
+  for (int mt = 0; mt < 8; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      const int q = mt * 8 + g, c = wid * 16 + nt * 8 + 2 * t;
+      const bool ok = q < ge.kpad;
+      *reinterpret_cast<double2*>(Ws + q * LDW + c) = make_double2(ok ? -acc[mt][nt][0] : 0.0, ok ? -acc[mt][nt][1] : 0.0);
+      acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+    }
+  __syncwarp();
+  const double* ap2 = Vt + g * WA_LDM + t;  // A[m=r][k=q] = V[j+r][q]
+#pragma unroll 1
+  for (int ks = 0; ks < ksteps; ++ks) {
+    const double b0 = bp[ks * 4 * LDW], b1 = bp[ks * 4 * LDW + 8];
+    double a[8];
+#pragma unroll
+    for (int mt = 0; mt < 8; ++mt) a[mt] = ap2[mt * 8 * WA_LDM + ks * 4];
+#pragma unroll
+    for (int mt = 0; mt < 8; ++mt) {
+      dmma884(acc[mt][0][0], acc[mt][0][1], a[mt], b0);
+      dmma884(acc[mt][1][0], acc[mt][1][1], a[mt], b1);
+    }
+  }
+  double* Cg = P.a + (size_t)(ge.j + ge.fjb) * P.lda + ge.j;
+#pragma unroll
+  for (int mt = 0; mt < 8; ++mt) {
+    const int r = mt * 8 + g;
+    if (r < ge.k && ge.j + r < P.m) {
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const int c = c0 + wid * 16 + nt * 8 + 2 * t;
+        if (c < ge.nc) Cg[(size_t)c * P.lda + r] += acc[mt][nt][0];
+        if (c + 1 < ge.nc) Cg[(size_t)(c + 1) * P.lda + r] += acc[mt][nt][1];
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------ k_rankk
@@ -489,22 +539,28 @@ __global__ void __launch_bounds__(RK_THREADS, 2) k_rankk(qrdm_prob P) {
     int nrb = rb, nct = ct + 1;
     if (nct == CT) { nct = 0; ++nrb; }
     if (more && nrb == rb) { issue_w(nct, buf ^ 1); cp_async_commit(); }
-    if (more) load_c(nrb, nct, Y);
     const double* ap = Wsb + buf * 64 * RK_LDW + a_off;
     const double* bp = Vs + b_off;
+    auto ksteps = [&](int ks0, int ks1) {
 #pragma unroll 2
-    for (int ks = 0; ks < kpad / 4; ++ks) {  // 8 LDS.64 feed 16 independent DMMAs
-      double a[4], b[4];
+      for (int ks = ks0; ks < ks1; ++ks) {  // 8 LDS.64 feed 16 independent DMMAs
+        double a[4], b[4];
 #pragma unroll
-      for (int x = 0; x < 4; ++x) {
-        a[x] = ap[ks * 4 * RK_LDW + x * 8];
-        b[x] = bp[ks * 4 * RK_LDV + x * 8];
+        for (int x = 0; x < 4; ++x) {
+          a[x] = ap[ks * 4 * RK_LDW + x * 8];
+          b[x] = bp[ks * 4 * RK_LDV + x * 8];
+        }
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) dmma884(X[mt][nt][0], X[mt][nt][1], a[mt], b[nt]);
       }
-#pragma unroll
-      for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) dmma884(X[mt][nt][0], X[mt][nt][1], a[mt], b[nt]);
-    }
+    };
+    // The prefetch of C(u+1) is issued only after the first use of X (see k_fused: a wait for X that sits
+    // behind freshly issued loads on the same scoreboard costs a full memory latency per unit).
+    ksteps(0, 2);
+    if (more) load_c(nrb, nct, Y);
+    ksteps(2, kpad / 4);
     store_c(rb, ct, X);
     if (more && nrb != rb) {
       __syncthreads();  // all warps finished reading the old V tile
@@ -600,8 +656,7 @@ __device__ __forceinline__ void fused_body(const qrdm_prob& P, const VtGeom& ge,
 #pragma unroll
     for (int c = 0; c < 2; ++c) acc[a][c][0] = acc[a][c][1] = 0.0;
 
-  auto issue = [&](long long u, int stage) {
-    const int T = (int)(u / ge.NCH), chunk = (int)(u - (long long)T * ge.NCH);
+  auto issue = [&](int T, int chunk, int stage) {
     double* Vp = stage0 + (size_t)stage * FU_STAGE_DOUBLES;
     double* Vn = Vp + 64 * FU_LDP;
     const int r0 = ge.jal + chunk * FU_BK;
@@ -629,8 +684,7 @@ __device__ __forceinline__ void fused_body(const qrdm_prob& P, const VtGeom& ge,
     const int R0 = ge.jal + chunk * FU_BK, c0 = (T - 1) * FU_BN;
     return VEC16 && T > 0 && R0 >= jrow && R0 + FU_BK <= P.m && c0 + FU_BN <= ge.nc;
   };
-  auto load_c = [&](long long u, double (&dst)[2][4][2]) {
-    const int T = (int)(u / ge.NCH), chunk = (int)(u - (long long)T * ge.NCH);
+  auto load_c = [&](int T, int chunk, double (&dst)[2][4][2]) {
     const int R0 = ge.jal + chunk * FU_BK;
     if (T == 0) {  // the "C" tile is V_cur itself: its product is V'V (k_tinv)
 #pragma unroll
@@ -709,56 +763,39 @@ __device__ __forceinline__ void fused_body(const qrdm_prob& P, const VtGeom& ge,
     }
   };
 
-  long long u = lo;
   int left = (int)(hi - lo), st = 0;
-  int curT = (int)(lo / ge.NCH);
+  int T = (int)(lo / ge.NCH), chunk = (int)(lo - (long long)T * ge.NCH);
+  int curT = T;
   if (curT > 0) load_w2(curT);
-  issue(lo, 0);
+  issue(T, chunk, 0);
   cp_async_commit();
+  const int KSA = FULLK ? 16 : (kp_prev >> 2);  // k-steps of phase A
 
   // one unit: X holds C(u) (prefetched), Y receives C(u+1) while the MMAs of u run
   auto step = [&](double (&X)[2][4][2], double (&Y)[2][4][2]) {
     cp_async_wait<0>();
     __syncthreads();  // V chunks of u (and the W2 tile) landed; everyone is done with unit u-1
-    const int T = (int)(u / ge.NCH), chunk = (int)(u - (long long)T * ge.NCH);
     if (T != curT) {
       flush(curT);
       curT = T;
       load_w2(T);
       __syncthreads();
     }
+    int nT = T, nchunk = chunk + 1;
+    if (nchunk == ge.NCH) { nchunk = 0; ++nT; }
     if (left > 1) {
-      issue(u + 1, st ^ 1);
+      issue(nT, nchunk, st ^ 1);
       cp_async_commit();
-      load_c(u + 1, Y);
     }
     const double* Vp = stage0 + (size_t)st * FU_STAGE_DOUBLES;
     const double* Vn = Vp + 64 * FU_LDP;
-    if (T > 0) {
-      // phase A: X[c][r] += sum_q W2[q][c] V_prev[r][q]   (M = columns, N = rows, K = q)
-      const double* ap = W2s + t * FU_LDW + wid * 16 + g;
-      const double* bp = Vp + t * FU_LDP + g;
-#pragma unroll 2
-      for (int ks = 0; ks < kp_prev / 4; ++ks) {
-        double a[2], bb[4];
-#pragma unroll
-        for (int x = 0; x < 2; ++x) a[x] = ap[ks * 4 * FU_LDW + x * 8];
-#pragma unroll
-        for (int x = 0; x < 4; ++x) bb[x] = bp[ks * 4 * FU_LDP + x * 8];
-#pragma unroll
-        for (int ct = 0; ct < 2; ++ct)
-#pragma unroll
-          for (int rt = 0; rt < 4; ++rt) dmma884(X[ct][rt][0], X[ct][rt][1], a[ct], bb[rt]);
-      }
-      store_c(T, chunk, X);
-    }
     // phase B: acc[q][c] += sum_r V_cur[r][q] X[c][r]     (M = q, N = columns, K = rows {2t+e})
-    {
+    auto phase_b = [&]() {
       const double* ap = Vn + g * FU_LDN + 2 * t;
 #pragma unroll
       for (int rt = 0; rt < 4; ++rt) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {  // 4 q-tiles at a time: 16 operand registers live, dependent DMMAs 8 apart
+        for (int h = 0; h < 2; ++h) {  // 4 q-tiles at a time
           double2 a[4];
 #pragma unroll
           for (int x = 0; x < 4; ++x)
@@ -779,12 +816,40 @@ __device__ __forceinline__ void fused_body(const qrdm_prob& P, const VtGeom& ge,
           }
         }
       }
+    };
+    // The prefetch of C(u+1) into Y is issued only AFTER the first use of X, and the V'V tile (T == 0, no
+    // phase A) gets its own copy of phase B: ptxas gives the loads of X and of Y the same scoreboard, so a
+    // first use of X that sits behind freshly issued loads of Y — which is what the merge point of the two
+    // paths looked like to the compiler — waits a full memory latency per unit (ncu: 8-10% of all stall
+    // samples on one DMMA).
+    if (T > 0) {
+      // phase A: X[c][r] += sum_q W2[q][c] V_prev[r][q]   (M = columns, N = rows, K = q)
+      const double* ap = W2s + t * FU_LDW + wid * 16 + g;
+      const double* bp = Vp + t * FU_LDP + g;
+#pragma unroll 4
+      for (int ks = 0; ks < KSA; ++ks) {
+        double a[2], bb[4];
+#pragma unroll
+        for (int x = 0; x < 2; ++x) a[x] = ap[ks * 4 * FU_LDW + x * 8];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) bb[x] = bp[ks * 4 * FU_LDP + x * 8];
+#pragma unroll
+        for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+          for (int rt = 0; rt < 4; ++rt) dmma884(X[ct][rt][0], X[ct][rt][1], a[ct], bb[rt]);
+      }
+      store_c(T, chunk, X);
+      if (left > 1) load_c(nT, nchunk, Y);
+      phase_b();
+    } else {
+      phase_b();
+      if (left > 1) load_c(nT, nchunk, Y);
     }
-    ++u; st ^= 1; --left;
+    T = nT; chunk = nchunk; st ^= 1; --left;
   };
 
   double XA[2][4][2], XB[2][4][2];
-  load_c(lo, XA);
+  load_c(T, chunk, XA);
   while (left > 0) {
     step(XA, XB);
     if (left > 0) step(XB, XA);
@@ -797,7 +862,7 @@ __global__ void __launch_bounds__(FU_THREADS, 2) k_fused(qrdm_prob P, int wslot_
   extern __shared__ __align__(16) double sm[];
   const VtGeom ge = vt_geom(P, FU_BN);
   if (ge.k <= 0 || ge.nc <= 0 || ge.jr >= P.m) return;
-  if (ge.kpad == 64) fused_body<VEC16, true>(P, ge, wslot_stride_cols, sm);  // the common case: no predicates
+  if (ge.kpad == 64 && P.ctrl->pend_k > 56) fused_body<VEC16, true>(P, ge, wslot_stride_cols, sm);  // the common case: both blocks full, no predicates
   else fused_body<VEC16, false>(P, ge, wslot_stride_cols, sm);
 }
 
@@ -849,7 +914,7 @@ __global__ void __launch_bounds__(256) k_rowupd(qrdm_prob P) {
 #define CU_GROUP 8
 template <int MODE>
 __global__ void __launch_bounds__(CU_ROWS) k_colupd(qrdm_prob P) {
-  __shared__ double Wc[CU_GROUP][64];
+  __shared__ __align__(16) double Wc[CU_GROUP][64];
   __shared__ int colof[CU_GROUP];
   const qrdm_ctrl* ctrl = P.ctrl;
   const int tid = threadIdx.x;
@@ -897,18 +962,22 @@ __global__ void __launch_bounds__(CU_ROWS) k_colupd(qrdm_prob P) {
       for (int q = 0; q < 64; ++q) v[q] = q < kprev ? P.vc_prev[(size_t)q * P.ldv + r] : 0.0;
       vloaded = true;
     }
+    double s[CU_GROUP];
+#pragma unroll
+    for (int x = 0; x < CU_GROUP; ++x) s[x] = 0.0;
+#pragma unroll
+    for (int q = 0; q < 64; q += 2) {  // 8 independent FMA chains, W2 broadcast from smem two q at a time
+#pragma unroll
+      for (int x = 0; x < CU_GROUP; ++x) {
+        const double2 w = *reinterpret_cast<const double2*>(&Wc[x][q]);
+        s[x] = fma(v[q], w.x, s[x]);
+        s[x] = fma(v[q + 1], w.y, s[x]);
+      }
+    }
 #pragma unroll
     for (int x = 0; x < CU_GROUP; ++x) {
       const int col = colof[x];
-      if (col < 0) continue;
-      double* ptr = P.a + (size_t)col * P.lda + r;
-      double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-      for (int q = 0; q < 64; q += 2) {
-        s0 = fma(v[q], Wc[x][q], s0);
-        s1 = fma(v[q + 1], Wc[x][q + 1], s1);
-      }
-      *ptr += s0 + s1;
+      if (col >= 0) P.a[(size_t)col * P.lda + r] += s[x];
     }
   }
 }
@@ -977,15 +1046,16 @@ extern "C" int qrdm_k_wreduce(const qrdm_prob* p, int j_host, int vt_grid, int s
 }
 
 // T' and W2 = -T' W from the partial-W slots of k_vtc (bn = 128) or k_fused (bn = 64)
-extern "C" int qrdm_k_w2(const qrdm_prob* p, int j_host, int vt_grid, int stride, int bn, void* stream) {
+extern "C" int qrdm_k_w2(const qrdm_prob* p, int j_host, int vt_grid, int stride, int bn_and_rows, void* stream) {
+  const int bn = bn_and_rows & 0xff0, rows_mode = bn_and_rows & 1;  // bit 0: also finish the k new R rows (deferred update)
   trailing_attrs();
   cudaStream_t s = (cudaStream_t)stream;
   const int ncmax = p->n - j_host - 1;
   if (ncmax <= 0 || stride <= 0) return 0;
   k_tinv<<<1, TI_THREADS, TI_SMEM, s>>>(*p, vt_grid, stride, bn);
   QRDM_LAUNCH_CHECK();
-  if (bn == 64) k_wapply<64><<<(ncmax + 63) / 64, 128, WA_SMEM_BN(64), s>>>(*p, vt_grid, stride);
-  else k_wapply<128><<<(ncmax + 127) / 128, 256, WA_SMEM_BN(128), s>>>(*p, vt_grid, stride);
+  if (bn == 64) k_wapply<64><<<(ncmax + 63) / 64, 128, WA_SMEM_BN(64), s>>>(*p, vt_grid, stride, rows_mode);
+  else k_wapply<128><<<(ncmax + 127) / 128, 256, WA_SMEM_BN(128), s>>>(*p, vt_grid, stride, rows_mode);
   QRDM_LAUNCH_CHECK();
   return 0;
 }
@@ -1061,8 +1131,9 @@ extern "C" int qrdm_k_colupd(const qrdm_prob* p, int mode, int j_host, void* str
   const int gx = (rows + CU_ROWS - 1) / CU_ROWS;
   qrdm_prob q = *p;
   q.vc_prev = p->vc;  // called in the iteration that created the pending block: its V is still "current"
-  if (mode == 0) k_colupd<0><<<dim3(gx, 16), CU_ROWS, 0, (cudaStream_t)stream>>>(q);
-  else k_colupd<1><<<dim3(gx, gx >= 64 ? 4 : 16), CU_ROWS, 0, (cudaStream_t)stream>>>(q);
+  const int gy = gx >= 64 ? 4 : 16;  // column groups walked by one CTA share its row of V_prev
+  if (mode == 0) k_colupd<0><<<dim3(gx, gy), CU_ROWS, 0, (cudaStream_t)stream>>>(q);
+  else k_colupd<1><<<dim3(gx, gy), CU_ROWS, 0, (cudaStream_t)stream>>>(q);
   QRDM_LAUNCH_CHECK();
   return 0;
 }

@@ -1,6 +1,6 @@
 """GPU suite, deferred trailing update (k_fused / k_rowupd / k_colupd / flush).
 
-By default the deferred path only engages while the trailing matrix is >= 1536 wide and tall, so the
+By default the deferred path only engages while the trailing matrix has >= 7168^2 elements, so the
 small fixtures of test_gpu_parity.py never reach it.  Here QRDM_B200_LAZY_MIN=1 forces it from the
 first iteration on (every block deferred until fewer than 65 columns remain), which covers:
 fused pass-2/pass-1, eager completion of the leading 64 positions + candidates, flagged-norm columns
@@ -17,8 +17,7 @@ import parity
 from golden.cases import CASES
 from qrdm_b200 import generators as g
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("QRDM_B200_TEST_LAZY") != "1", reason="deferred update not validated yet")]
+pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
@@ -71,7 +70,7 @@ LAZY_CASES = [
     ("kahan300_perturbed", lambda: g.kahan(300, theta=1.2, perturb=1e3, seed=1), {}, "1"),
     ("graded1024_stop1", lambda: g.graded(1024, seed=3), dict(stop_mode=1), "1"),  # flush on the early stop
     ("graded777x1200", lambda: g.graded(1200, seed=4, m=777), {}, "1"),
-    ("gauss3000x2600_default", lambda: g.gaussian(3000, 2600, 7), {}, None),    # default threshold: deferred, then eager
+    ("gauss3000x2600_min1500", lambda: g.gaussian(3000, 2600, 7), {}, "1500"),  # deferred first, then eager
 ]
 
 

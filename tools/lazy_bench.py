@@ -34,5 +34,5 @@ for lazy in ("0", "1", "0", "1"):
     else:
         same = f" jpvt_equal={bool(torch.equal(jp, ref[0]))} max_rel_diag_diff={float(torch.max(torch.abs(d - ref[1]) / ref[1])):.2e}"
     print(f"{m}x{n} lazy={lazy}: info {info} rank {int(nc.sum())} iters {st['iterations']} ms_total {st['ms_total']:.2f} "
-          f"panel {st["ms_stage"]["panel"]:.2f} trailing {st['ms_stage']['VTC']:.2f} ms = {tf:.2f} TFLOP/s, launches {st['launches']}{same}",
+          f"panel {st["ms_stage"]["panel"]:.2f} trailing {st['ms_stage']['trailing']:.2f} ms = {tf:.2f} TFLOP/s, launches {st['launches']}{same}",
           flush=True)
