@@ -93,22 +93,32 @@ __global__ void __launch_bounds__(64) k_gram_reduce(qrdm_prob P, int of_v, int n
   if (!of_v && P.ctrl->nc <= 1) return;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;  // 4096 entries
   const double* src = P.gram_part + e;
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  // 16 loads in flight per thread (the kernel is pure L2 latency); fixed association order: deterministic
+  double s[16];
+#pragma unroll
+  for (int u = 0; u < 16; ++u) s[u] = 0.0;
   int q = 0;
-  for (; q + 3 < nparts; q += 4) {  // fixed association order: deterministic
-    s0 += src[(size_t)q * 4096];
-    s1 += src[(size_t)(q + 1) * 4096];
-    s2 += src[(size_t)(q + 2) * 4096];
-    s3 += src[(size_t)(q + 3) * 4096];
+  for (; q + 15 < nparts; q += 16) {
+    double v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) v[u] = src[(size_t)(q + u) * 4096];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) s[u] += v[u];
   }
-  for (; q < nparts; ++q) s0 += src[(size_t)q * 4096];
-  P.gram[e] = (s0 + s1) + (s2 + s3);
+  for (; q < nparts; ++q) s[0] += src[(size_t)q * 4096];
+#pragma unroll
+  for (int w = 8; w > 0; w >>= 1)
+#pragma unroll
+    for (int u = 0; u < w; ++u) s[u] += s[u + w];
+  P.gram[e] = s[0];
 }
 
 // rows_hint: host-side upper bound of the number of rows (m - j) used to size the grid.
 extern "C" int qrdm_k_gram(const qrdm_prob* p, int of_v, int rows_hint, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
-  int g = (rows_hint + 63) / 64;
+  // >= 128 rows (two pipelined sub-chunks) per CTA: the reduce kernel then sums 128 partial blocks at
+  // m = 16384 instead of 256 (it was 30 us of pure L2 latency per iteration)
+  int g = (rows_hint + 127) / 128;
   if (g < 1) g = 1;
   if (g > QRDM_GRAM_MAXCTA) g = QRDM_GRAM_MAXCTA;
   if (g > 2 * p->sm_count) g = 2 * p->sm_count;

@@ -425,16 +425,34 @@ __global__ void __launch_bounds__(2 * BN) k_wapply(qrdm_prob P, int vt_grid, int
 #define RK_THREADS 128
 #define RK_SMEM ((64 * RK_LDV + 2 * 64 * RK_LDW) * 8)
 
-template <bool VEC16>
+// LIST = true (deferred update, with P.pend): the columns are not a contiguous range but the EAGER SET of the
+// pending block — the leading min(64, cols) positions of the new trailing matrix plus the candidates
+// k_select just chose, i.e. everything the next Gram / pick / permutation / panel touches.  They are
+// completed here (rows >= pend_r0) and stamped in upd_eager so that k_fused / the flush skip them.
+template <bool VEC16, bool LIST>
 __global__ void __launch_bounds__(RK_THREADS, 2) k_rankk(qrdm_prob P) {
   extern __shared__ __align__(16) double sm[];
   double* Vs = sm;                 // [q][RK_LDV]
   double* Wsb = sm + 64 * RK_LDV;  // 2 x [q][RK_LDW]
+  __shared__ int slist[LIST ? 128 : 1];  // absolute column of list entry e, or -1
   const qrdm_ctrl* ctrl = P.ctrl;
   const int tid = threadIdx.x, lane = tid & 31, wr = tid >> 5, g = lane >> 2, t = lane & 3;
   const QrdmGeom qg = qrdm_geom(P);
   const int jc = qg.j, fjb = qg.fjb, k = qg.k;
-  const int nc = qg.n_end - jc - fjb;
+  int nc = qg.n_end - jc - fjb;
+  if (LIST) {
+    const int jn = ctrl->j, cols = P.n - jn, ncand = ctrl->nc, c0p = jc + fjb;
+    int col = -1;
+    if (tid < 64) col = tid < cols ? jn + tid : -1;
+    else if (tid - 64 < ncand) { const int off = ctrl->cand[tid - 64]; col = off >= 64 ? jn + off : -1; }
+    if (col >= 0) {
+      if (blockIdx.x == 0) P.upd_eager[col] = P.stamp;
+      if (P.upd_flag[col] == P.stamp || col < c0p) col = -1;  // done by k_colupd<1> / leftover panel column
+    }
+    slist[tid] = col;
+    __syncthreads();
+    nc = 64 + ncand;
+  }
   if (nc <= 0 || k <= 0) return;
   (void)ctrl;
   const int j = qrdm_jr(P, jc);  // first active local row (== jc on a single GPU)
@@ -454,8 +472,18 @@ __global__ void __launch_bounds__(RK_THREADS, 2) k_rankk(qrdm_prob P) {
   const int w_iters = kpad >> 3;
 
   auto issue_w = [&](int ct, int buf) {
-    const double* src = P.w2 + (size_t)w_q * P.ldw + ct * RK_BN + w_cp;
     double* dst = Wsb + buf * 64 * RK_LDW + w_q * RK_LDW + w_cp;
+    if (LIST) {  // gathered columns: two 8-byte copies, zero-filled for masked entries
+      const int col0 = slist[ct * RK_BN + w_cp], col1 = slist[ct * RK_BN + w_cp + 1];
+      const double* s0 = P.w2 + (size_t)w_q * P.ldw + (col0 >= 0 ? col0 - (jc + fjb) : 0);
+      const double* s1 = P.w2 + (size_t)w_q * P.ldw + (col1 >= 0 ? col1 - (jc + fjb) : 0);
+      for (int i = 0; i < w_iters; ++i) {
+        cp_async8(dst + i * 8 * RK_LDW, s0 + (size_t)i * 8 * P.ldw, col0 >= 0 ? 8 : 0);
+        cp_async8(dst + i * 8 * RK_LDW + 1, s1 + (size_t)i * 8 * P.ldw, col1 >= 0 ? 8 : 0);
+      }
+      return;
+    }
+    const double* src = P.w2 + (size_t)w_q * P.ldw + ct * RK_BN + w_cp;
     for (int i = 0; i < w_iters; ++i) cp_async16(dst + i * 8 * RK_LDW, src + (size_t)i * 8 * P.ldw, 16);
   };
   auto issue_v = [&](int rb) {
@@ -469,7 +497,40 @@ __global__ void __launch_bounds__(RK_THREADS, 2) k_rankk(qrdm_prob P) {
     const int R0 = jal + rb * RK_BM, c0 = ct * RK_BN;
     return VEC16 && R0 >= j && R0 + RK_BM <= P.m && c0 + RK_BN <= nc;
   };
+  // LIST: lane (g, .) works on list entries c0 + mt*8 + g; per-column pointers, rows as usual
+  auto list_rw = [&](int rb, int ct, double (&x)[4][4][2], bool store) {
+    const int R0 = jal + rb * RK_BM, c0 = ct * RK_BN;
+    const bool rows_in = VEC16 && R0 >= j && R0 + RK_BM <= P.m;
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+      const int col = slist[c0 + mt * 8 + g];
+      double* base = P.a + (size_t)(col >= 0 ? col : 0) * lda + R0 + wr * 32 + 2 * t;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int r = R0 + wr * 32 + nt * 8 + 2 * t;
+        double* ptr = base + nt * 8;
+        if (!store) {
+          double v0 = 0.0, v1 = 0.0;
+          if (col >= 0) {
+            if (rows_in) { const double2 v = *reinterpret_cast<const double2*>(ptr); v0 = v.x; v1 = v.y; }
+            else {
+              if (r >= j && r < P.m) v0 = ptr[0];
+              if (r + 1 >= j && r + 1 < P.m) v1 = ptr[1];
+            }
+          }
+          x[mt][nt][0] = v0; x[mt][nt][1] = v1;
+        } else if (col >= 0) {
+          if (rows_in) *reinterpret_cast<double2*>(ptr) = make_double2(x[mt][nt][0], x[mt][nt][1]);
+          else {
+            if (r >= j && r < P.m) ptr[0] = x[mt][nt][0];
+            if (r + 1 >= j && r + 1 < P.m) ptr[1] = x[mt][nt][1];
+          }
+        }
+      }
+    }
+  };
   auto load_c = [&](int rb, int ct, double (&dst)[4][4][2]) {
+    if (LIST) { list_rw(rb, ct, dst, false); return; }
     if (P.debug & 2) {
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt)
@@ -502,7 +563,8 @@ __global__ void __launch_bounds__(RK_THREADS, 2) k_rankk(qrdm_prob P) {
       }
     }
   };
-  auto store_c = [&](int rb, int ct, const double (&src)[4][4][2]) {
+  auto store_c = [&](int rb, int ct, double (&src)[4][4][2]) {
+    if (LIST) { list_rw(rb, ct, src, true); return; }
     if (P.debug & 1) return;
     const int R0 = jal + rb * RK_BM, c0 = ct * RK_BN;
     double* base = Cg + (size_t)c0 * lda + R0 + lane_off;
@@ -826,8 +888,7 @@ __device__ __forceinline__ void fused_body(const qrdm_prob& P, const VtGeom& ge,
       // phase A: X[c][r] += sum_q W2[q][c] V_prev[r][q]   (M = columns, N = rows, K = q)
       const double* ap = W2s + t * FU_LDW + wid * 16 + g;
       const double* bp = Vp + t * FU_LDP + g;
-#pragma unroll 4
-      for (int ks = 0; ks < KSA; ++ks) {
+      auto kstep = [&](int ks) {
         double a[2], bb[4];
 #pragma unroll
         for (int x = 0; x < 2; ++x) a[x] = ap[ks * 4 * FU_LDW + x * 8];
@@ -837,7 +898,10 @@ __device__ __forceinline__ void fused_body(const qrdm_prob& P, const VtGeom& ge,
         for (int ct = 0; ct < 2; ++ct)
 #pragma unroll
           for (int rt = 0; rt < 4; ++rt) dmma884(X[ct][rt][0], X[ct][rt][1], a[ct], bb[rt]);
-      }
+      };
+      // (fully unrolling the 16 k-steps of a full block makes the kernel 8% SLOWER: 150 KB of code)
+#pragma unroll 4
+      for (int ks = 0; ks < KSA; ++ks) kstep(ks);
       store_c(T, chunk, X);
       if (left > 1) load_c(nT, nchunk, Y);
       phase_b();
@@ -1002,8 +1066,10 @@ static void trailing_attrs() {
   cudaFuncSetAttribute(k_tinv, cudaFuncAttributeMaxDynamicSharedMemorySize, TI_SMEM);
   cudaFuncSetAttribute(k_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FU_SMEM);
   cudaFuncSetAttribute(k_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FU_SMEM);
-  cudaFuncSetAttribute(k_rankk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RK_SMEM);
-  cudaFuncSetAttribute(k_rankk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RK_SMEM);
+  cudaFuncSetAttribute(k_rankk<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RK_SMEM);
+  cudaFuncSetAttribute(k_rankk<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RK_SMEM);
+  cudaFuncSetAttribute(k_rankk<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RK_SMEM);
+  cudaFuncSetAttribute(k_rankk<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RK_SMEM);
   attr_set = true;
 }
 static int host_jr(const qrdm_prob* p, int j) {
@@ -1070,8 +1136,8 @@ extern "C" int qrdm_k_rankk(const qrdm_prob* p, int j_host, void* stream) {
   if (p->m - jal > 0) {
     const long long units = (long long)((ncmax + RK_BN - 1) / RK_BN) * ((p->m - jal + RK_BM - 1) / RK_BM);
     const int grid = (int)(units < 2 * p->sm_count ? units : 2 * p->sm_count);
-    if (p->vec16) k_rankk<true><<<grid, RK_THREADS, RK_SMEM, s>>>(*p);
-    else k_rankk<false><<<grid, RK_THREADS, RK_SMEM, s>>>(*p);
+    if (p->vec16) k_rankk<true, false><<<grid, RK_THREADS, RK_SMEM, s>>>(*p);
+    else k_rankk<false, false><<<grid, RK_THREADS, RK_SMEM, s>>>(*p);
     QRDM_LAUNCH_CHECK();
   }
   return 0;
@@ -1124,16 +1190,25 @@ extern "C" int qrdm_k_rowupd(const qrdm_prob* p, int j_host, void* stream) {
   return 0;
 }
 
-// j_host: first column of the iteration that created the pending block (rows >= j_host + 1 may be active)
+// j_host: first column of the iteration that created the pending block (rows >= j_host + 1 may be active).
+// Called in that same iteration, so the block's V is still the "current" buffer p->vc.
 extern "C" int qrdm_k_colupd(const qrdm_prob* p, int mode, int j_host, void* stream) {
+  trailing_attrs();
   const int rows = p->m - j_host - 1;
   if (rows <= 0) return 0;
-  const int gx = (rows + CU_ROWS - 1) / CU_ROWS;
   qrdm_prob q = *p;
-  q.vc_prev = p->vc;  // called in the iteration that created the pending block: its V is still "current"
-  const int gy = gx >= 64 ? 4 : 16;  // column groups walked by one CTA share its row of V_prev
-  if (mode == 0) k_colupd<0><<<dim3(gx, gy), CU_ROWS, 0, (cudaStream_t)stream>>>(q);
-  else k_colupd<1><<<dim3(gx, gy), CU_ROWS, 0, (cudaStream_t)stream>>>(q);
+  if (mode == 0) {  // eager set: DMMA rank-k update on the gathered columns (<= 128 = 4 column tiles)
+    q.pend = 1;
+    const int jal = host_jr(p, j_host) & ~(QRDM_ROWALIGN - 1);
+    const long long units = 4LL * ((p->m - jal + RK_BM - 1) / RK_BM);
+    const int grid = (int)(units < 2 * p->sm_count ? units : 2 * p->sm_count);
+    if (p->vec16) k_rankk<true, true><<<grid, RK_THREADS, RK_SMEM, (cudaStream_t)stream>>>(q);
+    else k_rankk<false, true><<<grid, RK_THREADS, RK_SMEM, (cudaStream_t)stream>>>(q);
+  } else {          // flagged-norm list (arbitrary length, usually empty): FMA kernel
+    const int gx = (rows + CU_ROWS - 1) / CU_ROWS;
+    q.vc_prev = p->vc;
+    k_colupd<1><<<dim3(gx, gx >= 64 ? 4 : 16), CU_ROWS, 0, (cudaStream_t)stream>>>(q);
+  }
   QRDM_LAUNCH_CHECK();
   return 0;
 }
