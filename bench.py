@@ -11,7 +11,7 @@ value   = whole-job GFLOP/s with A resident in HBM (dgeqrdm_dev, CUDA events, ma
           algorithmic FLOPs F(m,n,r) = 4mnr - 2(m+n)r^2 + (4/3)r^3, r = sum(ncols).
 e2e     = the same metric through the reference-facing C ABI `dgeqrdm` with PINNED HOST buffers:
           H2D of A, the factorisation, D2H of A/jpvt/tau all inside the timed region.
-roofline= the trailing update (K6: k_vtc + k_tinv + k_wapply + k_rankk, FP64 DMMA) timed with CUDA events
+roofline= the trailing update (K6: k_fused / k_vtc + k_tinv + k_wapply + k_rankk, FP64 DMMA) timed with CUDA events
           on the launching stream inside the same timed steps, against the FP64 DMMA peak measured
           live by the library's micro-benchmark (MEASURED_PEAKS.json carries no FP64 figure).
 cpu_baseline / --impl reference = the UNMODIFIED reference (oracle/_ref, compiled from
@@ -543,7 +543,8 @@ def main():
                 "steps": e2e_steps, "api": "dgeqrdm (C ABI, pinned host buffers, wall clock around the blocking call)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"kernel": "K6 trailing update: k_vtc + k_tinv + k_wapply + k_rankk (DMMA.8x8x4)", "bound": "tensor",
+        "roofline": {"kernel": "K6 trailing update: k_fused (deferred pass 2 + pass 1; k_vtc/k_rankk below the 7168^2 break-even) "
+                               "+ k_tinv + k_wapply + eager k_rankk<list> (DMMA.8x8x4)", "bound": "tensor",
                      "achieved": achieved, "peak": peak_dmma, "unit": "TFLOP/s",
                      "frac": (achieved / peak_dmma) if achieved else None,
                      "peak_source": "FP64 DMMA peak measured live by qrdm_b200_measure_fp64_peak "
@@ -553,9 +554,10 @@ def main():
                      "launches_per_step": trailing_launches / args.steps,
                      "ms_per_step": trailing_ms / args.steps, "share_of_step": trailing_ms / ms,
                      "traffic": None,
-                     "traffic_note": "ncu --set full at iteration 10 (m_r=15744): k_vtc 2.03 GB read (algorithmic 1.97), "
-                                     "k_rankk 2.05 GB read + 1.92 GB written (algorithmic 1.97 + 1.97): no wasted re-reads; "
-                                     "per-launch traffic shrinks with the trailing matrix, see profiles/"},
+                     "traffic_note": "ncu --set full at iteration 10 (m_r=15744): k_fused 2.03 GB read + 1.93 GB written "
+                                     "(algorithmic 1.97 + 1.97; the unfused pair k_vtc + k_rankk moved 4.1 GB read + 1.9 GB "
+                                     "written): no wasted re-reads; per-launch traffic shrinks with the trailing matrix, "
+                                     "see profiles/r01_ncu_fused_v3.txt"},
         "stages": {"panel_ms_per_step": panel_ms / args.steps, "trailing_ms_per_step": trailing_ms / args.steps},
     }
     if row_sharded is not None:
