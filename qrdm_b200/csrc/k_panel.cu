@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(qrdm_prob P, int rpc
 // whole panel; only the two active columns (v and the next pivot column) pass through smem, the
 // scalars are computed once per warp with a single sqrt (beta^2 = alpha^2 + ||x||^2, stop test on
 // ||x||^2 < thres^2), and the exchange stays the LL reduce-scatter + broadcast of the kernel above.
-// RI = rows per lane: 4 (<= 128 rows per CTA) or 8 (<= 256 rows per CTA, twice the registers)
+// RI = rows per lane: 1, 2, 4 or 8 (32 ... 256 rows per CTA); the launcher picks the cheapest that fits
 template <int RI>
 __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_reg(qrdm_prob P, int rpc, unsigned epoch) {
   __shared__ double sred[PANEL_WARPS];
@@ -641,15 +641,29 @@ extern "C" int qrdm_k_panel(const qrdm_prob* p, int j_host, void* stream) {
   // both proportional to the CTA count; grow the grid only when the slab would not fit in smem
   const int gmax = p->sm_count < QRDM_PANEL_MAXCTA ? p->sm_count : QRDM_PANEL_MAXCTA;
   if (rows <= 256 * gmax && !getenv("QRDM_PANEL_NOREG")) {  // register-resident slabs, 128 (or 256) rows per CTA
-    const int per = rows <= 128 * gmax ? 128 : 256;
+    // Rows per CTA (32 x RI).  Per-column cost measured on B200 (panel ms / columns, square Gaussian inputs):
+    //   1000 rows: 2.75 / 2.96 / 3.38 us for RI = 1 / 2 / 4;  4096 rows: 3.83 / 3.30 / 3.46;  8192 rows: RI = 4 beats 2
+    //   by 7%;  16384 rows: 4.7 us with RI = 4 (123 CTAs), 5.8 us with RI = 8.
+    // i.e. ~0.23 us per RI (the in-CTA sweep) + ~0.012 us per CTA beyond 16 (LL reduce-scatter / broadcast fan-in).
+    int per = 256;
+    {
+      double best = 1e30;
+      for (int ri = 1; ri <= 8; ri *= 2) {
+        const int g = (rows + 32 * ri - 1) / (32 * ri);
+        if (g > gmax) continue;
+        const double cost = 0.23 * ri + 0.012 * (g > 16 ? g - 16 : 0);
+        if (cost < best) { best = cost; per = 32 * ri; }
+      }
+      static const char* e = getenv("QRDM_PANEL_PER");  // experiment switch
+      if (e) { const int v = atoi(e); if ((v == 32 || v == 64 || v == 128 || v == 256) && rows <= v * gmax) per = v; }
+    }
     int Gr = (rows + per - 1) / per, rpcr = (rows + Gr - 1) / Gr;
     static unsigned epoch_r = 0x400000;
     epoch_r = epoch_r + 1 >= 0x7fffff ? 0x400000 : epoch_r + 1;
     qrdm_prob prob_r = *p;
     void* args_r[] = {(void*)&prob_r, (void*)&rpcr, (void*)&epoch_r};
-    cudaError_t er = per == 128
-        ? cudaLaunchCooperativeKernel((void*)k_panel_reg<4>, dim3(Gr), dim3(PANEL_THREADS), args_r, 0, (cudaStream_t)stream)
-        : cudaLaunchCooperativeKernel((void*)k_panel_reg<8>, dim3(Gr), dim3(PANEL_THREADS), args_r, 0, (cudaStream_t)stream);
+    void* fn = per == 32 ? (void*)k_panel_reg<1> : per == 64 ? (void*)k_panel_reg<2> : per == 128 ? (void*)k_panel_reg<4> : (void*)k_panel_reg<8>;
+    cudaError_t er = cudaLaunchCooperativeKernel(fn, dim3(Gr), dim3(PANEL_THREADS), args_r, 0, (cudaStream_t)stream);
     ++g_qrdm_launches;
     return er == cudaSuccess ? 0 : (int)er;
   }
