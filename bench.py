@@ -32,6 +32,17 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# The driver reads ONE JSON line from stdout.  Libraries write there too (NCCL prints its version banner
+# to stdout under torchrun), so keep a private copy of the real stdout for the JSON line and point fd 1
+# at stderr for everybody else.
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
 WORKLOADS = {
     # name: (m, n, generator, stop_mode, description = the BASELINE.json config it is)
     "C1": (1000, 1000, "gaussian", 0, "1000x1000 random Gaussian double matrix (configs[0])"),
@@ -128,7 +139,7 @@ def run_reference(args, rank, world):
             "scaling": "weak", "vs_baseline": None}
     if not ref.have_ref():
         line["unavailable"] = "oracle/_ref/libqrdm_ref.so not present (build it where /root/reference exists)"
-        print(json.dumps(line))
+        emit(line)
         return
     ref.set_ref_threads(cores)
     # bounded sample: the leading sm x sn block of the same matrix family, sized for a few s per step
@@ -158,7 +169,7 @@ def run_reference(args, rank, world):
                  "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": cores, "kind": "reference",
                                   "sample": sample},
                  "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-    print(json.dumps(line))
+    emit(line)
 
 
 def cpu_baseline(args, m, n, kind, stop_mode, desc):
@@ -571,7 +582,7 @@ def main():
             line["cpu_baseline"] = cpu_baseline(args, m, n, kind, stop_mode, desc)
         except Exception as exc:  # the baseline must never sink the measurement
             line["cpu_baseline"] = {"value": None, "error": str(exc)[:200]}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
