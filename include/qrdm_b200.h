@@ -84,6 +84,16 @@ void qrdm_b200_comm_destroy(void);
 int dgeqrdm_dev_sharded(int m_local, int m_global, int row0, int nranks, int n, double *d_a, int lda,
                         int *d_jpvt, double *d_tau, int *ncols, const double *thres, int nb, void *stream);
 
+/* Addition: apply Q = H_0 H_1 ... H_{k-1} (trans = 'N') or Q' (trans = 'T') from the left to an
+ * m x n matrix C, the reflectors being the first k columns of a matrix factored by dgeqrdm / dgeqrf (vectors
+ * below the diagonal, unit diagonal implicit) and tau.  Replaces the LAPACKE_dormqr('L', trans, ...) behind the
+ * reference wrapper's DORMQR (reference QRDM_wrapper.c:104-126), which auxil.checkQR (reference auxil.py:20-105)
+ * uses to form Q and Q R; runs the K6 trailing-update kernels block by block (64 reflectors per block).
+ * _dev: every pointer is a DEVICE pointer, column-major, lda/ldc >= m.  Returns 0 (or -13 if NaNs went through). */
+int qrdm_b200_dormqr_dev(char trans, int m, int n, int k, const double *d_a, int lda, const double *d_tau, double *d_c,
+                         int ldc, void *stream);
+int qrdm_b200_dormqr(char trans, int m, int n, int k, const double *a, int lda, const double *tau, double *c, int ldc);
+
 /* Addition: per-call statistics of the last dgeqrdm*() on this thread's device. */
 typedef struct qrdm_b200_stats {
   int iterations;        /* DM iterations (= number of ncols entries written) */

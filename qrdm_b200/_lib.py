@@ -25,7 +25,8 @@ STAGES = ["norm_init", "select", "gram", "pick", "permute", "panel", "vtv", "tra
 # every symbol include/qrdm_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = ["dgeqrdm", "dgeqrdm_work", "dgeqrdm_dev", "dgeqrdm_dev_sharded", "dgeqrdm_batched", "dgeqrdm_batched_dev", "qrdm_b200_get_stats",
            "qrdm_b200_set_profile", "qrdm_b200_init", "qrdm_b200_shutdown", "qrdm_b200_measure_fp64_peak",
-           "qrdm_b200_version", "qrdm_b200_comm_unique_id", "qrdm_b200_comm_init", "qrdm_b200_comm_destroy"]
+           "qrdm_b200_version", "qrdm_b200_comm_unique_id", "qrdm_b200_comm_init", "qrdm_b200_comm_destroy",
+           "qrdm_b200_dormqr", "qrdm_b200_dormqr_dev"]
 
 
 def _load():
@@ -66,6 +67,12 @@ def _load():
     lib.dgeqrdm_dev_sharded.restype = C.c_int
     lib.dgeqrdm_dev_sharded.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.qrdm_b200_dormqr_dev.restype = C.c_int
+    lib.qrdm_b200_dormqr_dev.argtypes = [C.c_char, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_int, C.c_void_p]
+    lib.qrdm_b200_dormqr.restype = C.c_int
+    lib.qrdm_b200_dormqr.argtypes = [C.c_char, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                     C.c_int]
     return lib
 
 

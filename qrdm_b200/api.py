@@ -77,6 +77,31 @@ def dgeqrdm_batched_device(batch, m, n, d_a, lda, stride_a, d_jpvt, d_tau, d_nco
                                             C.c_void_p(int(stream)) if stream else None))
 
 
+def dormqr(F, tau, Cm, k=None, trans="N"):
+    """C <- Q C (trans "N") or Q' C ("T") on the GPU; F = factored matrix (host), reflectors in its first k
+    columns (default len(tau)); returns (info, new C).  ``qrdm_b200_dormqr`` (host pointers)."""
+    F = np.asfortranarray(F, dtype=np.float64)
+    Cm = np.array(Cm, dtype=np.float64, order="F", copy=True)
+    tau = np.ascontiguousarray(tau, dtype=np.float64)
+    m = F.shape[0]
+    k = len(tau) if k is None else int(k)
+    assert Cm.shape[0] == m and k <= F.shape[1]
+    info = _lib.lib.qrdm_b200_dormqr(trans.encode(), m, Cm.shape[1], k, F.ctypes.data, m, tau.ctypes.data,
+                                     Cm.ctypes.data, m)
+    return int(info), Cm
+
+
+def dormqr_device(trans, m, n, k, dA, lda, d_tau, dC, ldc, stream=None):
+    """Device-resident Q application (``qrdm_b200_dormqr_dev``): torch CUDA tensors or raw device pointers."""
+    def ptr(x):
+        return int(x.data_ptr()) if hasattr(x, "data_ptr") else int(x)
+    if stream is None:
+        import torch
+        stream = torch.cuda.current_stream().cuda_stream
+    return int(_lib.lib.qrdm_b200_dormqr_dev(trans.encode(), int(m), int(n), int(k), ptr(dA), int(lda), ptr(d_tau),
+                                             ptr(dC), int(ldc), C.c_void_p(int(stream))))
+
+
 def stats():
     return _lib.stats()
 

@@ -526,6 +526,100 @@ int dgeqrdm(int matrix_layout, int m, int n, double *a, int lda, int *jpvt, doub
   return dgeqrdm_work(matrix_layout, m, n, a, lda, jpvt, tau, ncols, thres, nb);
 }
 
+/* ---- Q application: C <- Q C or Q' C with the reflectors of a factored matrix, in blocks of 64
+ * through the trailing-update kernels (K6).  Replaces the LAPACKE_dormqr('L', .) call of the reference
+ * wrapper's DORMQR (QRDM_wrapper.c:104-126) and makes auxil.checkQR (auxil.py:20-105) possible at sizes whose
+ * m x m Q would never fit on the host.  Any partition of the k reflectors into blocks is valid: T is rebuilt per
+ * block from V'V and tau (k_tinv), so this does not depend on the block sizes of the factorisation. ---- */
+int qrdm_b200_dormqr_dev(char trans, int m, int n, int k, const double *d_a, int lda, const double *d_tau, double *d_c,
+                         int ldc, void *stream) {
+  const int transN = (trans == 'N' || trans == 'n');
+  if (!transN && trans != 'T' && trans != 't') return bad_argument(1);
+  if (m <= 0) return bad_argument(2);
+  if (n <= 0) return bad_argument(3);
+  if (k < 0 || k > m) return bad_argument(4);
+  if (lda < m) return bad_argument(6);
+  if (ldc < m) return bad_argument(9);
+  int rc = ws_ensure(m, n + QRDM_KMAX);
+  if (rc) return rc;
+  qrdm_workspace *w = &g_ws;
+  qrdm_prob P;
+  memset(&P, 0, sizeof(P));
+  P.m = m; P.lda = ldc; P.nb = QRDM_KMAX;
+  P.tau = (double *)d_tau;
+  P.vn1 = w->vn1; P.vn2 = w->vn2; P.ctrl = w->ctrl;
+  P.gram_part = w->gram_part; P.gram = w->gram;
+  P.vc = w->vc; P.vc_prev = w->vc; P.ldv = w->ldv;
+  P.wp = w->wp; P.wp_elems = w->wp_elems; P.w2 = w->w2; P.ldw = w->ldw;
+  P.nrm_part = w->nrm_part; P.nrm_splits = w->nrm_splits; P.flag_list = w->flag_list;
+  P.upd_flag = w->upd_marks; P.upd_eager = w->upd_marks + w->cap_n;
+  P.sm_count = w->sm_count;
+  P.vec16 = (((size_t)d_c & 15) == 0 && (ldc & 1) == 0) ? 1 : 0;
+  P.m_glob = m; P.nranks = 1;
+  memset(&g_stats, 0, sizeof(g_stats));
+  const long long launches0 = qrdm_rt_launch_count();
+  CU(qrdm_rt_event_record(w->ev[0], stream));
+  CU(qrdm_rt_memset(w->ctrl, 0, sizeof(qrdm_ctrl), stream));
+  CU(qrdm_rt_memset(w->vc, 0, sizeof(double) * (size_t)w->ldv * 64, stream));
+  const int nblk = (k + QRDM_KMAX - 1) / QRDM_KMAX;
+  for (int bi = 0; bi < nblk; ++bi) {
+    const int b = transN ? nblk - 1 - bi : bi; /* Q = H_0 H_1 ...: last block first; Q': first block first */
+    const int j0 = b * QRDM_KMAX, kb = k - j0 < QRDM_KMAX ? k - j0 : QRDM_KMAX;
+    int stride = 0, grid = 0;
+    /* the kernels update the columns right of the block, A[:, j0+kb : P.n): make that range be C */
+    P.n = j0 + kb + n;
+    P.a = (double *)((size_t)d_c - sizeof(double) * (size_t)(j0 + kb) * (size_t)ldc);
+    CU(qrdm_k_vc_build(&P, d_a, lda, j0, kb, stream));
+    CU(qrdm_k_vtc_only(&P, j0, &stride, &grid, stream));
+    if (stride > 0) {
+      CU(qrdm_k_w2(&P, j0, grid, stride, 128 | (transN ? 2 : 0), stream));
+      CU(qrdm_k_rankk(&P, j0, stream));
+    }
+    g_stats.trailing_flops += 4.0 * (double)(m - j0) * (double)n * (double)kb;
+  }
+  CU(qrdm_rt_event_record(w->ev[1], stream));
+  rc = read_mailbox(&P, stream);
+  if (rc) return rc;
+  g_stats.ms_total = qrdm_rt_event_ms(w->ev[0], w->ev[1]);
+  g_stats.iterations = nblk;
+  g_stats.rank = k;
+  g_stats.launches = qrdm_rt_launch_count() - launches0;
+  return w->mailbox->err; /* 0, or -13 if a NaN went through (the screen of k_wapply) */
+}
+
+/* Host-pointer variant: A (m x k reflector columns, as returned by dgeqrdm/dgeqrf), tau and C in host memory. */
+int qrdm_b200_dormqr(char trans, int m, int n, int k, const double *a, int lda, const double *tau, double *c, int ldc) {
+  if (m <= 0) return bad_argument(2);
+  if (n <= 0) return bad_argument(3);
+  if (k < 0 || k > m) return bad_argument(4);
+  if (lda < m) return bad_argument(6);
+  if (ldc < m) return bad_argument(9);
+  int rc = qrdm_b200_init(-1);
+  if (rc) return rc;
+  void *stream = g_ws.compute_stream;
+  const int ldd = (m + 1) & ~1;
+  double *d_a = NULL, *d_c = NULL, *d_tau = NULL;
+  const int kc = k > 0 ? k : 1;
+  CU(qrdm_rt_malloc((void **)&d_a, sizeof(double) * (size_t)ldd * kc));
+  CU(qrdm_rt_malloc((void **)&d_c, sizeof(double) * (size_t)ldd * n));
+  CU(qrdm_rt_malloc((void **)&d_tau, sizeof(double) * kc));
+  CU(qrdm_rt_memset(d_c, 0, sizeof(double) * (size_t)ldd * n, stream));
+  if (k > 0) {
+    CU(qrdm_rt_h2d_2d(d_a, sizeof(double) * ldd, a, sizeof(double) * lda, sizeof(double) * m, k, stream));
+    CU(qrdm_rt_h2d(d_tau, tau, sizeof(double) * k, stream));
+  }
+  CU(qrdm_rt_h2d_2d(d_c, sizeof(double) * ldd, c, sizeof(double) * ldc, sizeof(double) * m, n, stream));
+  int info = k > 0 ? qrdm_b200_dormqr_dev(trans, m, n, k, d_a, ldd, d_tau, d_c, ldd, stream) : 0;
+  if (info > QRDM_ERR_CUDA) {
+    CU(qrdm_rt_d2h_2d(c, sizeof(double) * ldc, d_c, sizeof(double) * ldd, sizeof(double) * m, n, stream));
+    CU(qrdm_rt_sync(stream));
+  }
+  qrdm_rt_free(d_a);
+  qrdm_rt_free(d_c);
+  qrdm_rt_free(d_tau);
+  return info;
+}
+
 /* ---- 1-D block-row sharded entry point (one process per GPU; NCCL communicator set up through
  * qrdm_b200_comm_unique_id / qrdm_b200_comm_init, e.g. with the id broadcast by torch.distributed) ---- */
 int qrdm_b200_comm_unique_id(char *out128) { return qrdm_rt_comm_unique_id(out128) ? QRDM_ERR_COMM : 0; }

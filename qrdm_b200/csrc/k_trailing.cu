@@ -294,12 +294,16 @@ __global__ void __launch_bounds__(2 * BN) k_wapply(qrdm_prob P, int vt_grid, int
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
   const VtGeom ge = vt_geom(P, BN);
   const int c0 = blockIdx.x * BN;
-  if (rows_mode && blockIdx.x == 0 && tid == 0) { ctrl->pend_k = ge.k; ctrl->pend_c0 = ge.j + ge.fjb; ctrl->pend_r0 = ge.j + ge.k; }
+  if ((rows_mode & 1) && blockIdx.x == 0 && tid == 0) { ctrl->pend_k = ge.k; ctrl->pend_c0 = ge.j + ge.fjb; ctrl->pend_r0 = ge.j + ge.k; }
   if (ge.k <= 0 || c0 >= ge.nc) return;
   const int T = blockIdx.x + 1;
   if (tid == 0) { if (P.w_reduced) { slots[0] = 0; nslots = 1; } else nslots = vt_slot_list(ge, vt_grid, T, slots, QRDM_PANEL_MAXCTA * 2 + 8); }
-  for (int e = tid; e < 4096; e += NT) Ms[(e >> 6) * WA_LDM + (e & 63)] = P.gram[e];
-  if (rows_mode)
+  if (rows_mode & 2) {  // apply Q instead of Q': T = (T')'
+    for (int e = tid; e < 4096; e += NT) Ms[(e & 63) * WA_LDM + (e >> 6)] = P.gram[e];
+  } else {
+    for (int e = tid; e < 4096; e += NT) Ms[(e >> 6) * WA_LDM + (e & 63)] = P.gram[e];
+  }
+  if (rows_mode & 1)
     for (int e = tid; e < 4096; e += NT) {
       const int q = e >> 6, r = e & 63;  // consecutive threads -> consecutive rows of one column of V
       Vt[r * WA_LDM + q] = (q < ge.k && r < ge.k && ge.j + r < P.m) ? P.vc[(size_t)(ge.voff + q) * P.ldv + ge.j + r] : 0.0;
@@ -360,7 +364,7 @@ __global__ void __launch_bounds__(2 * BN) k_wapply(qrdm_prob P, int vt_grid, int
     }
   }
   if (bad) atomicCAS(&ctrl->err, 0, -13);
-  if (!rows_mode) return;
+  if (!(rows_mode & 1)) return;
   // ---- the k new R rows of this tile.  Each warp keeps to its own 16 columns of Ws (the ones it read
   // above), so overwriting them with W2 needs no block barrier ----
   __syncwarp();
@@ -1114,7 +1118,8 @@ extern "C" int qrdm_k_wreduce(const qrdm_prob* p, int j_host, int vt_grid, int s
 
 // T' and W2 = -T' W from the partial-W slots of k_vtc (bn = 128) or k_fused (bn = 64)
 extern "C" int qrdm_k_w2(const qrdm_prob* p, int j_host, int vt_grid, int stride, int bn_and_rows, void* stream) {
-  const int bn = bn_and_rows & 0xff0, rows_mode = bn_and_rows & 1;  // bit 0: also finish the k new R rows (deferred update)
+  // bit 0: also finish the k new R rows (deferred update); bit 1: use T instead of T' (apply Q, qrdm_b200_dormqr)
+  const int bn = bn_and_rows & 0xff0, rows_mode = bn_and_rows & 3;
   trailing_attrs();
   cudaStream_t s = (cudaStream_t)stream;
   const int ncmax = p->n - j_host - 1;
@@ -1223,4 +1228,34 @@ extern "C" int qrdm_k_flush(const qrdm_prob* p, int j_host, void* stream) {
   q.pend = 1;
   q.vc = p->vc_prev;
   return qrdm_k_rankk(&q, j_host, stream);
+}
+
+// ---- Q application (qrdm_b200_dormqr*): the block reflector of columns j0 .. j0+k-1 of an already factored
+// matrix is rebuilt as the clean copy Vc (unit diagonal, zeros above, zero-padded to 8 columns) and ctrl is
+// pointed at that block, after which the trailing kernels above apply it to any m x n matrix C.
+__global__ void __launch_bounds__(256) k_vc_build(qrdm_prob P, const double* af, int ldf, int j0, int k) {
+  const int q = blockIdx.y;  // < kpad
+  if (blockIdx.x == 0 && q == 0 && threadIdx.x == 0) {
+    qrdm_ctrl* c = P.ctrl;
+    c->j = j0; c->fjb = k; c->fjb_cmp = k;
+  }
+  const int jal = j0 & ~(QRDM_ROWALIGN - 1);
+  const int r = jal + blockIdx.x * 256 + threadIdx.x;
+  if (r >= P.m) return;
+  double v = 0.0;
+  if (q < k) {
+    if (r == j0 + q) v = 1.0;
+    else if (r > j0 + q) v = af[(size_t)(j0 + q) * ldf + r];
+  }
+  P.vc[(size_t)q * P.ldv + r] = v;
+}
+
+extern "C" int qrdm_k_vc_build(const qrdm_prob* p, const double* d_af, int ldf, int j0, int k, void* stream) {
+  const int kpad = (k + 7) & ~7;
+  const int jal = j0 & ~(QRDM_ROWALIGN - 1);
+  const int rows = p->m - jal;
+  if (rows <= 0 || k <= 0) return 0;
+  k_vc_build<<<dim3((rows + 255) / 256, kpad), 256, 0, (cudaStream_t)stream>>>(*p, d_af, ldf, j0, k);
+  QRDM_LAUNCH_CHECK();
+  return 0;
 }

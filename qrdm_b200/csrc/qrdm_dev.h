@@ -121,12 +121,13 @@ int qrdm_k_wreduce(const qrdm_prob *p, int j_host, int vt_grid, int stride, void
 int qrdm_k_trailing_finish(const qrdm_prob *p, int j_host, int vt_grid, int stride, void *stream);
 /* deferred trailing update: pass 2 of the pending block fused into pass 1 of the current one */
 int qrdm_k_fused(const qrdm_prob *p, int j_host, int *stride_out, int *grid_out, void *stream);
-int qrdm_k_w2(const qrdm_prob *p, int j_host, int vt_grid, int stride, int bn, void *stream); /* T', W2 = -T'W */
+int qrdm_k_w2(const qrdm_prob *p, int j_host, int vt_grid, int stride, int bn_and_flags, void *stream); /* T', W2 = -T'W; bn | 1: + R rows, | 2: use T */
 int qrdm_k_rankk(const qrdm_prob *p, int j_host, void *stream);    /* pass 2 alone */
 int qrdm_k_rowupd(const qrdm_prob *p, int j_host, void *stream);   /* the k new R rows of the trailing columns */
 int qrdm_k_colupd(const qrdm_prob *p, int mode, int j_host, void *stream); /* 0: eager set, 1: flagged-norm list */
 int qrdm_k_norm_update_lazy(const qrdm_prob *p, int j_host, void *stream);
 int qrdm_k_flush(const qrdm_prob *p, int j_host, void *stream);    /* apply a pending block to the whole trailing matrix */
+int qrdm_k_vc_build(const qrdm_prob *p, const double *d_af, int ldf, int j0, int k, void *stream); /* Vc + ctrl of one block of a factored matrix */
 int qrdm_k_skinny_update(const qrdm_prob *p, int rows_hint, void *stream); /* tall panel: sub-panel -> rest of panel */
 int qrdm_k_skinny_part(const qrdm_prob *p, int rows_hint, void *stream);   /* row-sharded: before the all-reduce */
 int qrdm_k_skinny_finish(const qrdm_prob *p, int rows_hint, void *stream); /* row-sharded: after it */
