@@ -91,6 +91,23 @@ def dormqr(F, tau, Cm, k=None, trans="N"):
     return int(info), Cm
 
 
+def low_rank(F, tau, k=0):
+    """Rank-k approximation from a rank-revealing factorisation, the reference's ``auxil.low_rank``
+    (auxil.py:156-200) with the Q application on the GPU:  A P ~ A_k = Q [R11 R12; 0 0], R11 k x k.
+    F, tau: outputs of dgeqrdm (column-major convention); k = 0 or k > min(m, n) means min(m, n).
+    Returns A_k (m x n, columns in pivoted order)."""
+    F = np.asfortranarray(F, dtype=np.float64)
+    m, n = F.shape
+    if k == 0 or k > min(m, n):
+        k = min(m, n)
+    R = np.zeros((m, n), order="F")
+    R[:k, :] = np.triu(F)[:k, :]
+    info, Ak = dormqr(F, tau, R, k=k, trans="N")
+    if info != 0:
+        raise RuntimeError(f"qrdm_b200_dormqr failed: info={info}")
+    return Ak
+
+
 def dormqr_device(trans, m, n, k, dA, lda, d_tau, dC, ldc, stream=None):
     """Device-resident Q application (``qrdm_b200_dormqr_dev``): torch CUDA tensors or raw device pointers."""
     def ptr(x):

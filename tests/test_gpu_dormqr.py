@@ -106,3 +106,31 @@ def test_checkqr_at_full_size_on_device(m, n, q):
     print(f"checkQR {m}x{n}: residual {res:.2e} orthogonality {orth:.2e} (tol {tol:.2e}); Q R formed in "
           f"{st['ms_total']:.1f} ms = {st['trailing_flops'] / st['ms_total'] / 1e9:.1f} TFLOP/s")
     assert res <= tol and orth <= tol, (res, orth, tol)
+
+
+def test_low_rank_matches_host_evaluation(q):
+    """auxil.low_rank (reference auxil.py:156-200) with the GPU Q application: A_k = Q [R11 R12; 0 0]; its error
+    against A P is ||R22||, and it agrees with the LAPACK evaluation of the same product."""
+    A = g.graded(256, seed=1)                       # numerical rank 127
+    out = q.dgeqrdm(A)
+    k = 100
+    Ak = q.low_rank(out["A"], out["tau"], k)
+    R = np.zeros_like(A, order="F")
+    R[:k, :] = np.triu(out["A"])[:k, :]
+    exp = _lapack_ormqr(out["A"], out["tau"], R, k, "N")
+    assert np.linalg.norm(Ak - exp) <= 50 * 256 * parity.EPS * np.linalg.norm(A)
+    AP = A[:, out["jpvt"] - 1]
+    R22 = np.triu(out["A"])[k:, k:]
+    assert abs(np.linalg.norm(AP - Ak) - np.linalg.norm(R22)) <= 1e-10 * np.linalg.norm(A)
+
+
+def test_nb1_is_column_pivoted_qr(q):
+    """With one candidate per iteration (nb = 1) Deviation Maximisation degenerates to classical column pivoting:
+    the pivots and |diag R| of LAPACK dgeqp3 (the reference wrapper's QP3, QRDM_wrapper.c:15-41)."""
+    A = g.gaussian(300, 200, seed=8)
+    out = q.dgeqrdm(A, nb=1)
+    assert out["info"] == 0 and int(out["ncols"].sum()) == 200 and out["ncols"][:200].max() == 1
+    qr, jp, tau, _, info = sla.lapack.dgeqp3(np.asfortranarray(A))
+    assert info == 0
+    assert np.array_equal(out["jpvt"], jp)
+    assert np.allclose(np.abs(np.diag(out["A"])), np.abs(np.diag(qr)), rtol=1e-10, atol=0)
