@@ -641,10 +641,8 @@ int dgeqrdm_dev_sharded(int m_local, int m_global, int row0, int nranks, int n, 
 }
 
 /* ---- batched mode: `batch` independent m x n matrices, matrix b at
- * a + b*stride_a (column-major, lda), outputs at jpvt + b*n, tau + b*min(m,n), ncols + b*n.
- * Round 1: the whole batch is made device-resident with one H2D, then factored one matrix after
- * the other by the single-matrix driver (launch-latency bound for small matrices — the planned
- * replacement is one persistent CTA-cluster per matrix); multi-GPU = each rank passes its share. ---- */
+ * a + b*stride_a (column-major, lda), outputs at jpvt + b*n, tau + b*min(m,n), ncols + b*n;
+ * multi-GPU = each rank passes its share (independent units, no collective). ---- */
 /* Batched mode (BASELINE configs[4]): matrices with m, n <= 1024 run as ONE launch with one
  * CTA per matrix (k_small.cu); larger ones fall back to a loop over the one-matrix path. */
 int dgeqrdm_batched_dev(int batch, int m, int n, double *d_a, int lda, long long stride_a, int *d_jpvt,

@@ -64,6 +64,31 @@ def test_no_cpu_fallback(lib, capfd):
     assert "CUDA error" in capfd.readouterr().err
 
 
+def _ormqr(lib, trans, m, n, k, lda=None, ldc=None):
+    a = np.zeros((max(m, 1), max(k, 1)), order="F")
+    c = np.zeros((max(m, 1), max(n, 1)), order="F")
+    tau = np.zeros(max(k, 1))
+    return lib.qrdm_b200_dormqr(trans, m, n, k, a.ctypes.data, m if lda is None else lda, tau.ctypes.data,
+                                c.ctypes.data, m if ldc is None else ldc)
+
+
+@pytest.mark.parametrize("kw", [dict(trans=b"N", m=0, n=4, k=0), dict(trans=b"N", m=4, n=0, k=2),
+                                dict(trans=b"N", m=4, n=4, k=5), dict(trans=b"T", m=4, n=4, k=2, lda=3),
+                                dict(trans=b"T", m=4, n=4, k=2, ldc=3)])
+def test_dormqr_argument_errors(lib, kw, capfd):
+    """The Q application (include/qrdm_b200.h) checks its arguments before touching the device."""
+    assert _ormqr(lib, **kw) == -1
+    capfd.readouterr()
+
+
+def test_dormqr_has_no_cpu_fallback(lib, capfd):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    assert _ormqr(lib, b"N", 8, 8, 4) == -100
+    capfd.readouterr()
+
+
 def test_product_never_imports_oracle():
     """The shipped package must not reference oracle/ (parity claims are void otherwise)."""
     pkg = os.path.join(ROOT, "qrdm_b200")
