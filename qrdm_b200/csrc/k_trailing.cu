@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(RK_THREADS, 2) k_rankk(qrdm_prob P) {
     else if (tid - 64 < ncand) { const int off = ctrl->cand[tid - 64]; col = off >= 64 ? jn + off : -1; }
     if (col >= 0) {
       if (blockIdx.x == 0) P.upd_eager[col] = P.stamp;
-      if (P.upd_flag[col] == P.stamp || col < c0p) col = -1;  // done by k_colupd<1> / leftover panel column
+      if (P.upd_flag[col] == P.stamp || col < c0p) col = -1;  // done by k_colupd / leftover panel column
     }
     slist[tid] = col;
     __syncthreads();
@@ -680,8 +680,8 @@ __global__ void __launch_bounds__(256) k_wreduce(qrdm_prob P, int vt_grid, int w
 // 4k FLOPs = 16 flop/B at k = 64, against 8 flop/B for k_rankk alone, whose mixed read+write
 // stream bound it at 65% DMMA-active).  The columns the next selection touches (leading 64
 // positions, the candidates, columns whose norm is recomputed exactly) were brought up to date
-// eagerly by k_colupd and carry the block's stamp in upd_eager / upd_flag: their W2 column reads
-// as zero here.  The k new R rows were finished by k_rowupd; rows < j are never stored.
+// eagerly (k_rankk<., LIST>, k_colupd) and carry the block's stamp in upd_eager / upd_flag: their W2 column reads
+// as zero here.  The k new R rows were finished by k_wapply (rows mode); rows < j are never stored.
 //
 // Two 4-warp CTAs per SM; a unit is a 32-row chunk of a 64-column tile; warp w owns columns
 // 16w..16w+15 of the tile.  C goes global -> registers in DMMA fragment layout (prefetched one unit
@@ -935,63 +935,21 @@ __global__ void __launch_bounds__(FU_THREADS, 2) k_fused(qrdm_prob P, int wslot_
   else fused_body<VEC16, false>(P, ge, wslot_stride_cols, sm);
 }
 
-// The k new R rows of the trailing columns, finished right after W2 is known (the norm downdate
-// needs them before the next selection):  C[j:j+k, c] += V[j:j+k, :] W2[:, c].  Also records the
-// pending block in ctrl.  16 columns per CTA, thread <-> (row, 4 columns).
-__global__ void __launch_bounds__(256) k_rowupd(qrdm_prob P) {
-  __shared__ double Vt[64 * 65];  // [q][r]
-  __shared__ double Ws[64 * 17];  // [q][c]
-  qrdm_ctrl* ctrl = P.ctrl;
-  const int j = ctrl->j, fjb = ctrl->fjb, k = ctrl->fjb_cmp;
-  const int nc = P.n - j - fjb, tid = threadIdx.x;
-  if (blockIdx.x == 0 && tid == 0) { ctrl->pend_k = k; ctrl->pend_c0 = j + fjb; ctrl->pend_r0 = j + k; }
-  const int cb = blockIdx.x * 16;
-  if (k <= 0 || cb >= nc) return;
-  for (int e = tid; e < 64 * 64; e += 256) {
-    const int q = e >> 6, r = e & 63;
-    Vt[q * 65 + r] = (q < k && r < k && j + r < P.m) ? P.vc[(size_t)q * P.ldv + j + r] : 0.0;
-  }
-  for (int e = tid; e < 64 * 16; e += 256) {
-    const int q = e >> 4, c = e & 15;
-    Ws[q * 17 + c] = (q < k && cb + c < nc) ? P.w2[(size_t)q * P.ldw + cb + c] : 0.0;
-  }
-  __syncthreads();
-  const int r = tid & 63, cg = tid >> 6;
-  if (r >= k || j + r >= P.m) return;
-  double acc[4];
-#pragma unroll
-  for (int x = 0; x < 4; ++x) acc[x] = 0.0;
-  for (int q = 0; q < k; ++q) {
-    const double v = Vt[q * 65 + r];
-#pragma unroll
-    for (int x = 0; x < 4; ++x) acc[x] = fma(v, Ws[q * 17 + cg + 4 * x], acc[x]);
-  }
-#pragma unroll
-  for (int x = 0; x < 4; ++x) {
-    const int c = cb + cg + 4 * x;
-    if (c < nc) P.a[(size_t)(j + fjb + c) * P.lda + j + r] += acc[x];
-  }
-}
-
-// Eager completion of the pending update on a short list of columns (rows >= pend_r0), plain FMA:
-//   MODE 0  the leading min(64, cols) positions of the new trailing matrix + the candidates chosen
-//           by k_select (everything the Gram / pick / permutation / panel of the next iteration touches)
-//   MODE 1  the columns whose partial norm is about to be recomputed exactly (flag_list)
-// A finished column gets the block's stamp (upd_eager / upd_flag) so that nobody applies it twice.
-// Thread <-> row (its row of V_prev in registers), 8 list entries per CTA column group.
+// Completion of the pending update (rows >= pend_r0) on the columns whose partial norm is about to be recomputed
+// exactly (flag_list of k_norm_update: any length, usually empty), plain FMA.  A finished column gets the block's
+// stamp in upd_flag so that nobody applies the update twice.  (The other eager set — leading positions +
+// candidates — goes through the DMMA kernel, k_rankk<., LIST>.)
+// Thread <-> row (its row of the pending V in registers), 8 list entries per CTA column group.
 #define CU_ROWS 128
 #define CU_GROUP 8
-template <int MODE>
 __global__ void __launch_bounds__(CU_ROWS) k_colupd(qrdm_prob P) {
   __shared__ __align__(16) double Wc[CU_GROUP][64];
   __shared__ int colof[CU_GROUP];
   const qrdm_ctrl* ctrl = P.ctrl;
   const int tid = threadIdx.x;
   const int kprev = ctrl->pend_k, c0p = ctrl->pend_c0, r0p = ctrl->pend_r0;
-  if (kprev <= 0) return;
-  const int jn = ctrl->j;  // MODE 0 runs after k_select: the new first column
-  const int cols = P.n - jn;
-  const int nlist = MODE == 0 ? 64 + ctrl->nc : ctrl->nflag;
+  const int nlist = ctrl->nflag;
+  if (kprev <= 0 || nlist <= 0) return;
   const int ngroups = (nlist + CU_GROUP - 1) / CU_GROUP;
   const int r = r0p + blockIdx.x * CU_ROWS + tid;
   const bool rok = r < P.m;
@@ -1001,20 +959,8 @@ __global__ void __launch_bounds__(CU_ROWS) k_colupd(qrdm_prob P) {
     __syncthreads();
     if (tid < CU_GROUP) {
       const int e = gi * CU_GROUP + tid;
-      int col = -1;
-      if (e < nlist) {
-        if (MODE == 1) col = P.flag_list[e];
-        else if (e < 64) col = e < cols ? jn + e : -1;
-        else { const int off = ctrl->cand[e - 64]; col = off >= 64 ? jn + off : -1; }
-      }
-      if (col >= 0) {
-        if (MODE == 0) {
-          if (blockIdx.x == 0) P.upd_eager[col] = P.stamp;
-          if (P.upd_flag[col] == P.stamp) col = -1;  // already done by the MODE 1 launch of this block
-        } else if (blockIdx.x == 0) {
-          P.upd_flag[col] = P.stamp;
-        }
-      }
+      int col = e < nlist ? P.flag_list[e] : -1;
+      if (col >= 0 && blockIdx.x == 0) P.upd_flag[col] = P.stamp;
       if (col >= 0 && col - c0p < 0) col = -1;  // leftover panel column: nothing pending
       colof[tid] = col;
     }
@@ -1189,13 +1135,6 @@ extern "C" int qrdm_k_fused(const qrdm_prob* p, int j_host, int* stride_out, int
   return 0;
 }
 
-extern "C" int qrdm_k_rowupd(const qrdm_prob* p, int j_host, void* stream) {
-  const int ncmax = p->n - j_host - 1;
-  k_rowupd<<<ncmax > 0 ? (ncmax + 15) / 16 : 1, 256, 0, (cudaStream_t)stream>>>(*p);
-  QRDM_LAUNCH_CHECK();
-  return 0;
-}
-
 // j_host: first column of the iteration that created the pending block (rows >= j_host + 1 may be active).
 // Called in that same iteration, so the block's V is still the "current" buffer p->vc.
 extern "C" int qrdm_k_colupd(const qrdm_prob* p, int mode, int j_host, void* stream) {
@@ -1213,7 +1152,7 @@ extern "C" int qrdm_k_colupd(const qrdm_prob* p, int mode, int j_host, void* str
   } else {          // flagged-norm list (arbitrary length, usually empty): FMA kernel
     const int gx = (rows + CU_ROWS - 1) / CU_ROWS;
     q.vc_prev = p->vc;
-    k_colupd<1><<<dim3(gx, gx >= 64 ? 4 : 16), CU_ROWS, 0, (cudaStream_t)stream>>>(q);
+    k_colupd<<<dim3(gx, gx >= 64 ? 4 : 16), CU_ROWS, 0, (cudaStream_t)stream>>>(q);
   }
   QRDM_LAUNCH_CHECK();
   return 0;

@@ -53,7 +53,7 @@ typedef struct qrdm_ctrl {
   int cyc_start[QRDM_MAXPOS + 1];
   int cyc_pos[QRDM_MAXPOS];   /* cycle c: new[p_k] = old[p_{k+1}], new[p_last] = old[p_0] */
   /* deferred ("lazy") trailing update: block reflector whose pass 2 has not been applied to the bulk
-   * of the trailing matrix yet (written by k_rowupd, read by k_fused / k_colupd / the flush) */
+   * of the trailing matrix yet (written by k_wapply in rows mode, read by k_fused / k_colupd / k_rankk<list> / the flush) */
   int pend_k;   /* reflectors of the pending block */
   int pend_c0;  /* first column the pending update applies to (= j + fjb of its iteration) */
   int pend_r0;  /* first row still to be updated (= j + k of its iteration: the k new R rows are done) */
@@ -123,8 +123,7 @@ int qrdm_k_trailing_finish(const qrdm_prob *p, int j_host, int vt_grid, int stri
 int qrdm_k_fused(const qrdm_prob *p, int j_host, int *stride_out, int *grid_out, void *stream);
 int qrdm_k_w2(const qrdm_prob *p, int j_host, int vt_grid, int stride, int bn_and_flags, void *stream); /* T', W2 = -T'W; bn | 1: + R rows, | 2: use T */
 int qrdm_k_rankk(const qrdm_prob *p, int j_host, void *stream);    /* pass 2 alone */
-int qrdm_k_rowupd(const qrdm_prob *p, int j_host, void *stream);   /* the k new R rows of the trailing columns */
-int qrdm_k_colupd(const qrdm_prob *p, int mode, int j_host, void *stream); /* 0: eager set, 1: flagged-norm list */
+int qrdm_k_colupd(const qrdm_prob *p, int mode, int j_host, void *stream); /* 0: eager set (DMMA, gathered), 1: flagged-norm list (FMA) */
 int qrdm_k_norm_update_lazy(const qrdm_prob *p, int j_host, void *stream);
 int qrdm_k_flush(const qrdm_prob *p, int j_host, void *stream);    /* apply a pending block to the whole trailing matrix */
 int qrdm_k_vc_build(const qrdm_prob *p, const double *d_af, int ldf, int j0, int k, void *stream); /* Vc + ctrl of one block of a factored matrix */

@@ -1,4 +1,4 @@
-"""GPU suite, deferred trailing update (k_fused / k_rowupd / k_colupd / flush).
+"""GPU suite, deferred trailing update (k_fused / k_wapply rows mode / k_rankk<list> / k_colupd / flush).
 
 By default the deferred path only engages while the trailing matrix has >= 7168^2 elements, so the
 small fixtures of test_gpu_parity.py never reach it.  Here QRDM_B200_LAZY_MIN=1 forces it from the
