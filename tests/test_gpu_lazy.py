@@ -122,3 +122,44 @@ def test_deferred_bitwise_determinism(q, forced_lazy):
     a = q.dgeqrdm(A)
     b = q.dgeqrdm(A)
     assert np.array_equal(a["A"], b["A"]) and np.array_equal(a["jpvt"], b["jpvt"]) and np.array_equal(a["tau"], b["tau"])
+
+
+def test_deferred_device_entry_point_odd_lda(q, oracle_ref, forced_lazy):
+    """Odd leading dimension on the device with the deferred schedule forced on: k_fused<false> and
+    k_rankk<false, LIST> (8-byte copies, scalar C loads/stores); the padding rows must stay untouched."""
+    import torch
+    for (m, n, lda) in [(300, 210, 301), (1100, 700, 1103), (640, 900, 641)]:
+        A = g.gaussian(m, n, 40 + m)
+        buf = torch.full((n, lda), 3.25, dtype=torch.float64, device="cuda")
+        buf[:, :m] = torch.from_numpy(np.ascontiguousarray(A.T)).cuda()
+        d_jpvt = torch.zeros(n, dtype=torch.int32, device="cuda")
+        d_tau = torch.zeros(min(m, n), dtype=torch.float64, device="cuda")
+        info, ncols = q.dgeqrdm_device(buf, m, n, lda, d_jpvt, d_tau)
+        assert info == 0
+        out = buf.cpu().numpy()
+        assert np.all(out[:, m:] == 3.25)
+        got = dict(info=info, A=out[:, :m].T, jpvt=d_jpvt.cpu().numpy(), tau=d_tau.cpu().numpy(), ncols=ncols)
+        parity.check_against(got, oracle_ref.ref_dgeqrdm(A), (m, n))
+        res, orth = parity.qr_invariants(A, got)
+        tol = parity.invariant_tol(A.shape)
+        assert res <= tol and orth <= tol, (res, orth, tol)
+
+
+def test_deferred_dormqr_device_odd_ldc(q):
+    """Q application with an odd leading dimension of C on the device (non-vectorised K6 paths)."""
+    import scipy.linalg as sla
+    import torch
+    m, n, p, ldc = 500, 300, 77, 501
+    rng = np.random.default_rng(5)
+    F, tau, _, info = sla.lapack.dgeqrf(np.asfortranarray(rng.standard_normal((m, n))))
+    Cm = rng.standard_normal((m, p))
+    dF = torch.from_numpy(np.ascontiguousarray(F.T)).cuda()
+    dtau = torch.from_numpy(tau).cuda()
+    dC = torch.full((p, ldc), -1.5, dtype=torch.float64, device="cuda")
+    dC[:, :m] = torch.from_numpy(np.ascontiguousarray(Cm.T)).cuda()
+    assert q.dormqr_device("N", m, p, n, dF, m, dtau, dC, ldc) == 0
+    out = dC.cpu().numpy()
+    assert np.all(out[:, m:] == -1.5)
+    lw = int(sla.lapack.dormqr("L", "N", F, tau, np.asfortranarray(Cm), -1)[1][0])
+    exp = sla.lapack.dormqr("L", "N", F, tau, np.asfortranarray(Cm), lw)[0]
+    assert np.linalg.norm(out[:, :m].T - exp) <= 50 * m * parity.EPS * np.linalg.norm(Cm)
