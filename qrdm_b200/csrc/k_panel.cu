@@ -669,17 +669,17 @@ extern "C" int qrdm_k_panel(const qrdm_prob* p, int j_host, void* stream) {
   // both proportional to the CTA count; grow the grid only when the slab would not fit in smem
   const int gmax = p->sm_count < QRDM_PANEL_MAXCTA ? p->sm_count : QRDM_PANEL_MAXCTA;
   if (rows <= 256 * gmax && !getenv("QRDM_PANEL_NOREG")) {  // register-resident slabs, 128 (or 256) rows per CTA
-    // Rows per CTA (32 x RI).  Per-column cost measured on B200 (panel ms / columns, square Gaussian inputs):
-    //   1000 rows: 2.75 / 2.96 / 3.38 us for RI = 1 / 2 / 4;  4096 rows: 3.83 / 3.30 / 3.46;  8192 rows: RI = 4 beats 2
-    //   by 7%;  16384 rows: 4.7 us with RI = 4 (123 CTAs), 5.8 us with RI = 8.
-    // i.e. ~0.23 us per RI (the in-CTA sweep) + ~0.012 us per CTA beyond 16 (LL reduce-scatter / broadcast fan-in).
+    // Rows per CTA (32 x RI).  Per-column cost measured on B200 (panel ms / columns, square Gaussian inputs, after
+    // the one-round-trip gather): 2500 rows 3.12 / 3.25 / 3.68 us for RI = 1 / 2 / 4; 4096 rows 3.34 / 3.24 / 3.77;
+    // 8192 rows RI = 2 beats RI = 4 by 7%; 16384 rows 4.1 us with RI = 4 (123 CTAs), RI = 8 is 25% slower.
+    // i.e. ~0.25 us per RI (the in-CTA sweep) + ~0.0045 us per CTA (skew / fan-in of the LL exchange).
     int per = 256;
     {
       double best = 1e30;
       for (int ri = 1; ri <= 8; ri *= 2) {
         const int g = (rows + 32 * ri - 1) / (32 * ri);
         if (g > gmax) continue;
-        const double cost = 0.23 * ri + 0.012 * (g > 16 ? g - 16 : 0);
+        const double cost = 0.25 * ri + 0.0045 * g;
         if (cost < best) { best = cost; per = 32 * ri; }
       }
       static const char* e = getenv("QRDM_PANEL_PER");  // experiment switch
