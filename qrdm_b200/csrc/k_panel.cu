@@ -375,8 +375,9 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_reg(qrdm_prob P, int
     if (len > 1) {
       if (i > 0 && xn2 < thres2) { k = i; break; }  // DM early stop: column i left untouched
       // Only the warps that consume the scalars compute them: warps 0-1 (wv, tau), the owner of column i
-      // (scale, beta) and, in column 0, everybody (thres2 needs beta).  512 threads doing an FP64 sqrt and
-      // two divisions each cost 3500 cycles per column on the FP64 pipe (QRDM_B200_DEBUG=8 phase counts).
+      // (scale, beta) and, in column 0, everybody (thres2 needs beta).  The chain itself costs ~350 cycles
+      // (measured by running it twice); the 2.5-3.5 k cycles QRDM_B200_DEBUG=8 books under "scalars" are the
+      // broadcast wait: a clock read right after __syncthreads captures the barrier's ISSUE, not its release.
       if (xn2 != 0.0 && (i == 0 || wid < 2 || wid == (i & 15))) {
         const double h = sqrt(fma(alpha, alpha, xn2));
         beta = (alpha >= 0.0) ? -h : h;
