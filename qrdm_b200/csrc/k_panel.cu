@@ -21,6 +21,7 @@
 #define PANEL_WARPS (PANEL_THREADS / 32)
 #define PANEL_CPW ((63 + PANEL_WARPS - 1) / PANEL_WARPS)  // columns per warp in the sweep
 #define PANEL_RG (PANEL_THREADS / 64)                      // reduction groups
+#define QRDM_PANEL_AG_GAIN 0.45                            // us per column saved by the one-hop exchange (G <= 32), measured
 
 // Cross-CTA exchange without barriers: every value travels as a 16-byte "LL" packet
 // {lo32, tag, hi32, tag} (the scheme NCCL's low-latency protocol uses): an aligned 8-byte store is
@@ -66,6 +67,31 @@ __device__ __forceinline__ double ll_gather_sum(const LLPacket* base, size_t str
 #pragma unroll
   for (int u = 0; u < MAXU; ++u) {
     const int c = lane + 32 * u;
+    if (c < G) {
+      while (t0[u] != tag || t1[u] != tag)
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];\n"
+                     : "=r"(lo[u]), "=r"(t0[u]), "=r"(hi[u]), "=r"(t1[u]) : "l"(base + (size_t)c * stride) : "memory");
+      v += __longlong_as_double((long long)(((unsigned long long)hi[u] << 32) | lo[u]));
+    }
+  }
+  return v;
+}
+
+// all-gather variant: partials of CTAs start, start+step, ... (<= 5 of them), loads issued together
+__device__ __forceinline__ double ll_gather_sum_strided(const LLPacket* base, size_t stride, int start, int step, int G, unsigned tag) {
+  constexpr int MAXU = 5;
+  unsigned lo[MAXU], t0[MAXU], hi[MAXU], t1[MAXU];
+#pragma unroll
+  for (int u = 0; u < MAXU; ++u) {
+    const int c = start + step * u;
+    if (c < G)
+      asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];\n"
+                   : "=r"(lo[u]), "=r"(t0[u]), "=r"(hi[u]), "=r"(t1[u]) : "l"(base + (size_t)c * stride) : "memory");
+  }
+  double v = 0.0;
+#pragma unroll
+  for (int u = 0; u < MAXU; ++u) {
+    const int c = start + step * u;
     if (c < G) {
       while (t0[u] != tag || t1[u] != tag)
         asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];\n"
@@ -286,9 +312,15 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(qrdm_prob P, int rpc
 // scalars are computed once per warp with a single sqrt (beta^2 = alpha^2 + ||x||^2, stop test on
 // ||x||^2 < thres^2), and the exchange stays the LL reduce-scatter + broadcast of the kernel above.
 // RI = rows per lane: 1, 2, 4 or 8 (32 ... 256 rows per CTA); the launcher picks the cheapest that fits
+// Exchange per column: G <= 32 (allgather != 0): every CTA totals all columns itself from the G partial packets
+// — ONE cross-CTA hop; larger grids: reduce-scatter to CTA (jj mod G) + broadcast — two hops, G*64 instead
+// of G*G*64 packets per column.
 template <int RI>
-__global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_reg(qrdm_prob P, int rpc, unsigned epoch) {
+__global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_reg(qrdm_prob P, int rpc_and_mode, unsigned epoch) {
+  const int rpc = rpc_and_mode & 0xffffff;
+  const bool allgather = (rpc_and_mode >> 24) != 0;
   __shared__ double sred[PANEL_WARPS];
+  __shared__ double red[7][64];
   __shared__ double S_[64], rowv[64], wv[64];
   __shared__ double vbuf[32 * RI], xbuf[32 * RI];
   qrdm_ctrl* ctrl = P.ctrl;
@@ -349,6 +381,24 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_reg(qrdm_prob P, int
     const int cur = i & 1, nxt = cur ^ 1;
     const unsigned tag = tag_base + i + 1;
     long long tq0 = timing ? clock64() : 0;
+    if (allgather) {
+      // ---- one hop: thread (jj, grp) sums the partials of CTAs grp, grp+7, ... (<= 5) of column jj; threads
+      // 448..511 pick up the pivot row meanwhile; 64 threads then add the 7 group sums in fixed order.  Every
+      // CTA adds the same packets in the same order => bit-identical totals (and decisions) everywhere ----
+      const int jj = tid & 63, grp = tid >> 6;
+      if (grp < 7) {
+        double v = 0.0;
+        if (jj >= i && jj < fjb)
+          v = ll_gather_sum_strided(&part[(size_t)cur * QRDM_PANEL_MAXCTA * 64 + jj], 64, grp, 7, G, tag);
+        red[grp][jj] = v;
+      } else if (jj >= i && jj < fjb) {
+        rowv[jj] = ll_load(&bcast[cur * 128 + 64 + jj], tag);
+      }
+      __syncthreads();
+      if (tid < 64 && tid >= i && tid < fjb)
+        S_[tid] = (((((red[0][tid] + red[1][tid]) + red[2][tid]) + red[3][tid]) + red[4][tid]) + red[5][tid]) + red[6][tid];
+      if (timing) { const long long tq = clock64(); tph[0] += tq - tq0; tq0 = tq; }
+    } else {
     // ---- reduce-scatter: column jj is totalled by warp (jj - i - off) / G of CTA jj mod G, so a small
     // grid (few rows) spreads its columns over the warps instead of looping over them; lanes <-> CTAs,
     // fixed association order, no block barrier ----
@@ -365,6 +415,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_reg(qrdm_prob P, int
         const double v = ll_load(&bcast[cur * 128 + tid], tag);
         if (tid < 64) S_[jj] = v; else rowv[jj] = v;
       }
+    }
     }
     __syncthreads();
     if (timing) { const long long tq = clock64(); tph[1] += tq - tq0; tq0 = tq; }
@@ -673,14 +724,17 @@ extern "C" int qrdm_k_panel(const qrdm_prob* p, int j_host, void* stream) {
     // Rows per CTA (32 x RI).  Per-column cost measured on B200 (panel ms / columns, square Gaussian inputs, after
     // the one-round-trip gather): 2500 rows 3.12 / 3.25 / 3.68 us for RI = 1 / 2 / 4; 4096 rows 3.34 / 3.24 / 3.77;
     // 8192 rows RI = 2 beats RI = 4 by 7%; 16384 rows 4.1 us with RI = 4 (123 CTAs), RI = 8 is 25% slower.
-    // i.e. ~0.25 us per RI (the in-CTA sweep) + ~0.0045 us per CTA (skew / fan-in of the LL exchange).
+    // i.e. ~0.25-0.3 us per RI (the in-CTA sweep) + ~0.0045 us per CTA (skew / fan-in of the LL exchange);
+    // grids of <= 32 CTAs use the one-hop exchange: 1000 rows 2.90 -> 2.44 us per column.
     int per = 256;
+    static const char* e_ag = getenv("QRDM_PANEL_AG");  // experiment switch: 0 disables the one-hop exchange
+    const bool ag_ok = e_ag && atoi(e_ag) != 0;  /* opt-in until the full GPU suite has run with it */
     {
       double best = 1e30;
       for (int ri = 1; ri <= 8; ri *= 2) {
         const int g = (rows + 32 * ri - 1) / (32 * ri);
         if (g > gmax) continue;
-        const double cost = 0.25 * ri + 0.0045 * g;
+        const double cost = 0.30 * ri + 0.0045 * g - ((ag_ok && g <= 32) ? QRDM_PANEL_AG_GAIN : 0.0);
         if (cost < best) { best = cost; per = 32 * ri; }
       }
       static const char* e = getenv("QRDM_PANEL_PER");  // experiment switch
@@ -690,6 +744,7 @@ extern "C" int qrdm_k_panel(const qrdm_prob* p, int j_host, void* stream) {
     static unsigned epoch_r = 0x400000;
     epoch_r = epoch_r + 1 >= 0x7fffff ? 0x400000 : epoch_r + 1;
     qrdm_prob prob_r = *p;
+    if (ag_ok && Gr <= 32) rpcr |= 1 << 24;  // one-hop exchange
     void* args_r[] = {(void*)&prob_r, (void*)&rpcr, (void*)&epoch_r};
     void* fn = per == 32 ? (void*)k_panel_reg<1> : per == 64 ? (void*)k_panel_reg<2> : per == 128 ? (void*)k_panel_reg<4> : (void*)k_panel_reg<8>;
     cudaError_t er = cudaLaunchCooperativeKernel(fn, dim3(Gr), dim3(PANEL_THREADS), args_r, 0, (cudaStream_t)stream);
