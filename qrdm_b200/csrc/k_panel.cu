@@ -315,12 +315,11 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(qrdm_prob P, int rpc
 // Exchange per column: G <= 32 (allgather != 0): every CTA totals all columns itself from the G partial packets
 // — ONE cross-CTA hop; larger grids: reduce-scatter to CTA (jj mod G) + broadcast — two hops, G*64 instead
 // of G*G*64 packets per column.
-template <int RI>
-__global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_reg(qrdm_prob P, int rpc_and_mode, unsigned epoch) {
-  const int rpc = rpc_and_mode & 0xffffff;
-  const bool allgather = (rpc_and_mode >> 24) != 0;
+template <int RI, bool AG>
+__global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_reg(qrdm_prob P, int rpc, unsigned epoch) {
+  constexpr bool allgather = AG;
   __shared__ double sred[PANEL_WARPS];
-  __shared__ double red[7][64];
+  __shared__ double red[AG ? 7 : 1][64];
   __shared__ double S_[64], rowv[64], wv[64];
   __shared__ double vbuf[32 * RI], xbuf[32 * RI];
   qrdm_ctrl* ctrl = P.ctrl;
@@ -728,7 +727,7 @@ extern "C" int qrdm_k_panel(const qrdm_prob* p, int j_host, void* stream) {
     // grids of <= 32 CTAs use the one-hop exchange: 1000 rows 2.90 -> 2.44 us per column.
     int per = 256;
     static const char* e_ag = getenv("QRDM_PANEL_AG");  // experiment switch: 0 disables the one-hop exchange
-    const bool ag_ok = e_ag && atoi(e_ag) != 0;  /* opt-in until the full GPU suite has run with it */
+    const bool ag_ok = !(e_ag && atoi(e_ag) == 0);
     {
       double best = 1e30;
       for (int ri = 1; ri <= 8; ri *= 2) {
@@ -744,9 +743,12 @@ extern "C" int qrdm_k_panel(const qrdm_prob* p, int j_host, void* stream) {
     static unsigned epoch_r = 0x400000;
     epoch_r = epoch_r + 1 >= 0x7fffff ? 0x400000 : epoch_r + 1;
     qrdm_prob prob_r = *p;
-    if (ag_ok && Gr <= 32) rpcr |= 1 << 24;  // one-hop exchange
+    const bool ag = ag_ok && Gr <= 32;  // one-hop exchange
     void* args_r[] = {(void*)&prob_r, (void*)&rpcr, (void*)&epoch_r};
-    void* fn = per == 32 ? (void*)k_panel_reg<1> : per == 64 ? (void*)k_panel_reg<2> : per == 128 ? (void*)k_panel_reg<4> : (void*)k_panel_reg<8>;
+    void* fn = ag ? (per == 32 ? (void*)k_panel_reg<1, true> : per == 64 ? (void*)k_panel_reg<2, true>
+                                 : per == 128 ? (void*)k_panel_reg<4, true> : (void*)k_panel_reg<8, true>)
+                  : (per == 32 ? (void*)k_panel_reg<1, false> : per == 64 ? (void*)k_panel_reg<2, false>
+                                 : per == 128 ? (void*)k_panel_reg<4, false> : (void*)k_panel_reg<8, false>);
     cudaError_t er = cudaLaunchCooperativeKernel(fn, dim3(Gr), dim3(PANEL_THREADS), args_r, 0, (cudaStream_t)stream);
     ++g_qrdm_launches;
     return er == cudaSuccess ? 0 : (int)er;
