@@ -12,8 +12,10 @@
 // CTAs take bit-identical decisions (stop test, tau) and the result is run-to-run deterministic.
 // Also emits the clean copy Vc of the reflectors (unit diagonal, zeros above, zero-padded to a
 // multiple of 8 columns) that the trailing-update kernels consume.
+#include <cooperative_groups.h>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -312,14 +314,19 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(qrdm_prob P, int rpc
 // scalars are computed once per warp with a single sqrt (beta^2 = alpha^2 + ||x||^2, stop test on
 // ||x||^2 < thres^2), and the exchange stays the LL reduce-scatter + broadcast of the kernel above.
 // RI = rows per lane: 1, 2, 4 or 8 (32 ... 256 rows per CTA); the launcher picks the cheapest that fits
-// Exchange per column: G <= 32 (allgather != 0): every CTA totals all columns itself from the G partial packets
-// — ONE cross-CTA hop; larger grids: reduce-scatter to CTA (jj mod G) + broadcast — two hops, G*64 instead
-// of G*G*64 packets per column.
-template <int RI, bool AG>
+// Exchange per column (MODE):
+//   1  G <= 32: every CTA totals all columns itself from the G partial packets — ONE cross-CTA hop;
+//   2  larger grids, thread-block clusters of PANEL_CL: the CTAs of a cluster first add their partials in the
+//      leader's shared memory (DSMEM stores + one cluster barrier), the leader publishes ONE packet per column,
+//      and every CTA totals the G/PANEL_CL (<= 35) cluster packets itself — one cluster barrier + one global hop;
+//   0  fallback: reduce-scatter to CTA (jj mod G) + broadcast — two global hops.
+#define PANEL_CL 4
+template <int RI, int MODE>
 __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_reg(qrdm_prob P, int rpc, unsigned epoch) {
-  constexpr bool allgather = AG;
+  constexpr bool allgather = MODE != 0;
   __shared__ double sred[PANEL_WARPS];
-  __shared__ double red[AG ? 7 : 1][64];
+  __shared__ double red[MODE != 0 ? 7 : 1][64];
+  __shared__ double cpart[MODE == 2 ? 2 : 1][MODE == 2 ? PANEL_CL : 1][64];  // leader's copy: [buf][rank][column]
   __shared__ double S_[64], rowv[64], wv[64];
   __shared__ double vbuf[32 * RI], xbuf[32 * RI];
   qrdm_ctrl* ctrl = P.ctrl;
@@ -333,6 +340,31 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_reg(qrdm_prob P, int
   LLPacket* part = reinterpret_cast<LLPacket*>(P.panel_part);
   LLPacket* bcast = reinterpret_cast<LLPacket*>(P.panel_row);
   const unsigned tag_base = epoch << 8;
+  // MODE 2: publishers are clusters; pub = index of this CTA's packet row, GP = number of packet rows to gather
+  const int crank = MODE == 2 ? (int)cooperative_groups::this_cluster().block_rank() : 0;
+  const int pub = MODE == 2 ? b / PANEL_CL : b, GP = MODE == 2 ? G / PANEL_CL : G;
+  double* cpart_leader = MODE == 2 ? cooperative_groups::this_cluster().map_shared_rank(&cpart[0][0][0], 0) : nullptr;
+  // publish the block sums acc[c] of columns wid + 16c (c < 4, columns > lo only) for exchange buffer `buf`
+  auto publish = [&](double (&acc)[4], int buf, int lo, unsigned ptag) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int jj = wid + 16 * c;
+      const double a = warp_sum(acc[c]);
+      if (lane == 0 && jj > lo && jj < fjb) {
+        if (MODE == 2) cpart_leader[((size_t)buf * PANEL_CL + crank) * 64 + jj] = a;
+        else ll_store(&part[((size_t)buf * QRDM_PANEL_MAXCTA + b) * 64 + jj], a, ptag);
+      }
+    }
+  };
+  // MODE 2, after the cluster barrier: the leader adds the 8 partials of every column and publishes them
+  auto publish_cluster = [&](int buf, int lo, unsigned ptag) {
+    if (MODE == 2 && crank == 0 && tid < 64 && tid > lo && tid < fjb) {
+      double t = 0.0;
+#pragma unroll
+      for (int r = 0; r < PANEL_CL; ++r) t += cpart[buf][r][tid];
+      ll_store(&part[((size_t)buf * QRDM_PANEL_MAXCTA + pub) * 64 + tid], t, ptag);
+    }
+  };
 
   double reg[RI][4];  // [ri][c]: row r0 + lane + 32*ri, column wid + 16*c
 #pragma unroll
@@ -363,13 +395,9 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_reg(qrdm_prob P, int
         }
       }
     }
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int jj = wid + 16 * c;
-      const double a = warp_sum(acc[c]);
-      if (lane == 0 && jj < fjb) ll_store(&part[(size_t)b * 64 + jj], a, tag_base + 1);
-    }
+    publish(acc, 0, -1, tag_base + 1);
   }
+  if (MODE == 2) { cooperative_groups::this_cluster().sync(); publish_cluster(0, -1, tag_base + 1); }
   __syncthreads();
 
   double thres2 = 5e-14 * 5e-14;  // (reference src/dgeqr2.c:40)^2
@@ -388,7 +416,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_reg(qrdm_prob P, int
       if (grp < 7) {
         double v = 0.0;
         if (jj >= i && jj < fjb)
-          v = ll_gather_sum_strided(&part[(size_t)cur * QRDM_PANEL_MAXCTA * 64 + jj], 64, grp, 7, G, tag);
+          v = ll_gather_sum_strided(&part[(size_t)cur * QRDM_PANEL_MAXCTA * 64 + jj], 64, grp, 7, GP, tag);
         red[grp][jj] = v;
       } else if (jj >= i && jj < fjb) {
         rowv[jj] = ll_load(&bcast[cur * 128 + 64 + jj], tag);
@@ -501,15 +529,11 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_reg(qrdm_prob P, int
           }
         }
       }
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int jj = wid + 16 * c;
-        const double a = warp_sum(acc[c]);
-        if (lane == 0 && jj > i && jj < fjb) ll_store(&part[((size_t)nxt * QRDM_PANEL_MAXCTA + b) * 64 + jj], a, tag + 1);
-      }
+      publish(acc, nxt, i, tag + 1);
     }
     if (timing) { const long long tq = clock64(); tph[3] += tq - tq0; tq0 = tq; }
-    __syncthreads();  // vbuf / xbuf / S_ / rowv / wv are rewritten by the next step
+    if (MODE == 2) { cooperative_groups::this_cluster().sync(); publish_cluster(nxt, i, tag + 1); }
+    else __syncthreads();  // vbuf / xbuf / S_ / rowv / wv are rewritten by the next step
     if (timing) { const long long tq = clock64(); tph[4] += tq - tq0; tq0 = tq; }
   }
   if (timing && j == 640)
@@ -720,35 +744,78 @@ extern "C" int qrdm_k_panel(const qrdm_prob* p, int j_host, void* stream) {
   // both proportional to the CTA count; grow the grid only when the slab would not fit in smem
   const int gmax = p->sm_count < QRDM_PANEL_MAXCTA ? p->sm_count : QRDM_PANEL_MAXCTA;
   if (rows <= 256 * gmax && !getenv("QRDM_PANEL_NOREG")) {  // register-resident slabs, 128 (or 256) rows per CTA
-    // Rows per CTA (32 x RI).  Per-column cost measured on B200 (panel ms / columns, square Gaussian inputs, after
-    // the one-round-trip gather): 2500 rows 3.12 / 3.25 / 3.68 us for RI = 1 / 2 / 4; 4096 rows 3.34 / 3.24 / 3.77;
-    // 8192 rows RI = 2 beats RI = 4 by 7%; 16384 rows 4.1 us with RI = 4 (123 CTAs), RI = 8 is 25% slower.
-    // i.e. ~0.25-0.3 us per RI (the in-CTA sweep) + ~0.0045 us per CTA (skew / fan-in of the LL exchange);
-    // grids of <= 32 CTAs use the one-hop exchange: 1000 rows 2.90 -> 2.44 us per column.
-    int per = 256;
-    static const char* e_ag = getenv("QRDM_PANEL_AG");  // experiment switch: 0 disables the one-hop exchange
+    static const char* e_ag = getenv("QRDM_PANEL_AG");  // experiment switches: 0 disables the one-hop exchange
+    static const char* e_cl = getenv("QRDM_PANEL_CL");  //                      0 disables the cluster exchange
     const bool ag_ok = !(e_ag && atoi(e_ag) == 0);
+    // clusters of PANEL_CL CTAs (MODE 2): how many CTAs can be co-resident as whole clusters (GPC granularity:
+    // 33 clusters of 4 = 132 CTAs on a 148-SM B200, only 15 clusters of 8); queried once
+    static int cl_max_ctas = -1;
+    static cudaLaunchAttribute cl_attrs[2];
+    if (cl_max_ctas < 0) {
+      cl_max_ctas = 0;
+      if (!(e_cl && atoi(e_cl) == 0)) {
+        cudaLaunchConfig_t q;
+        memset(&q, 0, sizeof(q));
+        q.gridDim = dim3(PANEL_CL); q.blockDim = dim3(PANEL_THREADS);
+        cl_attrs[0].id = cudaLaunchAttributeClusterDimension;
+        cl_attrs[0].val.clusterDim.x = PANEL_CL; cl_attrs[0].val.clusterDim.y = 1; cl_attrs[0].val.clusterDim.z = 1;
+        cl_attrs[1].id = cudaLaunchAttributeCooperative;
+        cl_attrs[1].val.cooperative = 1;
+        q.attrs = cl_attrs; q.numAttrs = 2;
+        int ncl = 0;
+        if (cudaOccupancyMaxActiveClusters(&ncl, (void*)k_panel_reg<4, 2>, &q) == cudaSuccess) cl_max_ctas = ncl * PANEL_CL;
+        (void)cudaGetLastError();
+        if (cl_max_ctas > 35 * PANEL_CL) cl_max_ctas = 35 * PANEL_CL;  // gather width of the MODE 2 kernel
+      }
+    }
+    // Rows per CTA (32 x RI) and exchange mode by a measured cost model (us per column, B200, square Gaussian
+    // inputs): ~0.3 per RI (the in-CTA sweep) + 0.0045 per CTA (skew / fan-in of the LL exchange); the one-hop
+    // exchange (<= 32 CTAs) saves 0.45 (1000 rows: 2.90 -> 2.44), the cluster exchange 0.3 (8192 rows: 3.58 -> 3.27).
+    int per = 256, mode = 0;
     {
       double best = 1e30;
       for (int ri = 1; ri <= 8; ri *= 2) {
         const int g = (rows + 32 * ri - 1) / (32 * ri);
         if (g > gmax) continue;
-        const double cost = 0.30 * ri + 0.0045 * g - ((ag_ok && g <= 32) ? QRDM_PANEL_AG_GAIN : 0.0);
-        if (cost < best) { best = cost; per = 32 * ri; }
+        const int gpad = (g + PANEL_CL - 1) / PANEL_CL * PANEL_CL;
+        const int md = (ag_ok && g <= 32) ? 1 : (gpad <= cl_max_ctas ? 2 : 0);
+        const double cost = 0.30 * ri + 0.0045 * g - (md == 1 ? 0.45 : md == 2 ? 0.30 : 0.0);
+        if (cost < best) { best = cost; per = 32 * ri; mode = md; }
       }
       static const char* e = getenv("QRDM_PANEL_PER");  // experiment switch
-      if (e) { const int v = atoi(e); if ((v == 32 || v == 64 || v == 128 || v == 256) && rows <= v * gmax) per = v; }
+      if (e) {
+        const int v = atoi(e);
+        if ((v == 32 || v == 64 || v == 128 || v == 256) && rows <= v * gmax) {
+          per = v;
+          const int g = (rows + v - 1) / v, gpad = (g + PANEL_CL - 1) / PANEL_CL * PANEL_CL;
+          mode = (ag_ok && g <= 32) ? 1 : (gpad <= cl_max_ctas ? 2 : 0);
+        }
+      }
     }
     int Gr = (rows + per - 1) / per, rpcr = (rows + Gr - 1) / Gr;
     static unsigned epoch_r = 0x400000;
     epoch_r = epoch_r + 1 >= 0x7fffff ? 0x400000 : epoch_r + 1;
     qrdm_prob prob_r = *p;
-    const bool ag = ag_ok && Gr <= 32;  // one-hop exchange
     void* args_r[] = {(void*)&prob_r, (void*)&rpcr, (void*)&epoch_r};
-    void* fn = ag ? (per == 32 ? (void*)k_panel_reg<1, true> : per == 64 ? (void*)k_panel_reg<2, true>
-                                 : per == 128 ? (void*)k_panel_reg<4, true> : (void*)k_panel_reg<8, true>)
-                  : (per == 32 ? (void*)k_panel_reg<1, false> : per == 64 ? (void*)k_panel_reg<2, false>
-                                 : per == 128 ? (void*)k_panel_reg<4, false> : (void*)k_panel_reg<8, false>);
+#define PANEL_FN(MODE) (per == 32 ? (void*)k_panel_reg<1, MODE> : per == 64 ? (void*)k_panel_reg<2, MODE> \
+                        : per == 128 ? (void*)k_panel_reg<4, MODE> : (void*)k_panel_reg<8, MODE>)
+    if (mode == 2) {
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3((Gr + PANEL_CL - 1) / PANEL_CL * PANEL_CL);  // padded with CTAs that own no rows
+      cfg.blockDim = dim3(PANEL_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = (cudaStream_t)stream;
+      cfg.attrs = cl_attrs; cfg.numAttrs = 2;
+      const cudaError_t e2 = cudaLaunchKernelExC(&cfg, PANEL_FN(2), args_r);
+      if (e2 == cudaSuccess) { ++g_qrdm_launches; return 0; }
+      if (getenv("QRDM_PANEL_VERBOSE"))
+        fprintf(stderr, "qrdm_b200: cluster panel launch failed (%s, grid %d); two-hop kernel from now on\n",
+                cudaGetErrorString(e2), (int)cfg.gridDim.x);
+      (void)cudaGetLastError();
+      cl_max_ctas = 0;
+      mode = 0;
+    }
+    void* fn = mode == 1 ? PANEL_FN(1) : PANEL_FN(0);
+#undef PANEL_FN
     cudaError_t er = cudaLaunchCooperativeKernel(fn, dim3(Gr), dim3(PANEL_THREADS), args_r, 0, (cudaStream_t)stream);
     ++g_qrdm_launches;
     return er == cudaSuccess ? 0 : (int)er;
