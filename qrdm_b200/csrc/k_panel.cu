@@ -344,6 +344,9 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_reg(qrdm_prob P, int
   const int crank = MODE == 2 ? (int)cooperative_groups::this_cluster().block_rank() : 0;
   const int pub = MODE == 2 ? b / PANEL_CL : b, GP = MODE == 2 ? G / PANEL_CL : G;
   double* cpart_leader = MODE == 2 ? cooperative_groups::this_cluster().map_shared_rank(&cpart[0][0][0], 0) : nullptr;
+  // DSMEM rule: nobody may write into the leader's shared memory before the leader CTA has started running
+  // (found by compute-sanitizer racecheck and by a wrong factorisation under ncu, whose scheduling differs)
+  if (MODE == 2) cooperative_groups::this_cluster().sync();
   // publish the block sums acc[c] of columns wid + 16c (c < 4, columns > lo only) for exchange buffer `buf`
   auto publish = [&](double (&acc)[4], int buf, int lo, unsigned ptag) {
 #pragma unroll
@@ -561,6 +564,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_reg(qrdm_prob P, int
     if (b == 0 && jj < kpad)
       for (int g = jal + lane; g < j; g += 32) P.vc[(size_t)jj * P.ldv + g] = 0.0;
   }
+  if (MODE == 2) cooperative_groups::this_cluster().sync();  // no CTA of a cluster leaves while its shared memory may still be addressed
 }
 
 // ---------------------------------------------------------------------------------------------
