@@ -757,7 +757,16 @@ extern "C" int qrdm_k_panel(const qrdm_prob* p, int j_host, void* stream) {
     static cudaLaunchAttribute cl_attrs[2];
     if (cl_max_ctas < 0) {
       cl_max_ctas = 0;
-      if (!(e_cl && atoi(e_cl) == 0)) {
+      // Under Nsight Compute the cooperative + cluster launch does not keep all clusters co-resident (the
+      // factorisation came out wrong or hung with 32 clusters in flight, while plain runs, memcheck and
+      // racecheck are clean), so a process started by a CUDA injection tool (ncu, compute-sanitizer:
+      // CUDA_INJECTION64_PATH) profiles the two-hop kernel unless QRDM_PANEL_CL=2 insists.
+      const char* pre = getenv("LD_PRELOAD");
+      const bool injected = getenv("CUDA_INJECTION64_PATH") != NULL || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") != NULL ||
+                            getenv("NV_NSIGHT_INJECTION_TRANSPORT_TYPE") != NULL ||
+                            (pre && (strstr(pre, "njection") || strstr(pre, "TreeLauncher")));
+      const int want = e_cl ? atoi(e_cl) : 1;
+      if (want == 2 || (want == 1 && !injected)) {
         cudaLaunchConfig_t q;
         memset(&q, 0, sizeof(q));
         q.gridDim = dim3(PANEL_CL); q.blockDim = dim3(PANEL_THREADS);
