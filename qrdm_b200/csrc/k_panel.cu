@@ -744,10 +744,8 @@ extern "C" int qrdm_k_panel(const qrdm_prob* p, int j_host, void* stream) {
   }
   const int rows = p->m - j_host;
   if (rows <= 0) return 0;
-  // few, fat CTAs: the per-column cost is the grid barrier + the all-to-all read of the partials,
-  // both proportional to the CTA count; grow the grid only when the slab would not fit in smem
   const int gmax = p->sm_count < QRDM_PANEL_MAXCTA ? p->sm_count : QRDM_PANEL_MAXCTA;
-  if (rows <= 256 * gmax && !getenv("QRDM_PANEL_NOREG")) {  // register-resident slabs, 128 (or 256) rows per CTA
+  if (rows <= 256 * gmax && !getenv("QRDM_PANEL_NOREG")) {  // register-resident slabs, 32 ... 256 rows per CTA
     static const char* e_ag = getenv("QRDM_PANEL_AG");  // experiment switches: 0 disables the one-hop exchange
     static const char* e_cl = getenv("QRDM_PANEL_CL");  //                      0 disables the cluster exchange
     const bool ag_ok = !(e_ag && atoi(e_ag) == 0);
