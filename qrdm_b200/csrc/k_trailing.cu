@@ -4,11 +4,16 @@
 // Replaces: LAPACKE_dlarfb_mia -> LAPACKE_dlarfb_work -> dlarfb_ (reference src/dlarfb.c:40-151,
 // call at src/dgeqrdm_work.c:762-767) and the T factor of LAPACKE_dlarft (:751-754).
 //
-// Three kernels:
-//   k_vtc     W_s = V_s' C_s for row split s       DMMA, K = rows, 3-stage cp.async pipeline
-//   k_tinv    T' = (I + D N)^-1 D from V'V (k_vtc's tile 0) and tau, one CTA
-//   k_wapply  W2 = -T' (sum_s W_s) per 128-column tile, DMMA; also the NaN screen of C (-13)
-//   k_rankk   C -= V y                              DMMA, K = k (<= 64) resident in smem
+// Kernels:
+//   k_vtc      W_s = V_s' C_s per partial-W slot        DMMA, K = rows, 2-stage cp.async ring
+//   k_tinv     T' = (I + D N)^-1 D from V'V (k_vtc's / k_fused's tile 0) and tau, one CTA
+//   k_wapply   W2 = -T' (sum_s W_s) per column tile, DMMA; NaN screen of C (-13); optionally the k new R rows
+//              of the tile (deferred schedule) and T instead of T' (Q application)
+//   k_rankk    C += V W2                                  DMMA, K = k (<= 64) resident in smem; LIST mode = the same
+//              update on a gathered column list (eager set of the deferred schedule)
+//   k_fused    deferred schedule: pass 2 of the pending block fused into pass 1 of the current one (C read once,
+//              written once per iteration); k_colupd / k_w2mask: its small helpers
+//   k_vc_build rebuilds the clean V of one block of a factored matrix (Q application, qrdm_b200_dormqr)
 // FP64 math is mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4): measured 37.0 TFLOP/s = the B200 FP64 peak,
 // vs 33.5-34 for a DFMA loop (profiles/r01_fp64_peak_microbench.txt); tcgen05/wgmma have no FP64
 // kind.  Algorithmic FLOPs 4*m_r*n_c*k; minimum HBM traffic 24*m_r*n_c bytes (C read twice,
