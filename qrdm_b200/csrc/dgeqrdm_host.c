@@ -316,7 +316,10 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
       STAGE(QRDM_STAGE_PICK, qrdm_k_pick(&P, stream));
       STAGE(QRDM_STAGE_PERMUTE, qrdm_k_permute(&P, stream));
       STAGE(QRDM_STAGE_PANEL, qrdm_k_panel(&P, j, stream));
-      lazy = lazy_on && n - j - QRDM_KMAX >= 1 && m - j - QRDM_KMAX >= 1 &&
+      /* both dimensions must be large as well: with few trailing columns (tall-skinny, C4) the eager set of
+       * <= 128 columns is a large share of the matrix and the deferred schedule buys nothing */
+      const int lazy_dim = lazy_min < 1024 ? lazy_min : 1024;
+      lazy = lazy_on && n - j - QRDM_KMAX >= lazy_dim && m - j - QRDM_KMAX >= lazy_dim &&
              (double)(n - j - QRDM_KMAX) * (double)(m - j - QRDM_KMAX) >= (double)lazy_min * (double)lazy_min;
       if (!pending && !lazy) {
         STAGE(QRDM_STAGE_VTC, qrdm_k_trailing(&P, j, stream));
