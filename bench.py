@@ -35,13 +35,22 @@ sys.path.insert(0, ROOT)
 # The driver reads ONE JSON line from stdout.  Libraries write there too (NCCL prints its version banner
 # to stdout under torchrun), so keep a private copy of the real stdout for the JSON line and point fd 1
 # at stderr for everybody else.
-_JSON_OUT = os.fdopen(os.dup(1), "w")
-os.dup2(2, 1)
+_JSON_OUT = None
+
+
+def protect_stdout():
+    """Called by main() only (importing this module must not touch the caller's file descriptors)."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
 
 
 def emit(line):
-    _JSON_OUT.write(json.dumps(line) + "\n")
-    _JSON_OUT.flush()
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 WORKLOADS = {
     # name: (m, n, generator, stop_mode, description = the BASELINE.json config it is)
@@ -353,6 +362,7 @@ def main():
     ap.add_argument("--no-batched", action="store_true", help="skip the configs[4] batched leg")
     ap.add_argument("--batch-total", type=int, default=8192)
     args = ap.parse_args()
+    protect_stdout()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = max(args.warmup, 1)  # contract says W >= 3; honour smaller only for ncu captures
 
