@@ -35,6 +35,7 @@
 // Traffic per column ~ G*64 packets instead of the G*G*64 of an all-to-all read, latency two
 // round trips, and identical inputs on every CTA => bit-identical decisions (stop test, tau).
 struct __align__(16) LLPacket { unsigned lo, tag0, hi, tag1; };
+#define LL_SPIN_LIMIT (1u << 27)  // polls (~0.5 us each) before a waiting thread gives up with a trap
 
 __device__ __forceinline__ void ll_store(LLPacket* p, double v, unsigned tag) {
   const unsigned long long b = (unsigned long long)__double_as_longlong(v);
@@ -43,9 +44,10 @@ __device__ __forceinline__ void ll_store(LLPacket* p, double v, unsigned tag) {
                : "memory");
 }
 __device__ __forceinline__ double ll_load(const LLPacket* p, unsigned tag) {
-  unsigned lo, t0, hi, t1;
+  unsigned lo, t0, hi, t1, spins = 0;
   do {
     asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(lo), "=r"(t0), "=r"(hi), "=r"(t1) : "l"(p) : "memory");
+    if (++spins > LL_SPIN_LIMIT) __trap();  // a partner CTA never showed up: fail loudly instead of hanging the GPU
   } while (t0 != tag || t1 != tag);
   return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
 }
@@ -70,9 +72,12 @@ __device__ __forceinline__ double ll_gather_sum(const LLPacket* base, size_t str
   for (int u = 0; u < MAXU; ++u) {
     const int c = lane + 32 * u;
     if (c < G) {
-      while (t0[u] != tag || t1[u] != tag)
+      unsigned spins = 0;
+      while (t0[u] != tag || t1[u] != tag) {
         asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];\n"
                      : "=r"(lo[u]), "=r"(t0[u]), "=r"(hi[u]), "=r"(t1[u]) : "l"(base + (size_t)c * stride) : "memory");
+        if (++spins > LL_SPIN_LIMIT) __trap();
+      }
       v += __longlong_as_double((long long)(((unsigned long long)hi[u] << 32) | lo[u]));
     }
   }
@@ -95,9 +100,12 @@ __device__ __forceinline__ double ll_gather_sum_strided(const LLPacket* base, si
   for (int u = 0; u < MAXU; ++u) {
     const int c = start + step * u;
     if (c < G) {
-      while (t0[u] != tag || t1[u] != tag)
+      unsigned spins = 0;
+      while (t0[u] != tag || t1[u] != tag) {
         asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];\n"
                      : "=r"(lo[u]), "=r"(t0[u]), "=r"(hi[u]), "=r"(t1[u]) : "l"(base + (size_t)c * stride) : "memory");
+        if (++spins > LL_SPIN_LIMIT) __trap();
+      }
       v += __longlong_as_double((long long)(((unsigned long long)hi[u] << 32) | lo[u]));
     }
   }
