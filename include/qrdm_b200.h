@@ -12,6 +12,8 @@
 #ifndef QRDM_B200_H_
 #define QRDM_B200_H_
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -25,6 +27,11 @@ extern "C" {
 #define QRDM_ERR_CUDA (-100)       /* CUDA runtime failure (no device, launch error, OOM) */
 #define QRDM_ERR_COMM (-101)       /* NCCL failure in the row-sharded path */
 #define QRDM_ERR_UNSUPPORTED (-102) /* jpvt[j] != 0 on entry (fixed columns), nb > QRDM_NB_MAX */
+
+/* Threading: the reference keeps no global state (src/dgeqrdm_work.c:650-665, 816-826) and may be called from
+ * several host threads at once.  Here the device workspace is per process; every entry point below takes one
+ * process-wide recursive lock, so concurrent callers are safe and are served one after the other.  The workspace
+ * follows the caller's current CUDA device: a call made after cudaSetDevice(other) re-creates it there. */
 
 /* Replaces: reference include/QRDM.h:19-22, src/dgeqrdm.c:5-16.
  * QR factorisation with Deviation-Maximisation block pivoting, A P = Q R, FP64.
@@ -65,7 +72,8 @@ int dgeqrdm_batched(int batch, int m, int n, double *a, int lda, long long strid
                     int *ncols, double *thres, int nb, int *infos);
 
 /* Device-resident batched variant (m, n <= 1024, else QRDM_ERR_UNSUPPORTED): every array is a DEVICE
- * pointer except thres; d_ncols is [batch][n] with the stop-rule mode in [b][0] on entry and the block
+ * pointer except thres, which MUST hold 3 doubles here (the stop modes live on the device, so thres[2] is always
+ * read; the host-pointer variant above reads it only if some matrix asks for stop mode 3); d_ncols is [batch][n] with the stop-rule mode in [b][0] on entry and the block
  * sizes on exit; d_infos [batch] (may be NULL) receives the per-matrix info.  One launch; returns after
  * it has completed on the stream. */
 int dgeqrdm_batched_dev(int batch, int m, int n, double *d_a, int lda, long long stride_a, int *d_jpvt,
@@ -75,12 +83,21 @@ int dgeqrdm_batched_dev(int batch, int m, int n, double *d_a, int lda, long long
  * process per GPU.  Rank p passes its rows [row0, row0 + m_local) of all n columns (device memory,
  * column-major, lda >= m_local); d_jpvt / d_tau / ncols come back replicated on every rank.  The
  * all-reduces (column-norm partials, candidate Gram, one 128-double vector per panel column, the
- * V'C slots) run on NCCL over NVLink on `stream`.  Set the communicator up first:
- * rank 0 calls qrdm_b200_comm_unique_id, the 128 bytes are broadcast by the launcher
- * (e.g. torch.distributed), every rank calls qrdm_b200_comm_init. */
+ * V'C slots) run on `stream`.  Two transports (both may be set up; QRDM_B200_COLL=peer|nccl forces one):
+ *   NCCL   rank 0 calls qrdm_b200_comm_unique_id, the 128 bytes are broadcast by the launcher (e.g.
+ *          torch.distributed), every rank calls qrdm_b200_comm_init.  Carries the bandwidth-bound vectors.
+ *   peer   NVLink peer memory (CUDA IPC, one node, <= 8 ranks): every rank calls qrdm_b200_peer_handle, the launcher
+ *          all-gathers the 64-byte handles (rank order), every rank calls qrdm_b200_peer_open and the launcher
+ *          runs one barrier.  With peer memory open the panel's per-column reduction happens INSIDE one persistent
+ *          kernel per 8-column sub-panel (LL packets stored straight into the peers' buffers) and the small vectors
+ *          go through a one-kernel LL all-reduce; without it the round-1 path (one kernel + one 1-KB ncclAllReduce
+ *          per panel column) is used. */
 int qrdm_b200_comm_unique_id(char *out128);
 int qrdm_b200_comm_init(int rank, int nranks, const char *id128);
 void qrdm_b200_comm_destroy(void);
+int qrdm_b200_peer_handle(char *out64);
+int qrdm_b200_peer_open(int rank, int nranks, const char *handles64);
+void qrdm_b200_peer_close(void);
 int dgeqrdm_dev_sharded(int m_local, int m_global, int row0, int nranks, int n, double *d_a, int lda,
                         int *d_jpvt, double *d_tau, int *ncols, const double *thres, int nb, void *stream);
 
@@ -134,8 +151,10 @@ int qrdm_b200_init(int device);
 void qrdm_b200_shutdown(void);
 
 /* Micro-benchmarks used by bench.py for the roofline denominators (measured live, on the stream
- * given): FP64 FMA-pipe peak in TFLOP/s, and a device-to-device copy in GB/s. */
+ * given): FP64 peak in TFLOP/s (use_dmma = 1: DMMA.8x8x4 chains, 0: DFMA chains), and a device-to-device copy of
+ * `bytes` bytes in GB/s (bytes read + bytes written per second; best of 5). */
 double qrdm_b200_measure_fp64_peak(int use_dmma, void *stream);
+double qrdm_b200_measure_copy_gbs(size_t bytes, void *stream);
 const char *qrdm_b200_version(void);
 
 #ifdef __cplusplus

@@ -46,8 +46,11 @@ def QRDM(matrix_layout, m, n, A, lda, jpvt, tau, ncols, thres, nb):
     pn = _buf(ncols, np.int32, "ncols")
     ph = _buf(thres, np.float64, "thres")
     if m > 0 and n > 0 and (A.size < lda * (n - 1) + m or jpvt.size < n or tau.size < min(m, n)
-                            or thres.size < 2 or ncols.size < 1):
-        raise ValueError("array too small for the given m, n, lda")
+                            or thres.size < 2 or ncols.size < min(m, n)):
+        # ncols: the driver writes one entry per iteration, up to min(m, n) of them (reference doc: dimension N)
+        raise ValueError("array too small for the given m, n, lda (ncols needs min(m, n) entries)")
+    if thres.size < 3 and ncols.size > 0 and int(ncols.flat[0]) == 3:
+        raise ValueError("stop mode 3 reads thres[2]")
     return int(_lib.lib.dgeqrdm(int(matrix_layout), int(m), int(n), pa, int(lda), pj, pt, pn, ph, int(nb)))
 
 

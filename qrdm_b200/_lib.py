@@ -26,7 +26,8 @@ STAGES = ["norm_init", "select", "gram", "pick", "permute", "panel", "vtv", "tra
 EXPORTS = ["dgeqrdm", "dgeqrdm_work", "dgeqrdm_dev", "dgeqrdm_dev_sharded", "dgeqrdm_batched", "dgeqrdm_batched_dev", "qrdm_b200_get_stats",
            "qrdm_b200_set_profile", "qrdm_b200_init", "qrdm_b200_shutdown", "qrdm_b200_measure_fp64_peak",
            "qrdm_b200_version", "qrdm_b200_comm_unique_id", "qrdm_b200_comm_init", "qrdm_b200_comm_destroy",
-           "qrdm_b200_dormqr", "qrdm_b200_dormqr_dev"]
+           "qrdm_b200_dormqr", "qrdm_b200_dormqr_dev", "qrdm_b200_peer_handle", "qrdm_b200_peer_open",
+           "qrdm_b200_peer_close", "qrdm_b200_measure_copy_gbs"]
 
 
 def _load():
@@ -58,6 +59,13 @@ def _load():
     lib.qrdm_b200_comm_init.restype = C.c_int
     lib.qrdm_b200_comm_init.argtypes = [C.c_int, C.c_int, C.c_char_p]
     lib.qrdm_b200_comm_destroy.restype = None
+    lib.qrdm_b200_peer_handle.restype = C.c_int
+    lib.qrdm_b200_peer_handle.argtypes = [C.c_char_p]
+    lib.qrdm_b200_peer_open.restype = C.c_int
+    lib.qrdm_b200_peer_open.argtypes = [C.c_int, C.c_int, C.c_char_p]
+    lib.qrdm_b200_peer_close.restype = None
+    lib.qrdm_b200_measure_copy_gbs.restype = C.c_double
+    lib.qrdm_b200_measure_copy_gbs.argtypes = [C.c_size_t, C.c_void_p]
     lib.dgeqrdm_batched.restype = C.c_int
     lib.dgeqrdm_batched.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]

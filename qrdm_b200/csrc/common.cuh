@@ -6,6 +6,7 @@
 #include "qrdm_dev.h"
 
 extern long long g_qrdm_launches;  // kernels launched by this process (stats: gpu_launches)
+extern "C" int qrdm_rt_device_generation(void);  // bumped when the library (re)initialises on a device
 
 #define QRDM_LAUNCH_CHECK()                   \
   do {                                        \

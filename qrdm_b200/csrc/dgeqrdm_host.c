@@ -10,17 +10,20 @@
  */
 #include <float.h>
 #include <math.h>
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include "../../include/qrdm_b200.h"
+#include "hostio.h"
 #include "qrdm_dev.h"
 
-#define QRDM_VERSION "qrdm_b200 0.1 (round 1)"
+#define QRDM_VERSION "qrdm_b200 0.2 (round 2)"
 
 typedef struct {
   int ready, sm_count;
+  int device; /* the device the workspace lives on (a call on another current device re-creates it) */
   /* capacities */
   int cap_m, cap_n;
   size_t cap_a_bytes;
@@ -42,6 +45,7 @@ typedef struct {
   void *ev_stage[2];
   void *compute_stream, *copy_stream; /* non-blocking streams of the host-pointer entry points */
   void *h2d_stream;                   /* third stream of the batched pipeline (created on first use) */
+  qrdm_hostio *io;                    /* bounce pipeline for pageable host buffers (created on first use) */
 } qrdm_workspace;
 
 /* 1-D block-row sharding: this rank holds global rows [row0, row0 + m_local) */
@@ -55,11 +59,29 @@ typedef struct {
   int h_lda;
   void *copy_stream;
   int done_cols; /* columns [0, done_cols) already enqueued for D2H */
+  qrdm_hostio *io; /* non-NULL: pageable host buffer, finished columns go through the pinned ring of hostio.c */
 } qrdm_writeback;
 
 static qrdm_workspace g_ws;
 static qrdm_b200_stats g_stats;
 static int g_profile = -1;
+
+/* The reference allocates and frees its workspace per call and keeps no global state (src/dgeqrdm_work.c:650-665,
+ * 816-826), so two host threads may call it concurrently.  Here the device workspace, the statistics and the LL
+ * epochs of the kernel launchers are per process: every public entry point runs under one recursive lock, which
+ * makes concurrent callers safe (they are serialised — one GPU is one resource anyway). */
+static pthread_mutex_t g_api_lock;
+static pthread_once_t g_api_once = PTHREAD_ONCE_INIT;
+static void api_lock_init(void) {
+  pthread_mutexattr_t at;
+  pthread_mutexattr_init(&at);
+  pthread_mutexattr_settype(&at, PTHREAD_MUTEX_RECURSIVE);
+  pthread_mutex_init(&g_api_lock, &at);
+  pthread_mutexattr_destroy(&at);
+}
+static void api_lock(void) { pthread_once(&g_api_once, api_lock_init); pthread_mutex_lock(&g_api_lock); }
+static void api_unlock(void) { pthread_mutex_unlock(&g_api_lock); }
+#define API_BODY(call) do { api_lock(); int r__ = (call); api_unlock(); return r__; } while (0)
 
 static int roundup(int x, int a) { return (x + a - 1) / a * a; }
 
@@ -74,9 +96,20 @@ static int roundup(int x, int a) { return (x + a - 1) / a * a; }
   } while (0)
 
 const char *qrdm_b200_version(void) { return QRDM_VERSION; }
-void qrdm_b200_get_stats(qrdm_b200_stats *out) { *out = g_stats; }
-void qrdm_b200_set_profile(int mode) { g_profile = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }
-double qrdm_b200_measure_fp64_peak(int use_dmma, void *stream) { return qrdm_rt_fp64_peak(use_dmma, stream); }
+void qrdm_b200_get_stats(qrdm_b200_stats *out) { api_lock(); *out = g_stats; api_unlock(); }
+void qrdm_b200_set_profile(int mode) { api_lock(); g_profile = mode < 0 ? 0 : (mode > 2 ? 2 : mode); api_unlock(); }
+double qrdm_b200_measure_fp64_peak(int use_dmma, void *stream) {
+  api_lock();
+  const double r = qrdm_rt_fp64_peak(use_dmma, stream);
+  api_unlock();
+  return r;
+}
+double qrdm_b200_measure_copy_gbs(size_t bytes, void *stream) {
+  api_lock();
+  const double r = qrdm_rt_copy_gbs(bytes, stream);
+  api_unlock();
+  return r;
+}
 
 static void ws_free_sized(qrdm_workspace *w) {
   void *bufs[] = {w->vn1, w->vn2, w->vc, w->wp, w->w2, w->nrm_part, w->flag_list, w->upd_marks};
@@ -88,21 +121,41 @@ static void ws_free_sized(qrdm_workspace *w) {
   w->cap_m = w->cap_n = 0;
 }
 
-void qrdm_b200_shutdown(void) {
+static void shutdown_impl(void) {
   qrdm_workspace *w = &g_ws;
   if (!w->ready) return;
+  int cur = -1;
+  qrdm_rt_get_device(&cur);
+  if (cur != w->device) qrdm_rt_set_device(w->device); /* streams / events are destroyed on their own device */
+  qrdm_rt_peer_destroy();
   ws_free_sized(w);
   void *fixed[] = {w->ctrl, w->gram_part, w->gram, w->panel_part, w->panel_row, w->d_a, w->d_tau, w->d_jpvt, w->mg_buf, w->mg_cnt};
   for (size_t i = 0; i < sizeof(fixed) / sizeof(fixed[0]); ++i)
     if (fixed[i]) qrdm_rt_free(fixed[i]);
   if (w->mailbox) qrdm_rt_host_free(w->mailbox);
+  for (int i = 0; i < 4; ++i) qrdm_rt_event_destroy(w->ev[i]);
+  for (int i = 0; i < 2; ++i) qrdm_rt_event_destroy(w->ev_stage[i]);
+  if (w->compute_stream) qrdm_rt_stream_destroy(w->compute_stream);
+  if (w->copy_stream) qrdm_rt_stream_destroy(w->copy_stream);
+  if (w->h2d_stream) qrdm_rt_stream_destroy(w->h2d_stream);
+  if (w->io) qrdm_hostio_destroy(w->io);
   memset(w, 0, sizeof(*w));
+  if (cur >= 0 && cur != w->device) qrdm_rt_set_device(cur);
 }
+void qrdm_b200_shutdown(void) { api_lock(); shutdown_impl(); api_unlock(); }
 
-int qrdm_b200_init(int device) {
+static int init_impl(int device) {
   qrdm_workspace *w = &g_ws;
   if (device >= 0) CU(qrdm_rt_set_device(device));
-  if (w->ready) return 0;
+  int cur = 0;
+  CU(qrdm_rt_get_device(&cur));
+  if (w->ready && w->device == cur) return 0;
+  if (w->ready) { /* the caller switched devices: buffers, streams and kernel attributes belong to the old one */
+    shutdown_impl();
+    CU(qrdm_rt_set_device(cur));
+  }
+  qrdm_rt_new_device_generation(); /* launchers re-apply their per-device function attributes */
+  w->device = cur;
   size_t freeb = 0;
   CU(qrdm_rt_device_info(&w->sm_count, &freeb));
   CU(qrdm_rt_malloc((void **)&w->ctrl, sizeof(qrdm_ctrl)));
@@ -128,10 +181,11 @@ int qrdm_b200_init(int device) {
   }
   return 0;
 }
+int qrdm_b200_init(int device) { API_BODY(init_impl(device)); }
 
 static int ws_ensure(int m, int n) {
   qrdm_workspace *w = &g_ws;
-  int rc = qrdm_b200_init(-1);
+  int rc = init_impl(-1);
   if (rc) return rc;
   if (m <= w->cap_m && n <= w->cap_n) return 0;
   int cm = m > w->cap_m ? m : w->cap_m, cn = n > w->cap_n ? n : w->cap_n;
@@ -227,6 +281,29 @@ static int stage_end(int stage, long long launches_before, void *stream) {
     CU(stage_end(id, lb__, stream));                  \
   } while (0)
 
+/* Sum all-reduce of the row-sharded path.  Two transports:
+ *   peer  one-shot LL all-reduce over NVLink peer memory (k_peer.cu): one kernel, ~one NVLink store + one L2 poll of
+ *         latency — used for everything up to QRDM_COLL_PEER_MAX doubles (the per-iteration vectors of a tall-skinny
+ *         factorisation: Gram 4096, skinny products 512, folded W <= 64 x ~600, norm sums n);
+ *   nccl  ncclAllReduce (bandwidth-bound messages: W of wide matrices, norm partials of many columns; and whenever the
+ *         launcher did not open peer memory).
+ * QRDM_B200_COLL=peer|nccl forces one of them (tests run 2 ranks on ONE GPU with "peer": NCCL refuses that). */
+#define QRDM_COLL_PEER_MAX ((size_t)96 * 1024)
+static int mg_allreduce(double *buf, size_t count, void *stream) {
+  static int mode = -1; /* 0 auto, 1 peer, 2 nccl */
+  if (mode < 0) {
+    const char *e = getenv("QRDM_B200_COLL");
+    mode = !e ? 0 : (strcmp(e, "peer") == 0 ? 1 : (strcmp(e, "nccl") == 0 ? 2 : 0));
+  }
+  const int have_peer = qrdm_rt_peer_available() > 0;
+  if (mode == 1 && !have_peer) {
+    fprintf(stderr, "qrdm_b200: QRDM_B200_COLL=peer but no peer memory is open (qrdm_b200_peer_open)\n");
+    return -1;
+  }
+  if (have_peer && (mode == 1 || (mode == 0 && count <= QRDM_COLL_PEER_MAX))) return qrdm_k_peer_allreduce(buf, count, stream);
+  return qrdm_rt_allreduce(buf, count, stream);
+}
+
 static int read_mailbox(const qrdm_prob *p, void *stream) {
   CU(qrdm_rt_d2h(g_ws.mailbox, p->ctrl, QRDM_MAILBOX_BYTES, stream));
   CU(qrdm_rt_sync(stream));
@@ -295,7 +372,7 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
   } else { /* partial sums of squares -> all-reduce -> sqrt */
     int nsplit = 1;
     CU(qrdm_k_colnorm_part(&P, 0, &nsplit, stream));
-    if (qrdm_rt_allreduce(P.nrm_part, (size_t)nsplit * n, stream)) return QRDM_ERR_COMM;
+    if (mg_allreduce(P.nrm_part, (size_t)nsplit * n, stream)) return QRDM_ERR_COMM;
     CU(qrdm_k_colnorm_fin(&P, 0, nsplit, stream));
   }
   STAGE(QRDM_STAGE_SELECT, qrdm_k_select(&P, stream));
@@ -348,11 +425,29 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
       const int kmax_h = nb < n - j ? (nb < m_glob - j ? nb : m_glob - j) : (n - j < m_glob - j ? n - j : m_glob - j);
       int vt_stride = 0, vt_grid = 0, nsplit = 1;
       CU(qrdm_k_gram_part(&P, m - jr > 0 ? m - jr : 1, stream));
-      if (qrdm_rt_allreduce(P.gram, 4096, stream)) return QRDM_ERR_COMM;
+      if (mg_allreduce(P.gram, 4096, stream)) return QRDM_ERR_COMM;
       CU(qrdm_k_pick(&P, stream));
       CU(qrdm_k_permute(&P, stream));
-      if ((m_glob - j) / P.nranks <= 16384) {
-        /* one kernel + one 128-double all-reduce per panel column */
+      if (qrdm_rt_peer_available() == P.nranks && !getenv("QRDM_B200_MG_LEGACY")) {
+        /* Peer memory open: every sharded panel runs blocked, 8-column sub-panels factored by ONE persistent kernel
+         * each (k_panel_tall<true>) that exchanges the per-column vector [||x||^2, x'C_sub | pivot row] with the other
+         * GPUs as LL packets over NVLink from inside the kernel — no launch and no collective call per column
+         * (src/dgeqr2.c:148-189 is one tight loop upstream).  Each sub-panel's block reflector then updates the rest of
+         * the panel: V'[V | C_p] partials, one 512-double all-reduce, C_p += V W2. */
+        for (int sb = 0; sb < kmax_h; sb += QRDM_TALL_B) {
+          qrdm_prob Ps = P;
+          Ps.sub = sb + 1;
+          int jrs = j + sb - P.row0;
+          jrs = jrs < 0 ? 0 : (jrs > m ? m : jrs);
+          CU(qrdm_k_panel_tall_mg(&Ps, j, stream));
+          if (sb + QRDM_TALL_B < kmax_h) {
+            CU(qrdm_k_skinny_part(&Ps, m - jrs > 0 ? m - jrs : 1, stream));
+            if (mg_allreduce(P.gram_part, 512, stream)) return QRDM_ERR_COMM;
+            CU(qrdm_k_skinny_finish(&Ps, m - jrs > 0 ? m - jrs : 1, stream));
+          }
+        }
+      } else if ((m_glob - j) / P.nranks <= 16384) {
+        /* legacy transport (NCCL only): one kernel + one 128-double all-reduce per panel column */
         CU(qrdm_k_panel_mg_init(&P, j, stream));
         if (qrdm_rt_allreduce(P.mg_buf, 128, stream)) return QRDM_ERR_COMM;
         for (int i = 0; i < kmax_h; ++i) {
@@ -388,15 +483,15 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
       CU(qrdm_k_vtc_only(&P, j, &vt_stride, &vt_grid, stream));
       if (vt_stride > 0) {
         CU(qrdm_k_wreduce(&P, j, vt_grid, vt_stride, stream));
-        if (qrdm_rt_allreduce(P.wp, (size_t)64 * vt_stride, stream)) return QRDM_ERR_COMM;
+        if (mg_allreduce(P.wp, (size_t)64 * vt_stride, stream)) return QRDM_ERR_COMM;
         CU(qrdm_k_trailing_finish(&P, j, vt_grid, vt_stride, stream));
       }
       if (n - j - 1 > 0) {
         CU(qrdm_k_norm_dpart(&P, j, stream));
-        if (qrdm_rt_allreduce(P.nrm_part, (size_t)n, stream)) return QRDM_ERR_COMM;
+        if (mg_allreduce(P.nrm_part, (size_t)n, stream)) return QRDM_ERR_COMM;
         CU(qrdm_k_norm_apply(&P, j, stream));
         CU(qrdm_k_colnorm_part(&P, 2, &nsplit, stream));
-        if (qrdm_rt_allreduce(P.nrm_part, (size_t)nsplit * n, stream)) return QRDM_ERR_COMM;
+        if (mg_allreduce(P.nrm_part, (size_t)nsplit * n, stream)) return QRDM_ERR_COMM;
         CU(qrdm_k_colnorm_fin(&P, 2, nsplit, stream));
       }
     }
@@ -425,7 +520,13 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
     }
     g_stats.trailing_flops += 4.0 * (double)(m - jr) * (double)(cols - k) * (double)k;
     j += k;
-    if (wb) {
+    if (wb && wb->io) {
+      /* pageable host buffer: the same streaming through the pinned ring + drain thread of hostio.c; the ring
+       * may be full, then the columns wait for a later push or for the final download */
+      const int taken = qrdm_hostio_wb_push(wb->io, wb->done_cols, j);
+      if (taken < 0) return QRDM_ERR_CUDA;
+      wb->done_cols += taken;
+    } else if (wb) {
       /* columns [done, j) are final (later iterations only touch columns >= j, and the mailbox
        * sync above means every kernel of this iteration has finished): stream them to the host
        * while the next iterations compute */
@@ -457,25 +558,12 @@ int dgeqrdm_dev(int m, int n, double *d_a, int lda, int *d_jpvt, double *d_tau, 
                 const double *thres, int nb, void *stream) {
   int rc = check_args(QRDM_COL_MAJOR, m, n, lda, thres, nb);
   if (rc) return rc;
-  return factor_device(m, n, d_a, lda, d_jpvt, d_tau, ncols, thres, nb, stream, NULL, NULL);
+  API_BODY(factor_device(m, n, d_a, lda, d_jpvt, d_tau, ncols, thres, nb, stream, NULL, NULL));
 }
 
-int dgeqrdm_work(int matrix_layout, int m, int n, double *a, int lda, int *jpvt, double *tau,
-                 int *ncols, double *thres, int nb) {
+static int ensure_staging(int m, int n, int ldd) {
   qrdm_workspace *w = &g_ws;
-  int rc = check_args(matrix_layout, m, n, lda, thres, nb);
-  if (rc) return rc;
-  for (int c = 0; c < n; ++c)
-    if (jpvt[c] != 0) {
-      /* fixed columns: the reference's own path is broken for nfxd > 0 (SURVEY.md 2a) */
-      fprintf(stderr, "qrdm_b200: jpvt[%d] != 0 on entry (fixed columns) is not supported\n", c);
-      return QRDM_ERR_UNSUPPORTED;
-    }
-  rc = qrdm_b200_init(-1);
-  if (rc) return rc;
-  void *stream = w->compute_stream;
   const int minmn = m < n ? m : n;
-  const int ldd = (m + 1) & ~1; /* even leading dimension on the device: 16-byte aligned columns */
   const size_t a_bytes = sizeof(double) * (size_t)ldd * n;
   if (a_bytes > w->cap_a_bytes) {
     if (w->d_a) qrdm_rt_free(w->d_a);
@@ -486,42 +574,111 @@ int dgeqrdm_work(int matrix_layout, int m, int n, double *a, int lda, int *jpvt,
   }
   if ((size_t)minmn > w->cap_tau) {
     if (w->d_tau) qrdm_rt_free(w->d_tau);
+    w->d_tau = NULL;
     w->cap_tau = 0;
     CU(qrdm_rt_malloc((void **)&w->d_tau, sizeof(double) * minmn));
     w->cap_tau = minmn;
   }
   if ((size_t)n > w->cap_jpvt) {
     if (w->d_jpvt) qrdm_rt_free(w->d_jpvt);
+    w->d_jpvt = NULL;
     w->cap_jpvt = 0;
     CU(qrdm_rt_malloc((void **)&w->d_jpvt, sizeof(int) * n));
     w->cap_jpvt = n;
   }
-  CU(qrdm_rt_event_record(w->ev[2], stream));
-  if (ldd != m && ((size_t)ldd * n > (size_t)m * n)) CU(qrdm_rt_memset(w->d_a, 0, a_bytes, stream));
-  CU(qrdm_rt_h2d_2d(w->d_a, sizeof(double) * ldd, a, sizeof(double) * lda, sizeof(double) * m, n, stream));
-  CU(qrdm_rt_h2d(w->d_tau, tau, sizeof(double) * minmn, stream)); /* entries >= rank stay as given */
-  CU(qrdm_rt_event_record(w->ev[3], stream));
-  /* pinned host buffer: overlap the D2H of finished columns with the rest of the factorisation */
-  qrdm_writeback wb = {a, lda, w->copy_stream, 0};
-  const int overlap = qrdm_rt_is_pinned(a) && !getenv("QRDM_B200_NO_OVERLAP");
-  int info = factor_device(m, n, w->d_a, ldd, w->d_jpvt, w->d_tau, ncols, thres, nb, stream, overlap ? &wb : NULL, NULL);
-  if (info <= QRDM_ERR_CUDA) return info;
-  const double ms_h2d = qrdm_rt_event_ms(w->ev[2], w->ev[3]);
-  CU(qrdm_rt_event_record(w->ev[2], stream));
-  {
-    const int done = overlap ? wb.done_cols : 0; /* the unreduced tail (early stop / error) */
-    if (done < n)
-      CU(qrdm_rt_d2h_2d(a + (size_t)done * lda, sizeof(double) * lda, w->d_a + (size_t)done * ldd,
-                        sizeof(double) * ldd, sizeof(double) * m, (size_t)(n - done), stream));
-    if (overlap) CU(qrdm_rt_sync(w->copy_stream));
+  return 0;
+}
+
+/* Host-pointer entry point.  Three transfer modes, chosen from the caller's buffer:
+ *   pinned host memory      one async 2-D H2D; finished columns stream back D2H during the factorisation;
+ *   pageable (NumPy) memory multi-threaded pinned bounce pipeline both ways + the same streamed write-back through a
+ *                           pinned ring (hostio.c) — the reference's caller passes pageable arrays (QRDM_wrapper.c:155-159);
+ *   QRDM_B200_NO_BOUNCE=1   plain cudaMemcpy2D from pageable memory (the round-1 behaviour, kept for A/B timing). */
+static int dgeqrdm_work_locked(int m, int n, double *a, int lda, int *jpvt, double *tau, int *ncols, double *thres, int nb) {
+  qrdm_workspace *w = &g_ws;
+  int rc = init_impl(-1);
+  if (rc) return rc;
+  void *stream = w->compute_stream;
+  const int minmn = m < n ? m : n;
+  const int ldd = (m + 1) & ~1; /* even leading dimension on the device: 16-byte aligned columns */
+  const size_t a_bytes = sizeof(double) * (size_t)ldd * n;
+  rc = ensure_staging(m, n, ldd);
+  if (rc) return rc;
+  const int pinned = qrdm_rt_is_pinned(a);
+  const int bounce = !pinned && !getenv("QRDM_B200_NO_BOUNCE") && (size_t)m * n >= (size_t)1 << 16;
+  if (bounce && !w->io && qrdm_hostio_create(&w->io, w->device)) return QRDM_ERR_CUDA;
+  int info = QRDM_ERR_CUDA;
+#define CUX(call)                                                                             \
+  do {                                                                                        \
+    int e__ = (call);                                                                         \
+    if (e__ != 0) {                                                                           \
+      fprintf(stderr, "qrdm_b200: CUDA error %d (%s) at %s:%d\n", e__, qrdm_rt_errstr(e__), \
+              __FILE__, __LINE__);                                                            \
+      info = QRDM_ERR_CUDA;                                                                   \
+      goto fail;                                                                              \
+    }                                                                                         \
+  } while (0)
+  CUX(qrdm_rt_event_record(w->ev[2], stream));
+  if (ldd != m) CUX(qrdm_rt_memset(w->d_a, 0, a_bytes, stream));
+  if (bounce) {
+    CUX(qrdm_rt_sync(stream)); /* the memset of the padding row must not race with the workers' streams */
+    if (qrdm_hostio_upload(w->io, w->d_a, ldd, a, lda, m, n)) { info = QRDM_ERR_CUDA; goto fail; }
+  } else {
+    CUX(qrdm_rt_h2d_2d(w->d_a, sizeof(double) * ldd, a, sizeof(double) * lda, sizeof(double) * m, n, stream));
   }
-  CU(qrdm_rt_d2h(jpvt, w->d_jpvt, sizeof(int) * n, stream));
-  CU(qrdm_rt_d2h(tau, w->d_tau, sizeof(double) * minmn, stream));
-  CU(qrdm_rt_event_record(w->ev[3], stream));
-  CU(qrdm_rt_sync(stream));
-  g_stats.ms_h2d = ms_h2d;
-  g_stats.ms_d2h = qrdm_rt_event_ms(w->ev[2], w->ev[3]);
+  CUX(qrdm_rt_h2d(w->d_tau, tau, sizeof(double) * minmn, stream)); /* entries >= rank stay as given */
+  CUX(qrdm_rt_event_record(w->ev[3], stream));
+  {
+    /* overlap the D2H of finished columns with the rest of the factorisation */
+    qrdm_writeback wb = {a, lda, w->copy_stream, 0, NULL};
+    int overlap = (pinned || bounce) && !getenv("QRDM_B200_NO_OVERLAP");
+    if (overlap && bounce) {
+      const int r = qrdm_hostio_wb_begin(w->io, a, lda, w->d_a, ldd, m, w->copy_stream);
+      if (r < 0) { info = QRDM_ERR_CUDA; goto fail; }
+      if (r == 0) wb.io = w->io; else overlap = 0;
+    }
+    info = factor_device(m, n, w->d_a, ldd, w->d_jpvt, w->d_tau, ncols, thres, nb, stream, overlap ? &wb : NULL, NULL);
+    if (wb.io && qrdm_hostio_wb_end(wb.io) && info > QRDM_ERR_CUDA) info = QRDM_ERR_CUDA;
+    if (info <= QRDM_ERR_CUDA) goto fail;
+    const double ms_h2d = qrdm_rt_event_ms(w->ev[2], w->ev[3]);
+    CUX(qrdm_rt_event_record(w->ev[2], stream));
+    const int done = overlap ? wb.done_cols : 0; /* what is left: the unreduced tail (early stop / error), a full ring */
+    if (done < n) {
+      if (bounce) {
+        if (qrdm_hostio_download(w->io, a, lda, w->d_a, ldd, m, done, n)) { info = QRDM_ERR_CUDA; goto fail; }
+      } else {
+        CUX(qrdm_rt_d2h_2d(a + (size_t)done * lda, sizeof(double) * lda, w->d_a + (size_t)done * ldd,
+                           sizeof(double) * ldd, sizeof(double) * m, (size_t)(n - done), stream));
+      }
+    }
+    if (overlap) CUX(qrdm_rt_sync(w->copy_stream));
+    CUX(qrdm_rt_d2h(jpvt, w->d_jpvt, sizeof(int) * n, stream));
+    CUX(qrdm_rt_d2h(tau, w->d_tau, sizeof(double) * minmn, stream));
+    CUX(qrdm_rt_event_record(w->ev[3], stream));
+    CUX(qrdm_rt_sync(stream));
+    g_stats.ms_h2d = ms_h2d;
+    g_stats.ms_d2h = qrdm_rt_event_ms(w->ev[2], w->ev[3]);
+  }
   return info;
+fail:
+  /* nothing may still be writing into the caller's buffers (or reading ours) once we return */
+  qrdm_rt_sync(w->copy_stream);
+  qrdm_rt_sync(stream);
+  return info;
+#undef CUX
+}
+
+int dgeqrdm_work(int matrix_layout, int m, int n, double *a, int lda, int *jpvt, double *tau,
+                 int *ncols, double *thres, int nb) {
+  int rc = check_args(matrix_layout, m, n, lda, thres, nb);
+  if (rc) return rc;
+  for (int c = 0; c < n; ++c)
+    if (jpvt[c] != 0) {
+      /* fixed columns: the reference's own path is broken for nfxd > 0 (SURVEY.md 2a) */
+      fprintf(stderr, "qrdm_b200: jpvt[%d] != 0 on entry (fixed columns) is not supported\n", c);
+      return QRDM_ERR_UNSUPPORTED;
+    }
+  API_BODY(dgeqrdm_work_locked(m, n, a, lda, jpvt, tau, ncols, thres, nb));
 }
 
 int dgeqrdm(int matrix_layout, int m, int n, double *a, int lda, int *jpvt, double *tau, int *ncols,
@@ -534,8 +691,8 @@ int dgeqrdm(int matrix_layout, int m, int n, double *a, int lda, int *jpvt, doub
  * wrapper's DORMQR (QRDM_wrapper.c:104-126) and makes auxil.checkQR (auxil.py:20-105) possible at sizes whose
  * m x m Q would never fit on the host.  Any partition of the k reflectors into blocks is valid: T is rebuilt per
  * block from V'V and tau (k_tinv), so this does not depend on the block sizes of the factorisation. ---- */
-int qrdm_b200_dormqr_dev(char trans, int m, int n, int k, const double *d_a, int lda, const double *d_tau, double *d_c,
-                         int ldc, void *stream) {
+static int dormqr_dev_locked(char trans, int m, int n, int k, const double *d_a, int lda, const double *d_tau, double *d_c,
+                             int ldc, void *stream) {
   const int transN = (trans == 'N' || trans == 'n');
   if (!transN && trans != 'T' && trans != 't') return bad_argument(1);
   if (m <= 0) return bad_argument(2);
@@ -590,48 +747,89 @@ int qrdm_b200_dormqr_dev(char trans, int m, int n, int k, const double *d_a, int
   return w->mailbox->err; /* 0, or -13 if a NaN went through (the screen of k_wapply) */
 }
 
+int qrdm_b200_dormqr_dev(char trans, int m, int n, int k, const double *d_a, int lda, const double *d_tau, double *d_c,
+                         int ldc, void *stream) {
+  API_BODY(dormqr_dev_locked(trans, m, n, k, d_a, lda, d_tau, d_c, ldc, stream));
+}
+
 /* Host-pointer variant: A (m x k reflector columns, as returned by dgeqrdm/dgeqrf), tau and C in host memory. */
-int qrdm_b200_dormqr(char trans, int m, int n, int k, const double *a, int lda, const double *tau, double *c, int ldc) {
-  if (m <= 0) return bad_argument(2);
-  if (n <= 0) return bad_argument(3);
-  if (k < 0 || k > m) return bad_argument(4);
-  if (lda < m) return bad_argument(6);
-  if (ldc < m) return bad_argument(9);
-  int rc = qrdm_b200_init(-1);
+static int dormqr_locked(char trans, int m, int n, int k, const double *a, int lda, const double *tau, double *c, int ldc) {
+  int rc = init_impl(-1);
   if (rc) return rc;
   void *stream = g_ws.compute_stream;
   const int ldd = (m + 1) & ~1;
   double *d_a = NULL, *d_c = NULL, *d_tau = NULL;
   const int kc = k > 0 ? k : 1;
-  CU(qrdm_rt_malloc((void **)&d_a, sizeof(double) * (size_t)ldd * kc));
-  CU(qrdm_rt_malloc((void **)&d_c, sizeof(double) * (size_t)ldd * n));
-  CU(qrdm_rt_malloc((void **)&d_tau, sizeof(double) * kc));
-  CU(qrdm_rt_memset(d_c, 0, sizeof(double) * (size_t)ldd * n, stream));
+  int info = QRDM_ERR_CUDA;
+#define CUX(call)                                                                             \
+  do {                                                                                        \
+    int e__ = (call);                                                                         \
+    if (e__ != 0) {                                                                           \
+      fprintf(stderr, "qrdm_b200: CUDA error %d (%s) at %s:%d\n", e__, qrdm_rt_errstr(e__), \
+              __FILE__, __LINE__);                                                            \
+      info = QRDM_ERR_CUDA;                                                                   \
+      goto done;                                                                              \
+    }                                                                                         \
+  } while (0)
+  CUX(qrdm_rt_malloc((void **)&d_a, sizeof(double) * (size_t)ldd * kc));
+  CUX(qrdm_rt_malloc((void **)&d_c, sizeof(double) * (size_t)ldd * n));
+  CUX(qrdm_rt_malloc((void **)&d_tau, sizeof(double) * kc));
+  CUX(qrdm_rt_memset(d_c, 0, sizeof(double) * (size_t)ldd * n, stream));
   if (k > 0) {
-    CU(qrdm_rt_h2d_2d(d_a, sizeof(double) * ldd, a, sizeof(double) * lda, sizeof(double) * m, k, stream));
-    CU(qrdm_rt_h2d(d_tau, tau, sizeof(double) * k, stream));
+    CUX(qrdm_rt_h2d_2d(d_a, sizeof(double) * ldd, a, sizeof(double) * lda, sizeof(double) * m, k, stream));
+    CUX(qrdm_rt_h2d(d_tau, tau, sizeof(double) * k, stream));
   }
-  CU(qrdm_rt_h2d_2d(d_c, sizeof(double) * ldd, c, sizeof(double) * ldc, sizeof(double) * m, n, stream));
-  int info = k > 0 ? qrdm_b200_dormqr_dev(trans, m, n, k, d_a, ldd, d_tau, d_c, ldd, stream) : 0;
+  CUX(qrdm_rt_h2d_2d(d_c, sizeof(double) * ldd, c, sizeof(double) * ldc, sizeof(double) * m, n, stream));
+  info = k > 0 ? dormqr_dev_locked(trans, m, n, k, d_a, ldd, d_tau, d_c, ldd, stream) : 0;
   if (info > QRDM_ERR_CUDA) {
-    CU(qrdm_rt_d2h_2d(c, sizeof(double) * ldc, d_c, sizeof(double) * ldd, sizeof(double) * m, n, stream));
-    CU(qrdm_rt_sync(stream));
+    const int keep = info;
+    CUX(qrdm_rt_d2h_2d(c, sizeof(double) * ldc, d_c, sizeof(double) * ldd, sizeof(double) * m, n, stream));
+    info = keep;
   }
-  qrdm_rt_free(d_a);
-  qrdm_rt_free(d_c);
-  qrdm_rt_free(d_tau);
+done:
+  qrdm_rt_sync(stream); /* no copy may still touch the caller's buffers or ours */
+  if (d_a) qrdm_rt_free(d_a);
+  if (d_c) qrdm_rt_free(d_c);
+  if (d_tau) qrdm_rt_free(d_tau);
   return info;
+#undef CUX
+}
+int qrdm_b200_dormqr(char trans, int m, int n, int k, const double *a, int lda, const double *tau, double *c, int ldc) {
+  const int transN = (trans == 'N' || trans == 'n');
+  if (!transN && trans != 'T' && trans != 't') return bad_argument(1);
+  if (m <= 0) return bad_argument(2);
+  if (n <= 0) return bad_argument(3);
+  if (k < 0 || k > m) return bad_argument(4);
+  if (lda < m) return bad_argument(6);
+  if (ldc < m) return bad_argument(9);
+  API_BODY(dormqr_locked(trans, m, n, k, a, lda, tau, c, ldc));
 }
 
 /* ---- 1-D block-row sharded entry point (one process per GPU; NCCL communicator set up through
  * qrdm_b200_comm_unique_id / qrdm_b200_comm_init, e.g. with the id broadcast by torch.distributed) ---- */
-int qrdm_b200_comm_unique_id(char *out128) { return qrdm_rt_comm_unique_id(out128) ? QRDM_ERR_COMM : 0; }
-int qrdm_b200_comm_init(int rank, int nranks, const char *id128) {
-  int rc = qrdm_b200_init(-1);
+int qrdm_b200_comm_unique_id(char *out128) { API_BODY(qrdm_rt_comm_unique_id(out128) ? QRDM_ERR_COMM : 0); }
+static int comm_init_locked(int rank, int nranks, const char *id128) {
+  int rc = init_impl(-1);
   if (rc) return rc;
   return qrdm_rt_comm_init(rank, nranks, id128) ? QRDM_ERR_COMM : 0;
 }
-void qrdm_b200_comm_destroy(void) { qrdm_rt_comm_destroy(); }
+int qrdm_b200_comm_init(int rank, int nranks, const char *id128) { API_BODY(comm_init_locked(rank, nranks, id128)); }
+void qrdm_b200_comm_destroy(void) { api_lock(); qrdm_rt_comm_destroy(); api_unlock(); }
+
+/* Peer memory of the row-sharded path (SURVEY.md 8e "fusion with the collective"): every rank owns one receive
+ * buffer in HBM, exports it with CUDA IPC and maps its peers' buffers, so that kernels exchange LL packets by
+ * plain stores over NVLink (k_peer.cu).  The launcher moves the 64-byte handles between the processes
+ * (qrdm_b200/sharded.py: torch.distributed all_gather) — the same division of labour as for the NCCL unique id. */
+static int peer_handle_locked(char *out64) {
+  int rc = init_impl(-1);
+  if (rc) return rc;
+  return qrdm_rt_peer_export(out64) ? QRDM_ERR_COMM : 0;
+}
+int qrdm_b200_peer_handle(char *out64) { API_BODY(peer_handle_locked(out64)); }
+int qrdm_b200_peer_open(int rank, int nranks, const char *handles64) {
+  API_BODY(qrdm_rt_peer_open(rank, nranks, handles64) ? QRDM_ERR_COMM : 0);
+}
+void qrdm_b200_peer_close(void) { api_lock(); qrdm_rt_peer_destroy(); api_unlock(); }
 
 int dgeqrdm_dev_sharded(int m_local, int m_global, int row0, int nranks, int n, double *d_a, int lda,
                         int *d_jpvt, double *d_tau, int *ncols, const double *thres, int nb, void *stream) {
@@ -640,26 +838,25 @@ int dgeqrdm_dev_sharded(int m_local, int m_global, int row0, int nranks, int n, 
   if (rc) return rc;
   if (lda < (m_local > 1 ? m_local : 1)) return bad_argument(5);
   qrdm_shard sh = {row0, m_global, nranks};
-  return factor_device(m_local, n, d_a, lda, d_jpvt, d_tau, ncols, thres, nb, stream, NULL, &sh);
+  API_BODY(factor_device(m_local, n, d_a, lda, d_jpvt, d_tau, ncols, thres, nb, stream, NULL, &sh));
 }
 
 /* ---- batched mode: `batch` independent m x n matrices, matrix b at
  * a + b*stride_a (column-major, lda), outputs at jpvt + b*n, tau + b*min(m,n), ncols + b*n;
- * multi-GPU = each rank passes its share (independent units, no collective). ---- */
-/* Batched mode (BASELINE configs[4]): matrices with m, n <= 1024 run as ONE launch with one
- * CTA per matrix (k_small.cu); larger ones fall back to a loop over the one-matrix path. */
-int dgeqrdm_batched_dev(int batch, int m, int n, double *d_a, int lda, long long stride_a, int *d_jpvt,
-                        double *d_tau, int *d_ncols, int *d_infos, const double *thres, int nb, void *stream) {
-  if (batch <= 0 || stride_a < (long long)lda * n) return bad_argument(1);
-  int rc = check_args(QRDM_COL_MAJOR, m, n, lda, thres, nb);
-  if (rc) return rc;
-  rc = qrdm_b200_init(-1);
+ * multi-GPU = each rank passes its share (independent units, no collective).  Matrices with m, n <= 1024 run as
+ * ONE launch with one CTA per matrix (k_small.cu); larger ones fall back to a loop over the one-matrix path.
+ * thres[2] (the eta of stop mode 3) is read only when some matrix asks for mode 3 — the reference reads it under
+ * `ncols[0] == 3` only (src/dgeqrdm_work.c:539-543) and its notebook passes a 2-element thres. ---- */
+static int batched_dev_locked(int batch, int m, int n, double *d_a, int lda, long long stride_a, int *d_jpvt,
+                              double *d_tau, int *d_ncols, int *d_infos, const double *thres, int nb, void *stream) {
+  int rc = init_impl(-1);
   if (rc) return rc;
   if (!qrdm_k_small_supported(m, n)) return QRDM_ERR_UNSUPPORTED;
   qrdm_workspace *w = &g_ws;
   memset(&g_stats, 0, sizeof(g_stats));
   const long long launches0 = qrdm_rt_launch_count();
   CU(qrdm_rt_event_record(w->ev[0], stream));
+  /* the stop modes live on the device here: thres must hold 3 elements (documented in include/qrdm_b200.h) */
   CU(qrdm_k_small(batch, m, n, d_a, lda, stride_a, d_jpvt, d_tau, d_ncols, d_infos, thres[0], thres[1], thres[2], nb,
                   stream));
   CU(qrdm_rt_event_record(w->ev[1], stream));
@@ -668,22 +865,40 @@ int dgeqrdm_batched_dev(int batch, int m, int n, double *d_a, int lda, long long
   g_stats.launches = qrdm_rt_launch_count() - launches0;
   return 0;
 }
+int dgeqrdm_batched_dev(int batch, int m, int n, double *d_a, int lda, long long stride_a, int *d_jpvt,
+                        double *d_tau, int *d_ncols, int *d_infos, const double *thres, int nb, void *stream) {
+  if (batch <= 0 || stride_a < (long long)lda * n) return bad_argument(1);
+  int rc = check_args(QRDM_COL_MAJOR, m, n, lda, thres, nb);
+  if (rc) return rc;
+  API_BODY(batched_dev_locked(batch, m, n, d_a, lda, stride_a, d_jpvt, d_tau, d_ncols, d_infos, thres, nb, stream));
+}
 
 static int batched_loop(int batch, int m, int n, double *a, int lda, long long stride_a, int *jpvt, double *tau,
                         int *ncols, double *thres, int nb, int *infos);
 
 #define QRDM_BATCH_CHUNK 592 /* matrices per pipeline stage: 4 waves of 148 CTAs */
 
-int dgeqrdm_batched(int batch, int m, int n, double *a, int lda, long long stride_a, int *jpvt, double *tau,
-                    int *ncols, double *thres, int nb, int *infos) {
+#define CUX(call)                                                                             \
+  do {                                                                                        \
+    int e__ = (call);                                                                         \
+    if (e__ != 0) {                                                                           \
+      fprintf(stderr, "qrdm_b200: CUDA error %d (%s) at %s:%d\n", e__, qrdm_rt_errstr(e__), \
+              __FILE__, __LINE__);                                                            \
+      worst = QRDM_ERR_CUDA;                                                                  \
+      goto done;                                                                              \
+    }                                                                                         \
+  } while (0)
+
+static int batched_locked(int batch, int m, int n, double *a, int lda, long long stride_a, int *jpvt, double *tau,
+                          int *ncols, double *thres, int nb, int *infos) {
   qrdm_workspace *w = &g_ws;
-  if (batch <= 0 || stride_a < (long long)lda * n) return bad_argument(1);
-  int rc = check_args(QRDM_COL_MAJOR, m, n, lda, thres, nb);
-  if (rc) return rc;
-  rc = qrdm_b200_init(-1);
+  int rc = init_impl(-1);
   if (rc) return rc;
   if (!qrdm_k_small_supported(m, n) || getenv("QRDM_B200_BATCH_LOOP"))
     return batched_loop(batch, m, n, a, lda, stride_a, jpvt, tau, ncols, thres, nb, infos);
+  double eta3 = 0.0;
+  for (int b = 0; b < batch; ++b)
+    if (ncols[(size_t)n * b] == 3) { eta3 = thres[2]; break; }
   /* three streams: chunk c+1 is uploaded and chunk c-1 downloaded while chunk c is factored */
   if (!w->h2d_stream) CU(qrdm_rt_stream_create(&w->h2d_stream));
   void *s_up = w->h2d_stream, *s_k = w->compute_stream, *s_down = w->copy_stream;
@@ -693,75 +908,88 @@ int dgeqrdm_batched(int batch, int m, int n, double *a, int lda, long long strid
   const int chunk = batch < QRDM_BATCH_CHUNK ? batch : QRDM_BATCH_CHUNK;
   const int nbuf = batch > chunk ? 3 : 1; /* ring of device chunks */
   double *d_all = NULL, *d_tau = NULL;
-  int *d_jpvt = NULL, *d_ncols = NULL, *d_infos = NULL;
+  int *d_jpvt = NULL, *d_ncols = NULL, *d_infos = NULL, *h_infos = NULL;
   void *ev_up[3] = {0}, *ev_k[3] = {0}, *ev_down[3] = {0};
-  CU(qrdm_rt_malloc((void **)&d_all, sizeof(double) * per * chunk * nbuf));
-  CU(qrdm_rt_malloc((void **)&d_tau, sizeof(double) * (size_t)minmn * chunk * nbuf));
-  CU(qrdm_rt_malloc((void **)&d_jpvt, sizeof(int) * (size_t)n * chunk * nbuf));
-  CU(qrdm_rt_malloc((void **)&d_ncols, sizeof(int) * (size_t)n * chunk * nbuf));
-  CU(qrdm_rt_malloc((void **)&d_infos, sizeof(int) * (size_t)chunk * nbuf));
-  for (int q = 0; q < nbuf; ++q) {
-    CU(qrdm_rt_event_create(&ev_up[q]));
-    CU(qrdm_rt_event_create(&ev_k[q]));
-    CU(qrdm_rt_event_create(&ev_down[q]));
-  }
-  int *h_infos = (int *)malloc(sizeof(int) * (size_t)batch);
+  int worst = 0;
+  h_infos = (int *)malloc(sizeof(int) * (size_t)batch);
   if (!h_infos) return QRDM_ERR_CUDA;
+  CUX(qrdm_rt_malloc((void **)&d_all, sizeof(double) * per * chunk * nbuf));
+  CUX(qrdm_rt_malloc((void **)&d_tau, sizeof(double) * (size_t)minmn * chunk * nbuf));
+  CUX(qrdm_rt_malloc((void **)&d_jpvt, sizeof(int) * (size_t)n * chunk * nbuf));
+  CUX(qrdm_rt_malloc((void **)&d_ncols, sizeof(int) * (size_t)n * chunk * nbuf));
+  CUX(qrdm_rt_malloc((void **)&d_infos, sizeof(int) * (size_t)chunk * nbuf));
+  for (int q = 0; q < nbuf; ++q) {
+    CUX(qrdm_rt_event_create(&ev_up[q]));
+    CUX(qrdm_rt_event_create(&ev_k[q]));
+    CUX(qrdm_rt_event_create(&ev_down[q]));
+  }
   memset(&g_stats, 0, sizeof(g_stats));
   const long long launches0 = qrdm_rt_launch_count();
-  CU(qrdm_rt_event_record(w->ev[0], s_k));
-  int nchunks = (batch + chunk - 1) / chunk;
+  CUX(qrdm_rt_event_record(w->ev[0], s_k));
+  const int nchunks = (batch + chunk - 1) / chunk;
   for (int c = 0; c < nchunks; ++c) {
     const int q = c % nbuf, b0 = c * chunk, cnt = batch - b0 < chunk ? batch - b0 : chunk;
     double *da = d_all + per * chunk * q;
     double *dt = d_tau + (size_t)minmn * chunk * q;
     int *dj = d_jpvt + (size_t)n * chunk * q, *dn = d_ncols + (size_t)n * chunk * q, *di = d_infos + (size_t)chunk * q;
-    if (c >= nbuf) CU(qrdm_rt_stream_wait_event(s_up, ev_down[q])); /* ring slot free again */
+    if (c >= nbuf) CUX(qrdm_rt_stream_wait_event(s_up, ev_down[q])); /* ring slot free again */
     if (lda == m && ldd == m && stride_a == (long long)m * n) {
-      CU(qrdm_rt_h2d(da, a + (size_t)stride_a * b0, sizeof(double) * per * cnt, s_up));
+      CUX(qrdm_rt_h2d(da, a + (size_t)stride_a * b0, sizeof(double) * per * cnt, s_up));
     } else {
       for (int b = 0; b < cnt; ++b)
-        CU(qrdm_rt_h2d_2d(da + per * b, sizeof(double) * ldd, a + (size_t)stride_a * (b0 + b), sizeof(double) * lda,
-                          sizeof(double) * m, n, s_up));
+        CUX(qrdm_rt_h2d_2d(da + per * b, sizeof(double) * ldd, a + (size_t)stride_a * (b0 + b), sizeof(double) * lda,
+                           sizeof(double) * m, n, s_up));
     }
-    CU(qrdm_rt_h2d(dt, tau + (size_t)minmn * b0, sizeof(double) * (size_t)minmn * cnt, s_up));
-    CU(qrdm_rt_h2d(dn, ncols + (size_t)n * b0, sizeof(int) * (size_t)n * cnt, s_up));
-    CU(qrdm_rt_event_record(ev_up[q], s_up));
-    CU(qrdm_rt_stream_wait_event(s_k, ev_up[q]));
-    CU(qrdm_k_small(cnt, m, n, da, ldd, (long long)per, dj, dt, dn, di, thres[0], thres[1], thres[2], nb, s_k));
-    CU(qrdm_rt_event_record(ev_k[q], s_k));
-    CU(qrdm_rt_stream_wait_event(s_down, ev_k[q]));
+    CUX(qrdm_rt_h2d(dt, tau + (size_t)minmn * b0, sizeof(double) * (size_t)minmn * cnt, s_up));
+    CUX(qrdm_rt_h2d(dn, ncols + (size_t)n * b0, sizeof(int) * (size_t)n * cnt, s_up));
+    CUX(qrdm_rt_event_record(ev_up[q], s_up));
+    CUX(qrdm_rt_stream_wait_event(s_k, ev_up[q]));
+    CUX(qrdm_k_small(cnt, m, n, da, ldd, (long long)per, dj, dt, dn, di, thres[0], thres[1], eta3, nb, s_k));
+    CUX(qrdm_rt_event_record(ev_k[q], s_k));
+    CUX(qrdm_rt_stream_wait_event(s_down, ev_k[q]));
     if (lda == m && ldd == m && stride_a == (long long)m * n) {
-      CU(qrdm_rt_d2h(a + (size_t)stride_a * b0, da, sizeof(double) * per * cnt, s_down));
+      CUX(qrdm_rt_d2h(a + (size_t)stride_a * b0, da, sizeof(double) * per * cnt, s_down));
     } else {
       for (int b = 0; b < cnt; ++b)
-        CU(qrdm_rt_d2h_2d(a + (size_t)stride_a * (b0 + b), sizeof(double) * lda, da + per * b, sizeof(double) * ldd,
-                          sizeof(double) * m, n, s_down));
+        CUX(qrdm_rt_d2h_2d(a + (size_t)stride_a * (b0 + b), sizeof(double) * lda, da + per * b, sizeof(double) * ldd,
+                           sizeof(double) * m, n, s_down));
     }
-    CU(qrdm_rt_d2h(jpvt + (size_t)n * b0, dj, sizeof(int) * (size_t)n * cnt, s_down));
-    CU(qrdm_rt_d2h(tau + (size_t)minmn * b0, dt, sizeof(double) * (size_t)minmn * cnt, s_down));
-    CU(qrdm_rt_d2h(ncols + (size_t)n * b0, dn, sizeof(int) * (size_t)n * cnt, s_down));
-    CU(qrdm_rt_d2h(h_infos + b0, di, sizeof(int) * (size_t)cnt, s_down));
-    CU(qrdm_rt_event_record(ev_down[q], s_down));
+    CUX(qrdm_rt_d2h(jpvt + (size_t)n * b0, dj, sizeof(int) * (size_t)n * cnt, s_down));
+    CUX(qrdm_rt_d2h(tau + (size_t)minmn * b0, dt, sizeof(double) * (size_t)minmn * cnt, s_down));
+    CUX(qrdm_rt_d2h(ncols + (size_t)n * b0, dn, sizeof(int) * (size_t)n * cnt, s_down));
+    CUX(qrdm_rt_d2h(h_infos + b0, di, sizeof(int) * (size_t)cnt, s_down));
+    CUX(qrdm_rt_event_record(ev_down[q], s_down));
   }
-  CU(qrdm_rt_event_record(w->ev[1], s_k));
-  CU(qrdm_rt_sync(s_down));
-  CU(qrdm_rt_sync(s_k));
+  CUX(qrdm_rt_event_record(w->ev[1], s_k));
+  CUX(qrdm_rt_sync(s_down));
+  CUX(qrdm_rt_sync(s_k));
   g_stats.ms_total = qrdm_rt_event_ms(w->ev[0], w->ev[1]);
   g_stats.launches = qrdm_rt_launch_count() - launches0;
-  int worst = 0;
   for (int b = 0; b < batch; ++b) {
     if (infos) infos[b] = h_infos[b];
     if (h_infos[b] != 0 && worst == 0) worst = h_infos[b];
   }
+done:
+  /* every stream idle before the buffers go away / the caller gets its arrays back */
+  qrdm_rt_sync(s_up);
+  qrdm_rt_sync(s_k);
+  qrdm_rt_sync(s_down);
   free(h_infos);
   for (int q = 0; q < nbuf; ++q) { qrdm_rt_event_destroy(ev_up[q]); qrdm_rt_event_destroy(ev_k[q]); qrdm_rt_event_destroy(ev_down[q]); }
-  qrdm_rt_free(d_all);
-  qrdm_rt_free(d_tau);
-  qrdm_rt_free(d_jpvt);
-  qrdm_rt_free(d_ncols);
-  qrdm_rt_free(d_infos);
+  if (d_all) qrdm_rt_free(d_all);
+  if (d_tau) qrdm_rt_free(d_tau);
+  if (d_jpvt) qrdm_rt_free(d_jpvt);
+  if (d_ncols) qrdm_rt_free(d_ncols);
+  if (d_infos) qrdm_rt_free(d_infos);
   return worst;
+}
+
+int dgeqrdm_batched(int batch, int m, int n, double *a, int lda, long long stride_a, int *jpvt, double *tau,
+                    int *ncols, double *thres, int nb, int *infos) {
+  if (batch <= 0 || stride_a < (long long)lda * n) return bad_argument(1);
+  int rc = check_args(QRDM_COL_MAJOR, m, n, lda, thres, nb);
+  if (rc) return rc;
+  API_BODY(batched_locked(batch, m, n, a, lda, stride_a, jpvt, tau, ncols, thres, nb, infos));
 }
 
 /* matrices too large for the one-CTA kernel: one after the other through the one-matrix path */
@@ -774,35 +1002,42 @@ static int batched_loop(int batch, int m, int n, double *a, int lda, long long s
   double *d_all = NULL, *d_tau = NULL;
   int *d_jpvt = NULL;
   const size_t per = (size_t)ldd * n;
-  CU(qrdm_rt_malloc((void **)&d_all, sizeof(double) * per * batch));
-  CU(qrdm_rt_malloc((void **)&d_tau, sizeof(double) * (size_t)minmn * batch));
-  CU(qrdm_rt_malloc((void **)&d_jpvt, sizeof(int) * (size_t)n * batch));
-  for (int b = 0; b < batch; ++b)
-    CU(qrdm_rt_h2d_2d(d_all + per * b, sizeof(double) * ldd, a + (size_t)stride_a * b, sizeof(double) * lda,
-                      sizeof(double) * m, n, stream));
-  CU(qrdm_rt_h2d(d_tau, tau, sizeof(double) * (size_t)minmn * batch, stream));
   int worst = 0;
   double ms = 0.0;
   long long launches = 0;
+  CUX(qrdm_rt_malloc((void **)&d_all, sizeof(double) * per * batch));
+  CUX(qrdm_rt_malloc((void **)&d_tau, sizeof(double) * (size_t)minmn * batch));
+  CUX(qrdm_rt_malloc((void **)&d_jpvt, sizeof(int) * (size_t)n * batch));
+  for (int b = 0; b < batch; ++b)
+    CUX(qrdm_rt_h2d_2d(d_all + per * b, sizeof(double) * ldd, a + (size_t)stride_a * b, sizeof(double) * lda,
+                       sizeof(double) * m, n, stream));
+  CUX(qrdm_rt_h2d(d_tau, tau, sizeof(double) * (size_t)minmn * batch, stream));
   for (int b = 0; b < batch; ++b) {
     int info = factor_device(m, n, d_all + per * b, ldd, d_jpvt + (size_t)n * b, d_tau + (size_t)minmn * b,
                              ncols + (size_t)n * b, thres, nb, stream, NULL, NULL);
     if (infos) infos[b] = info;
-    if (info <= QRDM_ERR_CUDA) { worst = info; break; }
+    if (info <= QRDM_ERR_CUDA) { worst = info; goto done; }
     if (info != 0 && worst == 0) worst = info;
     ms += g_stats.ms_total;
     launches += g_stats.launches;
   }
-  for (int b = 0; b < batch; ++b)
-    CU(qrdm_rt_d2h_2d(a + (size_t)stride_a * b, sizeof(double) * lda, d_all + per * b, sizeof(double) * ldd,
-                      sizeof(double) * m, n, stream));
-  CU(qrdm_rt_d2h(jpvt, d_jpvt, sizeof(int) * (size_t)n * batch, stream));
-  CU(qrdm_rt_d2h(tau, d_tau, sizeof(double) * (size_t)minmn * batch, stream));
-  CU(qrdm_rt_sync(stream));
+  {
+    const int keep = worst;
+    for (int b = 0; b < batch; ++b)
+      CUX(qrdm_rt_d2h_2d(a + (size_t)stride_a * b, sizeof(double) * lda, d_all + per * b, sizeof(double) * ldd,
+                         sizeof(double) * m, n, stream));
+    CUX(qrdm_rt_d2h(jpvt, d_jpvt, sizeof(int) * (size_t)n * batch, stream));
+    CUX(qrdm_rt_d2h(tau, d_tau, sizeof(double) * (size_t)minmn * batch, stream));
+    CUX(qrdm_rt_sync(stream));
+    worst = keep;
+  }
   g_stats.ms_total = ms;
   g_stats.launches = launches;
-  qrdm_rt_free(d_all);
-  qrdm_rt_free(d_tau);
-  qrdm_rt_free(d_jpvt);
+done:
+  qrdm_rt_sync(stream);
+  if (d_all) qrdm_rt_free(d_all);
+  if (d_tau) qrdm_rt_free(d_tau);
+  if (d_jpvt) qrdm_rt_free(d_jpvt);
   return worst;
 }
+#undef CUX

@@ -18,99 +18,13 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "ll.cuh"
 
 #define PANEL_THREADS 512
 #define PANEL_WARPS (PANEL_THREADS / 32)
 #define PANEL_CPW ((63 + PANEL_WARPS - 1) / PANEL_WARPS)  // columns per warp in the sweep
 #define PANEL_RG (PANEL_THREADS / 64)                      // reduction groups
 #define QRDM_PANEL_AG_GAIN 0.45                            // us per column saved by the one-hop exchange (G <= 32), measured
-
-// Cross-CTA exchange without barriers: every value travels as a 16-byte "LL" packet
-// {lo32, tag, hi32, tag} (the scheme NCCL's low-latency protocol uses): an aligned 8-byte store is
-// atomic, so a reader that sees the expected tag in both halves has the payload — no fence, no
-// counter, one L2 round trip.  tag = (panel launch epoch << 8) + step + 1 is never reused.
-// Per column the reduction is a reduce-scatter + broadcast: CTA (jj mod G) gathers the G partials of
-// column jj, sums them in a fixed order (deterministic) and publishes the total; everybody then
-// polls the 64 totals + the 64 entries of the pivot row published by the CTA that owns that row.
-// Traffic per column ~ G*64 packets instead of the G*G*64 of an all-to-all read, latency two
-// round trips, and identical inputs on every CTA => bit-identical decisions (stop test, tau).
-struct __align__(16) LLPacket { unsigned lo, tag0, hi, tag1; };
-#define LL_SPIN_LIMIT (1u << 27)  // polls (~0.5 us each) before a waiting thread gives up with a trap
-
-__device__ __forceinline__ void ll_store(LLPacket* p, double v, unsigned tag) {
-  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
-  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "r"((unsigned)b), "r"(tag),
-               "r"((unsigned)(b >> 32)), "r"(tag)
-               : "memory");
-}
-__device__ __forceinline__ double ll_load(const LLPacket* p, unsigned tag) {
-  unsigned lo, t0, hi, t1, spins = 0;
-  do {
-    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(lo), "=r"(t0), "=r"(hi), "=r"(t1) : "l"(p) : "memory");
-    if (++spins > LL_SPIN_LIMIT) __trap();  // a partner CTA never showed up: fail loudly instead of hanging the GPU
-  } while (t0 != tag || t1 != tag);
-  return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
-}
-
-// Sum over the partials of all G CTAs for one column, lane l taking CTAs l, l+32, ...  A lane has up to
-// ceil(148/32) = 5 packets to read: all loads are issued first and only then checked (re-polling the ones that
-// had not arrived), so they cost ONE L2 round trip instead of one each — the blocking ll_load in a loop
-// serialised them, which is where the 0.012 us per CTA of the panel's per-column cost came from.
-// The packets are added in the same order as before: results are bit-identical.
-__device__ __forceinline__ double ll_gather_sum(const LLPacket* base, size_t stride, int lane, int G, unsigned tag) {
-  constexpr int MAXU = (QRDM_PANEL_MAXCTA + 31) / 32;
-  unsigned lo[MAXU], t0[MAXU], hi[MAXU], t1[MAXU];
-#pragma unroll
-  for (int u = 0; u < MAXU; ++u) {
-    const int c = lane + 32 * u;
-    if (c < G)
-      asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];\n"
-                   : "=r"(lo[u]), "=r"(t0[u]), "=r"(hi[u]), "=r"(t1[u]) : "l"(base + (size_t)c * stride) : "memory");
-  }
-  double v = 0.0;
-#pragma unroll
-  for (int u = 0; u < MAXU; ++u) {
-    const int c = lane + 32 * u;
-    if (c < G) {
-      unsigned spins = 0;
-      while (t0[u] != tag || t1[u] != tag) {
-        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];\n"
-                     : "=r"(lo[u]), "=r"(t0[u]), "=r"(hi[u]), "=r"(t1[u]) : "l"(base + (size_t)c * stride) : "memory");
-        if (++spins > LL_SPIN_LIMIT) __trap();
-      }
-      v += __longlong_as_double((long long)(((unsigned long long)hi[u] << 32) | lo[u]));
-    }
-  }
-  return v;
-}
-
-// all-gather variant: partials of CTAs start, start+step, ... (<= 5 of them), loads issued together
-__device__ __forceinline__ double ll_gather_sum_strided(const LLPacket* base, size_t stride, int start, int step, int G, unsigned tag) {
-  constexpr int MAXU = 5;
-  unsigned lo[MAXU], t0[MAXU], hi[MAXU], t1[MAXU];
-#pragma unroll
-  for (int u = 0; u < MAXU; ++u) {
-    const int c = start + step * u;
-    if (c < G)
-      asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];\n"
-                   : "=r"(lo[u]), "=r"(t0[u]), "=r"(hi[u]), "=r"(t1[u]) : "l"(base + (size_t)c * stride) : "memory");
-  }
-  double v = 0.0;
-#pragma unroll
-  for (int u = 0; u < MAXU; ++u) {
-    const int c = start + step * u;
-    if (c < G) {
-      unsigned spins = 0;
-      while (t0[u] != tag || t1[u] != tag) {
-        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];\n"
-                     : "=r"(lo[u]), "=r"(t0[u]), "=r"(hi[u]), "=r"(t1[u]) : "l"(base + (size_t)c * stride) : "memory");
-        if (++spins > LL_SPIN_LIMIT) __trap();
-      }
-      v += __longlong_as_double((long long)(((unsigned long long)hi[u] << 32) | lo[u]));
-    }
-  }
-  return v;
-}
 
 template <bool SMEM>
 __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(qrdm_prob P, int rpc, unsigned epoch) {
@@ -582,7 +496,17 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_reg(qrdm_prob P, int
 // for the whole sweep, and the per-column sums are reduced block-wide once per step.  The cross-CTA
 // exchange is a single hop: every CTA reads all G partials of the <= 8 columns (G*8 LL packets).
 #define TALL_B QRDM_TALL_B
-__global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_tall(qrdm_prob P, int rpc, unsigned epoch) {
+// MG = true: the rows of the panel live on several GPUs (1-D block-row sharding).  Same kernel, but
+// the per-column exchange has a second level that crosses NVLink INSIDE the kernel: CTA 0 (the rank leader) totals
+// the rank's G partial packets, stores the <= 8 rank sums and the pivot-row entries it owns (zeros otherwise) as LL
+// packets into slot [rank] of EVERY rank's receive buffer (k_peer.cu), and every CTA of every rank then polls the
+// nranks slots of its own buffer and adds them in rank order.  Same packets, same order everywhere => all CTAs of
+// all ranks compute bit-identical tau / beta / stop decisions; no kernel boundary, no ncclAllReduce per column
+// (the round-1 sharded panel paid one launch + one 1-KB ncclAllReduce per column: ~70 us x 512 columns on C4).
+// Row bookkeeping: this rank holds global rows [row0, row0 + m); lr0 = first local row of the sub-panel, goff = the
+// panel-relative index of that row (0 on the rank that owns the diagonal block).  Single GPU: lr0 = j, goff = 0.
+template <bool MG>
+__global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_tall(qrdm_prob P, int rpc, unsigned epoch, PeerCtx pc) {
   __shared__ double S_[TALL_B], rowv[TALL_B];
   __shared__ double sacc[PANEL_WARPS][TALL_B];
   qrdm_ctrl* ctrl = P.ctrl;
@@ -591,13 +515,22 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_tall(qrdm_prob P, in
   const int j = qg.j, fjb = qg.fjb, sub_s = P.sub - 1;
   const int jmain = ctrl->j, fjb_main = ctrl->fjb;
   if (fjb <= 0) return;
-  const int rows = P.m - j, lda = P.lda;
+  const int lr0 = qrdm_jr(P, j);          // first local active row
+  const int goff = P.row0 + lr0 - j;      // its index relative to the sub-panel's first row (>= 0)
+  const int rows_l = P.m - lr0;           // local active rows
+  const int rows = P.m_glob - j;          // active rows of the whole (global) panel
+  const int lda = P.lda;
   const int G = gridDim.x, b = blockIdx.x;
-  const int r0 = min(rows, b * rpc), r1 = min(rows, r0 + rpc), nr = r1 - r0;
-  double* Ap = P.a + (size_t)j * lda + j + r0;  // local row r, sub-panel column c: Ap[c*lda + r]
+  const int r0 = min(rows_l, b * rpc), r1 = min(rows_l, r0 + rpc), nr = r1 - r0;
+  double* Ap = P.a + (size_t)j * lda + lr0 + r0;  // local row r of this CTA, sub-panel column c: Ap[c*lda + r]
   LLPacket* part = reinterpret_cast<LLPacket*>(P.panel_part);  // [2][PANEL_MAXCTA][64]
   LLPacket* bcast = reinterpret_cast<LLPacket*>(P.panel_row);  // [2][128]
   const unsigned tag_base = epoch << 8;
+  const int me = MG ? pc.rank : 0, NR = MG ? pc.nranks : 1;
+  // cross-GPU exchanges are numbered by a counter that lives on the device and advances identically on every rank
+  // (it counts the exchanges actually performed — the DM early stop makes that data dependent): exchange x uses slot
+  // parity x & 1 and tag x + 1, so consecutive exchanges never share a slot, within or across launches
+  const unsigned px0 = MG ? *pc.xseq : 0u;
 
   // block-wide sums of acc[0..TALL_B) -> LL packets part[buf][b][jj] for jj in [lo, fjb)
   auto publish = [&](double (&acc)[TALL_B], int buf, int lo, unsigned tag) {
@@ -622,7 +555,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_tall(qrdm_prob P, in
 #pragma unroll
     for (int c = 0; c < TALL_B; ++c) acc[c] = 0.0;
     for (int r = tid; r < nr; r += PANEL_THREADS) {
-      const int R = r0 + r;
+      const int R = goff + r0 + r;
       double v[TALL_B];
 #pragma unroll
       for (int c = 0; c < TALL_B; ++c) v[c] = c < fjb ? Ap[(size_t)c * lda + r] : 0.0;
@@ -644,11 +577,40 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_tall(qrdm_prob P, in
     const int cur = i & 1, nxt = cur ^ 1;
     const unsigned tag = tag_base + i + 1;
     // ---- gather: warp jj totals column jj over all CTAs (lanes <-> CTAs, fixed order); pivot row ----
-    if (wid < TALL_B && wid >= i && wid < fjb) {
-      double v = 0.0;
-      v += ll_gather_sum(&part[(size_t)cur * QRDM_PANEL_MAXCTA * 64 + wid], 64, lane, G, tag);
-      v = warp_sum(v);
-      if (lane == 0) { S_[wid] = v; rowv[wid] = ll_load(&bcast[cur * 128 + 64 + wid], tag); }
+    if (!MG) {
+      if (wid < TALL_B && wid >= i && wid < fjb) {
+        double v = 0.0;
+        v += ll_gather_sum(&part[(size_t)cur * QRDM_PANEL_MAXCTA * 64 + wid], 64, lane, G, tag);
+        v = warp_sum(v);
+        if (lane == 0) { S_[wid] = v; rowv[wid] = ll_load(&bcast[cur * 128 + 64 + wid], tag); }
+      }
+    } else if (wid < TALL_B && wid >= i && wid < fjb) {
+      const unsigned ptag = px0 + (unsigned)i + 1u;
+      const int pcur = (int)((px0 + (unsigned)i) & 1u);
+      if (b == 0) {
+        // rank leader: total of this rank's CTAs, then one packet per (column, peer) over NVLink.  Only the rank that
+        // owns global row j + i has a pivot-row entry; the others contribute an exact 0.
+        double v = ll_gather_sum(&part[(size_t)cur * QRDM_PANEL_MAXCTA * 64 + wid], 64, lane, G, tag);
+        v = warp_sum(v);
+        const int grow = j + i;  // global row of the pivot
+        double rv = 0.0;
+        if (grow >= P.row0 && grow < P.row0 + P.m) {
+          if (lane == 0) rv = ll_load(&bcast[cur * 128 + 64 + wid], tag);
+          rv = __shfl_sync(0xffffffffu, rv, 0);
+        }
+        if (lane < NR) ll_store(peer_panel_slot(pc.recv[lane], pcur, me, wid), v, ptag);
+        else if (lane >= 8 && lane < 8 + NR) ll_store(peer_panel_slot(pc.recv[lane - 8], pcur, me, 64 + wid), rv, ptag);
+      }
+      // everybody: the nranks rank sums from the local receive buffer, added in rank order
+      double x = 0.0;
+      if (lane < NR) x = ll_load(peer_panel_slot(pc.recv[me], pcur, lane, wid), ptag);
+      else if (lane >= 8 && lane < 8 + NR) x = ll_load(peer_panel_slot(pc.recv[me], pcur, lane - 8, 64 + wid), ptag);
+      double sv = 0.0, rvs = 0.0;
+      for (int r = 0; r < NR; ++r) {
+        sv += __shfl_sync(0xffffffffu, x, r);
+        rvs += __shfl_sync(0xffffffffu, x, 8 + r);
+      }
+      if (lane == 0) { S_[wid] = sv; rowv[wid] = rvs; }
     }
     __syncthreads();
     // ---- reflector scalars (dlarfg_mia) ----
@@ -679,7 +641,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_tall(qrdm_prob P, in
 #pragma unroll
     for (int c = 0; c < TALL_B; ++c) acc[c] = 0.0;
     for (int r = tid; r < nr; r += PANEL_THREADS) {
-      const int R = r0 + r;
+      const int R = goff + r0 + r;
       if (R < i) continue;
       double v = 1.0;
       if (R > i) {
@@ -723,32 +685,76 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_tall(qrdm_prob P, in
     ctrl->tall_done = (k < fjb) ? 1 : 0;
     ctrl->tall_thres = thres;
     ctrl->fjb_cmp = tk;
+    if (MG) *pc.xseq = px0 + (unsigned)(k < fjb ? k + 1 : fjb);  // exchanges performed by this launch
   }
-  // ---- clean copy of the sub-panel's reflectors into Vc columns voff .. voff + 7 ----
+  // ---- clean copy of the sub-panel's reflectors into Vc columns voff .. voff + 7 (Vc is indexed by LOCAL row) ----
   const int kpad = min(TALL_B, 64 - qg.voff);
-  const int jal = jmain & ~(QRDM_ROWALIGN - 1);
+  const int jal = qrdm_jr(P, jmain) & ~(QRDM_ROWALIGN - 1);
   for (int q = 0; q < kpad; ++q) {
-    double* vcol = P.vc + (size_t)(qg.voff + q) * P.ldv + j + r0;
+    double* vcol = P.vc + (size_t)(qg.voff + q) * P.ldv + lr0 + r0;
     for (int r = tid; r < nr; r += PANEL_THREADS) {
-      const int R = r0 + r;
+      const int R = goff + r0 + r;
       double v = 0.0;
       if (q < k) v = (R > q) ? Ap[(size_t)q * lda + r] : (R == q ? 1.0 : 0.0);
       vcol[r] = v;
     }
     if (b == 0)
-      for (int g = jal + tid; g < j; g += PANEL_THREADS) P.vc[(size_t)(qg.voff + q) * P.ldv + g] = 0.0;
+      for (int g = jal + tid; g < lr0; g += PANEL_THREADS) P.vc[(size_t)(qg.voff + q) * P.ldv + g] = 0.0;
   }
 }
 
+// LL tags = (epoch << 8) + step.  Three disjoint epoch ranges share the exchange buffers: [1, 2^21) blocked tall
+// panel, [2^21, 2^22) smem/global panel, [2^22, 2^23) register panel.  When a range wraps, packets of its previous
+// cycle could carry tags that match again, so the buffers are cleared (stream-ordered, between two panel launches no
+// packet is live) before the range restarts.
+static unsigned panel_next_epoch(unsigned& e, unsigned lo, unsigned hi, const qrdm_prob* p, void* stream) {
+  if (e + 1 >= hi) {
+    cudaMemsetAsync(p->panel_part, 0, (size_t)16 * 2 * QRDM_PANEL_MAXCTA * 64, (cudaStream_t)stream);
+    cudaMemsetAsync(p->panel_row, 0, (size_t)16 * 2 * 128, (cudaStream_t)stream);
+    e = lo;
+  } else {
+    ++e;
+  }
+  return e;
+}
+static unsigned g_epoch_tall = 0, g_epoch_plain = 0x200000, g_epoch_reg = 0x400000;
+static unsigned qrdm_panel_tall_epoch(const qrdm_prob* p, void* stream) { return panel_next_epoch(g_epoch_tall, 1, 0x200000, p, stream); }
+
+// Row-sharded panel: every sharded panel is run BLOCKED — 8-column sub-panels by k_panel_tall<true>
+// with the cross-GPU exchange inside the kernel; the caller (dgeqrdm_host.c) applies each sub-panel's block
+// reflector to the rest of the panel with the skinny kernels + one small all-reduce.  One launch per sub-panel.
+extern "C" int qrdm_k_panel_tall_mg(const qrdm_prob* p, int j_host, void* stream) {
+  const PeerCtx* pc = qrdm_peer_ctx();
+  if (!pc || p->sub <= 0) return (int)cudaErrorInvalidValue;
+  const int jsub = j_host + p->sub - 1;
+  int lr0 = jsub - p->row0;
+  lr0 = lr0 < 0 ? 0 : (lr0 > p->m ? p->m : lr0);
+  const int rows_l = p->m - lr0;
+  const int gmax = p->sm_count < QRDM_PANEL_MAXCTA ? p->sm_count : QRDM_PANEL_MAXCTA;
+  int Gs = (rows_l + 1023) / 1024;
+  if (Gs > gmax) Gs = gmax;
+  if (Gs < 1) Gs = 1;  // a rank without active rows still runs its leader CTA: it contributes zeros
+  int rpcs = (rows_l + Gs - 1) / Gs;
+  unsigned epoch = qrdm_panel_tall_epoch(p, stream);
+  qrdm_prob prob_s = *p;
+  PeerCtx pcv = *pc;
+  void* args_s[] = {(void*)&prob_s, (void*)&rpcs, (void*)&epoch, (void*)&pcv};
+  cudaError_t es = cudaLaunchCooperativeKernel((void*)k_panel_tall<true>, dim3(Gs), dim3(PANEL_THREADS), args_s, 0, (cudaStream_t)stream);
+  ++g_qrdm_launches;
+  return es == cudaSuccess ? 0 : (int)es;
+}
+
 extern "C" int qrdm_k_panel(const qrdm_prob* p, int j_host, void* stream) {
-  static bool attr_set = false;
+  static int attr_gen = -1;  // per-device function attributes: re-applied when the library moves to another device
   static int rows_per_cta = 128;
+  static int cl_max_ctas = -1;
   const int smem_cap = 200 * 1024;
-  if (!attr_set) {
+  if (attr_gen != qrdm_rt_device_generation()) {
     cudaFuncSetAttribute(k_panel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap);
     const char* e = getenv("QRDM_PANEL_ROWS");
     if (e && atoi(e) >= 32) rows_per_cta = atoi(e);
-    attr_set = true;
+    cl_max_ctas = -1;  // cluster occupancy is a per-device figure too
+    attr_gen = qrdm_rt_device_generation();
   }
   const int rows = p->m - j_host;
   if (rows <= 0) return 0;
@@ -759,20 +765,15 @@ extern "C" int qrdm_k_panel(const qrdm_prob* p, int j_host, void* stream) {
     const bool ag_ok = !(e_ag && atoi(e_ag) == 0);
     // clusters of PANEL_CL CTAs (MODE 2): how many CTAs can be co-resident as whole clusters (GPC granularity:
     // 33 clusters of 4 = 132 CTAs on a 148-SM B200, only 15 clusters of 8); queried once
-    static int cl_max_ctas = -1;
     static cudaLaunchAttribute cl_attrs[2];
     if (cl_max_ctas < 0) {
       cl_max_ctas = 0;
-      // Under Nsight Compute the cooperative + cluster launch does not keep all clusters co-resident (the
-      // factorisation came out wrong or hung with 32 clusters in flight, while plain runs, memcheck and
-      // racecheck are clean), so a process started by a CUDA injection tool (ncu, compute-sanitizer:
-      // CUDA_INJECTION64_PATH) profiles the two-hop kernel unless QRDM_PANEL_CL=2 insists.
-      const char* pre = getenv("LD_PRELOAD");
-      const bool injected = getenv("CUDA_INJECTION64_PATH") != NULL || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") != NULL ||
-                            getenv("NV_NSIGHT_INJECTION_TRANSPORT_TYPE") != NULL ||
-                            (pre && (strstr(pre, "njection") || strstr(pre, "TreeLauncher")));
+      // The library never looks at its environment to guess whether a tool is attached (round 1 did, and profiled a
+      // kernel it does not ship).  Nsight Compute's KERNEL replay re-runs a kernel that communicates through global
+      // memory flags out of context; profile the cluster panel with a single-pass metric set or with
+      // --replay-mode application (profiles/README), or force the two-hop kernel with QRDM_PANEL_CL=0.
       const int want = e_cl ? atoi(e_cl) : 1;
-      if (want == 2 || (want == 1 && !injected)) {
+      if (want >= 1) {
         cudaLaunchConfig_t q;
         memset(&q, 0, sizeof(q));
         q.gridDim = dim3(PANEL_CL); q.blockDim = dim3(PANEL_THREADS);
@@ -812,8 +813,7 @@ extern "C" int qrdm_k_panel(const qrdm_prob* p, int j_host, void* stream) {
       }
     }
     int Gr = (rows + per - 1) / per, rpcr = (rows + Gr - 1) / Gr;
-    static unsigned epoch_r = 0x400000;
-    epoch_r = epoch_r + 1 >= 0x7fffff ? 0x400000 : epoch_r + 1;
+    unsigned epoch_r = panel_next_epoch(g_epoch_reg, 0x400000, 0x7fffff, p, stream);
     qrdm_prob prob_r = *p;
     void* args_r[] = {(void*)&prob_r, (void*)&rpcr, (void*)&epoch_r};
 #define PANEL_FN(MODE) (per == 32 ? (void*)k_panel_reg<1, MODE> : per == 64 ? (void*)k_panel_reg<2, MODE> \
@@ -850,7 +850,7 @@ extern "C" int qrdm_k_panel(const qrdm_prob* p, int j_host, void* stream) {
     int kmax_h = p->nb;
     if (kmax_h > p->n - j_host) kmax_h = p->n - j_host;
     if (kmax_h > p->m_glob - j_host) kmax_h = p->m_glob - j_host;
-    static unsigned epoch_t = 0;
+    const PeerCtx nopeer{};
     for (int sb = 0; sb < kmax_h; sb += QRDM_TALL_B) {
       const int rows_s = rows - sb;
       if (rows_s <= 0) break;
@@ -858,11 +858,11 @@ extern "C" int qrdm_k_panel(const qrdm_prob* p, int j_host, void* stream) {
       if (Gs > gmax) Gs = gmax;
       if (Gs < 1) Gs = 1;
       int rpcs = (rows_s + Gs - 1) / Gs;
-      epoch_t = epoch_t + 1 >= 0x200000 ? 1 : epoch_t + 1;
+      unsigned epoch_t = qrdm_panel_tall_epoch(p, stream);
       qrdm_prob prob_s = *p;
       prob_s.sub = sb + 1;
-      void* args_s[] = {(void*)&prob_s, (void*)&rpcs, (void*)&epoch_t};
-      cudaError_t es = cudaLaunchCooperativeKernel((void*)k_panel_tall, dim3(Gs), dim3(PANEL_THREADS), args_s, 0, (cudaStream_t)stream);
+      void* args_s[] = {(void*)&prob_s, (void*)&rpcs, (void*)&epoch_t, (void*)&nopeer};
+      cudaError_t es = cudaLaunchCooperativeKernel((void*)k_panel_tall<false>, dim3(Gs), dim3(PANEL_THREADS), args_s, 0, (cudaStream_t)stream);
       ++g_qrdm_launches;
       if (es != cudaSuccess) return (int)es;
       if (sb + QRDM_TALL_B < kmax_h) {  // apply the sub-panel's reflectors to the rest of the panel
@@ -878,8 +878,7 @@ extern "C" int qrdm_k_panel(const qrdm_prob* p, int j_host, void* stream) {
   if (G > gmax) G = gmax;
   if (G < 1) G = 1;
   int rpc = (rows + G - 1) / G;
-  static unsigned epoch = 0x200000;
-  epoch = epoch + 1 >= 0x400000 ? 0x200000 : epoch + 1;  // tags (epoch << 8) + step: [1,2^21) blocked, [2^21,2^22) unblocked, upper half register kernel
+  unsigned epoch = panel_next_epoch(g_epoch_plain, 0x200000, 0x400000, p, stream);
   qrdm_prob prob = *p;
   void* args[] = {(void*)&prob, (void*)&rpc, (void*)&epoch};
   const size_t smem = (size_t)rpc * 64 * sizeof(double);

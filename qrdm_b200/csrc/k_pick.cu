@@ -36,10 +36,10 @@ __global__ void __launch_bounds__(256) k_permute(qrdm_prob P) {
 }
 
 extern "C" int qrdm_k_pick(const qrdm_prob* p, void* stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static int attr_gen = -1;  // per-device attribute, see qrdm_rt_device_generation
+  if (attr_gen != qrdm_rt_device_generation()) {
     cudaFuncSetAttribute(k_pick, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PickShared));
-    attr_set = true;
+    attr_gen = qrdm_rt_device_generation();
   }
   k_pick<<<1, 256, sizeof(PickShared), (cudaStream_t)stream>>>(*p);
   QRDM_LAUNCH_CHECK();

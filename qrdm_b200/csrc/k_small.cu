@@ -715,11 +715,11 @@ extern "C" int qrdm_k_small_supported(int m, int n) { return m <= SM_MAXDIM && n
 
 extern "C" int qrdm_k_small(int batch, int m, int n, double* d_a, int lda, long long stride_a, int* d_jpvt, double* d_tau,
                             int* d_ncols, int* d_infos, double delta, double tau_, double eta3, int nb, void* stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static int attr_gen = -1;  // per-device attribute, see qrdm_rt_device_generation
+  if (attr_gen != qrdm_rt_device_generation()) {
     cudaError_t e = cudaFuncSetAttribute(k_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallShared));
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
+    attr_gen = qrdm_rt_device_generation();
   }
   SmallArgs A;
   A.batch = batch; A.m = m; A.n = n; A.lda = lda; A.nb = nb;

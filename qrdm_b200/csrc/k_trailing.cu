@@ -1013,8 +1013,8 @@ __global__ void __launch_bounds__(256) k_w2mask(qrdm_prob P) {
 }
 
 static void trailing_attrs() {
-  static bool attr_set = false;
-  if (attr_set) return;
+  static int attr_gen = -1;  // per-device attributes, see qrdm_rt_device_generation
+  if (attr_gen == qrdm_rt_device_generation()) return;
   cudaFuncSetAttribute(k_vtc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VT_SMEM);
   cudaFuncSetAttribute(k_vtc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VT_SMEM);
   cudaFuncSetAttribute(k_wapply<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_SMEM_BN(128));
@@ -1026,7 +1026,7 @@ static void trailing_attrs() {
   cudaFuncSetAttribute(k_rankk<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RK_SMEM);
   cudaFuncSetAttribute(k_rankk<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RK_SMEM);
   cudaFuncSetAttribute(k_rankk<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RK_SMEM);
-  attr_set = true;
+  attr_gen = qrdm_rt_device_generation();
 }
 static int host_jr(const qrdm_prob* p, int j) {
   const int x = j - p->row0;

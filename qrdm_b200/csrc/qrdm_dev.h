@@ -165,6 +165,18 @@ int qrdm_rt_event_sync(void *ev);
 double qrdm_rt_event_ms(void *ev0, void *ev1);
 int qrdm_rt_device_info(int *sm_count, size_t *free_bytes);
 int qrdm_rt_set_device(int dev);
+int qrdm_rt_get_device(int *dev);
+int qrdm_rt_device_generation(void);
+void qrdm_rt_new_device_generation(void);
+int qrdm_rt_stream_destroy(void *stream);
+double qrdm_rt_copy_gbs(size_t bytes, void *stream);
+/* peer memory of the row-sharded path (k_peer.cu): CUDA-IPC receive buffers + the one-shot LL all-reduce */
+int qrdm_rt_peer_export(char *out64);
+int qrdm_rt_peer_open(int rank, int nranks, const char *handles64);
+int qrdm_rt_peer_destroy(void);
+int qrdm_rt_peer_available(void);              /* number of ranks of the open peer context, 0 = none */
+int qrdm_k_peer_allreduce(double *buf, size_t count, void *stream);
+int qrdm_k_panel_tall_mg(const qrdm_prob *p, int j_host, void *stream); /* sharded sub-panel, exchange inside the kernel */
 const char *qrdm_rt_errstr(int code);
 long long qrdm_rt_launch_count(void);
 double qrdm_rt_fp64_peak(int use_dmma, void *stream);

@@ -8,6 +8,7 @@
 #include "common.cuh"
 
 long long g_qrdm_launches = 0;
+static int g_qrdm_dev_gen = 0;
 
 extern "C" {
 
@@ -64,6 +65,10 @@ int qrdm_rt_device_info(int* sm_count, size_t* free_bytes) {
   return (int)e;
 }
 int qrdm_rt_set_device(int dev) { return (int)cudaSetDevice(dev); }
+int qrdm_rt_get_device(int* dev) { return (int)cudaGetDevice(dev); }
+int qrdm_rt_device_generation(void) { return g_qrdm_dev_gen; }
+void qrdm_rt_new_device_generation(void) { ++g_qrdm_dev_gen; }
+int qrdm_rt_stream_destroy(void* stream) { return stream ? (int)cudaStreamDestroy((cudaStream_t)stream) : 0; }
 const char* qrdm_rt_errstr(int code) { return cudaGetErrorString((cudaError_t)code); }
 long long qrdm_rt_launch_count(void) { return g_qrdm_launches; }
 
@@ -117,6 +122,43 @@ extern "C" double qrdm_rt_fp64_peak(int use_dmma, void* stream) {
   const double flops = use_dmma ? 2.0 * 256 * 8 * (double)iters * 8.0 * grid   /* 8 warps x 8 mma x 256 fma */
                                 : 2.0 * 16 * (double)iters * 256.0 * grid;
   return flops / (best * 1e-3) / 1e12;
+}
+
+// ---- device-to-device copy bandwidth (read + written bytes per second): the HBM roofline denominator bench.py measures
+// live next to MEASURED_PEAKS.json's hbm_gbs ----
+__global__ void __launch_bounds__(256) k_copy_bw(const double2* __restrict__ src, double2* __restrict__ dst, size_t n2) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+extern "C" double qrdm_rt_copy_gbs(size_t bytes, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (bytes < ((size_t)1 << 20)) bytes = (size_t)1 << 20;
+  bytes &= ~(size_t)15;
+  double2 *a = nullptr, *b = nullptr;
+  if (cudaMalloc(&a, bytes) != cudaSuccess) { cudaGetLastError(); return -1.0; }
+  if (cudaMalloc(&b, bytes) != cudaSuccess) { cudaGetLastError(); cudaFree(a); return -1.0; }
+  cudaMemsetAsync(a, 0, bytes, s);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 6; ++rep) {
+    cudaEventRecord(e0, s);
+    k_copy_bw<<<sms * 8, 256, 0, s>>>(a, b, bytes / 16);
+    cudaEventRecord(e1, s);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(a);
+  cudaFree(b);
+  if (cudaGetLastError() != cudaSuccess) return -1.0;
+  return 2.0 * (double)bytes / (best * 1e-3) / 1e9;
 }
 
 // ---- NCCL, bound at run time (dlopen) so that libqrdm_b200.so has no link-time dependency and a

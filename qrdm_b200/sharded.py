@@ -1,8 +1,10 @@
 """1-D block-row sharded dgeqrdm across the GPUs of one node, one process per GPU.
 
 `torch.distributed` is only the launcher-side plumbing (rendezvous, broadcasting the NCCL unique
-id); the data-path collectives are `ncclAllReduce` calls issued by the C host driver on the
-compute stream (`dgeqrdm_dev_sharded` in include/qrdm_b200.h).
+id, all-gathering the CUDA-IPC handles of the peer receive buffers); the data-path exchanges are
+issued by the C host driver on the compute stream (`dgeqrdm_dev_sharded` in include/qrdm_b200.h):
+LL packets over NVLink peer memory from inside the panel kernel and a one-kernel LL all-reduce for
+the small vectors, `ncclAllReduce` for the bandwidth-bound ones.
 """
 from __future__ import annotations
 
@@ -55,8 +57,35 @@ def broadcast_unique_id(make_id, rank: int, group=None, device=None) -> bytes:
     return bytes(buf.cpu().numpy().tobytes())
 
 
-def init_comm(rank: int, world: int, group=None, device=None) -> None:
-    """Create the library's NCCL communicator for this process (idempotent per process)."""
+def allgather_handles(my_handle: bytes, rank: int, world: int, group=None, device=None) -> bytes:
+    """All-gather of the 64-byte CUDA-IPC handles, rank order (gloo or nccl backend)."""
+    import torch
+    import torch.distributed as dist
+    if len(my_handle) != 64:
+        raise ValueError("a CUDA IPC handle is 64 bytes")
+    mine = torch.frombuffer(bytearray(my_handle), dtype=torch.uint8).clone()
+    if device is not None:
+        mine = mine.to(device)
+    parts = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    return b"".join(bytes(p.cpu().numpy().tobytes()) for p in parts)
+
+
+def init_peer(rank: int, world: int, group=None, device=None) -> None:
+    """Open NVLink peer memory between the ranks (include/qrdm_b200.h: qrdm_b200_peer_handle / _open)."""
+    import torch.distributed as dist
+    from . import _lib
+    raw = C.create_string_buffer(64)
+    if _lib.lib.qrdm_b200_peer_handle(raw) != 0:
+        raise RuntimeError("qrdm_b200_peer_handle failed (cudaIpcGetMemHandle)")
+    allh = allgather_handles(raw.raw, rank, world, group=group, device=device)
+    if _lib.lib.qrdm_b200_peer_open(int(rank), int(world), allh) != 0:
+        raise RuntimeError("qrdm_b200_peer_open failed (cudaIpcOpenMemHandle: no peer access between the GPUs?)")
+    dist.barrier(group=group)   # nobody sends before everybody has mapped and zeroed
+
+
+def init_comm(rank: int, world: int, group=None, device=None, nccl: bool = True, peer: bool = True) -> None:
+    """Set up the library's transports for this process: the NCCL communicator and NVLink peer memory."""
     from . import _lib
 
     def make_id():
@@ -65,9 +94,12 @@ def init_comm(rank: int, world: int, group=None, device=None) -> None:
             raise RuntimeError("qrdm_b200_comm_unique_id failed (libnccl.so.2 not loadable?)")
         return raw.raw
 
-    uid = broadcast_unique_id(make_id, rank, group=group, device=device)
-    if _lib.lib.qrdm_b200_comm_init(int(rank), int(world), uid) != 0:
-        raise RuntimeError("qrdm_b200_comm_init failed")
+    if nccl:
+        uid = broadcast_unique_id(make_id, rank, group=group, device=device)
+        if _lib.lib.qrdm_b200_comm_init(int(rank), int(world), uid) != 0:
+            raise RuntimeError("qrdm_b200_comm_init failed")
+    if peer:
+        init_peer(rank, world, group=group, device=device)
 
 
 def dgeqrdm_sharded(dA_local, m_local, m_global, row0, world, n, lda, d_jpvt, d_tau,

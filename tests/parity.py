@@ -101,3 +101,56 @@ def _ormqr(F, tau, C, r):
 
 def invariant_tol(shape):
     return 10.0 * max(shape) * 2 * EPS
+
+
+# ---------------------------------------------------------------------------------------------
+# Explicit bookkeeping of the margin exemption: every comparison against the
+# reference goes through `graded_check`, which records whether the case matched the reference
+# EXACTLY (all blocks, all pivots) or needed the 1e-12 margin rule, and how many blocks the rule
+# excluded.  conftest.py prints the table at the end of the session and writes it to
+# gpurun_out/parity_report.json when that directory is writable.
+REPORT = []
+
+
+def graded_check(name, got, exp, shape, margins_fn=None, require_full=False, family="gaussian"):
+    """Compare `got` with the reference output `exp`.
+
+    1. exact pass: every block size and every pivot equal, |diag R| to 1e-10 on all columns;
+    2. only if that fails and `require_full` is False: the trusted-prefix rule, first with the
+       |R_jj| noise floor alone, then (margins_fn() = decision margins logged by the C port) with the
+       1e-12 margin exemption.  `require_full=True` (Gaussian inputs: no decision is ever within
+       1e-12 of a tie and nothing sinks to the noise floor) forbids step 2 altogether."""
+    nblk_total = int(np.count_nonzero(exp["ncols"]))
+    entry = dict(case=name, shape=list(shape), family=family, blocks_total=nblk_total, mode=None,
+                 blocks_trusted=None, blocks_excluded=None, cols_trusted=None, margins_used=False)
+    try:
+        st = check_against(got, exp, shape, exact=True)
+        entry.update(mode="exact", blocks_trusted=nblk_total, blocks_excluded=0, cols_trusted=st["cols"])
+        REPORT.append(entry)
+        return entry
+    except AssertionError as first:
+        if require_full:
+            entry.update(mode="FAILED (full-prefix equality required)")
+            REPORT.append(entry)
+            raise
+        first_msg = str(first)
+    margins = None
+    try:
+        st = check_against(got, exp, shape, margins=None)
+    except AssertionError:
+        if margins_fn is None:
+            entry.update(mode="FAILED (noise-floor prefix)")
+            REPORT.append(entry)
+            raise
+        margins = margins_fn()
+        try:
+            st = check_against(got, exp, shape, margins=margins)
+        except AssertionError:
+            entry.update(mode="FAILED (margin prefix)", margins_used=True)
+            REPORT.append(entry)
+            raise
+    entry.update(mode="prefix+margins" if margins is not None else "prefix(noise floor)",
+                 blocks_trusted=st["blocks"], blocks_excluded=nblk_total - st["blocks"], cols_trusted=st["cols"],
+                 margins_used=margins is not None, exact_failure=first_msg[:120])
+    REPORT.append(entry)
+    return entry
