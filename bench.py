@@ -11,6 +11,11 @@ value   = whole-job GFLOP/s with A resident in HBM (dgeqrdm_dev, CUDA events, ma
           algorithmic FLOPs F(m,n,r) = 4mnr - 2(m+n)r^2 + (4/3)r^3, r = sum(ncols).
 e2e     = the same metric through the reference-facing C ABI `dgeqrdm` with PINNED HOST buffers:
           H2D of A, the factorisation, D2H of A/jpvt/tau all inside the timed region.
+e2e_pageable = the same call the reference's user makes: `QRDM.QRDM(...)` on PAGEABLE NumPy arrays (the library's
+          multi-threaded pinned bounce pipeline + streamed write-back, hostio.c), wall clock.
+roofline_hbm = the bandwidth-bound stages (K1 norms, K3b candidate Gram, K3d column exchange, K4 tall panel, K2 norm
+          downdate) of configs[3] on one GPU: algorithmic bytes / CUDA-event stage time against
+          MEASURED_PEAKS.json's hbm_gbs.
 roofline= the trailing update (K6: k_fused / k_vtc + k_tinv + k_wapply + k_rankk, FP64 DMMA) timed with CUDA events
           on the launching stream inside the same timed steps, against the FP64 DMMA peak measured
           live by the library's micro-benchmark (MEASURED_PEAKS.json carries no FP64 figure).
@@ -170,11 +175,15 @@ def run_reference(args, rank, world):
             break
     tot = sum(times)
     val = flops(sm_, sn_, rk) * len(times) / tot / 1e9
-    sample = (f"reference dgeqrdm (oracle/_ref, unmodified sources, OpenBLAS {cores} threads) on a "
-              f"{sm_}x{sn_} {kind} matrix (leading-block sample of {desc}), rank {rk}, {len(times)} timed runs")
+    whole = (sm_, sn_) == (m, n)
+    sample = (f"reference dgeqrdm (oracle/_ref, unmodified sources, OpenBLAS {cores} threads) on "
+              + (f"the FULL {sm_}x{sn_} {kind} matrix of the workload" if whole else
+                 f"a {sm_}x{sn_} {kind} matrix (leading-block sample of {desc})")
+              + f", rank {rk}, {len(times)} timed run(s)"
+              + ("" if len(times) > 1 else " (a single run: warm-up + steps would exceed the few-minute budget)"))
     line.update({"value": val, "ms_per_step": tot / len(times) * 1e3,
-                 "config": {"workload": desc, "sample_shape": [sm_, sn_], "thres": list(THRES), "nb": NB,
-                            "stop_mode": stop_mode},
+                 "config": {"workload": desc, "shape": [m, n], "sample_shape": [sm_, sn_], "same_config": whole,
+                            "thres": list(THRES), "nb": NB, "stop_mode": stop_mode},
                  "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": cores, "kind": "reference",
                                   "sample": sample},
                  "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
@@ -218,10 +227,40 @@ def cpu_baseline(args, m, n, kind, stop_mode, desc):
             "seconds": dt, "sample": f"scalar C port (oracle/qrdm_port.c) on a {sm_}x{sn_} Gaussian sample"}
 
 
-def run_row_sharded(torch, dist, qrdm_b200, rank, world, dev, m, n, steps, warmup):
-    """BASELINE config C4: tall-skinny m x n Gaussian, 1-D block-row sharded over `world` GPUs with
-    NCCL all-reduces in the data path (strong scaling: the matrix is fixed, each rank holds m/world
-    rows).  world == 1 runs the ordinary single-GPU path on the whole matrix."""
+def sharded_parity(torch, dist, qrdm_b200, rank, world, dev, m=200_000, n=512):
+    """parity_vs_single_gpu: one seeded m x n Gaussian matrix factored row-sharded over `world`
+    GPUs and on ONE GPU (every rank does the single-GPU run itself, it fits); jpvt / ncols must be equal and every
+    rank's rows of the factor must agree with the single-GPU rows."""
+    from qrdm_b200 import sharded
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(777)                               # the same matrix on every rank
+    A0 = torch.randn((n, m), dtype=torch.float64, device=dev, generator=gen)
+    row0, ml = sharded.row_partition(m, world)[rank]
+    loc = A0[:, row0:row0 + ml].clone()                # .contiguous() would alias A0 when world == 1
+    jp, tau = torch.zeros(n, dtype=torch.int32, device=dev), torch.zeros(n, dtype=torch.float64, device=dev)
+    info, nc = sharded.dgeqrdm_sharded(loc, ml, m, row0, world, n, ml, jp, tau, thres=THRES, nb=NB)
+    one = A0.clone()
+    jp1, tau1 = torch.zeros(n, dtype=torch.int32, device=dev), torch.zeros(n, dtype=torch.float64, device=dev)
+    info1, nc1 = qrdm_b200.dgeqrdm_device(one, m, n, m, jp1, tau1, thres=THRES, nb=NB)
+    scale = float(torch.linalg.norm(one))
+    diff = float(torch.linalg.norm(loc - one[:, row0:row0 + ml])) / scale
+    stat = torch.tensor([float(info != 0 or info1 != 0), float(not torch.equal(jp, jp1)),
+                         float(not np.array_equal(nc, nc1)), diff,
+                         float(torch.max(torch.abs(tau - tau1)))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(stat, op=dist.ReduceOp.MAX)
+    bad, jd, nd, diff, td = (float(x) for x in stat.tolist())
+    del A0, one, loc
+    return {"matrix": f"{m}x{n} Gaussian, seed 777, the same on every rank", "info_ok": bad == 0.0,
+            "jpvt_equal": jd == 0.0, "ncols_equal": nd == 0.0, "rows_rel_diff": diff, "tau_max_abs_diff": td,
+            "revealed_rank": int(nc.sum()), "reduced_over_ranks": "max"}
+
+
+def run_row_sharded(torch, dist, qrdm_b200, rank, world, dev, m, n, steps, warmup, with_cpu=False):
+    """BASELINE config C4: tall-skinny m x n Gaussian, 1-D block-row sharded over `world` GPUs (strong scaling: the
+    matrix is fixed, each rank holds m/world rows).  Exchanges in the data path: LL packets over NVLink peer memory
+    from inside the panel kernel + a one-kernel LL all-reduce for the small vectors, ncclAllReduce for the rest.
+    world == 1 runs the ordinary single-GPU path on the whole matrix."""
     from qrdm_b200 import sharded
     row0, ml = sharded.row_partition(m, world)[rank]
     gen = torch.Generator(device=dev)
@@ -231,8 +270,13 @@ def run_row_sharded(torch, dist, qrdm_b200, rank, world, dev, m, n, steps, warmu
     d_jpvt = torch.zeros(n, dtype=torch.int32, device=dev)
     d_tau = torch.zeros(min(m, n), dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream()
+    transport = "none"
     if world > 1:
         sharded.init_comm(rank, world, device=dev)
+        transport = ("NVLink peer memory (CUDA IPC): LL packets inside k_panel_tall<true> per panel column + one-kernel "
+                     "LL all-reduce for vectors <= 96 Ki doubles; ncclAllReduce above that")
+        if os.environ.get("QRDM_B200_MG_LEGACY"):
+            transport = "ncclAllReduce per panel column (round-1 path, QRDM_B200_MG_LEGACY)"
 
     def step():
         A.copy_(A0)
@@ -252,9 +296,11 @@ def run_row_sharded(torch, dist, qrdm_b200, rank, world, dev, m, n, steps, warmu
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
     e0.record(stream)
     for _ in range(steps):
         ncols = step()
+        launches += qrdm_b200.stats()["launches"]
     e1.record(stream)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
@@ -263,23 +309,80 @@ def run_row_sharded(torch, dist, qrdm_b200, rank, world, dev, m, n, steps, warmu
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     rk = int(ncols.sum())
+    out = {"workload": f"tall-skinny {m}x{n} Gaussian, row-sharded over {world} GPU(s) (configs[3])",
+           "n_gpus": world, "scaling": "strong", "ms_per_step": ms / steps, "seconds": ms / steps / 1e3,
+           "value": steps * flops(m, n, rk) / (ms * 1e-3) / 1e9, "unit": "GFLOP/s", "revealed_rank": rk,
+           "rows_per_gpu": ml, "steps": steps, "warmup": warmup, "gpu_launches_per_step": launches / steps,
+           "collectives": transport}
+    # ---- per-stage split + HBM rooflines of the bandwidth-bound stages (one GPU, every stage event-timed with a sync) ----
+    if world == 1:
+        try:
+            qrdm_b200.set_profile(1)
+            step()
+            st = qrdm_b200.stats()
+            qrdm_b200.set_profile(0)
+            out["stage_profile"] = {"ms_total": st["ms_total"], "ms_stage": st["ms_stage"], "stage_bytes": st["stage_bytes"],
+                                    "trailing_flops": st["trailing_flops"],
+                                    "note": "profile mode 1: event pair + sync around every stage (perturbs the total)"}
+        except Exception as exc:
+            out["stage_profile"] = {"error": str(exc)[:200]}
     del A0, A
     torch.cuda.empty_cache()
-    return {"workload": f"tall-skinny {m}x{n} Gaussian, row-sharded over {world} GPU(s) (configs[3])",
-            "n_gpus": world, "scaling": "strong", "ms_per_step": ms / steps, "seconds": ms / steps / 1e3,
-            "value": steps * flops(m, n, rk) / (ms * 1e-3) / 1e9, "unit": "GFLOP/s", "revealed_rank": rk,
-            "rows_per_gpu": ml, "collectives": "ncclAllReduce (f64 sum) on the compute stream" if world > 1 else "none"}
+    try:
+        out["parity_vs_single_gpu"] = sharded_parity(torch, dist, qrdm_b200, rank, world, dev)
+    except SystemExit:
+        raise
+    except Exception as exc:
+        out["parity_vs_single_gpu"] = {"error": str(exc)[:300]}
+    torch.cuda.empty_cache()
+    if with_cpu and rank == 0:
+        try:
+            from oracle import ref as oracle
+            from qrdm_b200 import generators as g
+            cores = len(os.sched_getaffinity(0))
+            oracle.set_ref_threads(cores)
+            cm = min(m, 500_000)
+            Ac = g.gaussian(cm, n, 0)
+            t0 = time.perf_counter()
+            o = oracle.ref_dgeqrdm(Ac, thres=THRES, nb=NB)
+            dt = time.perf_counter() - t0
+            rkc = int(o["ncols"].sum())
+            out["cpu_reference"] = {"seconds": dt, "gflops": flops(cm, n, rkc) / dt / 1e9, "cores": cores, "shape": [cm, n],
+                                    "seconds_extrapolated_to_full_rows": dt * m / cm,
+                                    "sample": f"unmodified reference dgeqrdm (oracle/_ref, OpenBLAS {cores} threads) on a {cm}x{n} "
+                                              f"Gaussian matrix (a quarter of the rows of configs[3]; cost is linear in m)"}
+            del Ac, o
+        except Exception as exc:
+            out["cpu_reference"] = {"error": str(exc)[:200]}
+    return out
 
 
-def run_batched(torch, dist, qrdm_b200, rank, world, dev, total, n, steps, warmup, with_cpu):
-    """BASELINE config C5: `total` Kahan-type n x n matrices (per-matrix theta in [1.1, 1.3], seeded diagonal
-    perturbation 1e3*eps*(n..1)), split evenly over `world` GPUs as independent units (no collective); every
-    rank factors its share with ONE launch of the one-CTA-per-matrix kernel (dgeqrdm_batched_dev)."""
+def _cpu_one_matrix(args):
+    """Pool worker of the C5 CPU baseline: one matrix, one BLAS thread."""
+    theta, seed, n, pert = args
+    from oracle import ref as oracle
+    from qrdm_b200 import generators as g
+    oracle.set_ref_threads(1)
+    A = g.kahan(n, theta=theta, perturb=pert, seed=seed)
+    t0 = time.perf_counter()
+    o = oracle.ref_dgeqrdm(A, thres=THRES, nb=NB)
+    return time.perf_counter() - t0, int(np.count_nonzero(o["ncols"]))
+
+
+def run_batched(torch, dist, qrdm_b200, rank, world, dev, total, n, steps, warmup, with_cpu, pure_theta=None):
+    """BASELINE config C5: `total` Kahan-type n x n matrices with the seeded diagonal perturbation 1e3*eps*(n..1), split
+    evenly over `world` GPUs as independent units (no collective); every rank factors its share with ONE launch of the
+    one-CTA-per-matrix kernel (dgeqrdm_batched_dev).  pure_theta=None: per-matrix theta in [1.1, 1.3] with the seeded
+    perturbation (mixed block sizes, ~55 iterations per matrix); pure_theta=1.25: the survey's unperturbed Kahan matrix,
+    511 one-column iterations per matrix."""
     from qrdm_b200 import generators as g
     from qrdm_b200 import sharded
     per = sharded.batch_partition(total, world)[rank][1]
     distinct = 37
-    base = np.stack([np.ascontiguousarray(g.kahan(n, theta=1.1 + 0.2 * b / distinct, perturb=1e3, seed=1000 * rank + b).T)
+    thetas = [pure_theta if pure_theta is not None else 1.1 + 0.2 * b / distinct for b in range(distinct)]
+    # the pure-theta batch is the survey's UNPERTURBED Kahan matrix (jpvt = identity, 511 one-column iterations at n = 512)
+    pert = 0.0 if pure_theta is not None else 1e3
+    base = np.stack([np.ascontiguousarray(g.kahan(n, theta=thetas[b], perturb=pert, seed=1000 * rank + b).T)
                      for b in range(distinct)])
     d_base = torch.from_numpy(base).to(dev)
     idx = torch.arange(per, device=dev) % distinct
@@ -321,24 +424,44 @@ def run_batched(torch, dist, qrdm_b200, rank, world, dev, total, n, steps, warmu
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         dist.all_reduce(agg, op=dist.ReduceOp.SUM)
         ms, fl, bad = float(mx[0]), float(agg[1]), int(agg[2])
-    out = {"workload": f"{total} Kahan-type {n}x{n} matrices split over {world} GPU(s), independent units (configs[4])",
+    out = {"workload": f"{total} Kahan-type {n}x{n} matrices ("
+                       + (f"theta = {pure_theta}, unperturbed" if pure_theta is not None else "theta in [1.1, 1.3], perturbed diagonal")
+                       + f") split over {world} GPU(s), independent units (configs[4])",
            "n_gpus": world, "scaling": "strong", "matrices_per_gpu": per, "ms_per_step": ms / steps,
            "matrices_per_s": total * steps / (ms * 1e-3), "value": steps * fl / (ms * 1e-3) / 1e9, "unit": "GFLOP/s",
            "mean_iterations_per_matrix": iters, "nonzero_infos": bad, "gpu_launches_per_step": 1,
            "timed_region": "K x (device-side restore of the batch + one k_small launch), CUDA events, max over ranks"}
+    # L2/HBM view of the one-CTA-per-matrix kernel: every iteration streams the trailing matrix of every matrix once in
+    # and once out (16 * m_r * n_c bytes, SURVEY.md 8d K6 minimum); with 148 x 2 MB in flight the set exceeds L2
+    if rank == 0:
+        itv = d_ncols[:distinct].cpu().numpy()
+        tb = 0.0
+        for b in range(distinct):
+            jj = 0
+            for k_ in itv[b][itv[b] > 0]:
+                tb += 16.0 * (n - jj) * (n - jj - int(k_))
+                jj += int(k_)
+        tb = tb / distinct * total
+        out["roofline"] = {"bound": "hbm", "kernel": "k_small (whole factorisation of one matrix per CTA)",
+                           "algorithmic_bytes_per_step": tb, "achieved": tb / (ms / steps * 1e-3) / 1e9, "unit": "GB/s",
+                           "note": "16*m_r*n_c bytes per iteration per matrix summed over the batch; peak = MEASURED_PEAKS hbm_gbs"}
     if with_cpu and rank == 0:
         try:
-            from oracle import ref as oracle
-            oracle.set_ref_threads(1)
-            t0 = time.perf_counter()
-            cnt = 6
-            for b in range(cnt):
-                oracle.ref_dgeqrdm(np.asfortranarray(base[b].T), thres=THRES, nb=NB)
-            dt = (time.perf_counter() - t0) / cnt
+            import multiprocessing as mp
             cores = len(os.sched_getaffinity(0))
-            out["cpu_reference"] = {"ms_per_matrix_1_thread": dt * 1e3, "cores": cores,
-                                    "matrices_per_s_all_cores_extrapolated": cores / dt,
-                                    "sample": f"{cnt} of the matrices, unmodified reference, 1 BLAS thread each"}
+            cnt = 256 if pure_theta is None else 64          # ~0.1 s (mixed) / ~0.1-0.2 s (pure) per matrix and thread
+            jobs = [(thetas[b % distinct], 1000 * rank + (b % distinct), n, pert) for b in range(cnt)]
+            with mp.get_context("spawn").Pool(cores) as pool:
+                pool.map(_cpu_one_matrix, jobs[:cores])      # start the workers, load the libraries
+                t0 = time.perf_counter()
+                res = pool.map(_cpu_one_matrix, jobs, chunksize=1)
+                wall = time.perf_counter() - t0
+            out["cpu_reference"] = {"matrices": cnt, "pool_processes": cores, "blas_threads_each": 1, "wall_seconds": wall,
+                                    "matrices_per_s": cnt / wall, "seconds_for_the_whole_batch_extrapolated": total * wall / cnt,
+                                    "mean_ms_per_matrix_1_thread": 1e3 * sum(r[0] for r in res) / cnt,
+                                    "mean_iterations": sum(r[1] for r in res) / cnt,
+                                    "sample": f"{cnt}-matrix subsample of the batch, unmodified reference (oracle/_ref), process "
+                                              f"pool of {cores} x 1 BLAS thread, extrapolated to {total} matrices (SURVEY.md 8d)"}
         except Exception as exc:
             out["cpu_reference"] = {"error": str(exc)[:200]}
     del d_a, d_base
@@ -354,7 +477,8 @@ def main():
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=6144, help="edge of the CPU-baseline sample block")
-    ap.add_argument("--ref-sample", type=int, default=6144, help="edge of the --impl reference sample block")
+    ap.add_argument("--ref-sample", type=int, default=16384,
+                    help="edge of the --impl reference sample block (default = the full configs[2] matrix: same config as the GPU arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-row-sharded", action="store_true", help="skip the configs[3] row-sharded leg")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the C1/C2 context timings")
@@ -487,6 +611,46 @@ def main():
         e2e_t = float(t.item())
     e2e_rank = int(h_ncols.sum())
     e2e_val = world * e2e_steps * flops(m, n, e2e_rank) / e2e_t / 1e9
+
+    # ---- the call a user of the reference makes: QRDM.QRDM on pageable NumPy arrays (QRDM_wrapper.c:89-96) ----
+    e2e_pg = None
+    try:
+        from qrdm_b200 import QRDM as shim
+        A_np = np.empty((n, m), dtype=np.float64)          # C-ordered (n, m) buffer = column-major m x n, pageable
+        src_np = hA0.numpy()
+        th2 = np.array([THRES[0], THRES[1]])                # the notebook passes a 2-element thres
+
+        def pg_step():
+            np.copyto(A_np, src_np)                        # host-side restore, NOT timed
+            h_jpvt[:] = 0
+            h_ncols[:] = 0
+            h_ncols[0] = stop_mode
+            t0 = time.perf_counter()
+            info = shim.QRDM(102, m, n, A_np, m, h_jpvt, h_tau, h_ncols, th2, NB)
+            dt = time.perf_counter() - t0
+            if info != 0:
+                raise SystemExit(f"QRDM.QRDM failed: info={info}")
+            return dt
+
+        pg_step()
+        if world > 1:
+            dist.barrier()
+        pg_t = sum(pg_step() for _ in range(e2e_steps))
+        if world > 1:
+            t = torch.tensor([pg_t], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            pg_t = float(t.item())
+        same = bool(np.array_equal(A_np, hA.numpy()))      # bit-identical to the pinned-buffer result
+        e2e_pg = {"value": world * e2e_steps * flops(m, n, int(h_ncols.sum())) / pg_t / 1e9, "unit": "GFLOP/s",
+                  "ms_per_step": pg_t / e2e_steps * 1e3, "steps": e2e_steps, "ratio_to_pinned_time": pg_t / e2e_t,
+                  "result_bit_identical_to_pinned": same,
+                  "api": "qrdm_b200.QRDM.QRDM (the reference's Python call, QRDM_wrapper.c:71-101) on pageable NumPy arrays: "
+                         "multi-threaded pinned bounce H2D, streamed D2H through a pinned ring (hostio.c)"}
+        del A_np
+    except SystemExit:
+        raise
+    except Exception as exc:
+        e2e_pg = {"error": str(exc)[:300]}
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- configs[3]: the row-sharded tall-skinny case (every rank takes part) ----
@@ -496,7 +660,7 @@ def main():
         torch.cuda.empty_cache()
         try:
             row_sharded = run_row_sharded(torch, dist, qrdm_b200, rank, world, dev, args.sharded_rows, 512,
-                                          steps=2, warmup=1)
+                                          steps=3, warmup=2, with_cpu=(world == 1 and not args.no_cpu_baseline))
         except SystemExit:
             raise
         except Exception as exc:  # never sink the headline measurement
@@ -511,32 +675,55 @@ def main():
             raise
         except Exception as exc:
             batched = {"error": str(exc)[:300]}
+        try:
+            pure = run_batched(torch, dist, qrdm_b200, rank, world, dev, args.batch_total, 512, steps=1, warmup=1,
+                               with_cpu=(world == 1 and not args.no_cpu_baseline), pure_theta=1.25)
+            if isinstance(batched, dict):
+                batched["pure_theta_1.25"] = pure
+        except SystemExit:
+            raise
+        except Exception as exc:
+            if isinstance(batched, dict):
+                batched["pure_theta_1.25"] = {"error": str(exc)[:300]}
 
     # ---- the other single-GPU BASELINE configs (parity-test cases, reported for context) ----
     other = {}
     if world == 1 and not args.no_other_configs and not os.environ.get("QRDM_BENCH_SHAPE"):
-        for name in ("C1", "C2"):
+        extra = dict(WORKLOADS)
+        extra["G8192"] = (8192, 8192, "gaussian", 0, "8192x8192 dense Gaussian (north_star: K6 >= 60 % of FP64 peak for n >= 8192)")
+        for name in ("C1", "C2", "G8192"):
             try:
-                om, on, okind, ostop, odesc = WORKLOADS[name]
+                om, on, okind, ostop, odesc = extra[name]
                 B0 = make_matrix_torch(torch, om, on, okind, seed=0, device=dev)
                 B = torch.empty_like(B0)
                 bj = torch.zeros(on, dtype=torch.int32, device=dev)
                 bt = torch.zeros(min(om, on), dtype=torch.float64, device=dev)
                 best = None
+                k6 = None
+                qrdm_b200.set_profile(2)   # event pairs around the panel and trailing stages only, no syncs
                 for _ in range(4):
                     B.copy_(B0)
                     torch.cuda.synchronize()
                     oinfo, oncols = qrdm_b200.dgeqrdm_device(B, om, on, om, bj, bt, thres=THRES, nb=NB, stop_mode=ostop,
                                                              stream=stream.cuda_stream)
                     st = qrdm_b200.stats()
-                    best = st["ms_total"] if best is None else min(best, st["ms_total"])
+                    if best is None or st["ms_total"] < best:
+                        best = st["ms_total"]
+                        k6 = (st["trailing_flops"], st["ms_stage"]["trailing"], st["ms_stage"]["panel"])
+                qrdm_b200.set_profile(0)
                 ork = int(oncols.sum())
+                k6_tf = k6[0] / (k6[1] * 1e-3) / 1e12 if k6 and k6[1] > 0 else None
                 other[name] = {"workload": odesc, "ms": best, "revealed_rank": ork, "stop_mode": ostop,
                                "gflops": flops(om, on, ork) / (best * 1e-3) / 1e9, "iterations": int(np.count_nonzero(oncols)),
+                               "roofline": {"kernel": "K6 trailing update", "bound": "tensor", "achieved": k6_tf, "peak": peak_dmma,
+                                            "unit": "TFLOP/s", "frac": (k6_tf / peak_dmma) if k6_tf else None,
+                                            "ms": k6[1] if k6 else None, "panel_ms": k6[2] if k6 else None,
+                                            "whole_step_frac_of_peak": flops(om, on, ork) / (best * 1e-3) / 1e12 / peak_dmma},
                                "timing": "best of 3 after 1 warm-up, device-resident (CUDA events inside dgeqrdm_dev)"}
                 del B0, B
             except Exception as exc:
                 other[name] = {"error": str(exc)[:200]}
+        qrdm_b200.set_profile(0)
 
     if rank != 0:
         if world > 1:
@@ -581,6 +768,31 @@ def main():
                                      "see profiles/r01_ncu_fused_v3.txt"},
         "stages": {"panel_ms_per_step": panel_ms / args.steps, "trailing_ms_per_step": trailing_ms / args.steps},
     }
+    if e2e_pg is not None:
+        line["e2e_pageable"] = e2e_pg
+    # ---- HBM rooflines of the bandwidth-bound stages, measured on configs[3] (one GPU) ----
+    if row_sharded is not None and isinstance(row_sharded.get("stage_profile"), dict) and "ms_stage" in row_sharded["stage_profile"]:
+        sp = row_sharded["stage_profile"]
+        hbm_peak = float(peaks_file.get("hbm_gbs") or 6550.0)
+        copy_live = qrdm_b200.copy_gbs(1 << 30, stream.cuda_stream)
+        names = {"norm_init": "K1 initial column norms (k_colnorm_partial/finalize), 8mn bytes",
+                 "gram": "K3b candidate Gram, 8*m_r*nc bytes per iteration",
+                 "permute": "K3d column exchange (k_permute), 32*m bytes per exchange",
+                 "panel": "K4 tall panel (k_panel_tall + k_skinny), >= 16*m_r*fjb bytes per iteration",
+                 "norm_update": "K2 norm downdate, 8*k*n_r bytes per iteration",
+                 "trailing": "K6 trailing update at n = 512 (24*m_r*n_c bytes per iteration; compute-bound, for reference)"}
+        rl = []
+        for key, label in names.items():
+            ms_ = sp["ms_stage"].get(key, 0.0)
+            by_ = sp["stage_bytes"].get(key, 0.0)
+            if ms_ > 0 and by_ > 0:
+                gbs = by_ / (ms_ * 1e-3) / 1e9
+                rl.append({"stage": key, "kernel": label, "bound": "hbm", "algorithmic_bytes": by_, "ms": ms_,
+                           "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak})
+        line["roofline_hbm"] = {"workload": row_sharded["workload"], "peak_source": "MEASURED_PEAKS.json hbm_gbs"
+                                if peaks_file.get("hbm_gbs") else "fallback 6550 GB/s (B200_PROFILING.md)",
+                                "copy_gbs_measured_live": copy_live, "stages": rl,
+                                "timing": "CUDA event pair + sync around every stage of one factorisation (profile mode 1)"}
     if row_sharded is not None:
         line["row_sharded"] = row_sharded
     if batched is not None:

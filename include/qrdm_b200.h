@@ -124,6 +124,9 @@ typedef struct qrdm_b200_stats {
   long long stage_launches[12];
   double trailing_flops; /* FLOPs executed by the trailing-update kernels (4*rows*cols*k summed) */
   double panel_cols;     /* total panel columns processed */
+  /* algorithmic bytes per stage, summed by the host from the mailbox: K1 8mn; K3b 8*m_r*nc;
+   * K3d 32*m per exchange; K4 16*m_r*fjb; K2 8*k*n_r; K6 16*m_r*n_c (deferred schedule) or 24*m_r*n_c */
+  double stage_bytes[12];
 } qrdm_b200_stats;
 
 enum {

@@ -131,3 +131,8 @@ def set_profile(mode: int):
 def fp64_peak(use_dmma=True, stream=0):
     """Measured FP64 peak of this GPU in TFLOP/s (DMMA.8x8x4 or DFMA chains on every SM)."""
     return float(_lib.lib.qrdm_b200_measure_fp64_peak(1 if use_dmma else 0, C.c_void_p(int(stream))))
+
+
+def copy_gbs(nbytes=1 << 30, stream=0):
+    """Measured device-to-device copy bandwidth in GB/s (bytes read + written per second)."""
+    return float(_lib.lib.qrdm_b200_measure_copy_gbs(int(nbytes), C.c_void_p(int(stream))))

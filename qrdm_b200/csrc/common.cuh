@@ -40,7 +40,11 @@ __device__ __forceinline__ QrdmGeom qrdm_geom(const qrdm_prob& P) {
     g.j = c->j; g.fjb = c->fjb; g.k = c->fjb_cmp; g.n_end = P.n; g.voff = 0;
   } else {
     const int s = P.sub - 1;
-    const bool dead = s >= c->fjb || (s > 0 && c->tall_done);
+    // After a DM early stop only the sub-panels BEHIND the one that stopped are dead.  The stopping sub-panel itself
+    // still owes its k = sub_k reflectors to the rest of the panel (the reference applies every reflector to all
+    // remaining panel columns as it goes, src/dgeqr2.c:179-186) — round 1 marked it dead as well, so a stop in a
+    // sub-panel s > 0 left the panel columns behind it one block reflector short.
+    const bool dead = s >= c->fjb || (s > 0 && c->tall_done && s > c->tall_stop_s);
     g.j = c->j + s;
     g.fjb = dead ? 0 : min(QRDM_TALL_B, c->fjb - s);
     g.k = dead ? 0 : c->sub_k;

@@ -379,6 +379,7 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
   rc = read_mailbox(&P, stream);
   if (rc) return rc;
   eta *= w->mailbox->maxnrm; /* :684 */
+  g_stats.stage_bytes[QRDM_STAGE_NORM_INIT] = 8.0 * (double)m * (double)n;
 
   int info = 0, it = 0, j = 0;
   while (j < minmn) { /* :694 */
@@ -386,6 +387,8 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
     int jr = j - P.row0;
     jr = jr < 0 ? 0 : (jr > m ? m : jr); /* first active local row */
     int lazy = 0;
+    /* the mailbox read at the end of the previous iteration already holds this iteration's candidate count */
+    if (w->mailbox->nc > 1) g_stats.stage_bytes[QRDM_STAGE_GRAM] += 8.0 * (double)(m - jr) * (double)w->mailbox->nc;
     if (!mg) {
       P.vc = vcbuf[it & 1];          /* V of this block; the pending block's V sits in the other buffer */
       P.vc_prev = vcbuf[(it & 1) ^ 1];
@@ -519,6 +522,9 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
       break;
     }
     g_stats.trailing_flops += 4.0 * (double)(m - jr) * (double)(cols - k) * (double)k;
+    g_stats.stage_bytes[QRDM_STAGE_PANEL] += 16.0 * (double)(m - jr) * (double)k; /* >= 16 m_r k: k <= fjb columns read + written once */
+    g_stats.stage_bytes[QRDM_STAGE_NORM_UPDATE] += 8.0 * (double)k * (double)(cols - k);
+    g_stats.stage_bytes[QRDM_STAGE_VTC] += (lazy ? 16.0 : 24.0) * (double)(m - jr) * (double)(cols - k);
     j += k;
     if (wb && wb->io) {
       /* pageable host buffer: the same streaming through the pinned ring + drain thread of hostio.c; the ring
@@ -542,7 +548,12 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
     STAGE(QRDM_STAGE_VTC, qrdm_k_flush(&P, pend_j, stream));
   }
   CU(qrdm_rt_event_record(w->ev[1], stream));
+  if (g_profile) CU(qrdm_rt_d2h(w->mailbox, w->ctrl, sizeof(qrdm_ctrl), stream)); /* device-side statistics (after the timed region) */
   CU(qrdm_rt_event_sync(w->ev[1]));
+  if (g_profile) {
+    CU(qrdm_rt_sync(stream));
+    g_stats.stage_bytes[QRDM_STAGE_PERMUTE] = 16.0 * (double)m * (double)w->mailbox->stat_perm_cols;
+  }
   g_stats.ms_total = qrdm_rt_event_ms(w->ev[0], w->ev[1]);
   for (int e = 0; e + 1 < g_ev_used; e += 2) /* light profile: sum the pooled event pairs */
     g_stats.ms_stage[g_ev_stage_of[e / 2]] += qrdm_rt_event_ms(g_ev_pool[e], g_ev_pool[e + 1]);
@@ -831,14 +842,32 @@ int qrdm_b200_peer_open(int rank, int nranks, const char *handles64) {
 }
 void qrdm_b200_peer_close(void) { api_lock(); qrdm_rt_peer_destroy(); api_unlock(); }
 
+static int sharded_locked(int m_local, int m_global, int row0, int nranks, int n, double *d_a, int lda,
+                          int *d_jpvt, double *d_tau, int *ncols, const double *thres, int nb, void *stream) {
+  qrdm_shard sh = {row0, m_global, nranks};
+  if (m_local > 0) return factor_device(m_local, n, d_a, lda, d_jpvt, d_tau, ncols, thres, nb, stream, NULL, &sh);
+  /* A rank that holds no rows at all (m_global < 32 * nranks or so) still has to take part in every exchange and to
+   * keep its replicated jpvt / tau / ncols.  It runs the ordinary path on ONE internal all-zero row placed below the
+   * matrix (row0 = m_global): a zero row contributes exact zeros to every sum, stays zero under every reflector
+   * (v = 0), and no kernel ever sees a local matrix without rows. */
+  double *dummy = NULL;
+  CU(qrdm_rt_malloc((void **)&dummy, sizeof(double) * 2 * (size_t)n));
+  int info = QRDM_ERR_CUDA;
+  if (qrdm_rt_memset(dummy, 0, sizeof(double) * 2 * (size_t)n, stream) == 0) {
+    sh.row0 = m_global;
+    info = factor_device(1, n, dummy, 2, d_jpvt, d_tau, ncols, thres, nb, stream, NULL, &sh);
+  }
+  qrdm_rt_sync(stream);
+  qrdm_rt_free(dummy);
+  return info;
+}
 int dgeqrdm_dev_sharded(int m_local, int m_global, int row0, int nranks, int n, double *d_a, int lda,
                         int *d_jpvt, double *d_tau, int *ncols, const double *thres, int nb, void *stream) {
   if (m_local < 0 || row0 < 0 || row0 + m_local > m_global || nranks < 1) return bad_argument(2);
   int rc = check_args(QRDM_COL_MAJOR, m_global, n, lda > m_global ? lda : m_global, thres, nb);
   if (rc) return rc;
   if (lda < (m_local > 1 ? m_local : 1)) return bad_argument(5);
-  qrdm_shard sh = {row0, m_global, nranks};
-  API_BODY(factor_device(m_local, n, d_a, lda, d_jpvt, d_tau, ncols, thres, nb, stream, NULL, &sh));
+  API_BODY(sharded_locked(m_local, m_global, row0, nranks, n, d_a, lda, d_jpvt, d_tau, ncols, thres, nb, stream));
 }
 
 /* ---- batched mode: `batch` independent m x n matrices, matrix b at

@@ -9,6 +9,8 @@
 // Rows are split over CTAs (split-K); partial 64x64 blocks go to gram_part[cta] and are summed in
 // fixed order by k_gram_reduce (deterministic; row-sharded build: all-reduce in between).
 // HBM/L2-bound: algorithmic bytes 8 * rows * nc.
+#include <cstdlib>
+
 #include "common.cuh"
 
 #define GR_ROWS 64
@@ -89,6 +91,157 @@ __global__ void __launch_bounds__(256) k_gram_partial(qrdm_prob P, int of_v) {
     for (int b = 0; b < 4; ++b) out[(4 * ty + a) * 64 + 4 * tx + b] = acc[a][b];
 }
 
+// ---------------------------------------------------------------------------------------------
+// K3b on the TMA + DMMA path (candidates' Gram, 16-byte aligned even-lda matrices: every production shape).
+//
+// The m_r x nc candidate panel is gathered column by column — a column chunk of a column-major matrix is one
+// contiguous run of bytes — by `cp.async.bulk` (SASS UBLKCP) into a 3-stage shared-memory ring, each stage
+// 128 rows x 64 columns, completion signalled on an mbarrier (expect_tx / complete_tx); a dedicated producer warp
+// issues the copies and waits on the stage's "empty" barrier, the 8 consumer warps wait on "full".  The product
+// runs on the FP64 tensor pipe: mma.sync.m8n8k4.f64 (DMMA) with M = N = candidate index, K = row index.  A lane's A
+// fragment for column block bi and its B fragment for block bj are the SAME register when bi = bj's block, so a
+// k-step costs NB8 shared-memory loads for NB8 (NB8 + 1) / 2 DMMAs (upper block triangle only: G is symmetric).
+// Consumer warp w owns the k-steps w, w + 8, ... of every stage (split-K inside the CTA, all warps balanced) and
+// keeps the whole upper triangle in registers (72 doubles at nc = 64); the 8 partial triangles are added in warp
+// order through shared memory (deterministic) and the CTA writes one 64 x 64 partial block; k_gram_reduce sums the
+// CTAs' blocks in fixed order as before.  Column stride GT_TRP = 132 doubles: 16-byte aligned bulk-copy
+// destinations and conflict-free fragment loads (lane (g, t) reads word g * 132 + t: banks 8g + 2t mod 32).
+// Bound: FP64 tensor pipe at nc = 64 (9 DMMA per row: 36 clk/row/SM against 23 B/clk/SM of HBM = 22 clk per
+// 512-byte row) — 0.25 ms per 2,000,000-row Gram against 0.16 ms of pure HBM time; HBM-bound for nc <= 32.
+#define GT_TR 128
+#define GT_TRP (GT_TR + 4)
+#define GT_STAGES 3
+#define GT_CONSUMERS 8
+#define GT_THREADS ((GT_CONSUMERS + 1) * 32)
+#define GT_STAGE_DOUBLES (64 * GT_TRP)
+#define GT_SMEM (GT_STAGES * GT_STAGE_DOUBLES * 8 + 128)
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned done = 0, spins = 0;
+  while (!done) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (!done && ++spins > (1u << 26)) __trap();  // a copy that never lands must not hang the GPU
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int NB8>
+__global__ void __launch_bounds__(GT_THREADS, 1) k_gram_tma(qrdm_prob P, int chunk) {
+  extern __shared__ __align__(128) unsigned char gt_smem[];
+  double* stage = reinterpret_cast<double*>(gt_smem);
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(gt_smem + (size_t)GT_STAGES * GT_STAGE_DOUBLES * 8);
+  unsigned long long* empty = full + GT_STAGES;
+  __shared__ int scol[64];
+  const qrdm_ctrl* ctrl = P.ctrl;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int nc = ctrl->nc;
+  if (nc <= 1) return;  // a single candidate is always taken, no cosines needed
+  const int j = ctrl->j;
+  const int r_lo = qrdm_jr(P, j), r_hi = P.m;
+  const int r_al = r_lo & ~1;  // bulk copies need 16-byte aligned sources: start on an even row, mask the extra one
+  const int my_lo = r_al + blockIdx.x * chunk, my_hi = min(r_hi, my_lo + chunk);
+  const int nchunks = my_hi > my_lo ? (my_hi - my_lo + GT_TR - 1) / GT_TR : 0;
+  const double* base = P.a + (size_t)j * P.lda;
+  if (tid < 64) scol[tid] = tid < nc ? ctrl->cand[tid] : 0;
+  if (tid == 0) {
+    for (int s = 0; s < GT_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], GT_CONSUMERS); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  constexpr int NBLK = NB8 * (NB8 + 1) / 2;
+  if (wid == GT_CONSUMERS) {
+    // ---- producer warp: one bulk copy per candidate column and stage ----
+    for (int it = 0; it < nchunks; ++it) {
+      const int s = it % GT_STAGES;
+      const unsigned ph = (unsigned)(it / GT_STAGES) & 1u;
+      if (it >= GT_STAGES) mbar_wait(&empty[s], ph ^ 1u);
+      const int r0 = my_lo + it * GT_TR;
+      const int vr = min(GT_TR, my_hi - r0);
+      const unsigned bytes = (unsigned)((vr + 1) & ~1) * 8u;  // an odd tail reads one padding row (lda > m there), masked below
+      if (lane == 0) mbar_expect_tx(&full[s], bytes * (unsigned)nc);
+      __syncwarp();
+      for (int c = lane; c < nc; c += 32)
+        bulk_g2s(stage + (size_t)s * GT_STAGE_DOUBLES + (size_t)c * GT_TRP, base + (size_t)scol[c] * P.lda + r0, bytes, &full[s]);
+    }
+    return;
+  }
+
+  // ---- consumer warps ----
+  const int g = lane >> 2, t = lane & 3;
+  double acc[NBLK][2];
+#pragma unroll
+  for (int b = 0; b < NBLK; ++b) { acc[b][0] = 0.0; acc[b][1] = 0.0; }
+  for (int it = 0; it < nchunks; ++it) {
+    const int s = it % GT_STAGES;
+    const unsigned ph = (unsigned)(it / GT_STAGES) & 1u;
+    const int r0 = my_lo + it * GT_TR;
+    const int vr = min(GT_TR, my_hi - r0);
+    const int lo = r0 < r_lo ? r_lo - r0 : 0;
+    const double* st = stage + (size_t)s * GT_STAGE_DOUBLES;
+    mbar_wait(&full[s], ph);
+    const int nks = (vr + 3) >> 2;
+    for (int ks = wid; ks < nks; ks += GT_CONSUMERS) {
+      const int row = ks * 4 + t;
+      const bool rv = row >= lo && row < vr;
+      double f[NB8];
+#pragma unroll
+      for (int b = 0; b < NB8; ++b) {
+        const int c = 8 * b + g;
+        const double x = st[(size_t)c * GT_TRP + row];
+        f[b] = (rv && c < nc) ? x : 0.0;
+      }
+      int q = 0;
+#pragma unroll
+      for (int bi = 0; bi < NB8; ++bi)
+#pragma unroll
+        for (int bj = bi; bj < NB8; ++bj, ++q) dmma884(acc[q][0], acc[q][1], f[bi], f[bj]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
+  // ---- add the 8 warps' partial triangles in warp order (deterministic), then write the CTA's 64 x 64 block ----
+  asm volatile("bar.sync 1, %0;\n" ::"n"(GT_CONSUMERS * 32) : "memory");  // every stage consumed, no copy in flight: reuse stage 0
+  double* Gs = stage;  // [64][66]
+  for (int w = 0; w < GT_CONSUMERS; ++w) {
+    if (wid == w) {
+      int q = 0;
+#pragma unroll
+      for (int bi = 0; bi < NB8; ++bi)
+#pragma unroll
+        for (int bj = bi; bj < NB8; ++bj, ++q) {
+          double* d = &Gs[(8 * bi + g) * 66 + 8 * bj + 2 * t];
+          if (w == 0) { d[0] = acc[q][0]; d[1] = acc[q][1]; }
+          else { d[0] += acc[q][0]; d[1] += acc[q][1]; }
+        }
+    }
+    asm volatile("bar.sync 1, %0;\n" ::"n"(GT_CONSUMERS * 32) : "memory");
+  }
+  double* out = P.gram_part + (size_t)blockIdx.x * 4096;
+  for (int e = tid; e < 4096; e += GT_CONSUMERS * 32) {
+    const int r = e >> 6, c = e & 63;
+    double v = 0.0;
+    if (r < 8 * NB8 && c < 8 * NB8) v = ((r >> 3) <= (c >> 3)) ? Gs[r * 66 + c] : Gs[c * 66 + r];
+    out[e] = v;
+  }
+}
+
 __global__ void __launch_bounds__(64) k_gram_reduce(qrdm_prob P, int of_v, int nparts) {
   if (!of_v && P.ctrl->nc <= 1) return;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;  // 4096 entries
@@ -122,6 +275,32 @@ extern "C" int qrdm_k_gram(const qrdm_prob* p, int of_v, int rows_hint, void* st
   if (g < 1) g = 1;
   if (g > QRDM_GRAM_MAXCTA) g = QRDM_GRAM_MAXCTA;
   if (g > 2 * p->sm_count) g = 2 * p->sm_count;
+  static const char* e_old = getenv("QRDM_GRAM_OLD");  // experiment switch: the round-1 FMA kernel
+  if (!of_v && p->vec16 && !(e_old && atoi(e_old))) {
+    // TMA + DMMA path: one CTA per SM at most, contiguous row ranges that are multiples of the 128-row stage
+    static int attr_gen = -1;
+    if (attr_gen != qrdm_rt_device_generation()) {
+      cudaFuncSetAttribute(k_gram_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM);
+      cudaFuncSetAttribute(k_gram_tma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM);
+      cudaFuncSetAttribute(k_gram_tma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM);
+      attr_gen = qrdm_rt_device_generation();
+    }
+    int gt = (rows_hint + 1 + GT_TR - 1) / GT_TR;  // + 1: the range may start one row early (even alignment)
+    if (gt > p->sm_count) gt = p->sm_count;
+    if (gt < 1) gt = 1;
+    int chunk = (rows_hint + 1 + gt - 1) / gt;
+    chunk = (chunk + GT_TR - 1) / GT_TR * GT_TR;
+    // nc is only known on the device: the widest variant is always correct (narrower ones are an optimisation the
+    // host can take when nb bounds the candidate count)
+    const int nbmax = p->nb < QRDM_KMAX ? p->nb : QRDM_KMAX;
+    if (nbmax <= 16) k_gram_tma<2><<<gt, GT_THREADS, GT_SMEM, s>>>(*p, chunk);
+    else if (nbmax <= 32) k_gram_tma<4><<<gt, GT_THREADS, GT_SMEM, s>>>(*p, chunk);
+    else k_gram_tma<8><<<gt, GT_THREADS, GT_SMEM, s>>>(*p, chunk);
+    QRDM_LAUNCH_CHECK();
+    k_gram_reduce<<<64, 64, 0, s>>>(*p, of_v, gt);
+    QRDM_LAUNCH_CHECK();
+    return 0;
+  }
   k_gram_partial<<<g, 256, 0, s>>>(*p, of_v);
   QRDM_LAUNCH_CHECK();
   k_gram_reduce<<<64, 64, 0, s>>>(*p, of_v, g);

@@ -196,6 +196,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(qrdm_prob P, int rpc
       ctrl->sub_k = k;
       ctrl->tall_k = tk;
       ctrl->tall_done = (k < fjb) ? 1 : 0;  // dead sub-panels never get here, so 0 is right after a full one
+      if (k < fjb) ctrl->tall_stop_s = sub_s;
       ctrl->tall_thres = thres;
       ctrl->fjb_cmp = tk;
     } else {
@@ -683,6 +684,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_tall(qrdm_prob P, in
     ctrl->sub_k = k;
     ctrl->tall_k = tk;
     ctrl->tall_done = (k < fjb) ? 1 : 0;
+    if (k < fjb) ctrl->tall_stop_s = sub_s;
     ctrl->tall_thres = thres;
     ctrl->fjb_cmp = tk;
     if (MG) *pc.xseq = px0 + (unsigned)(k < fjb ? k + 1 : fjb);  // exchanges performed by this launch

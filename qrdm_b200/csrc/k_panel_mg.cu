@@ -173,6 +173,7 @@ __global__ void __launch_bounds__(MG_THREADS) k_panel_mg_finish(qrdm_prob P) {
       ctrl->sub_k = k;
       ctrl->tall_k = tk;
       ctrl->tall_done = (k < g.fjb) ? 1 : 0;
+      if (k < g.fjb) ctrl->tall_stop_s = g.sub_s;
       ctrl->fjb_cmp = tk;
     } else {
       ctrl->fjb_cmp = k;

@@ -13,6 +13,9 @@
 __global__ void __launch_bounds__(256) k_pick(qrdm_prob P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   qrdm_pick_body(P, *reinterpret_cast<PickShared*>(smem_raw));
+  // statistics for the HBM roofline of K3d: columns moved so far (every one is read once and written once)
+  __syncthreads();
+  if (threadIdx.x == 0) P.ctrl->stat_perm_cols += P.ctrl->cyc_start[P.ctrl->ncyc];
 }
 
 // K3d: rotate the full-height columns along each cycle.  grid = (row chunks, cycles).

@@ -45,7 +45,7 @@ typedef struct qrdm_ctrl {
   int sub_k;              /* reflectors produced by the current sub-panel */
   int tall_k;             /* reflectors produced so far by this panel */
   int tall_done;          /* 1 once the early stop fired: later sub-panels are no-ops */
-  int pad4_;
+  int tall_stop_s;        /* panel column at which the sub-panel that stopped early starts (valid when tall_done) */
   double tall_thres;      /* stop threshold (set by the panel's first column) */
   int cand[QRDM_KMAX];        /* candidate column offsets (relative to j), by norm descending */
   double candnrm[QRDM_KMAX];  /* their partial norms */
@@ -58,6 +58,7 @@ typedef struct qrdm_ctrl {
   int pend_c0;  /* first column the pending update applies to (= j + fjb of its iteration) */
   int pend_r0;  /* first row still to be updated (= j + k of its iteration: the k new R rows are done) */
   int pad5_;
+  long long stat_perm_cols; /* statistics: columns moved by k_permute since the start of the factorisation */
 } qrdm_ctrl;
 #define QRDM_MAILBOX_BYTES 64
 

@@ -34,6 +34,19 @@ def graded(n: int, r: int | None = None, seed: int = 0, m: int | None = None) ->
     return np.asfortranarray(X)
 
 
+def graded_tall(m: int, n: int, r: int | None = None, seed: int = 0) -> np.ndarray:
+    """Tall graded-spectrum rank-deficient matrix: the ``graded`` recipe with a THIN left factor (Q of an m x n
+    Gaussian, so m can be 10^5 without an m x m QR).  Exercises the DM early stop inside the blocked tall panel."""
+    r = n // 2 if r is None else r
+    rng = np.random.default_rng(seed)
+    U, _ = np.linalg.qr(rng.standard_normal((m, n)))
+    V, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    i = np.arange(1, n + 1, dtype=np.float64)
+    sv = 2.0 ** (1.0 - i) + 1e-17
+    sv[:r] += 0.01 * (r - i[:r])
+    return np.asfortranarray((U * sv) @ V.T)
+
+
 def kahan(n: int, theta: float = 1.25, perturb: float = 0.0, seed: int | None = None) -> np.ndarray:
     """Kahan matrix ``K = diag(s^0..s^(n-1)) (I - c triu(ones,1))``, c = cos(theta), s = sin(theta)
     (config C5; not in the reference — defined in SURVEY.md §8d).  ``perturb`` scales the
