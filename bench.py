@@ -210,8 +210,14 @@ def cpu_baseline(args, m, n, kind, stop_mode, desc):
         t1 = time.perf_counter()
         ref.ref_dgeqp3(A0)
         dt3 = time.perf_counter() - t1
+        split = None
+        if ref.have_ref_timed():   # the same sources with call-site timers (oracle/ref_timing_shim.c)
+            try:
+                split = ref.ref_dgeqrdm_timed(A0, thres=THRES, nb=NB, stop_mode=stop_mode)["split"]
+            except Exception as exc:
+                split = {"error": str(exc)[:120]}
         return {"value": flops(sm_, sn_, rk) / dt / 1e9, "unit": "GFLOP/s", "cores": cores, "kind": "reference",
-                "seconds": dt, "dgeqp3_seconds": dt3,
+                "seconds": dt, "dgeqp3_seconds": dt3, "stage_split_seconds": split,
                 "dgeqp3_gflops": flops(sm_, sn_, min(sm_, sn_)) / dt3 / 1e9,
                 "sample": f"one run of the unmodified reference dgeqrdm (oracle/_ref, OpenBLAS {cores} threads) on a "
                           f"{sm_}x{sn_} {kind} matrix = leading-block sample of {desc}; rank {rk}; "
@@ -369,7 +375,7 @@ def _cpu_one_matrix(args):
     return time.perf_counter() - t0, int(np.count_nonzero(o["ncols"]))
 
 
-def run_batched(torch, dist, qrdm_b200, rank, world, dev, total, n, steps, warmup, with_cpu, pure_theta=None):
+def run_batched(torch, dist, qrdm_b200, rank, world, dev, total, n, steps, warmup, with_cpu, pure_theta=None, nb=None):
     """BASELINE config C5: `total` Kahan-type n x n matrices with the seeded diagonal perturbation 1e3*eps*(n..1), split
     evenly over `world` GPUs as independent units (no collective); every rank factors its share with ONE launch of the
     one-CTA-per-matrix kernel (dgeqrdm_batched_dev).  pure_theta=None: per-matrix theta in [1.1, 1.3] with the seeded
@@ -377,6 +383,7 @@ def run_batched(torch, dist, qrdm_b200, rank, world, dev, total, n, steps, warmu
     511 one-column iterations per matrix."""
     from qrdm_b200 import generators as g
     from qrdm_b200 import sharded
+    nb = NB if nb is None else nb
     per = sharded.batch_partition(total, world)[rank][1]
     distinct = 37
     thetas = [pure_theta if pure_theta is not None else 1.1 + 0.2 * b / distinct for b in range(distinct)]
@@ -397,7 +404,7 @@ def run_batched(torch, dist, qrdm_b200, rank, world, dev, total, n, steps, warmu
         torch.index_select(d_base, 0, idx, out=d_a)
         d_ncols.zero_()
         rc = qrdm_b200.api.dgeqrdm_batched_device(per, n, n, d_a.data_ptr(), n, n * n, d_jpvt.data_ptr(), d_tau.data_ptr(),
-                                                  d_ncols.data_ptr(), d_infos.data_ptr(), thres=THRES, nb=NB,
+                                                  d_ncols.data_ptr(), d_infos.data_ptr(), thres=THRES, nb=nb,
                                                   stream=stream.cuda_stream)
         if rc != 0:
             raise SystemExit(f"dgeqrdm_batched_dev failed: {rc}")
@@ -426,6 +433,7 @@ def run_batched(torch, dist, qrdm_b200, rank, world, dev, total, n, steps, warmu
         ms, fl, bad = float(mx[0]), float(agg[1]), int(agg[2])
     out = {"workload": f"{total} Kahan-type {n}x{n} matrices ("
                        + (f"theta = {pure_theta}, unperturbed" if pure_theta is not None else "theta in [1.1, 1.3], perturbed diagonal")
+                       + (f", nb = {nb}" if nb != NB else "")
                        + f") split over {world} GPU(s), independent units (configs[4])",
            "n_gpus": world, "scaling": "strong", "matrices_per_gpu": per, "ms_per_step": ms / steps,
            "matrices_per_s": total * steps / (ms * 1e-3), "value": steps * fl / (ms * 1e-3) / 1e9, "unit": "GFLOP/s",
@@ -445,7 +453,7 @@ def run_batched(torch, dist, qrdm_b200, rank, world, dev, total, n, steps, warmu
         out["roofline"] = {"bound": "hbm", "kernel": "k_small (whole factorisation of one matrix per CTA)",
                            "algorithmic_bytes_per_step": tb, "achieved": tb / (ms / steps * 1e-3) / 1e9, "unit": "GB/s",
                            "note": "16*m_r*n_c bytes per iteration per matrix summed over the batch; peak = MEASURED_PEAKS hbm_gbs"}
-    if with_cpu and rank == 0:
+    if with_cpu and rank == 0 and nb == NB:
         try:
             import multiprocessing as mp
             cores = len(os.sched_getaffinity(0))
@@ -685,6 +693,24 @@ def main():
         except Exception as exc:
             if isinstance(batched, dict):
                 batched["pure_theta_1.25"] = {"error": str(exc)[:300]}
+        if isinstance(batched, dict) and isinstance(batched.get("pure_theta_1.25"), dict):
+            batched["pure_theta_1.25"]["note"] = (
+                "unperturbed Kahan: all trailing partial norms are equal to the last bit (ORDER margin 0 in every iteration, "
+                "the 1e-12 rule exempts it).  The reference (and the one-matrix GPU path, tests kahan512: 511/511 blocks exact) "
+                "break the ties towards 511 one-column iterations; the one-CTA kernel sums the norms in another order and "
+                "breaks them differently (see mean_iterations_per_matrix).  The forced one-column case is the nb = 1 batch below.")
+        try:
+            one = run_batched(torch, dist, qrdm_b200, rank, world, dev, args.batch_total // 8, 512, steps=1, warmup=1,
+                              with_cpu=False, pure_theta=1.25, nb=1)
+            if isinstance(batched, dict):
+                one["note"] = ("nb = 1: every iteration triangularises exactly one column (512 iterations per matrix, the "
+                               "latency-bound worst case of the kernel); an eighth of the batch to bound the run time")
+                batched["one_column_iterations_nb1"] = one
+        except SystemExit:
+            raise
+        except Exception as exc:
+            if isinstance(batched, dict):
+                batched["one_column_iterations_nb1"] = {"error": str(exc)[:300]}
 
     # ---- the other single-GPU BASELINE configs (parity-test cases, reported for context) ----
     other = {}

@@ -19,6 +19,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(HERE, "_ref", "libqrdm_ref.so")
+REF_TIMED_SO = os.path.join(HERE, "_ref", "libqrdm_ref_timed.so")
 PORT_SO = os.path.join(HERE, "_build", "libqrdm_port.so")
 
 _dp = C.POINTER(C.c_double)
@@ -113,6 +114,41 @@ def port_dgeqrdm(A, thres=(0.9, 0.15), nb=64, stop_mode=0, layout=102, lda=None)
                                  ncols.ctypes.data_as(_ip), th.ctypes.data_as(_dp), nb,
                                  margins.ctypes.data_as(_dp))
     return dict(info=info, A=A, jpvt=jpvt, tau=tau, ncols=ncols, margins=margins)
+
+
+_ref_timed = None
+
+
+def have_ref_timed() -> bool:
+    return os.path.exists(REF_TIMED_SO)
+
+
+def ref_dgeqrdm_timed(A, thres=(0.9, 0.15), nb=64, stop_mode=0):
+    """The reference again, built with call-site timers (oracle/ref_timing_shim.c, sources untouched): returns the
+    usual outputs plus ``split`` = seconds in dgeqr2_mia / LAPACKE_dlarft / LAPACKE_dlarfb_mia and the total."""
+    global _ref_timed
+    import time
+    if _ref_timed is None:
+        lib = C.CDLL(REF_TIMED_SO)
+        lib.dgeqrdm.restype = C.c_int
+        lib.dgeqrdm.argtypes = [C.c_int, C.c_int, C.c_int, _dp, C.c_int, _ip, _dp, _ip, _dp, C.c_int]
+        lib.qt_reset.restype = None
+        lib.qt_get.restype = None
+        lib.qt_get.argtypes = [_dp]
+        _ref_timed = lib
+    lib = _ref_timed
+    A, m, n, jpvt, tau, ncols, th = _prep(A, thres, stop_mode)
+    lib.qt_reset()
+    t0 = time.perf_counter()
+    info = lib.dgeqrdm(102, m, n, A.ctypes.data_as(_dp), m, jpvt.ctypes.data_as(_ip), tau.ctypes.data_as(_dp),
+                       ncols.ctypes.data_as(_ip), th.ctypes.data_as(_dp), nb)
+    total = time.perf_counter() - t0
+    t = np.zeros(3)
+    lib.qt_get(t.ctypes.data_as(_dp))
+    split = {"dgeqr2_mia (panel)": float(t[0]), "LAPACKE_dlarft (T factor)": float(t[1]),
+             "LAPACKE_dlarfb_mia (trailing update)": float(t[2]),
+             "DM_perm + norm_update + driver (remainder)": float(total - t.sum()), "total": float(total)}
+    return dict(info=info, A=A, jpvt=jpvt, tau=tau, ncols=ncols, split=split)
 
 
 def ref_dgeqp3(A):
