@@ -304,6 +304,46 @@ static int mg_allreduce(double *buf, size_t count, void *stream) {
   return qrdm_rt_allreduce(buf, count, stream);
 }
 
+static int read_mailbox(const qrdm_prob *p, void *stream);
+
+/* Badly scaled input (largest column norm Inf, or below 2^-300 where squares underflow): find max |a_ij|, and if it is
+ * finite and far from 1 multiply A by the power of two that brings it to [1, 2).  Exact, so pivots / tau / V are those
+ * of the unscaled matrix and R is off by the same factor, which factor_device divides out at the end.  The reference
+ * gets there with scaled norms (cblas_dnrm2) and dlarfg's safmin loop (src/dlarfg.c:144-182). */
+static int mg_allreduce(double *buf, size_t count, void *stream);
+static int prescale_input(qrdm_prob *P, int mg, double *scale_out, void *stream) {
+  qrdm_workspace *w = &g_ws;
+  int nparts = 0;
+  *scale_out = 1.0;
+  CU(qrdm_k_amax(P, P->nrm_part, &nparts, stream));
+  double *h = (double *)malloc(sizeof(double) * (size_t)(nparts > 16 ? nparts : 16));
+  if (!h) return QRDM_ERR_CUDA;
+  int rc = qrdm_rt_d2h(h, P->nrm_part, sizeof(double) * (size_t)nparts, stream);
+  if (!rc) rc = qrdm_rt_sync(stream);
+  double amax = 0.0;
+  for (int i = 0; i < nparts && !rc; ++i) amax = h[i] > amax ? h[i] : amax;
+  if (!rc && mg && P->nranks > 1) {
+    /* the all-reduce sums: sum_r amax_r lies in [max, nranks * max] — as good as the max for picking a power of two,
+     * and bit-identical on every rank, so all ranks scale by the same factor */
+    double v[2] = {amax, 0.0};
+    rc = qrdm_rt_h2d(P->mg_buf, v, sizeof(v), stream);
+    if (!rc) rc = mg_allreduce(P->mg_buf, 2, stream) ? QRDM_ERR_COMM : 0;
+    if (!rc) rc = qrdm_rt_d2h(v, P->mg_buf, sizeof(v), stream);
+    if (!rc) rc = qrdm_rt_sync(stream);
+    if (!rc) amax = v[0];
+  }
+  free(h);
+  if (rc) return rc == QRDM_ERR_COMM ? rc : QRDM_ERR_CUDA;
+  if (!(amax > 0.0) || isinf(amax) || isnan(amax)) return 0; /* zero matrix, Inf or NaN input: nothing to gain */
+  const int e = ilogb(amax);
+  if (e > -200 && e < 200) return 0;                         /* a lone tiny or huge column: the matrix itself is fine */
+  const double sc = ldexp(1.0, -e);
+  CU(qrdm_k_scale(P, sc, 0, 0, stream));
+  *scale_out = sc;
+  (void)w;
+  return 0;
+}
+
 static int read_mailbox(const qrdm_prob *p, void *stream) {
   CU(qrdm_rt_d2h(g_ws.mailbox, p->ctrl, QRDM_MAILBOX_BYTES, stream));
   CU(qrdm_rt_sync(stream));
@@ -345,6 +385,7 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
   P.row0 = sh ? sh->row0 : 0; P.m_glob = m_glob; P.nranks = sh ? sh->nranks : 1;
   P.w_reduced = mg; P.mg_buf = w->mg_buf; P.mg_cnt = w->mg_cnt;
   { const char *dbg = getenv("QRDM_B200_DEBUG"); P.debug = dbg ? atoi(dbg) : 0; }
+  P.thres0 = 5e-14; /* src/dgeqr2.c:40 */
   P.vc_prev = w->vc + (size_t)w->ldv * 64;
   P.upd_flag = w->upd_marks; P.upd_eager = w->upd_marks + w->cap_n;
   /* Deferred ("lazy") trailing update, single GPU: pass 2 of a block is postponed and fused into pass 1
@@ -378,6 +419,27 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
   STAGE(QRDM_STAGE_SELECT, qrdm_k_select(&P, stream));
   rc = read_mailbox(&P, stream);
   if (rc) return rc;
+  double in_scale = 1.0; /* power of two the input was multiplied by (1: the normal case) */
+  if (!(w->mailbox->maxnrm <= 0x1p300) || w->mailbox->maxnrm < 0x1p-300) {
+    rc = prescale_input(&P, mg, &in_scale, stream);
+    if (rc) return rc;
+    if (in_scale != 1.0) { /* norms and selection again, now on representable squares */
+      P.thres0 = 5e-14 * in_scale;
+      wb = NULL; /* finished columns are only final after the unscaling at the end */
+      CU(qrdm_rt_memset(w->ctrl, 0, sizeof(qrdm_ctrl), stream));
+      if (!mg) {
+        CU(qrdm_k_colnorm(&P, 0, stream));
+      } else {
+        int nsplit = 1;
+        CU(qrdm_k_colnorm_part(&P, 0, &nsplit, stream));
+        if (mg_allreduce(P.nrm_part, (size_t)nsplit * n, stream)) return QRDM_ERR_COMM;
+        CU(qrdm_k_colnorm_fin(&P, 0, nsplit, stream));
+      }
+      CU(qrdm_k_select(&P, stream));
+      rc = read_mailbox(&P, stream);
+      if (rc) return rc;
+    }
+  }
   eta *= w->mailbox->maxnrm; /* :684 */
   g_stats.stage_bytes[QRDM_STAGE_NORM_INIT] = 8.0 * (double)m * (double)n;
 
@@ -427,10 +489,15 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
        * kernel: all ranks hold identical vn1/jpvt/ctrl and take identical decisions */
       const int kmax_h = nb < n - j ? (nb < m_glob - j ? nb : m_glob - j) : (n - j < m_glob - j ? n - j : m_glob - j);
       int vt_stride = 0, vt_grid = 0, nsplit = 1;
+      long long lbm = qrdm_rt_launch_count();
+      CU(stage_begin(QRDM_STAGE_GRAM, stream));
       CU(qrdm_k_gram_part(&P, m - jr > 0 ? m - jr : 1, stream));
       if (mg_allreduce(P.gram, 4096, stream)) return QRDM_ERR_COMM;
-      CU(qrdm_k_pick(&P, stream));
-      CU(qrdm_k_permute(&P, stream));
+      CU(stage_end(QRDM_STAGE_GRAM, lbm, stream));
+      STAGE(QRDM_STAGE_PICK, qrdm_k_pick(&P, stream));
+      STAGE(QRDM_STAGE_PERMUTE, qrdm_k_permute(&P, stream));
+      lbm = qrdm_rt_launch_count();
+      CU(stage_begin(QRDM_STAGE_PANEL, stream));
       if (qrdm_rt_peer_available() == P.nranks && !getenv("QRDM_B200_MG_LEGACY")) {
         /* Peer memory open: every sharded panel runs blocked, 8-column sub-panels factored by ONE persistent kernel
          * each (k_panel_tall<true>) that exchanges the per-column vector [||x||^2, x'C_sub | pivot row] with the other
@@ -483,12 +550,18 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
           }
         }
       }
+      CU(stage_end(QRDM_STAGE_PANEL, lbm, stream));
+      lbm = qrdm_rt_launch_count();
+      CU(stage_begin(QRDM_STAGE_VTC, stream));
       CU(qrdm_k_vtc_only(&P, j, &vt_stride, &vt_grid, stream));
       if (vt_stride > 0) {
         CU(qrdm_k_wreduce(&P, j, vt_grid, vt_stride, stream));
         if (mg_allreduce(P.wp, (size_t)64 * vt_stride, stream)) return QRDM_ERR_COMM;
         CU(qrdm_k_trailing_finish(&P, j, vt_grid, vt_stride, stream));
       }
+      CU(stage_end(QRDM_STAGE_VTC, lbm, stream));
+      lbm = qrdm_rt_launch_count();
+      CU(stage_begin(QRDM_STAGE_NORM_UPDATE, stream));
       if (n - j - 1 > 0) {
         CU(qrdm_k_norm_dpart(&P, j, stream));
         if (mg_allreduce(P.nrm_part, (size_t)n, stream)) return QRDM_ERR_COMM;
@@ -497,6 +570,7 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
         if (mg_allreduce(P.nrm_part, (size_t)nsplit * n, stream)) return QRDM_ERR_COMM;
         CU(qrdm_k_colnorm_fin(&P, 2, nsplit, stream));
       }
+      CU(stage_end(QRDM_STAGE_NORM_UPDATE, lbm, stream));
     }
     STAGE(QRDM_STAGE_SELECT, qrdm_k_select(&P, stream)); /* next iteration's prologue + max norm */
     if (lazy) { /* complete the update on everything the next Gram / pick / permutation / panel touches */
@@ -547,6 +621,7 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
     P.vc_prev = vcbuf[(it - 1) & 1];
     STAGE(QRDM_STAGE_VTC, qrdm_k_flush(&P, pend_j, stream));
   }
+  if (in_scale != 1.0) CU(qrdm_k_scale(&P, 1.0 / in_scale, 1, j, stream)); /* R back to the caller's scale */
   CU(qrdm_rt_event_record(w->ev[1], stream));
   if (g_profile) CU(qrdm_rt_d2h(w->mailbox, w->ctrl, sizeof(qrdm_ctrl), stream)); /* device-side statistics (after the timed region) */
   CU(qrdm_rt_event_sync(w->ev[1]));

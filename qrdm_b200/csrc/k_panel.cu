@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(qrdm_prob P, int rpc
     if (lane == 0) ll_store(&part[(size_t)b * 64 + jj], acc, tag_base + 1);
   }
 
-  double thres = (sub_s == 0) ? 5e-14 : ctrl->tall_thres;  // reference src/dgeqr2.c:40
+  double thres = (sub_s == 0) ? P.thres0 : ctrl->tall_thres;  // reference src/dgeqr2.c:40 (5e-14 x input scale)
   int k = fjb;
   long long tph[5] = {0, 0, 0, 0, 0};  // QRDM_B200_DEBUG & 8: per-phase cycle counts of CTA 0
   const bool timing = (P.debug & 8) && b == 0 && tid == 0;
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_reg(qrdm_prob P, int
   if (MODE == 2) { cooperative_groups::this_cluster().sync(); publish_cluster(0, -1, tag_base + 1); }
   __syncthreads();
 
-  double thres2 = 5e-14 * 5e-14;  // (reference src/dgeqr2.c:40)^2
+  double thres2 = P.thres0 * P.thres0;  // (reference src/dgeqr2.c:40)^2, 5e-14 x input scale
   int k = fjb;
   long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // QRDM_B200_DEBUG & 8: per-phase cycle counts of one CTA
   const bool timing = (P.debug & 8) && b == (G > 40 ? 40 : 0) && tid == 0;
@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_tall(qrdm_prob P, in
     publish(acc, 0, 0, tag_base + 1);
   }
 
-  double thres = (sub_s == 0) ? 5e-14 : ctrl->tall_thres;
+  double thres = (sub_s == 0) ? P.thres0 : ctrl->tall_thres;
   int k = fjb;
   for (int i = 0; i < fjb; ++i) {
     const int cur = i & 1, nxt = cur ^ 1;

@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(MG_THREADS) k_panel_mg_init(qrdm_prob P) {
   const MgGeom g = mg_geom(P);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, lda = P.lda;
   if (g.fjb <= 0) return;
-  if (blockIdx.x == 0 && tid == 0) { P.ctrl->mg_k = -1; if (g.sub_s == 0) P.ctrl->mg_thres2 = 5e-14 * 5e-14; }
+  if (blockIdx.x == 0 && tid == 0) { P.ctrl->mg_k = -1; if (g.sub_s == 0) P.ctrl->mg_thres2 = P.thres0 * P.thres0; }
   double* Ap = P.a + (size_t)g.j * lda + g.jr;
   double* mine = P.mg_buf + 512 + (size_t)blockIdx.x * 128;
   for (int e = tid; e < 128; e += MG_THREADS) mine[e] = 0.0;

@@ -421,7 +421,7 @@ __device__ __forceinline__ void small_panel(const qrdm_prob& P, SmallShared& S) 
   double* part = S.part;
   double* Sd = S.S_;    // [2][8] reduced dots, double-buffered by column parity
   double* Rv = S.rowv;  // [2][8] pivot-row entries
-  double thres2 = 5e-14 * 5e-14;  // (src/dgeqr2.c:40)^2
+  double thres2 = P.thres0 * P.thres0;  // (src/dgeqr2.c:40)^2, 5e-14 x the input scale
   int k = fjb;
   bool stopped = false;
   SM_PT(0);
@@ -611,6 +611,59 @@ __device__ __forceinline__ void small_norm_update(const qrdm_prob& P, SmallShare
   }
 }
 
+// initial norms (src/dgeqrdm_work.c:672-682), jpvt = identity (:596-609 with every column free)
+__device__ __noinline__ void small_init_norms(const qrdm_prob& P, SmallShared& S) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int c = wid; c < P.n; c += SM_NW) {
+    const double* col = P.a + (size_t)c * P.lda;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int r = lane;
+    for (; r + 96 < P.m; r += 128) {
+      s0 = fma(col[r], col[r], s0);
+      s1 = fma(col[r + 32], col[r + 32], s1);
+      s2 = fma(col[r + 64], col[r + 64], s2);
+      s3 = fma(col[r + 96], col[r + 96], s3);
+    }
+    for (; r < P.m; r += 32) s0 = fma(col[r], col[r], s0);
+    const double v = sqrt(warp_sum((s0 + s1) + (s2 + s3)));
+    if (lane == 0) { S.vn1[c] = v; S.vn2[c] = v; P.jpvt[c] = c + 1; }
+  }
+}
+
+// max |a_ij| of the matrix; if it is finite and its exponent is beyond +-200, multiply the matrix by the power of two
+// that brings it into [1, 2) and return that factor (1.0 otherwise).  Every thread returns the same value.
+__device__ __noinline__ double small_prescale(const qrdm_prob& P, SmallShared& S) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  double mx = 0.0;
+  for (int c = wid; c < P.n; c += SM_NW) {
+    const double* col = P.a + (size_t)c * P.lda;
+    for (int r = lane; r < P.m; r += 32) mx = fmax(mx, fabs(col[r]));  // fmax drops NaNs (the NaN screen's business)
+  }
+  mx = warp_max(mx);
+  __syncthreads();
+  if (lane == 0) S.red[wid] = mx;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int w = 0; w < SM_NW; ++w) t = fmax(t, S.red[w]);
+    double sc = 1.0;
+    if (t > 0.0 && !isinf(t)) {
+      const int e = ilogb(t);
+      if (e <= -200 || e >= 200) sc = ldexp(1.0, -e);
+    }
+    S.red[0] = sc;
+  }
+  __syncthreads();
+  const double sc = S.red[0];
+  __syncthreads();
+  if (sc != 1.0)
+    for (int c = wid; c < P.n; c += SM_NW) {
+      double* col = P.a + (size_t)c * P.lda;
+      for (int r = lane; r < P.m; r += 32) col[r] *= sc;
+    }
+  return sc;
+}
+
 __global__ void __launch_bounds__(SM_NT, 1) k_small(SmallArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmallShared& S = *reinterpret_cast<SmallShared*>(smem_raw);
@@ -637,24 +690,27 @@ __global__ void __launch_bounds__(SM_NT, 1) k_small(SmallArgs A) {
     S.it = 0;
     S.bad = 0;
   }
-  // initial norms (src/dgeqrdm_work.c:672-682), jpvt = identity (:596-609 with every column free)
-  for (int c = wid; c < A.n; c += SM_NW) {
-    const double* col = P.a + (size_t)c * A.lda;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int r = lane;
-    for (; r + 96 < A.m; r += 128) {
-      s0 = fma(col[r], col[r], s0);
-      s1 = fma(col[r + 32], col[r + 32], s1);
-      s2 = fma(col[r + 64], col[r + 64], s2);
-      s3 = fma(col[r + 96], col[r + 96], s3);
-    }
-    for (; r < A.m; r += 32) s0 = fma(col[r], col[r], s0);
-    const double v = sqrt(warp_sum((s0 + s1) + (s2 + s3)));
-    if (lane == 0) { S.vn1[c] = v; S.vn2[c] = v; P.jpvt[c] = c + 1; }
-  }
+  small_init_norms(P, S);
   __syncthreads();
   qrdm_select_body<SM_NT>(P, S.u.sel);
   __syncthreads();
+  // badly scaled matrix (largest column norm Inf / NaN, or so small that squares underflow): one exact power-of-two
+  // scaling of the whole matrix, undone on the R-like entries at the end (same scheme as the one-matrix driver,
+  // dgeqrdm_host.c prescale_input; the reference gets there with cblas_dnrm2 and dlarfg's safmin loop)
+  double in_scale = 1.0;
+  if (!(S.ctrl.maxnrm <= 0x1p300) || S.ctrl.maxnrm < 0x1p-300) {
+    in_scale = small_prescale(P, S);
+    if (in_scale != 1.0) {
+      __syncthreads();
+      for (int i = tid; i < (int)(sizeof(qrdm_ctrl) / sizeof(int)); i += SM_NT) reinterpret_cast<int*>(&S.ctrl)[i] = 0;
+      __syncthreads();
+      small_init_norms(P, S);
+      __syncthreads();
+      qrdm_select_body<SM_NT>(P, S.u.sel);
+      __syncthreads();
+    }
+  }
+  P.thres0 = 5e-14 * in_scale;  // src/dgeqr2.c:40
   if (tid == 0) S.eta *= S.ctrl.maxnrm;  // :684
   __syncthreads();
 
@@ -707,6 +763,15 @@ __global__ void __launch_bounds__(SM_NT, 1) k_small(SmallArgs A) {
     if (S.stop_mode && S.ctrl.maxnrm * sqrt((double)(cols - kk)) <= S.eta) break;  // :782-785
   }
   __syncthreads();
+  if (in_scale != 1.0) {  // R back to the caller's scale: rows <= c of the columns c < rank, whole columns c >= rank
+    const int rk = S.ctrl.j;
+    const double inv = 1.0 / in_scale;
+    for (int c = wid; c < A.n; c += SM_NW) {
+      double* col = P.a + (size_t)c * A.lda;
+      const int hi = c < rk ? min(c + 1, A.m) : A.m;
+      for (int r = lane; r < hi; r += 32) col[r] *= inv;
+    }
+  }
   SM_TPRINT;
   if (tid == 0 && A.infos) A.infos[b] = S.ctrl.err;
 }

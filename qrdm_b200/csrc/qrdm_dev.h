@@ -101,9 +101,16 @@ typedef struct qrdm_prob {
   int *upd_eager;     /* [n] == stamp: likewise for the eager set (leading 64 positions + candidates) */
   int stamp;          /* id of the pending block (> 0) */
   int pend;           /* 1: kernels take their geometry from ctrl->pend_* (flush of a pending block) */
+  double thres0;      /* the panel's initial absolute stop threshold 5e-14 (src/dgeqr2.c:40) times the power-of-two input
+                         scale (1 unless the matrix was pre-scaled, see qrdm_k_scale) */
 } qrdm_prob;
 
 int qrdm_k_colnorm(const qrdm_prob *p, int use_flag_list, void *stream);   /* K1 / K2 recompute */
+/* badly scaled inputs (max column norm beyond 2^+-300, where sums of squares leave the double range): max |a_ij| per
+ * CTA -> out[0..*nparts), and A *= s (mode 0: every entry; mode 1: the R-like entries of a factored matrix of rank r —
+ * rows <= c of the columns c < r, whole columns c >= r — the Householder vectors are scale invariant) */
+int qrdm_k_amax(const qrdm_prob *p, double *out, int *nparts, void *stream);
+int qrdm_k_scale(const qrdm_prob *p, double s, int mode, int r, void *stream);
 int qrdm_k_select(const qrdm_prob *p, void *stream);                        /* K3a */
 int qrdm_k_gram(const qrdm_prob *p, int of_v, int rows_hint, void *stream); /* K3b / K5 */
 int qrdm_k_pick(const qrdm_prob *p, void *stream);                          /* K3c + plan */

@@ -50,6 +50,14 @@ for mode in ("peer", "legacy_nccl_per_column", "peer"):
             times.append(float(t))
     out.setdefault(mode, []).append({"ms": times, "launches": qrdm_b200.stats()["launches"], "rank": int(nc.sum())})
 os.environ.pop("QRDM_B200_MG_LEGACY", None)
+# per-stage split of the sharded path (profile mode 1: event pair + sync around every stage, every rank alike)
+qrdm_b200.set_profile(1)
+A.copy_(A0)
+torch.cuda.synchronize(); dist.barrier()
+info, nc = sharded.dgeqrdm_sharded(A, ml, m, row0, world, n, ml, jp, tau, stream=stream.cuda_stream)
+st = qrdm_b200.stats()
+qrdm_b200.set_profile(0)
+out["stage_profile_rank0"] = {"ms_total": st["ms_total"], "ms_stage": st["ms_stage"], "stage_launches": st["stage_launches"]}
 del A0, A
 torch.cuda.empty_cache()
 out["parity_vs_single_gpu"] = bench.sharded_parity(torch, dist, qrdm_b200, rank, world, dev)
