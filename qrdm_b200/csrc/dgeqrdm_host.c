@@ -386,6 +386,7 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
   P.w_reduced = mg; P.mg_buf = w->mg_buf; P.mg_cnt = w->mg_cnt;
   { const char *dbg = getenv("QRDM_B200_DEBUG"); P.debug = dbg ? atoi(dbg) : 0; }
   P.thres0 = 5e-14; /* src/dgeqr2.c:40 */
+  P.inv_scale = 1.0;
   P.vc_prev = w->vc + (size_t)w->ldv * 64;
   P.upd_flag = w->upd_marks; P.upd_eager = w->upd_marks + w->cap_n;
   /* Deferred ("lazy") trailing update, single GPU: pass 2 of a block is postponed and fused into pass 1
@@ -425,6 +426,7 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
     if (rc) return rc;
     if (in_scale != 1.0) { /* norms and selection again, now on representable squares */
       P.thres0 = 5e-14 * in_scale;
+      P.inv_scale = 1.0 / in_scale;
       wb = NULL; /* finished columns are only final after the unscaling at the end */
       CU(qrdm_rt_memset(w->ctrl, 0, sizeof(qrdm_ctrl), stream));
       if (!mg) {
@@ -503,18 +505,14 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
          * each (k_panel_tall<true>) that exchanges the per-column vector [||x||^2, x'C_sub | pivot row] with the other
          * GPUs as LL packets over NVLink from inside the kernel — no launch and no collective call per column
          * (src/dgeqr2.c:148-189 is one tight loop upstream).  Each sub-panel's block reflector then updates the rest of
-         * the panel: V'[V | C_p] partials, one 512-double all-reduce, C_p += V W2. */
+         * the panel: V'[V | C_p] partials, their sum over the GPUs inside the W2 kernel (LL packets again), C_p += V W2. */
         for (int sb = 0; sb < kmax_h; sb += QRDM_TALL_B) {
           qrdm_prob Ps = P;
           Ps.sub = sb + 1;
           int jrs = j + sb - P.row0;
           jrs = jrs < 0 ? 0 : (jrs > m ? m : jrs);
           CU(qrdm_k_panel_tall_mg(&Ps, j, stream));
-          if (sb + QRDM_TALL_B < kmax_h) {
-            CU(qrdm_k_skinny_part(&Ps, m - jrs > 0 ? m - jrs : 1, stream));
-            if (mg_allreduce(P.gram_part, 512, stream)) return QRDM_ERR_COMM;
-            CU(qrdm_k_skinny_finish(&Ps, m - jrs > 0 ? m - jrs : 1, stream));
-          }
+          if (sb + QRDM_TALL_B < kmax_h) CU(qrdm_k_skinny_update_mg(&Ps, m - jrs > 0 ? m - jrs : 1, stream));
         }
       } else if ((m_glob - j) / P.nranks <= 16384) {
         /* legacy transport (NCCL only): one kernel + one 128-double all-reduce per panel column */

@@ -140,24 +140,41 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                : "memory");
 }
 
-template <int NB8>
+// SUBW = true: the same machinery computes the skinny product of the blocked tall panel (k_skinny.cu),
+//   W_ext = V' [V | C_p]   (8 x (8 + ncp)) = the first 8 ROWS of the Gram matrix of X = [V_sub | C_p],
+// where V_sub = the 8 clean reflector columns of the sub-panel (Vc) and C_p = the <= 56 panel columns behind it: only
+// the block row bi = 0 is accumulated (NB8 DMMAs per k-step) and every column is read exactly once — the round-1 FMA
+// kernel re-read V once per 8 columns and spent more shuffles on its per-chunk reductions than FMAs on the product
+// (402 us per call at 2,000,000 rows against 98 us of HBM time, profiles/r02_launches_c4_summary.txt).
+// Output: the CTA's partial in the layout k_sub_w2 folds, gram_part[cta * 512 + group * 64 + q * 8 + c].
+template <int NB8, bool SUBW>
 __global__ void __launch_bounds__(GT_THREADS, 1) k_gram_tma(qrdm_prob P, int chunk) {
   extern __shared__ __align__(128) unsigned char gt_smem[];
   double* stage = reinterpret_cast<double*>(gt_smem);
   unsigned long long* full = reinterpret_cast<unsigned long long*>(gt_smem + (size_t)GT_STAGES * GT_STAGE_DOUBLES * 8);
   unsigned long long* empty = full + GT_STAGES;
-  __shared__ int scol[64];
+  __shared__ const double* scolp[64];  // column c of X, local row 0
   const qrdm_ctrl* ctrl = P.ctrl;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int nc = ctrl->nc;
-  if (nc <= 1) return;  // a single candidate is always taken, no cosines needed
-  const int j = ctrl->j;
-  const int r_lo = qrdm_jr(P, j), r_hi = P.m;
+  int nc, r_lo;
+  if (SUBW) {
+    const QrdmGeom q = qrdm_geom(P);
+    const int c0 = q.j + q.fjb, ncp = q.n_end - c0;
+    if (q.fjb <= 0 || q.k <= 0 || ncp <= 0) return;  // dead sub-panel / nothing behind it (k_sub_w2 returns alike)
+    nc = 8 + ncp;
+    r_lo = qrdm_jr(P, q.j);
+    if (tid < 64) scolp[tid] = tid < 8 ? P.vc + (size_t)(q.voff + tid) * P.ldv : P.a + (size_t)(c0 + (tid < nc ? tid - 8 : 0)) * P.lda;
+  } else {
+    nc = ctrl->nc;
+    if (nc <= 1) return;  // a single candidate is always taken, no cosines needed
+    const int j = ctrl->j;
+    r_lo = qrdm_jr(P, j);
+    if (tid < 64) scolp[tid] = P.a + (size_t)(j + (tid < nc ? ctrl->cand[tid] : 0)) * P.lda;
+  }
+  const int r_hi = P.m;
   const int r_al = r_lo & ~1;  // bulk copies need 16-byte aligned sources: start on an even row, mask the extra one
   const int my_lo = r_al + blockIdx.x * chunk, my_hi = min(r_hi, my_lo + chunk);
   const int nchunks = my_hi > my_lo ? (my_hi - my_lo + GT_TR - 1) / GT_TR : 0;
-  const double* base = P.a + (size_t)j * P.lda;
-  if (tid < 64) scol[tid] = tid < nc ? ctrl->cand[tid] : 0;
   if (tid == 0) {
     for (int s = 0; s < GT_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], GT_CONSUMERS); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -165,7 +182,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gram_tma(qrdm_prob P, int chu
   }
   __syncthreads();
 
-  constexpr int NBLK = NB8 * (NB8 + 1) / 2;
+  constexpr int NBLK = SUBW ? NB8 : NB8 * (NB8 + 1) / 2;
   if (wid == GT_CONSUMERS) {
     // ---- producer warp: one bulk copy per candidate column and stage ----
     for (int it = 0; it < nchunks; ++it) {
@@ -178,7 +195,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gram_tma(qrdm_prob P, int chu
       if (lane == 0) mbar_expect_tx(&full[s], bytes * (unsigned)nc);
       __syncwarp();
       for (int c = lane; c < nc; c += 32)
-        bulk_g2s(stage + (size_t)s * GT_STAGE_DOUBLES + (size_t)c * GT_TRP, base + (size_t)scol[c] * P.lda + r0, bytes, &full[s]);
+        bulk_g2s(stage + (size_t)s * GT_STAGE_DOUBLES + (size_t)c * GT_TRP, scolp[c] + r0, bytes, &full[s]);
     }
     return;
   }
@@ -209,7 +226,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gram_tma(qrdm_prob P, int chu
       }
       int q = 0;
 #pragma unroll
-      for (int bi = 0; bi < NB8; ++bi)
+      for (int bi = 0; bi < (SUBW ? 1 : NB8); ++bi)
 #pragma unroll
         for (int bj = bi; bj < NB8; ++bj, ++q) dmma884(acc[q][0], acc[q][1], f[bi], f[bj]);
     }
@@ -223,7 +240,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gram_tma(qrdm_prob P, int chu
     if (wid == w) {
       int q = 0;
 #pragma unroll
-      for (int bi = 0; bi < NB8; ++bi)
+      for (int bi = 0; bi < (SUBW ? 1 : NB8); ++bi)
 #pragma unroll
         for (int bj = bi; bj < NB8; ++bj, ++q) {
           double* d = &Gs[(8 * bi + g) * 66 + 8 * bj + 2 * t];
@@ -232,6 +249,14 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gram_tma(qrdm_prob P, int chu
         }
     }
     asm volatile("bar.sync 1, %0;\n" ::"n"(GT_CONSUMERS * 32) : "memory");
+  }
+  if (SUBW) {
+    double* out = P.gram_part + (size_t)blockIdx.x * 512;
+    for (int e = tid; e < 512; e += GT_CONSUMERS * 32) {  // e = group * 64 + q * 8 + c  <->  G[q][8 * group + c]
+      const int gi = e >> 6, q = (e >> 3) & 7, c = e & 7;
+      out[e] = gi < NB8 ? Gs[q * 66 + 8 * gi + c] : 0.0;
+    }
+    return;
   }
   double* out = P.gram_part + (size_t)blockIdx.x * 4096;
   for (int e = tid; e < 4096; e += GT_CONSUMERS * 32) {
@@ -266,6 +291,35 @@ __global__ void __launch_bounds__(64) k_gram_reduce(qrdm_prob P, int of_v, int n
   P.gram[e] = s[0];
 }
 
+static void gram_tma_attrs() {
+  cudaFuncSetAttribute(k_gram_tma<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM);
+  cudaFuncSetAttribute(k_gram_tma<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM);
+  cudaFuncSetAttribute(k_gram_tma<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM);
+  cudaFuncSetAttribute(k_gram_tma<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM);
+}
+
+// Skinny product of the blocked tall panel on the TMA + DMMA path; *nparts = number of 512-double partials written to
+// gram_part (one per CTA, CTAs without rows write zeros).  Returns -1 when the matrix is not 16-byte aligned with an
+// even lda (the caller then uses the FMA kernel k_sub_w).
+extern "C" int qrdm_k_subw_tma(const qrdm_prob* p, int rows_hint, int* nparts, void* stream) {
+  static const char* e_old = getenv("QRDM_SUBW_OLD");  // experiment switch: the round-1 FMA kernel
+  if (!p->vec16 || (e_old && atoi(e_old))) return -1;
+  static int attr_gen = -1;
+  if (attr_gen != qrdm_rt_device_generation()) {
+    gram_tma_attrs();
+    attr_gen = qrdm_rt_device_generation();
+  }
+  int gt = (rows_hint + 1 + GT_TR - 1) / GT_TR;
+  if (gt > p->sm_count) gt = p->sm_count;
+  if (gt < 1) gt = 1;
+  int chunk = (rows_hint + 1 + gt - 1) / gt;
+  chunk = (chunk + GT_TR - 1) / GT_TR * GT_TR;
+  k_gram_tma<8, true><<<gt, GT_THREADS, GT_SMEM, (cudaStream_t)stream>>>(*p, chunk);
+  QRDM_LAUNCH_CHECK();
+  *nparts = gt;
+  return 0;
+}
+
 // rows_hint: host-side upper bound of the number of rows (m - j) used to size the grid.
 extern "C" int qrdm_k_gram(const qrdm_prob* p, int of_v, int rows_hint, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
@@ -280,9 +334,7 @@ extern "C" int qrdm_k_gram(const qrdm_prob* p, int of_v, int rows_hint, void* st
     // TMA + DMMA path: one CTA per SM at most, contiguous row ranges that are multiples of the 128-row stage
     static int attr_gen = -1;
     if (attr_gen != qrdm_rt_device_generation()) {
-      cudaFuncSetAttribute(k_gram_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM);
-      cudaFuncSetAttribute(k_gram_tma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM);
-      cudaFuncSetAttribute(k_gram_tma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM);
+      gram_tma_attrs();
       attr_gen = qrdm_rt_device_generation();
     }
     int gt = (rows_hint + 1 + GT_TR - 1) / GT_TR;  // + 1: the range may start one row early (even alignment)
@@ -293,9 +345,9 @@ extern "C" int qrdm_k_gram(const qrdm_prob* p, int of_v, int rows_hint, void* st
     // nc is only known on the device: the widest variant is always correct (narrower ones are an optimisation the
     // host can take when nb bounds the candidate count)
     const int nbmax = p->nb < QRDM_KMAX ? p->nb : QRDM_KMAX;
-    if (nbmax <= 16) k_gram_tma<2><<<gt, GT_THREADS, GT_SMEM, s>>>(*p, chunk);
-    else if (nbmax <= 32) k_gram_tma<4><<<gt, GT_THREADS, GT_SMEM, s>>>(*p, chunk);
-    else k_gram_tma<8><<<gt, GT_THREADS, GT_SMEM, s>>>(*p, chunk);
+    if (nbmax <= 16) k_gram_tma<2, false><<<gt, GT_THREADS, GT_SMEM, s>>>(*p, chunk);
+    else if (nbmax <= 32) k_gram_tma<4, false><<<gt, GT_THREADS, GT_SMEM, s>>>(*p, chunk);
+    else k_gram_tma<8, false><<<gt, GT_THREADS, GT_SMEM, s>>>(*p, chunk);
     QRDM_LAUNCH_CHECK();
     k_gram_reduce<<<64, 64, 0, s>>>(*p, of_v, gt);
     QRDM_LAUNCH_CHECK();

@@ -157,7 +157,9 @@ __global__ void __launch_bounds__(256) k_norm_update(qrdm_prob P, double tol3z) 
     d = P.nrm_part[c];  // row-sharded, part 2: all-reduced sum
   }
   if (lane == 0) {
-    double t = sqrt(fabs(d)) / v1;
+    // in the caller's scale (inv_scale = 1 unless the input was pre-scaled: then x * 1.0 is exact and nothing changes)
+    const double dt = (d * P.inv_scale) * P.inv_scale;
+    double t = sqrt(fabs(dt)) / (v1 * P.inv_scale);
     t = (t + 1.0) * (1.0 - t);
     t = (0.0 >= t) ? 0.0 : t;
     const double q = v1 / P.vn2[c];

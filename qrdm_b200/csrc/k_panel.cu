@@ -641,9 +641,9 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_tall(qrdm_prob P, in
     double acc[TALL_B];
 #pragma unroll
     for (int c = 0; c < TALL_B; ++c) acc[c] = 0.0;
-    for (int r = tid; r < nr; r += PANEL_THREADS) {
+    auto do_row = [&](int r) {  // general row (may be the pivot row, the next pivot row, or above the diagonal)
       const int R = goff + r0 + r;
-      if (R < i) continue;
+      if (R < i) return;
       double v = 1.0;
       if (R > i) {
         v = Ap[(size_t)i * lda + r];
@@ -651,7 +651,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_tall(qrdm_prob P, in
       } else {
         Ap[(size_t)i * lda + r] = beta;
       }
-      if (last) continue;
+      if (last) return;
       double pv[TALL_B];
 #pragma unroll
       for (int c = 0; c < TALL_B; ++c)
@@ -674,7 +674,37 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_tall(qrdm_prob P, in
         for (int c = 0; c < TALL_B; ++c)
           if (c > i && c < fjb) ll_store(&bcast[nxt * 128 + 64 + c], pv[c], tag + 1);
       }
+    };
+    // Two rows per trip whenever both lie strictly below the next pivot row (all but the first few rows of the rank
+    // that owns the diagonal block): 2 x (8 - i) independent loads in flight per thread before the first FMA — the
+    // one-row loop left the kernel latency-bound at ~2 TB/s (profiles/r02_launches_c4_summary.txt).  Same per-row
+    // arithmetic and the same per-thread accumulation order (rows ascending), so results are bit-identical.
+    int r = tid;
+    for (; r + PANEL_THREADS < nr; r += 2 * PANEL_THREADS) {
+      const int rb = r + PANEL_THREADS;
+      if (goff + r0 + r <= i + 1 || last) { do_row(r); do_row(rb); continue; }
+      double va = Ap[(size_t)i * lda + r], vb = Ap[(size_t)i * lda + rb];
+      double pa[TALL_B], pb[TALL_B];
+#pragma unroll
+      for (int c = 0; c < TALL_B; ++c)
+        if (c > i && c < fjb) { pa[c] = Ap[(size_t)c * lda + r]; pb[c] = Ap[(size_t)c * lda + rb]; }
+      if (tau != 0.0) { va *= scale; vb *= scale; Ap[(size_t)i * lda + r] = va; Ap[(size_t)i * lda + rb] = vb; }
+      double xa = 0.0, xb = 0.0;
+#pragma unroll
+      for (int c = 0; c < TALL_B; ++c) {
+        if (c > i && c < fjb) {
+          pa[c] = fma(-va, w[c], pa[c]);
+          pb[c] = fma(-vb, w[c], pb[c]);
+          Ap[(size_t)c * lda + r] = pa[c];
+          Ap[(size_t)c * lda + rb] = pb[c];
+          if (c == i + 1) { xa = pa[c]; xb = pb[c]; }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < TALL_B; ++c)
+        if (c > i && c < fjb) { acc[c] = fma(xa, pa[c], acc[c]); acc[c] = fma(xb, pb[c], acc[c]); }
     }
+    for (; r < nr; r += PANEL_THREADS) do_row(r);
     if (last) break;
     publish(acc, nxt, i + 1, tag + 1);
   }

@@ -40,6 +40,11 @@ struct PeerState {
 }  // namespace
 
 const PeerCtx* qrdm_peer_ctx() { return g_peer.open ? &g_peer.ctx : nullptr; }
+void qrdm_peer_next_gen(unsigned* tag, int* parity) {
+  g_peer.gen_seq = g_peer.gen_seq + 1 == 0 ? 1u : g_peer.gen_seq + 1;
+  *tag = g_peer.gen_seq;
+  *parity = (int)(g_peer.gen_seq & 1u);
+}
 
 __global__ void __launch_bounds__(256) k_peer_allreduce(double* __restrict__ buf, int count, PeerCtx pc, unsigned tag, int parity) {
   const int me = pc.rank, N = pc.nranks;
@@ -83,10 +88,12 @@ int qrdm_k_peer_allreduce(double* buf, size_t count, void* stream) {
   if (g_peer.ctx.nranks == 1) return 0;
   for (size_t off = 0; off < count; off += QRDM_PEER_CAP) {
     const int cnt = (int)(count - off < (size_t)QRDM_PEER_CAP ? count - off : (size_t)QRDM_PEER_CAP);
-    g_peer.gen_seq = g_peer.gen_seq + 1 == 0 ? 1u : g_peer.gen_seq + 1;
+    unsigned tag = 0;
+    int parity = 0;
+    qrdm_peer_next_gen(&tag, &parity);
     int grid = (cnt + 255) / 256;
     if (grid > 592) grid = 592;
-    k_peer_allreduce<<<grid, 256, 0, (cudaStream_t)stream>>>(buf + off, cnt, g_peer.ctx, g_peer.gen_seq, (int)(g_peer.gen_seq & 1u));
+    k_peer_allreduce<<<grid, 256, 0, (cudaStream_t)stream>>>(buf + off, cnt, g_peer.ctx, tag, parity);
     QRDM_LAUNCH_CHECK();
   }
   return 0;

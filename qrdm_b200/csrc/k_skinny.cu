@@ -8,6 +8,7 @@
 //   k_sub_apply  C_p += V W2
 // Algorithmic bytes: 8*m_r*(2*ncp + 16) read + 8*m_r*ncp written.
 #include "common.cuh"
+#include "ll.cuh"
 
 #define SK_RC 2048           // rows per CTA chunk
 #define SK_THREADS 256       // thread <-> rows tid, tid+256, ... of the chunk (coalesced per column)
@@ -81,15 +82,43 @@ __global__ void __launch_bounds__(SK_THREADS, 1) k_sub_w(qrdm_prob P) {
   }
 }
 
-__global__ void __launch_bounds__(512) k_sub_w2(qrdm_prob P, int nchunks_max) {
+// MG = true (row-sharded, peer memory open): the fold of this rank's chunk partials, the sum over the ranks and the
+// T' / W2 step in ONE single-CTA kernel — thread e stores its folded value as an LL packet into every peer's receive
+// buffer (k_peer.cu, generic region) and adds the nranks packets of its own buffer in rank order, so all ranks hold
+// bit-identical W; replaces k_sub_wred + all-reduce kernel + k_sub_w2 (three launches per sub-panel).
+template <bool MG>
+__global__ void __launch_bounds__(512) k_sub_w2(qrdm_prob P, int nchunks_max, PeerCtx pc, unsigned ptag, int pparity) {
   __shared__ double W[8 * 64];   // [group][q][c]
   __shared__ double T[64];       // T'[q][p]
   const SkGeom g = sk_geom(P);
-  if (g.k <= 0 || g.ncp <= 0) return;
+  if (g.k <= 0 || g.ncp <= 0) return;  // replicated decision: every rank returns alike, nobody waits for a packet
   const int tid = threadIdx.x;
-  const int nchunks = P.w_reduced ? 1 : min(nchunks_max, (g.rows + SK_RC - 1) / SK_RC);  // w_reduced: chunk 0 = all-reduced sum
+  // nchunks_max < 0: exactly -nchunks_max partials were written (TMA + DMMA producer, CTAs without rows write zeros);
+  // > 0: the FMA producer k_sub_w, whose CTAs beyond the last row chunk do not write
+  const int nchunks = nchunks_max < 0 ? -nchunks_max
+                      : MG ? min(nchunks_max, g.rows > 0 ? (g.rows + SK_RC - 1) / SK_RC : 0)
+                           : (P.w_reduced ? 1 : min(nchunks_max, (g.rows + SK_RC - 1) / SK_RC));  // w_reduced: chunk 0 = all-reduced sum
   const int ngroups = 1 + (g.ncp + 7) / 8;
-  if (tid < ngroups * 64) {
+  if (MG) {
+    if (tid < ngroups * 64) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int b = 0;
+    for (; b + 3 < nchunks; b += 4) {  // the association order of k_sub_wred
+      s0 += P.gram_part[(size_t)b * 512 + tid];
+      s1 += P.gram_part[(size_t)(b + 1) * 512 + tid];
+      s2 += P.gram_part[(size_t)(b + 2) * 512 + tid];
+      s3 += P.gram_part[(size_t)(b + 3) * 512 + tid];
+    }
+    for (; b < nchunks; ++b) s0 += P.gram_part[(size_t)b * 512 + tid];
+    const double mine = (s0 + s1) + (s2 + s3);
+    const int me = pc.rank, N = pc.nranks;
+    for (int r = 0; r < N; ++r)
+      if (r != me) ll_store(peer_gen_slot(pc.recv[r], pparity, me, (size_t)tid), mine, ptag);
+    double tot = 0.0;
+    for (int r = 0; r < N; ++r) tot += (r == me) ? mine : ll_load(peer_gen_slot(pc.recv[me], pparity, r, (size_t)tid), ptag);
+    W[tid] = tot;
+    }
+  } else if (tid < ngroups * 64) {
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     int b = 0;
     for (; b + 3 < nchunks; b += 4) {  // fixed association order
@@ -193,13 +222,18 @@ __global__ void __launch_bounds__(512) k_sub_wred(qrdm_prob P, int nchunks_max) 
 }
 
 // rows_hint: host-side upper bound of the rows of the sub-panel
+extern "C" int qrdm_k_subw_tma(const qrdm_prob* p, int rows_hint, int* nparts, void* stream);  // k_gram.cu
+
 extern "C" int qrdm_k_skinny_update(const qrdm_prob* p, int rows_hint, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   int nch = (rows_hint + SK_RC - 1) / SK_RC;
   if (nch < 1) nch = 1;
-  k_sub_w<<<nch, SK_THREADS, 0, s>>>(*p);
-  QRDM_LAUNCH_CHECK();
-  k_sub_w2<<<1, 512, 0, s>>>(*p, nch);
+  int nparts = 0, fold = nch;
+  const int rc = qrdm_k_subw_tma(p, rows_hint, &nparts, stream);
+  if (rc > 0) return rc;
+  if (rc == 0) fold = -nparts;
+  else { k_sub_w<<<nch, SK_THREADS, 0, s>>>(*p); QRDM_LAUNCH_CHECK(); }
+  k_sub_w2<false><<<1, 512, 0, s>>>(*p, fold, PeerCtx{}, 0u, 0);
   QRDM_LAUNCH_CHECK();
   k_sub_apply<<<nch, SK_THREADS, 0, s>>>(*p);
   QRDM_LAUNCH_CHECK();
@@ -221,7 +255,28 @@ extern "C" int qrdm_k_skinny_finish(const qrdm_prob* p, int rows_hint, void* str
   cudaStream_t s = (cudaStream_t)stream;
   int nch = (rows_hint + SK_RC - 1) / SK_RC;
   if (nch < 1) nch = 1;
-  k_sub_w2<<<1, 512, 0, s>>>(*p, 1);
+  k_sub_w2<false><<<1, 512, 0, s>>>(*p, 1, PeerCtx{}, 0u, 0);
+  QRDM_LAUNCH_CHECK();
+  k_sub_apply<<<nch, SK_THREADS, 0, s>>>(*p);
+  QRDM_LAUNCH_CHECK();
+  return 0;
+}
+// row-sharded with peer memory: partial products, then fold + cross-GPU sum + W2 in one kernel, then the update
+extern "C" int qrdm_k_skinny_update_mg(const qrdm_prob* p, int rows_hint, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  const PeerCtx* pc = qrdm_peer_ctx();
+  if (!pc) return (int)cudaErrorInvalidValue;
+  int nch = (rows_hint + SK_RC - 1) / SK_RC;
+  if (nch < 1) nch = 1;
+  int nparts = 0, fold = nch;
+  const int rc = qrdm_k_subw_tma(p, rows_hint, &nparts, stream);
+  if (rc > 0) return rc;
+  if (rc == 0) fold = -nparts;
+  else { k_sub_w<<<nch, SK_THREADS, 0, s>>>(*p); QRDM_LAUNCH_CHECK(); }
+  unsigned tag = 0;
+  int parity = 0;
+  qrdm_peer_next_gen(&tag, &parity);
+  k_sub_w2<true><<<1, 512, 0, s>>>(*p, fold, *pc, tag, parity);
   QRDM_LAUNCH_CHECK();
   k_sub_apply<<<nch, SK_THREADS, 0, s>>>(*p);
   QRDM_LAUNCH_CHECK();

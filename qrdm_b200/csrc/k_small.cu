@@ -585,7 +585,8 @@ __device__ __forceinline__ void small_norm_update(const qrdm_prob& P, SmallShare
     for (; r + 1 < j + k; r += 2) { d0 = fma(col[r], col[r], d0); d1 = fma(col[r + 1], col[r + 1], d1); }
     if (r < j + k) d0 = fma(col[r], col[r], d0);
     const double d = d0 + d1;
-    double t = sqrt(fabs(d)) / v1;
+    const double dt = (d * P.inv_scale) * P.inv_scale;  // caller's scale, see qrdm_prob::inv_scale
+    double t = sqrt(fabs(dt)) / (v1 * P.inv_scale);
     t = (t + 1.0) * (1.0 - t);
     t = (0.0 >= t) ? 0.0 : t;
     const double q = v1 / S.vn2[c];
@@ -679,6 +680,7 @@ __global__ void __launch_bounds__(SM_NT, 1) k_small(SmallArgs A) {
   P.tau = A.tau + (size_t)min(A.m, A.n) * b;
   P.vn1 = S.vn1; P.vn2 = S.vn2; P.ctrl = &S.ctrl; P.gram = S.gram;
   P.row0 = 0; P.m_glob = A.m; P.nranks = 1; P.sub = 0; P.debug = 0;
+  P.thres0 = 5e-14; P.inv_scale = 1.0;
   int* ncols = A.ncols + (size_t)A.n * b;
   const int minmn = min(A.m, A.n);
 
@@ -711,6 +713,7 @@ __global__ void __launch_bounds__(SM_NT, 1) k_small(SmallArgs A) {
     }
   }
   P.thres0 = 5e-14 * in_scale;  // src/dgeqr2.c:40
+  P.inv_scale = 1.0 / in_scale;
   if (tid == 0) S.eta *= S.ctrl.maxnrm;  // :684
   __syncthreads();
 

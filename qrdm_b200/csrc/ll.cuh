@@ -117,3 +117,4 @@ __device__ __forceinline__ LLPacket* peer_gen_slot(LLPacket* base, int parity, i
 // reader that sees the tag in both halves has the payload whatever the arrival order of the halves.
 // host side (k_peer.cu)
 const PeerCtx* qrdm_peer_ctx();          // NULL until qrdm_rt_peer_open succeeded
+void qrdm_peer_next_gen(unsigned* tag, int* parity);  // next exchange of the generic region (same sequence on every rank)

@@ -103,6 +103,9 @@ typedef struct qrdm_prob {
   int pend;           /* 1: kernels take their geometry from ctrl->pend_* (flush of a pending block) */
   double thres0;      /* the panel's initial absolute stop threshold 5e-14 (src/dgeqr2.c:40) times the power-of-two input
                          scale (1 unless the matrix was pre-scaled, see qrdm_k_scale) */
+  double inv_scale;   /* 1 / that scale (MUST be 1.0, never 0, for an unscaled matrix): the norm downdate evaluates its
+                         sum of squares in the CALLER's scale, where the reference's unscaled sum (src/dgeqrdm_work.c:81-86)
+                         underflows to 0 for ~1e-200 entries (no downdate) and overflows for ~1e+200 (forced recompute) */
 } qrdm_prob;
 
 int qrdm_k_colnorm(const qrdm_prob *p, int use_flag_list, void *stream);   /* K1 / K2 recompute */
@@ -185,6 +188,7 @@ int qrdm_rt_peer_destroy(void);
 int qrdm_rt_peer_available(void);              /* number of ranks of the open peer context, 0 = none */
 int qrdm_k_peer_allreduce(double *buf, size_t count, void *stream);
 int qrdm_k_panel_tall_mg(const qrdm_prob *p, int j_host, void *stream); /* sharded sub-panel, exchange inside the kernel */
+int qrdm_k_skinny_update_mg(const qrdm_prob *p, int rows_hint, void *stream); /* sharded skinny update, cross-GPU sum inside k_sub_w2 */
 const char *qrdm_rt_errstr(int code);
 long long qrdm_rt_launch_count(void);
 double qrdm_rt_fp64_peak(int use_dmma, void *stream);
