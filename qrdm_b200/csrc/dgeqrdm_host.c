@@ -353,7 +353,7 @@ static int read_mailbox(const qrdm_prob *p, void *stream) {
 /* The factorisation proper on device-resident data. */
 static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double *d_tau, int *ncols,
                          const double *thres, int nb, void *stream, qrdm_writeback *wb,
-                         const qrdm_shard *sh) {
+                         const qrdm_shard *sh, int nfxd_in) {
   qrdm_workspace *w = &g_ws;
   const double eps = DBL_EPSILON * 0.5; /* dlamch('e'), src/dgeqrdm_work.c:528 */
   /* row-sharded over several GPUs (QRDM_B200_FORCE_MG=1 exercises that path on a 1-rank communicator) */
@@ -387,6 +387,11 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
   { const char *dbg = getenv("QRDM_B200_DEBUG"); P.debug = dbg ? atoi(dbg) : 0; }
   P.thres0 = 5e-14; /* src/dgeqr2.c:40 */
   P.inv_scale = 1.0;
+  /* fixed columns (already moved to the front, d_jpvt holds the matching permutation): factored first, as they stand,
+   * in blocks of <= nb columns through the same kernels — the reference's dgeqrf + dormqr, src/dgeqrdm_work.c:612-635 */
+  const int nfxd = nfxd_in < minmn ? nfxd_in : minmn; /* na = min(m, nfxd), :613 */
+  P.nfxd = nfxd;
+  P.keep_jpvt = nfxd_in > 0;
   P.vc_prev = w->vc + (size_t)w->ldv * 64;
   P.upd_flag = w->upd_marks; P.upd_eager = w->upd_marks + w->cap_n;
   /* Deferred ("lazy") trailing update, single GPU: pass 2 of a block is postponed and fused into pass 1
@@ -442,10 +447,11 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
       if (rc) return rc;
     }
   }
-  eta *= w->mailbox->maxnrm; /* :684 */
+  const double eta_factor = eta;
+  eta *= w->mailbox->maxnrm; /* :684 (with fixed columns: re-evaluated on the free columns once they are done) */
   g_stats.stage_bytes[QRDM_STAGE_NORM_INIT] = 8.0 * (double)m * (double)n;
 
-  int info = 0, it = 0, j = 0;
+  int info = 0, it = 0, j = 0, sweep = 0; /* it: DM iterations (index into ncols); sweep: all iterations (V buffer parity) */
   while (j < minmn) { /* :694 */
     const int cols = n - j;
     int jr = j - P.row0;
@@ -454,8 +460,8 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
     /* the mailbox read at the end of the previous iteration already holds this iteration's candidate count */
     if (w->mailbox->nc > 1) g_stats.stage_bytes[QRDM_STAGE_GRAM] += 8.0 * (double)(m - jr) * (double)w->mailbox->nc;
     if (!mg) {
-      P.vc = vcbuf[it & 1];          /* V of this block; the pending block's V sits in the other buffer */
-      P.vc_prev = vcbuf[(it & 1) ^ 1];
+      P.vc = vcbuf[sweep & 1];       /* V of this block; the pending block's V sits in the other buffer */
+      P.vc_prev = vcbuf[(sweep & 1) ^ 1];
       STAGE(QRDM_STAGE_GRAM, qrdm_k_gram(&P, 0, m - jr, stream));
       STAGE(QRDM_STAGE_PICK, qrdm_k_pick(&P, stream));
       STAGE(QRDM_STAGE_PERMUTE, qrdm_k_permute(&P, stream));
@@ -463,7 +469,7 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
       /* both dimensions must be large as well: with few trailing columns (tall-skinny, C4) the eager set of
        * <= 128 columns is a large share of the matrix and the deferred schedule buys nothing */
       const int lazy_dim = lazy_min < 1024 ? lazy_min : 1024;
-      lazy = lazy_on && n - j - QRDM_KMAX >= lazy_dim && m - j - QRDM_KMAX >= lazy_dim &&
+      lazy = lazy_on && j >= nfxd && n - j - QRDM_KMAX >= lazy_dim && m - j - QRDM_KMAX >= lazy_dim &&
              (double)(n - j - QRDM_KMAX) * (double)(m - j - QRDM_KMAX) >= (double)lazy_min * (double)lazy_min;
       if (!pending && !lazy) {
         STAGE(QRDM_STAGE_VTC, qrdm_k_trailing(&P, j, stream));
@@ -483,6 +489,9 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
       if (lazy) {
         P.stamp = ++stamp;
         STAGE(QRDM_STAGE_NORM_UPDATE, qrdm_k_norm_update_lazy(&P, j, stream));
+      } else if (j < nfxd && j + (nb < nfxd - j ? nb : nfxd - j) >= nfxd) {
+        /* last block of fixed columns: the free columns' norms from scratch, as :672-682 computes them */
+        STAGE(QRDM_STAGE_NORM_UPDATE, qrdm_k_norm_recompute_all(&P, j, stream));
       } else {
         STAGE(QRDM_STAGE_NORM_UPDATE, qrdm_k_norm_update(&P, j, stream));
       }
@@ -585,7 +594,9 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
     }
     const qrdm_ctrl *mb = w->mailbox;
     const int k = mb->last_k;
-    ncols[it++] = k; /* :740 */
+    const int was_fixed = j < nfxd;
+    ++sweep;
+    if (!was_fixed) ncols[it++] = k; /* :740 (the reference counts DM iterations only: it starts after the fixed part) */
     g_stats.panel_cols += k;
     if (mb->err != 0) { info = mb->err; break; }
     if (k <= 0 || mb->j != j + k) {
@@ -613,10 +624,14 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
                         (size_t)(j - wb->done_cols), wb->copy_stream));
       wb->done_cols = j;
     }
+    if (was_fixed) {
+      if (j >= nfxd) eta = eta_factor * mb->maxnrm; /* :684 — max norm of the free columns below the fixed block */
+      continue;
+    }
     if (stop_mode && mb->maxnrm * sqrt((double)(cols - k)) <= eta) break; /* :782-785 */
   }
   if (pending) { /* early exit (stop rule / error) with a block still deferred: finish it */
-    P.vc_prev = vcbuf[(it - 1) & 1];
+    P.vc_prev = vcbuf[(sweep - 1) & 1];
     STAGE(QRDM_STAGE_VTC, qrdm_k_flush(&P, pend_j, stream));
   }
   if (in_scale != 1.0) CU(qrdm_k_scale(&P, 1.0 / in_scale, 1, j, stream)); /* R back to the caller's scale */
@@ -642,7 +657,7 @@ int dgeqrdm_dev(int m, int n, double *d_a, int lda, int *d_jpvt, double *d_tau, 
                 const double *thres, int nb, void *stream) {
   int rc = check_args(QRDM_COL_MAJOR, m, n, lda, thres, nb);
   if (rc) return rc;
-  API_BODY(factor_device(m, n, d_a, lda, d_jpvt, d_tau, ncols, thres, nb, stream, NULL, NULL));
+  API_BODY(factor_device(m, n, d_a, lda, d_jpvt, d_tau, ncols, thres, nb, stream, NULL, NULL, 0));
 }
 
 static int ensure_staging(int m, int n, int ldd) {
@@ -678,7 +693,8 @@ static int ensure_staging(int m, int n, int ldd) {
  *   pageable (NumPy) memory multi-threaded pinned bounce pipeline both ways + the same streamed write-back through a
  *                           pinned ring (hostio.c) — the reference's caller passes pageable arrays (QRDM_wrapper.c:155-159);
  *   QRDM_B200_NO_BOUNCE=1   plain cudaMemcpy2D from pageable memory (the round-1 behaviour, kept for A/B timing). */
-static int dgeqrdm_work_locked(int m, int n, double *a, int lda, int *jpvt, double *tau, int *ncols, double *thres, int nb) {
+static int dgeqrdm_work_locked(int m, int n, double *a, int lda, int *jpvt, double *tau, int *ncols, double *thres, int nb,
+                               int nfxd, const int *src_col, const int *jpvt0) {
   qrdm_workspace *w = &g_ws;
   int rc = init_impl(-1);
   if (rc) return rc;
@@ -711,6 +727,14 @@ static int dgeqrdm_work_locked(int m, int n, double *a, int lda, int *jpvt, doub
     CUX(qrdm_rt_h2d_2d(w->d_a, sizeof(double) * ldd, a, sizeof(double) * lda, sizeof(double) * m, n, stream));
   }
   CUX(qrdm_rt_h2d(w->d_tau, tau, sizeof(double) * minmn, stream)); /* entries >= rank stay as given */
+  if (nfxd > 0) {
+    /* fixed columns: the reference swaps them to the front on the host (src/dgeqrdm_work.c:592-607); here device column
+     * pos simply receives the caller's column src_col[pos], and d_jpvt starts as the permutation those swaps produce */
+    for (int pos = 0; pos < n; ++pos)
+      if (src_col[pos] != pos)
+        CUX(qrdm_rt_h2d(w->d_a + (size_t)pos * ldd, a + (size_t)src_col[pos] * lda, sizeof(double) * m, stream));
+    CUX(qrdm_rt_h2d(w->d_jpvt, jpvt0, sizeof(int) * n, stream));
+  }
   CUX(qrdm_rt_event_record(w->ev[3], stream));
   {
     /* overlap the D2H of finished columns with the rest of the factorisation */
@@ -721,7 +745,7 @@ static int dgeqrdm_work_locked(int m, int n, double *a, int lda, int *jpvt, doub
       if (r < 0) { info = QRDM_ERR_CUDA; goto fail; }
       if (r == 0) wb.io = w->io; else overlap = 0;
     }
-    info = factor_device(m, n, w->d_a, ldd, w->d_jpvt, w->d_tau, ncols, thres, nb, stream, overlap ? &wb : NULL, NULL);
+    info = factor_device(m, n, w->d_a, ldd, w->d_jpvt, w->d_tau, ncols, thres, nb, stream, overlap ? &wb : NULL, NULL, nfxd);
     if (wb.io && qrdm_hostio_wb_end(wb.io) && info > QRDM_ERR_CUDA) info = QRDM_ERR_CUDA;
     if (info <= QRDM_ERR_CUDA) goto fail;
     const double ms_h2d = qrdm_rt_event_ms(w->ev[2], w->ev[3]);
@@ -756,13 +780,36 @@ int dgeqrdm_work(int matrix_layout, int m, int n, double *a, int lda, int *jpvt,
                  int *ncols, double *thres, int nb) {
   int rc = check_args(matrix_layout, m, n, lda, thres, nb);
   if (rc) return rc;
-  for (int c = 0; c < n; ++c)
-    if (jpvt[c] != 0) {
-      /* fixed columns: the reference's own path is broken for nfxd > 0 */
-      fprintf(stderr, "qrdm_b200: jpvt[%d] != 0 on entry (fixed columns) is not supported\n", c);
-      return QRDM_ERR_UNSUPPORTED;
+  /* Fixed columns, jpvt[j] != 0 on entry (LAPACK dgeqp3 convention): the reference moves them to the front with the
+   * swap sequence of src/dgeqrdm_work.c:592-607 — replayed here on index arrays — factors them without pivoting and
+   * runs DM on the rest.  (Its own continuation mis-indexes the auxiliary arrays for nfxd > 0; what is
+   * implemented is what :592-635 sets out to do.)  ncols counts DM iterations only, as upstream's `it` does. */
+  int nfxd = 0, any = 0;
+  for (int c = 0; c < n; ++c) any |= (jpvt[c] != 0);
+  if (!any) API_BODY(dgeqrdm_work_locked(m, n, a, lda, jpvt, tau, ncols, thres, nb, 0, NULL, NULL));
+  int *src_col = (int *)malloc(sizeof(int) * (size_t)n * 2);
+  if (!src_col) return QRDM_ERR_CUDA;
+  int *jp = src_col + n;
+  for (int c = 0; c < n; ++c) { src_col[c] = c; jp[c] = jpvt[c]; }
+  for (int c = 0; c < n; ++c) { /* 0-based replay of :594-607 */
+    if (jp[c] != 0) {
+      if (c != nfxd) {
+        const int t = src_col[c]; src_col[c] = src_col[nfxd]; src_col[nfxd] = t;
+        jp[c] = jp[nfxd];
+        jp[nfxd] = c + 1;
+      } else {
+        jp[c] = c + 1;
+      }
+      ++nfxd;
+    } else {
+      jp[c] = c + 1;
     }
-  API_BODY(dgeqrdm_work_locked(m, n, a, lda, jpvt, tau, ncols, thres, nb));
+  }
+  api_lock();
+  rc = dgeqrdm_work_locked(m, n, a, lda, jpvt, tau, ncols, thres, nb, nfxd, src_col, jp);
+  api_unlock();
+  free(src_col);
+  return rc;
 }
 
 int dgeqrdm(int matrix_layout, int m, int n, double *a, int lda, int *jpvt, double *tau, int *ncols,
@@ -918,7 +965,7 @@ void qrdm_b200_peer_close(void) { api_lock(); qrdm_rt_peer_destroy(); api_unlock
 static int sharded_locked(int m_local, int m_global, int row0, int nranks, int n, double *d_a, int lda,
                           int *d_jpvt, double *d_tau, int *ncols, const double *thres, int nb, void *stream) {
   qrdm_shard sh = {row0, m_global, nranks};
-  if (m_local > 0) return factor_device(m_local, n, d_a, lda, d_jpvt, d_tau, ncols, thres, nb, stream, NULL, &sh);
+  if (m_local > 0) return factor_device(m_local, n, d_a, lda, d_jpvt, d_tau, ncols, thres, nb, stream, NULL, &sh, 0);
   /* A rank that holds no rows at all (m_global < 32 * nranks or so) still has to take part in every exchange and to
    * keep its replicated jpvt / tau / ncols.  It runs the ordinary path on ONE internal all-zero row placed below the
    * matrix (row0 = m_global): a zero row contributes exact zeros to every sum, stays zero under every reflector
@@ -928,7 +975,7 @@ static int sharded_locked(int m_local, int m_global, int row0, int nranks, int n
   int info = QRDM_ERR_CUDA;
   if (qrdm_rt_memset(dummy, 0, sizeof(double) * 2 * (size_t)n, stream) == 0) {
     sh.row0 = m_global;
-    info = factor_device(1, n, dummy, 2, d_jpvt, d_tau, ncols, thres, nb, stream, NULL, &sh);
+    info = factor_device(1, n, dummy, 2, d_jpvt, d_tau, ncols, thres, nb, stream, NULL, &sh, 0);
   }
   qrdm_rt_sync(stream);
   qrdm_rt_free(dummy);
@@ -1116,7 +1163,7 @@ static int batched_loop(int batch, int m, int n, double *a, int lda, long long s
   CUX(qrdm_rt_h2d(d_tau, tau, sizeof(double) * (size_t)minmn * batch, stream));
   for (int b = 0; b < batch; ++b) {
     int info = factor_device(m, n, d_all + per * b, ldd, d_jpvt + (size_t)n * b, d_tau + (size_t)minmn * b,
-                             ncols + (size_t)n * b, thres, nb, stream, NULL, NULL);
+                             ncols + (size_t)n * b, thres, nb, stream, NULL, NULL, 0);
     if (infos) infos[b] = info;
     if (info <= QRDM_ERR_CUDA) { worst = info; goto done; }
     if (info != 0 && worst == 0) worst = info;

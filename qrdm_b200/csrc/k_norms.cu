@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256) k_colnorm_finalize(qrdm_prob P, int use_l
   const int c = use_list ? P.flag_list[idx] : idx;
   P.vn1[c] = v;
   P.vn2[c] = v;
-  if (!use_list) P.jpvt[c] = c + 1;  // src/dgeqrdm_work.c:596-609 with every column free
+  if (!use_list && !P.keep_jpvt) P.jpvt[c] = c + 1;  // src/dgeqrdm_work.c:596-609 with every column free
 }
 
 static int colnorm_nsplit(const qrdm_prob* p, int* gx_out) {
@@ -185,6 +185,22 @@ extern "C" int qrdm_k_norm_update(const qrdm_prob* p, int j_host, void* stream) 
   const int maxcols = p->n - j_host - 1;  // k >= 1
   if (maxcols <= 0) return 0;
   k_norm_update<0><<<(maxcols + 7) / 8, 256, 0, s>>>(*p, 1.0536712127723509e-08 /* tol3z = sqrt(dlamch('e')) = sqrt(2^-53), src/dgeqrdm_work.c:528-529 */);
+  QRDM_LAUNCH_CHECK();
+  return qrdm_k_colnorm(p, 1, stream);
+}
+
+// End of the fixed-column phase: the reference computes the norms of the free columns from scratch on the rows below
+// the fixed block (src/dgeqrdm_work.c:672-682) — flag every remaining column and run the exact recompute of K2.
+__global__ void __launch_bounds__(256) k_flag_all(qrdm_prob P) {
+  qrdm_ctrl* ctrl = P.ctrl;
+  const int c0 = ctrl->j + ctrl->fjb_cmp, cnt = P.n - c0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) P.flag_list[i] = c0 + i;
+  if (blockIdx.x == 0 && threadIdx.x == 0) ctrl->nflag = cnt > 0 ? cnt : 0;
+}
+extern "C" int qrdm_k_norm_recompute_all(const qrdm_prob* p, int j_host, void* stream) {
+  const int maxcols = p->n - j_host - 1;
+  if (maxcols <= 0) return 0;
+  k_flag_all<<<(maxcols + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*p);
   QRDM_LAUNCH_CHECK();
   return qrdm_k_colnorm(p, 1, stream);
 }

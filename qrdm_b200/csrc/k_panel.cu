@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel(qrdm_prob P, int rpc
     double tau = 0.0, beta = alpha, scale = 1.0;
     if (len > 1) {
       const double xnorm = sqrt(S_[i]);
-      if (sub_s + i > 0 && xnorm < thres) { k = i; break; }  // DM early stop: column i left untouched
+      if (sub_s + i > 0 && xnorm < thres && !ctrl->forced) { k = i; break; }  // DM early stop: column i left untouched
       if (xnorm != 0.0) {
         const double h = hypot(alpha, xnorm);
         beta = (alpha >= 0.0) ? -h : h;
@@ -256,6 +256,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_reg(qrdm_prob P, int
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int j = ctrl->j, fjb = ctrl->fjb;
   if (fjb <= 0) return;
+  const bool forced = ctrl->forced != 0;  // fixed columns: plain Householder QR, no early stop
   const int rows = P.m - j, lda = P.lda;
   const int G = gridDim.x, b = blockIdx.x;
   const int r0 = min(rows, b * rpc), r1 = min(rows, r0 + rpc), nr = r1 - r0;  // nr <= 128
@@ -377,7 +378,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_reg(qrdm_prob P, int
     const int len = rows - i;
     double tau = 0.0, beta = alpha, scale = 1.0;
     if (len > 1) {
-      if (i > 0 && xn2 < thres2) { k = i; break; }  // DM early stop: column i left untouched
+      if (i > 0 && xn2 < thres2 && !forced) { k = i; break; }  // DM early stop: column i left untouched
       // Only the warps that consume the scalars compute them: warps 0-1 (wv, tau), the owner of column i
       // (scale, beta) and, in column 0, everybody (thres2 needs beta).  The chain itself costs ~350 cycles
       // (measured by running it twice); the 2.5-3.5 k cycles QRDM_B200_DEBUG=8 books under "scalars" are the
@@ -516,6 +517,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_tall(qrdm_prob P, in
   const int j = qg.j, fjb = qg.fjb, sub_s = P.sub - 1;
   const int jmain = ctrl->j, fjb_main = ctrl->fjb;
   if (fjb <= 0) return;
+  const bool forced = ctrl->forced != 0;  // fixed columns: plain Householder QR, no early stop
   const int lr0 = qrdm_jr(P, j);          // first local active row
   const int goff = P.row0 + lr0 - j;      // its index relative to the sub-panel's first row (>= 0)
   const int rows_l = P.m - lr0;           // local active rows
@@ -620,7 +622,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_tall(qrdm_prob P, in
     double tau = 0.0, beta = alpha, scale = 1.0;
     if (len > 1) {
       const double xnorm = sqrt(S_[i]);
-      if (sub_s + i > 0 && xnorm < thres) { k = i; break; }  // DM early stop
+      if (sub_s + i > 0 && xnorm < thres && !forced) { k = i; break; }  // DM early stop (never for fixed columns)
       if (xnorm != 0.0) {
         const double h = hypot(alpha, xnorm);
         beta = (alpha >= 0.0) ? -h : h;

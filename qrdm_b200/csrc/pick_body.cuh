@@ -30,6 +30,15 @@ __device__ __forceinline__ void qrdm_pick_body(const qrdm_prob& P, PickShared& S
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int j = ctrl->j, kmax = ctrl->kmax, nc = ctrl->nc, cols = P.n - j;
   if (kmax == 0) return;
+  if (ctrl->forced) {  // fixed columns: all nc leading columns, in place (no greedy test, no exchange)
+    for (int s = tid; s < nc; s += blockDim.x) ctrl->sel[s] = s;
+    if (tid == 0) {
+      S.fjb = nc; S.ncyc = 0; S.cyc_start[0] = 0;
+      ctrl->fjb = nc; ctrl->ncyc = 0; ctrl->cyc_start[0] = 0; ctrl->panel_bar = 0u;
+    }
+    __syncthreads();
+    return;
+  }
 
   if (tid < 64) {
     S.cand[tid] = tid < kmax ? ctrl->cand[tid] : -1;

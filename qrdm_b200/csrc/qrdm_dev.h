@@ -57,7 +57,8 @@ typedef struct qrdm_ctrl {
   int pend_k;   /* reflectors of the pending block */
   int pend_c0;  /* first column the pending update applies to (= j + fjb of its iteration) */
   int pend_r0;  /* first row still to be updated (= j + k of its iteration: the k new R rows are done) */
-  int pad5_;
+  int forced;   /* 1: this iteration factors FIXED columns (jpvt != 0 on entry): the next columns as they stand, no DM
+                   selection, no permutation, no early stop in the panel */
   long long stat_perm_cols; /* statistics: columns moved by k_permute since the start of the factorisation */
 } qrdm_ctrl;
 #define QRDM_MAILBOX_BYTES 64
@@ -101,6 +102,8 @@ typedef struct qrdm_prob {
   int *upd_eager;     /* [n] == stamp: likewise for the eager set (leading 64 positions + candidates) */
   int stamp;          /* id of the pending block (> 0) */
   int pend;           /* 1: kernels take their geometry from ctrl->pend_* (flush of a pending block) */
+  int nfxd;           /* number of fixed columns, already moved to the front (src/dgeqrdm_work.c:592-607); 0 = none */
+  int keep_jpvt;      /* 1: d_jpvt holds the caller's initial permutation, K1 must not reset it to the identity */
   double thres0;      /* the panel's initial absolute stop threshold 5e-14 (src/dgeqr2.c:40) times the power-of-two input
                          scale (1 unless the matrix was pre-scaled, see qrdm_k_scale) */
   double inv_scale;   /* 1 / that scale (MUST be 1.0, never 0, for an unscaled matrix): the norm downdate evaluates its
@@ -121,6 +124,7 @@ int qrdm_k_permute(const qrdm_prob *p, void *stream);                       /* K
 int qrdm_k_panel(const qrdm_prob *p, int j_host, void *stream);             /* K4 */
 int qrdm_k_trailing(const qrdm_prob *p, int j_host, void *stream);          /* K6: vtc, wsolve, rankk */
 int qrdm_k_norm_update(const qrdm_prob *p, int j_host, void *stream);       /* K2 */
+int qrdm_k_norm_recompute_all(const qrdm_prob *p, int j_host, void *stream); /* exact norms of every column right of the block (end of the fixed-column phase, src/dgeqrdm_work.c:672-682) */
 /* row-sharded variants: each stage is split at the point where the all-reduce sits */
 int qrdm_k_colnorm_part(const qrdm_prob *p, int use_flag_list, int *nsplit_out, void *stream);
 int qrdm_k_colnorm_fin(const qrdm_prob *p, int use_flag_list, int nsplit, void *stream);

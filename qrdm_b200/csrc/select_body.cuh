@@ -47,6 +47,7 @@ __device__ __forceinline__ void qrdm_select_body(const qrdm_prob& P, SelShared& 
     ctrl->nc = 0;
     ctrl->ncyc = 0;
     ctrl->nflag = 0;
+    ctrl->forced = 0;
     ctrl->kmax = kmax;
     if (k > 0) ctrl->it += 1;
     S.count = 0;
@@ -89,6 +90,16 @@ __device__ __forceinline__ void qrdm_select_body(const qrdm_prob& P, SelShared& 
   kmn = S.red[0];
   if (tid == 0) ctrl->maxnrm = __longlong_as_double((long long)kmx);
   if (kmax == 0) return;
+  if (j < P.nfxd) {
+    // Fixed columns (jpvt[j] != 0 on entry, moved up front by the driver as src/dgeqrdm_work.c:592-607 does): the
+    // reference factors them with LAPACKE_dgeqrf and applies Q' with LAPACKE_dormqr (:612-635).  Here they go through
+    // the same panel + trailing-update kernels in blocks of <= nb columns, taken as they stand.
+    const int kf = min(kmax, P.nfxd - j);
+    for (int c = tid; c < kf; c += NT) { ctrl->cand[c] = c; ctrl->candnrm[c] = P.vn1[j + c]; }
+    __syncthreads();
+    if (tid == 0) { ctrl->nc = kf; ctrl->forced = 1; }
+    return;
+  }
 
   // ---- narrow down to <= SELCAP survivors containing the top kmax ----
   bool collect_all = cols <= QRDM_SELCAP;

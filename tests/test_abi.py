@@ -51,7 +51,15 @@ def test_argument_errors_return_minus_one(lib, kw, entry, capfd):
 
 def test_unsupported_inputs(lib, capfd):
     assert _call(lib, 4, 4, nb=65) == -102
-    assert _call(lib, 4, 4, jpvt0=1) == -102  # fixed columns: broken upstream, out of scope
+    capfd.readouterr()
+
+
+def test_fixed_columns_take_the_gpu_path(lib, capfd):
+    """jpvt != 0 on entry (fixed columns, reference src/dgeqrdm_work.c:592-635) is a supported input since round 2: on a
+    box without a GPU it must therefore fail like every other valid call (no CPU fallback), not with -102."""
+    import torch
+    rc = _call(lib, 4, 4, jpvt0=1)
+    assert rc == (0 if torch.cuda.is_available() else -100)
     capfd.readouterr()
 
 
