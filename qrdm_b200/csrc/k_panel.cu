@@ -507,8 +507,13 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_reg(qrdm_prob P, int
 // (the round-1 sharded panel paid one launch + one 1-KB ncclAllReduce per column: ~70 us x 512 columns on C4).
 // Row bookkeeping: this rank holds global rows [row0, row0 + m); lr0 = first local row of the sub-panel, goff = the
 // panel-relative index of that row (0 on the rank that owns the diagonal block).  Single GPU: lr0 = j, goff = 0.
-template <bool MG>
+// SM = true: the CTA's rows of the 8-column sub-panel fit in shared memory (rpc * 64 bytes <= 200 KB: up to ~3200 rows
+// per CTA, 470,000 rows per GPU — every rank of configs[3] from 4 GPUs on): the slab is loaded once, the 8 sweeps run
+// out of shared memory and it is written back once, instead of streaming the remaining columns through L2 / HBM for
+// every column (16 column passes instead of 64).
+template <bool MG, bool SM>
 __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_tall(qrdm_prob P, int rpc, unsigned epoch, PeerCtx pc) {
+  extern __shared__ __align__(16) double tall_slab[];  // SM: [TALL_B][lds]
   __shared__ double S_[TALL_B], rowv[TALL_B];
   __shared__ double sacc[PANEL_WARPS][TALL_B];
   qrdm_ctrl* ctrl = P.ctrl;
@@ -525,7 +530,14 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_tall(qrdm_prob P, in
   const int lda = P.lda;
   const int G = gridDim.x, b = blockIdx.x;
   const int r0 = min(rows_l, b * rpc), r1 = min(rows_l, r0 + rpc), nr = r1 - r0;
-  double* Ap = P.a + (size_t)j * lda + lr0 + r0;  // local row r of this CTA, sub-panel column c: Ap[c*lda + r]
+  double* Ag = P.a + (size_t)j * lda + lr0 + r0;  // local row r of this CTA, sub-panel column c: Ag[c*lda + r]
+  const int ldp = SM ? ((rpc + 1) & ~1) : lda;
+  double* Ap = SM ? tall_slab : Ag;                // the working copy: Ap[c*ldp + r]
+  if (SM) {
+    for (int c = 0; c < fjb; ++c)
+      for (int r = threadIdx.x; r < nr; r += PANEL_THREADS) Ap[(size_t)c * ldp + r] = Ag[(size_t)c * lda + r];
+    __syncthreads();
+  }
   LLPacket* part = reinterpret_cast<LLPacket*>(P.panel_part);  // [2][PANEL_MAXCTA][64]
   LLPacket* bcast = reinterpret_cast<LLPacket*>(P.panel_row);  // [2][128]
   const unsigned tag_base = epoch << 8;
@@ -561,7 +573,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_tall(qrdm_prob P, in
       const int R = goff + r0 + r;
       double v[TALL_B];
 #pragma unroll
-      for (int c = 0; c < TALL_B; ++c) v[c] = c < fjb ? Ap[(size_t)c * lda + r] : 0.0;
+      for (int c = 0; c < TALL_B; ++c) v[c] = c < fjb ? Ap[(size_t)c * ldp + r] : 0.0;
       if (R > 0) {
 #pragma unroll
         for (int c = 0; c < TALL_B; ++c) acc[c] = fma(v[0], v[c], acc[c]);
@@ -648,22 +660,22 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_tall(qrdm_prob P, in
       if (R < i) return;
       double v = 1.0;
       if (R > i) {
-        v = Ap[(size_t)i * lda + r];
-        if (tau != 0.0) { v *= scale; Ap[(size_t)i * lda + r] = v; }
+        v = Ap[(size_t)i * ldp + r];
+        if (tau != 0.0) { v *= scale; Ap[(size_t)i * ldp + r] = v; }
       } else {
-        Ap[(size_t)i * lda + r] = beta;
+        Ap[(size_t)i * ldp + r] = beta;
       }
       if (last) return;
       double pv[TALL_B];
 #pragma unroll
       for (int c = 0; c < TALL_B; ++c)
-        if (c > i && c < fjb) pv[c] = Ap[(size_t)c * lda + r];
+        if (c > i && c < fjb) pv[c] = Ap[(size_t)c * ldp + r];
       double x1 = 0.0;
 #pragma unroll
       for (int c = 0; c < TALL_B; ++c) {
         if (c > i && c < fjb) {
           pv[c] = fma(-v, w[c], pv[c]);
-          Ap[(size_t)c * lda + r] = pv[c];
+          Ap[(size_t)c * ldp + r] = pv[c];
           if (c == i + 1) x1 = pv[c];
         }
       }
@@ -682,23 +694,23 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_tall(qrdm_prob P, in
     // one-row loop left the kernel latency-bound at ~2 TB/s (profiles/r02_launches_c4_summary.txt).  Same per-row
     // arithmetic and the same per-thread accumulation order (rows ascending), so results are bit-identical.
     int r = tid;
-    for (; r + PANEL_THREADS < nr; r += 2 * PANEL_THREADS) {
+    for (; !SM && r + PANEL_THREADS < nr; r += 2 * PANEL_THREADS) {
       const int rb = r + PANEL_THREADS;
       if (goff + r0 + r <= i + 1 || last) { do_row(r); do_row(rb); continue; }
-      double va = Ap[(size_t)i * lda + r], vb = Ap[(size_t)i * lda + rb];
+      double va = Ap[(size_t)i * ldp + r], vb = Ap[(size_t)i * ldp + rb];
       double pa[TALL_B], pb[TALL_B];
 #pragma unroll
       for (int c = 0; c < TALL_B; ++c)
-        if (c > i && c < fjb) { pa[c] = Ap[(size_t)c * lda + r]; pb[c] = Ap[(size_t)c * lda + rb]; }
-      if (tau != 0.0) { va *= scale; vb *= scale; Ap[(size_t)i * lda + r] = va; Ap[(size_t)i * lda + rb] = vb; }
+        if (c > i && c < fjb) { pa[c] = Ap[(size_t)c * ldp + r]; pb[c] = Ap[(size_t)c * ldp + rb]; }
+      if (tau != 0.0) { va *= scale; vb *= scale; Ap[(size_t)i * ldp + r] = va; Ap[(size_t)i * ldp + rb] = vb; }
       double xa = 0.0, xb = 0.0;
 #pragma unroll
       for (int c = 0; c < TALL_B; ++c) {
         if (c > i && c < fjb) {
           pa[c] = fma(-va, w[c], pa[c]);
           pb[c] = fma(-vb, w[c], pb[c]);
-          Ap[(size_t)c * lda + r] = pa[c];
-          Ap[(size_t)c * lda + rb] = pb[c];
+          Ap[(size_t)c * ldp + r] = pa[c];
+          Ap[(size_t)c * ldp + rb] = pb[c];
           if (c == i + 1) { xa = pa[c]; xb = pb[c]; }
         }
       }
@@ -721,6 +733,10 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_tall(qrdm_prob P, in
     ctrl->fjb_cmp = tk;
     if (MG) *pc.xseq = px0 + (unsigned)(k < fjb ? k + 1 : fjb);  // exchanges performed by this launch
   }
+  if (SM) {  // the factored slab goes back to global memory once (the block-wide barrier above ordered the last sweep)
+    for (int c = 0; c < fjb; ++c)
+      for (int r = tid; r < nr; r += PANEL_THREADS) Ag[(size_t)c * lda + r] = Ap[(size_t)c * ldp + r];
+  }
   // ---- clean copy of the sub-panel's reflectors into Vc columns voff .. voff + 7 (Vc is indexed by LOCAL row) ----
   const int kpad = min(TALL_B, 64 - qg.voff);
   const int jal = qrdm_jr(P, jmain) & ~(QRDM_ROWALIGN - 1);
@@ -729,7 +745,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_tall(qrdm_prob P, in
     for (int r = tid; r < nr; r += PANEL_THREADS) {
       const int R = goff + r0 + r;
       double v = 0.0;
-      if (q < k) v = (R > q) ? Ap[(size_t)q * lda + r] : (R == q ? 1.0 : 0.0);
+      if (q < k) v = (R > q) ? Ap[(size_t)q * ldp + r] : (R == q ? 1.0 : 0.0);
       vcol[r] = v;
     }
     if (b == 0)
@@ -752,6 +768,21 @@ static unsigned panel_next_epoch(unsigned& e, unsigned lo, unsigned hi, const qr
   return e;
 }
 static unsigned g_epoch_tall = 0, g_epoch_plain = 0x200000, g_epoch_reg = 0x400000;
+// dynamic shared memory of the slab-resident sub-panel kernel for `rpc` rows per CTA, or 0 when the slab does not fit
+#define TALL_SLAB_CAP (200 * 1024)
+static size_t tall_slab_bytes(int rpc) {
+  static int attr_gen = -1;
+  static const char* e_off = getenv("QRDM_PANEL_TALL_SM");  // experiment switch: 0 = always stream from global memory
+  if (e_off && atoi(e_off) == 0) return 0;
+  const size_t bytes = (size_t)((rpc + 1) & ~1) * QRDM_TALL_B * sizeof(double);
+  if (bytes == 0 || bytes > TALL_SLAB_CAP) return 0;
+  if (attr_gen != qrdm_rt_device_generation()) {
+    cudaFuncSetAttribute(k_panel_tall<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TALL_SLAB_CAP);
+    cudaFuncSetAttribute(k_panel_tall<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TALL_SLAB_CAP);
+    attr_gen = qrdm_rt_device_generation();
+  }
+  return bytes;
+}
 static unsigned qrdm_panel_tall_epoch(const qrdm_prob* p, void* stream) { return panel_next_epoch(g_epoch_tall, 1, 0x200000, p, stream); }
 
 // Row-sharded panel: every sharded panel is run BLOCKED — 8-column sub-panels by k_panel_tall<true>
@@ -773,7 +804,9 @@ extern "C" int qrdm_k_panel_tall_mg(const qrdm_prob* p, int j_host, void* stream
   qrdm_prob prob_s = *p;
   PeerCtx pcv = *pc;
   void* args_s[] = {(void*)&prob_s, (void*)&rpcs, (void*)&epoch, (void*)&pcv};
-  cudaError_t es = cudaLaunchCooperativeKernel((void*)k_panel_tall<true>, dim3(Gs), dim3(PANEL_THREADS), args_s, 0, (cudaStream_t)stream);
+  const size_t slab = tall_slab_bytes(rpcs);
+  cudaError_t es = slab ? cudaLaunchCooperativeKernel((void*)k_panel_tall<true, true>, dim3(Gs), dim3(PANEL_THREADS), args_s, slab, (cudaStream_t)stream)
+                        : cudaLaunchCooperativeKernel((void*)k_panel_tall<true, false>, dim3(Gs), dim3(PANEL_THREADS), args_s, 0, (cudaStream_t)stream);
   ++g_qrdm_launches;
   return es == cudaSuccess ? 0 : (int)es;
 }
@@ -896,7 +929,9 @@ extern "C" int qrdm_k_panel(const qrdm_prob* p, int j_host, void* stream) {
       qrdm_prob prob_s = *p;
       prob_s.sub = sb + 1;
       void* args_s[] = {(void*)&prob_s, (void*)&rpcs, (void*)&epoch_t, (void*)&nopeer};
-      cudaError_t es = cudaLaunchCooperativeKernel((void*)k_panel_tall<false>, dim3(Gs), dim3(PANEL_THREADS), args_s, 0, (cudaStream_t)stream);
+      const size_t slab = tall_slab_bytes(rpcs);
+      cudaError_t es = slab ? cudaLaunchCooperativeKernel((void*)k_panel_tall<false, true>, dim3(Gs), dim3(PANEL_THREADS), args_s, slab, (cudaStream_t)stream)
+                            : cudaLaunchCooperativeKernel((void*)k_panel_tall<false, false>, dim3(Gs), dim3(PANEL_THREADS), args_s, 0, (cudaStream_t)stream);
       ++g_qrdm_launches;
       if (es != cudaSuccess) return (int)es;
       if (sb + QRDM_TALL_B < kmax_h) {  // apply the sub-panel's reflectors to the rest of the panel

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) k_sub_w(qrdm_prob P) {
 // buffer (k_peer.cu, generic region) and adds the nranks packets of its own buffer in rank order, so all ranks hold
 // bit-identical W; replaces k_sub_wred + all-reduce kernel + k_sub_w2 (three launches per sub-panel).
 template <bool MG>
-__global__ void __launch_bounds__(512) k_sub_w2(qrdm_prob P, int nchunks_max, PeerCtx pc, unsigned ptag, int pparity) {
+__global__ void __launch_bounds__(1024) k_sub_w2(qrdm_prob P, int nchunks_max, PeerCtx pc, unsigned ptag, int pparity) {
   __shared__ double W[8 * 64];   // [group][q][c]
   __shared__ double T[64];       // T'[q][p]
   const SkGeom g = sk_geom(P);
@@ -99,36 +99,37 @@ __global__ void __launch_bounds__(512) k_sub_w2(qrdm_prob P, int nchunks_max, Pe
                       : MG ? min(nchunks_max, g.rows > 0 ? (g.rows + SK_RC - 1) / SK_RC : 0)
                            : (P.w_reduced ? 1 : min(nchunks_max, (g.rows + SK_RC - 1) / SK_RC));  // w_reduced: chunk 0 = all-reduced sum
   const int ngroups = 1 + (g.ncp + 7) / 8;
-  if (MG) {
-    if (tid < ngroups * 64) {
+  // fold of the partials: the CTA has 1024 threads, half h sums the partials b = h, h + 2, ... of entry e with four
+  // loads in flight, then the two halves are added (fixed order: deterministic)
+  __shared__ double Wh[2][512];
+  {
+    const int h = tid >> 9, e = tid & 511;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int b = 0;
-    for (; b + 3 < nchunks; b += 4) {  // the association order of k_sub_wred
-      s0 += P.gram_part[(size_t)b * 512 + tid];
-      s1 += P.gram_part[(size_t)(b + 1) * 512 + tid];
-      s2 += P.gram_part[(size_t)(b + 2) * 512 + tid];
-      s3 += P.gram_part[(size_t)(b + 3) * 512 + tid];
+    if (e < ngroups * 64) {
+      int b = h;
+      for (; b + 6 < nchunks; b += 8) {
+        s0 += P.gram_part[(size_t)b * 512 + e];
+        s1 += P.gram_part[(size_t)(b + 2) * 512 + e];
+        s2 += P.gram_part[(size_t)(b + 4) * 512 + e];
+        s3 += P.gram_part[(size_t)(b + 6) * 512 + e];
+      }
+      for (; b < nchunks; b += 2) s0 += P.gram_part[(size_t)b * 512 + e];
     }
-    for (; b < nchunks; ++b) s0 += P.gram_part[(size_t)b * 512 + tid];
-    const double mine = (s0 + s1) + (s2 + s3);
-    const int me = pc.rank, N = pc.nranks;
-    for (int r = 0; r < N; ++r)
-      if (r != me) ll_store(peer_gen_slot(pc.recv[r], pparity, me, (size_t)tid), mine, ptag);
-    double tot = 0.0;
-    for (int r = 0; r < N; ++r) tot += (r == me) ? mine : ll_load(peer_gen_slot(pc.recv[me], pparity, r, (size_t)tid), ptag);
-    W[tid] = tot;
+    Wh[h][e] = (s0 + s1) + (s2 + s3);
+  }
+  __syncthreads();
+  if (tid < ngroups * 64) {
+    const double mine = Wh[0][tid] + Wh[1][tid];
+    if (MG) {
+      const int me = pc.rank, N = pc.nranks;
+      for (int r = 0; r < N; ++r)
+        if (r != me) ll_store(peer_gen_slot(pc.recv[r], pparity, me, (size_t)tid), mine, ptag);
+      double tot = 0.0;
+      for (int r = 0; r < N; ++r) tot += (r == me) ? mine : ll_load(peer_gen_slot(pc.recv[me], pparity, r, (size_t)tid), ptag);
+      W[tid] = tot;
+    } else {
+      W[tid] = mine;
     }
-  } else if (tid < ngroups * 64) {
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int b = 0;
-    for (; b + 3 < nchunks; b += 4) {  // fixed association order
-      s0 += P.gram_part[(size_t)b * 512 + tid];
-      s1 += P.gram_part[(size_t)(b + 1) * 512 + tid];
-      s2 += P.gram_part[(size_t)(b + 2) * 512 + tid];
-      s3 += P.gram_part[(size_t)(b + 3) * 512 + tid];
-    }
-    for (; b < nchunks; ++b) s0 += P.gram_part[(size_t)b * 512 + tid];
-    W[tid] = (s0 + s1) + (s2 + s3);
   }
   __syncthreads();
   if (tid < 8) {  // column p = tid of X = (I + D N)^-1, N = strictly-lower V'V, D = diag(tau); T' = X D
@@ -233,7 +234,7 @@ extern "C" int qrdm_k_skinny_update(const qrdm_prob* p, int rows_hint, void* str
   if (rc > 0) return rc;
   if (rc == 0) fold = -nparts;
   else { k_sub_w<<<nch, SK_THREADS, 0, s>>>(*p); QRDM_LAUNCH_CHECK(); }
-  k_sub_w2<false><<<1, 512, 0, s>>>(*p, fold, PeerCtx{}, 0u, 0);
+  k_sub_w2<false><<<1, 1024, 0, s>>>(*p, fold, PeerCtx{}, 0u, 0);
   QRDM_LAUNCH_CHECK();
   k_sub_apply<<<nch, SK_THREADS, 0, s>>>(*p);
   QRDM_LAUNCH_CHECK();
@@ -255,7 +256,7 @@ extern "C" int qrdm_k_skinny_finish(const qrdm_prob* p, int rows_hint, void* str
   cudaStream_t s = (cudaStream_t)stream;
   int nch = (rows_hint + SK_RC - 1) / SK_RC;
   if (nch < 1) nch = 1;
-  k_sub_w2<false><<<1, 512, 0, s>>>(*p, 1, PeerCtx{}, 0u, 0);
+  k_sub_w2<false><<<1, 1024, 0, s>>>(*p, 1, PeerCtx{}, 0u, 0);
   QRDM_LAUNCH_CHECK();
   k_sub_apply<<<nch, SK_THREADS, 0, s>>>(*p);
   QRDM_LAUNCH_CHECK();
@@ -276,7 +277,7 @@ extern "C" int qrdm_k_skinny_update_mg(const qrdm_prob* p, int rows_hint, void* 
   unsigned tag = 0;
   int parity = 0;
   qrdm_peer_next_gen(&tag, &parity);
-  k_sub_w2<true><<<1, 512, 0, s>>>(*p, fold, *pc, tag, parity);
+  k_sub_w2<true><<<1, 1024, 0, s>>>(*p, fold, *pc, tag, parity);
   QRDM_LAUNCH_CHECK();
   k_sub_apply<<<nch, SK_THREADS, 0, s>>>(*p);
   QRDM_LAUNCH_CHECK();

@@ -656,6 +656,11 @@ __global__ void __launch_bounds__(RK_THREADS, 2) k_rankk(qrdm_prob P) {
 // Row-sharded build: fold the partial-W slots of every tile into slot 0 (fixed order) so that ONE
 // contiguous [64][stride] block can be all-reduced over NVLink; ranks that have no rows left
 // contribute zeros.  k_tinv / k_wapply then read slot 0 only (P.w_reduced).
+// Tall-skinny matrices have few column tiles and many CTAs per tile (296 CTAs over <= 4 tiles at n = 512: ~74 slots per
+// tile), so the fold is spread over gridDim.y = 16 row groups of the 64 x 128 tile and every thread keeps four slot
+// loads in flight (fixed association order ((s0 + s1) + (s2 + s3)), deterministic).  Also used on one GPU when a tile
+// has more than 8 slots: k_tinv / k_wapply then read one slot instead of summing 74 serially on 1 + CT CTAs.
+#define WR_GY 16
 __global__ void __launch_bounds__(256) k_wreduce(qrdm_prob P, int vt_grid, int wslot_stride_cols) {
   __shared__ int slots[QRDM_PANEL_MAXCTA * 2 + 8];
   __shared__ int nslots;
@@ -667,13 +672,21 @@ __global__ void __launch_bounds__(256) k_wreduce(qrdm_prob P, int vt_grid, int w
   __syncthreads();
   const size_t sstride = (size_t)64 * wslot_stride_cols;
   const int ns = nslots;
-  for (int e = threadIdx.x; e < 64 * VT_BN; e += 256) {
-    const int q = e / VT_BN, c = e % VT_BN;
+  constexpr int QPG = 64 / WR_GY;  // rows of the tile per row group
+  for (int e = threadIdx.x; e < QPG * VT_BN; e += 256) {
+    const int q = blockIdx.y * QPG + e / VT_BN, c = e % VT_BN;
     double* dst = P.wp + (size_t)q * wslot_stride_cols + (size_t)T * VT_BN + c;
-    double s2 = 0.0;
-    if (q < ge.kpad)
-      for (int i = 0; i < ns; ++i) s2 += dst[(size_t)slots[i] * sstride];
-    dst[0] = s2;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    if (q < ge.kpad) {
+      int i = 0;
+      for (; i + 3 < ns; i += 4) {
+        const double v0 = dst[(size_t)slots[i] * sstride], v1 = dst[(size_t)slots[i + 1] * sstride];
+        const double v2 = dst[(size_t)slots[i + 2] * sstride], v3 = dst[(size_t)slots[i + 3] * sstride];
+        s0 += v0; s1 += v1; s2 += v2; s3 += v3;
+      }
+      for (; i < ns; ++i) s0 += dst[(size_t)slots[i] * sstride];
+    }
+    dst[0] = (s0 + s1) + (s2 + s3);
   }
 }
 
@@ -1062,7 +1075,7 @@ extern "C" int qrdm_k_vtc_only(const qrdm_prob* p, int j_host, int* stride_out, 
 
 extern "C" int qrdm_k_wreduce(const qrdm_prob* p, int j_host, int vt_grid, int stride, void* stream) {
   if (stride <= 0) return 0;
-  k_wreduce<<<stride / VT_BN, 256, 0, (cudaStream_t)stream>>>(*p, vt_grid, stride);
+  k_wreduce<<<dim3(stride / VT_BN, WR_GY), 256, 0, (cudaStream_t)stream>>>(*p, vt_grid, stride);
   QRDM_LAUNCH_CHECK();
   return 0;
 }
@@ -1113,6 +1126,14 @@ extern "C" int qrdm_k_trailing(const qrdm_prob* p, int j_host, void* stream) {
   int stride = 0, grid = 0;
   int rc = qrdm_k_vtc_only(p, j_host, &stride, &grid, stream);
   if (rc) return rc;
+  // tall-skinny: many CTAs per column tile => fold the partial-W slots in parallel first (see k_wreduce)
+  if (stride > 0 && !p->w_reduced && grid > 8 * (stride / VT_BN)) {
+    rc = qrdm_k_wreduce(p, j_host, grid, stride, stream);
+    if (rc) return rc;
+    qrdm_prob p2 = *p;
+    p2.w_reduced = 1;
+    return qrdm_k_trailing_finish(&p2, j_host, grid, stride, stream);
+  }
   return qrdm_k_trailing_finish(p, j_host, grid, stride, stream);
 }
 
