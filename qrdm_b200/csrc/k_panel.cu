@@ -586,7 +586,10 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_tall(qrdm_prob P, in
     publish(acc, 0, 0, tag_base + 1);
   }
 
-  double thres = (sub_s == 0) ? P.thres0 : ctrl->tall_thres;
+  // squared stop threshold (carried across the sub-panels in ctrl->tall_thres): the test runs on ||x||^2 and the
+  // reflector needs ONE square root, beta^2 = alpha^2 + ||x||^2 — the same scalar chain as k_panel_reg (the
+  // sqrt + hypot pair of the first version cost more than the sweep of a slab-resident sub-panel)
+  double thres2 = (sub_s == 0) ? P.thres0 * P.thres0 : ctrl->tall_thres;
   int k = fjb;
   for (int i = 0; i < fjb; ++i) {
     const int cur = i & 1, nxt = cur ^ 1;
@@ -629,20 +632,19 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_tall(qrdm_prob P, in
     }
     __syncthreads();
     // ---- reflector scalars (dlarfg_mia) ----
-    const double alpha = rowv[i];
+    const double alpha = rowv[i], xn2 = S_[i];
     const int len = rows - i;
     double tau = 0.0, beta = alpha, scale = 1.0;
     if (len > 1) {
-      const double xnorm = sqrt(S_[i]);
-      if (sub_s + i > 0 && xnorm < thres && !forced) { k = i; break; }  // DM early stop (never for fixed columns)
-      if (xnorm != 0.0) {
-        const double h = hypot(alpha, xnorm);
+      if (sub_s + i > 0 && xn2 < thres2 && !forced) { k = i; break; }  // DM early stop (never for fixed columns)
+      if (xn2 != 0.0) {
+        const double h = sqrt(fma(alpha, alpha, xn2));
         beta = (alpha >= 0.0) ? -h : h;
         tau = (beta - alpha) / beta;
         scale = 1.0 / (alpha - beta);
       }
     }
-    if (sub_s + i == 0 && fjb_main > 1 && P.tau_ > 0.0) thres = P.tau_ * fabs(beta);
+    if (sub_s + i == 0 && fjb_main > 1 && P.tau_ > 0.0) { const double th = P.tau_ * fabs(beta); thres2 = th * th; }
     if (b == 0 && tid == 0) {
       P.tau[j + i] = tau;
       if (tau != tau && ctrl->err == 0) ctrl->err = -8;
@@ -729,7 +731,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_tall(qrdm_prob P, in
     ctrl->tall_k = tk;
     ctrl->tall_done = (k < fjb) ? 1 : 0;
     if (k < fjb) ctrl->tall_stop_s = sub_s;
-    ctrl->tall_thres = thres;
+    ctrl->tall_thres = thres2;
     ctrl->fjb_cmp = tk;
     if (MG) *pc.xseq = px0 + (unsigned)(k < fjb ? k + 1 : fjb);  // exchanges performed by this launch
   }

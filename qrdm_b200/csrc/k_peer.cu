@@ -20,7 +20,9 @@
 //
 // Slot reuse: two parities (generic: sequence number & 1; panel: a device-side exchange counter & 1).  A rank can only send for exchange e+2 after it has finished exchange e+1, which needed
 // every peer's e+1 contribution, which each peer sends only after it has finished READING exchange e (stream / program
-// order) — so a slot is never overwritten before its last reader is done.  Tags never repeat within 2^32
+// order) — so a slot is never overwritten before its last reader is done.  This needs consecutive PERFORMED exchanges
+// to alternate parity: a kernel that draws a sequence number (qrdm_peer_next_gen) must perform the exchange even when
+// it has nothing to send (k_sub_w2<true> exchanges one dummy element for a dead sub-panel).  Tags never repeat within 2^32
 // exchanges and the buffers start zeroed (tag 0 is never used).
 #include <cstdio>
 #include <cstdlib>

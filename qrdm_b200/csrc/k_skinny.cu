@@ -91,8 +91,22 @@ __global__ void __launch_bounds__(1024) k_sub_w2(qrdm_prob P, int nchunks_max, P
   __shared__ double W[8 * 64];   // [group][q][c]
   __shared__ double T[64];       // T'[q][p]
   const SkGeom g = sk_geom(P);
-  if (g.k <= 0 || g.ncp <= 0) return;  // replicated decision: every rank returns alike, nobody waits for a packet
   const int tid = threadIdx.x;
+  if (g.k <= 0 || g.ncp <= 0) {
+    // Nothing to update (replicated decision: every rank gets here alike).  The host has already drawn a sequence
+    // number for this exchange, and the two-parity slot scheme of k_peer.cu is only safe if consecutive PERFORMED
+    // exchanges alternate parity — so the exchange is still performed, on one dummy element.  (Skipping it let a fast
+    // rank overwrite, two sequence numbers later, a slot a slow rank had not read yet: the waiting rank then spun into
+    // its trap — seen with two ranks time-slicing one GPU on Kahan inputs, where every panel has one column.)
+    if (MG && tid == 0) {
+      const int me = pc.rank, N = pc.nranks;
+      for (int r = 0; r < N; ++r)
+        if (r != me) ll_store(peer_gen_slot(pc.recv[r], pparity, me, 0), 0.0, ptag);
+      for (int r = 0; r < N; ++r)
+        if (r != me) (void)ll_load(peer_gen_slot(pc.recv[me], pparity, r, 0), ptag);
+    }
+    return;
+  }
   // nchunks_max < 0: exactly -nchunks_max partials were written (TMA + DMMA producer, CTAs without rows write zeros);
   // > 0: the FMA producer k_sub_w, whose CTAs beyond the last row chunk do not write
   const int nchunks = nchunks_max < 0 ? -nchunks_max

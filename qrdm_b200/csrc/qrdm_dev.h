@@ -46,7 +46,7 @@ typedef struct qrdm_ctrl {
   int tall_k;             /* reflectors produced so far by this panel */
   int tall_done;          /* 1 once the early stop fired: later sub-panels are no-ops */
   int tall_stop_s;        /* panel column at which the sub-panel that stopped early starts (valid when tall_done) */
-  double tall_thres;      /* stop threshold (set by the panel's first column) */
+  double tall_thres;      /* SQUARED stop threshold (set by the panel's first column), carried across sub-panels */
   int cand[QRDM_KMAX];        /* candidate column offsets (relative to j), by norm descending */
   double candnrm[QRDM_KMAX];  /* their partial norms */
   int sel[QRDM_KMAX];         /* accepted offsets, acceptance order */
