@@ -71,6 +71,7 @@ struct SmallShared {
   int xcol[64], xdiag[64], ycol[64], ydiag[64];
   int flag[SM_MAXDIM];
   double eta;
+  double thres0, inv_scale;  // 5e-14 x the input scale / its reciprocal (1 unless the matrix was pre-scaled)
   long long ptq, ptq2;
   int stop_mode, it, bad, keep[64];
   union alignas(16) {
@@ -421,7 +422,7 @@ __device__ __forceinline__ void small_panel(const qrdm_prob& P, SmallShared& S) 
   double* part = S.part;
   double* Sd = S.S_;    // [2][8] reduced dots, double-buffered by column parity
   double* Rv = S.rowv;  // [2][8] pivot-row entries
-  double thres2 = P.thres0 * P.thres0;  // (src/dgeqr2.c:40)^2, 5e-14 x the input scale
+  double thres2 = S.thres0 * S.thres0;  // (src/dgeqr2.c:40)^2, 5e-14 x the input scale
   int k = fjb;
   bool stopped = false;
   SM_PT(0);
@@ -585,8 +586,8 @@ __device__ __forceinline__ void small_norm_update(const qrdm_prob& P, SmallShare
     for (; r + 1 < j + k; r += 2) { d0 = fma(col[r], col[r], d0); d1 = fma(col[r + 1], col[r + 1], d1); }
     if (r < j + k) d0 = fma(col[r], col[r], d0);
     const double d = d0 + d1;
-    const double dt = (d * P.inv_scale) * P.inv_scale;  // caller's scale, see qrdm_prob::inv_scale
-    double t = sqrt(fabs(dt)) / (v1 * P.inv_scale);
+    const double dt = (d * S.inv_scale) * S.inv_scale;  // caller's scale, see qrdm_prob::inv_scale
+    double t = sqrt(fabs(dt)) / (v1 * S.inv_scale);
     t = (t + 1.0) * (1.0 - t);
     t = (0.0 >= t) ? 0.0 : t;
     const double q = v1 / S.vn2[c];
@@ -613,8 +614,11 @@ __device__ __forceinline__ void small_norm_update(const qrdm_prob& P, SmallShare
 }
 
 // initial norms (src/dgeqrdm_work.c:672-682), jpvt = identity (:596-609 with every column free)
-__device__ __noinline__ void small_init_norms(const qrdm_prob& P, SmallShared& S) {
+// (the noinline helpers take scalars, not the qrdm_prob: taking its address would move the whole descriptor to local
+// memory for the hot loops of the kernel as well)
+__device__ __noinline__ void small_init_norms(const double* a, int lda, int m, int n, int* jpvt, SmallShared& S) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  struct { const double* a; int lda, m, n; int* jpvt; } P = {a, lda, m, n, jpvt};
   for (int c = wid; c < P.n; c += SM_NW) {
     const double* col = P.a + (size_t)c * P.lda;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
@@ -633,8 +637,9 @@ __device__ __noinline__ void small_init_norms(const qrdm_prob& P, SmallShared& S
 
 // max |a_ij| of the matrix; if it is finite and its exponent is beyond +-200, multiply the matrix by the power of two
 // that brings it into [1, 2) and return that factor (1.0 otherwise).  Every thread returns the same value.
-__device__ __noinline__ double small_prescale(const qrdm_prob& P, SmallShared& S) {
+__device__ __noinline__ double small_prescale(double* a, int lda, int m, int n, SmallShared& S) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  struct { double* a; int lda, m, n; } P = {a, lda, m, n};
   double mx = 0.0;
   for (int c = wid; c < P.n; c += SM_NW) {
     const double* col = P.a + (size_t)c * P.lda;
@@ -692,7 +697,7 @@ __global__ void __launch_bounds__(SM_NT, 1) k_small(SmallArgs A) {
     S.it = 0;
     S.bad = 0;
   }
-  small_init_norms(P, S);
+  small_init_norms(P.a, A.lda, A.m, A.n, P.jpvt, S);
   __syncthreads();
   qrdm_select_body<SM_NT>(P, S.u.sel);
   __syncthreads();
@@ -701,20 +706,22 @@ __global__ void __launch_bounds__(SM_NT, 1) k_small(SmallArgs A) {
   // dgeqrdm_host.c prescale_input; the reference gets there with cblas_dnrm2 and dlarfg's safmin loop)
   double in_scale = 1.0;
   if (!(S.ctrl.maxnrm <= 0x1p300) || S.ctrl.maxnrm < 0x1p-300) {
-    in_scale = small_prescale(P, S);
+    in_scale = small_prescale(P.a, A.lda, A.m, A.n, S);
     if (in_scale != 1.0) {
       __syncthreads();
       for (int i = tid; i < (int)(sizeof(qrdm_ctrl) / sizeof(int)); i += SM_NT) reinterpret_cast<int*>(&S.ctrl)[i] = 0;
       __syncthreads();
-      small_init_norms(P, S);
+      small_init_norms(P.a, A.lda, A.m, A.n, P.jpvt, S);
       __syncthreads();
       qrdm_select_body<SM_NT>(P, S.u.sel);
       __syncthreads();
     }
   }
-  P.thres0 = 5e-14 * in_scale;  // src/dgeqr2.c:40
-  P.inv_scale = 1.0 / in_scale;
-  if (tid == 0) S.eta *= S.ctrl.maxnrm;  // :684
+  if (tid == 0) {
+    S.thres0 = 5e-14 * in_scale;  // src/dgeqr2.c:40
+    S.inv_scale = 1.0 / in_scale;
+    S.eta *= S.ctrl.maxnrm;  // :684
+  }
   __syncthreads();
 
   SM_TDECL;
