@@ -20,7 +20,7 @@ extern "C" {
 
 #define QRDM_COL_MAJOR 102 /* reference include/cblas.h:10, src/dgeqrdm_work.c:17-18 */
 #define QRDM_ROW_MAJOR 101 /* accepted by the reference's check but never worked there: rejected */
-#define QRDM_NB_MAX 64     /* largest supported block size / candidate count */
+#define QRDM_NB_MAX 256    /* largest supported block size / candidate count (above 64: micro-panels of 64 columns) */
 
 /* error codes beyond the reference's (0, -1 bad argument, -8/-6/-13 NaN screens of
  * LAPACKE_dlarft / LAPACKE_dlarfb_mia, reference src/dlarfb.c:73-86) */

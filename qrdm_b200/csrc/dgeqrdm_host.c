@@ -33,6 +33,10 @@ typedef struct {
   int *flag_list, *upd_marks; /* upd_marks: [2][cap_n] stamps of the deferred trailing update */
   double *mg_buf;
   unsigned *mg_cnt;
+  /* nb > 64 (k_wide.cu), allocated on first use */
+  double *wide_part, *wide_gram;
+  int *wide_marks, *wide_swaps;
+  int wide_marks_cap;
   size_t wp_elems;
   int ldv, ldw, nrm_splits;
   /* staging for the host-pointer entry points */
@@ -129,7 +133,8 @@ static void shutdown_impl(void) {
   if (cur != w->device) qrdm_rt_set_device(w->device); /* streams / events are destroyed on their own device */
   qrdm_rt_peer_destroy();
   ws_free_sized(w);
-  void *fixed[] = {w->ctrl, w->gram_part, w->gram, w->panel_part, w->panel_row, w->d_a, w->d_tau, w->d_jpvt, w->mg_buf, w->mg_cnt};
+  void *fixed[] = {w->ctrl, w->gram_part, w->gram, w->panel_part, w->panel_row, w->d_a, w->d_tau, w->d_jpvt, w->mg_buf, w->mg_cnt,
+                   w->wide_part, w->wide_gram, w->wide_marks, w->wide_swaps};
   for (size_t i = 0; i < sizeof(fixed) / sizeof(fixed[0]); ++i)
     if (fixed[i]) qrdm_rt_free(fixed[i]);
   if (w->mailbox) qrdm_rt_host_free(w->mailbox);
@@ -350,6 +355,25 @@ static int read_mailbox(const qrdm_prob *p, void *stream) {
   return 0;
 }
 
+/* nb > 64: workspace of the wide selection (k_wide.cu) */
+static int ws_ensure_wide(int n) {
+  qrdm_workspace *w = &g_ws;
+  if (!w->wide_part) {
+    const size_t pairs = (QRDM_CANDMAX / 64) * (QRDM_CANDMAX / 64 + 1) / 2;
+    CU(qrdm_rt_malloc((void **)&w->wide_part, sizeof(double) * pairs * QRDM_WIDE_ROWCTAS * 4096));
+    CU(qrdm_rt_malloc((void **)&w->wide_gram, sizeof(double) * QRDM_CANDMAX * QRDM_CANDMAX));
+    CU(qrdm_rt_malloc((void **)&w->wide_swaps, sizeof(int) * (2 * (2 * QRDM_CANDMAX + 4) + 1)));
+  }
+  if (n > w->wide_marks_cap) {
+    if (w->wide_marks) qrdm_rt_free(w->wide_marks);
+    w->wide_marks = NULL;
+    w->wide_marks_cap = 0;
+    CU(qrdm_rt_malloc((void **)&w->wide_marks, sizeof(int) * (size_t)n));
+    w->wide_marks_cap = n;
+  }
+  return 0;
+}
+
 /* The factorisation proper on device-resident data. */
 static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double *d_tau, int *ncols,
                          const double *thres, int nb, void *stream, qrdm_writeback *wb,
@@ -402,7 +426,18 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
    * k_vtc + k_rankk, the eager completion costs ~0.09 ms: break-even near a 7000 x 7000 trailing matrix */
   int lazy_min = 7168;
   { const char *e = getenv("QRDM_B200_LAZY_MIN"); if (e) lazy_min = atoi(e); if (lazy_min < 1) lazy_min = 1; }
-  const int lazy_on = !mg && !(getenv("QRDM_B200_LAZY") && atoi(getenv("QRDM_B200_LAZY")) == 0);
+  /* nb > 64: selection at full width, factorisation in micro-panels of 64 columns (k_wide.cu); eager schedule only */
+  const int wide = nb > QRDM_KMAX;
+  if (wide) {
+    if (mg) {
+      fprintf(stderr, "qrdm_b200: nb = %d > %d is not supported in the row-sharded entry point\n", nb, QRDM_KMAX);
+      return QRDM_ERR_UNSUPPORTED;
+    }
+    rc = ws_ensure_wide(n);
+    if (rc) return rc;
+    CU(qrdm_rt_memset(w->wide_marks, 0, sizeof(int) * (size_t)n, stream));
+  }
+  const int lazy_on = !mg && !wide && !(getenv("QRDM_B200_LAZY") && atoi(getenv("QRDM_B200_LAZY")) == 0);
   int pending = 0, pend_j = 0, stamp = 0;
   double *vcbuf[2] = {w->vc, w->vc + (size_t)w->ldv * 64};
 
@@ -459,7 +494,25 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
     int lazy = 0;
     /* the mailbox read at the end of the previous iteration already holds this iteration's candidate count */
     if (w->mailbox->nc > 1) g_stats.stage_bytes[QRDM_STAGE_GRAM] += 8.0 * (double)(m - jr) * (double)w->mailbox->nc;
-    if (!mg) {
+    if (wide) {
+      const int kmax_h = nb < n - j ? (nb < m - j ? nb : m - j) : (n - j < m - j ? n - j : m - j);
+      P.vc = vcbuf[0];
+      P.vc_prev = vcbuf[1];
+      STAGE(QRDM_STAGE_GRAM, qrdm_k_gram_wide(&P, w->wide_part, w->wide_gram, m - jr, stream));
+      STAGE(QRDM_STAGE_PICK, qrdm_k_pick_wide(&P, w->wide_gram, w->wide_marks, w->wide_swaps, stream));
+      for (int t = 0; t * QRDM_KMAX < kmax_h; ++t) { /* micro-panels; those behind a DM stop are no-ops on the device */
+        const int jt = j + t * QRDM_KMAX;
+        CU(qrdm_k_micro_begin(&P, t, stream));
+        STAGE(QRDM_STAGE_PANEL, qrdm_k_panel(&P, jt, stream));
+        STAGE(QRDM_STAGE_VTC, qrdm_k_trailing(&P, jt, stream));
+      }
+      CU(qrdm_k_micro_end(&P, stream));
+      if (j < nfxd && j + (nb < nfxd - j ? nb : nfxd - j) >= nfxd) {
+        STAGE(QRDM_STAGE_NORM_UPDATE, qrdm_k_norm_recompute_all(&P, j, stream));
+      } else {
+        STAGE(QRDM_STAGE_NORM_UPDATE, qrdm_k_norm_update(&P, j, stream));
+      }
+    } else if (!mg) {
       P.vc = vcbuf[sweep & 1];       /* V of this block; the pending block's V sits in the other buffer */
       P.vc_prev = vcbuf[(sweep & 1) ^ 1];
       STAGE(QRDM_STAGE_GRAM, qrdm_k_gram(&P, 0, m - jr, stream));

@@ -327,7 +327,10 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_reg(qrdm_prob P, int
   if (MODE == 2) { cooperative_groups::this_cluster().sync(); publish_cluster(0, -1, tag_base + 1); }
   __syncthreads();
 
-  double thres2 = P.thres0 * P.thres0;  // (reference src/dgeqr2.c:40)^2, 5e-14 x input scale
+  // nb > 64: this panel may CONTINUE a wider block (micro-panel t > 0, k_wide.cu): the stop test then applies from its
+  // first column on and the threshold set by the block's first column is carried in ctrl
+  const bool cont = ctrl->micro_t > 0;
+  double thres2 = cont ? ctrl->micro_thres2 : P.thres0 * P.thres0;  // (reference src/dgeqr2.c:40)^2, 5e-14 x input scale
   int k = fjb;
   long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // QRDM_B200_DEBUG & 8: per-phase cycle counts of one CTA
   const bool timing = (P.debug & 8) && b == (G > 40 ? 40 : 0) && tid == 0;
@@ -378,7 +381,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_reg(qrdm_prob P, int
     const int len = rows - i;
     double tau = 0.0, beta = alpha, scale = 1.0;
     if (len > 1) {
-      if (i > 0 && xn2 < thres2 && !forced) { k = i; break; }  // DM early stop: column i left untouched
+      if ((i > 0 || cont) && xn2 < thres2 && !forced) { k = i; break; }  // DM early stop: column i left untouched
       // Only the warps that consume the scalars compute them: warps 0-1 (wv, tau), the owner of column i
       // (scale, beta) and, in column 0, everybody (thres2 needs beta).  The chain itself costs ~350 cycles
       // (measured by running it twice); the 2.5-3.5 k cycles QRDM_B200_DEBUG=8 books under "scalars" are the
@@ -390,7 +393,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_reg(qrdm_prob P, int
         scale = 1.0 / (alpha - beta);
       }
     }
-    if (i == 0 && fjb > 1 && P.tau_ > 0.0) { const double th = P.tau_ * fabs(beta); thres2 = th * th; }
+    if (i == 0 && !cont && fjb > 1 && P.tau_ > 0.0) { const double th = P.tau_ * fabs(beta); thres2 = th * th; }
     if (b == 0 && tid == 0) {
       P.tau[j + i] = tau;
       if (tau != tau && ctrl->err == 0) ctrl->err = -8;  // LAPACKE_dlarft's NaN screen of tau
@@ -467,7 +470,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_reg(qrdm_prob P, int
     printf("panel_reg j=%d G=%d rpc=%d fjb=%d cycles: reduce %lld bcast %lld scalars+publish %lld (scalars %lld, to-sync %lld) sweep %lld endsync %lld\n", j, G, rpc, fjb,
            tph[0], tph[1], tph[2], tph[5], tph[6], tph[3], tph[4]);
   __syncthreads();
-  if (b == 0 && tid == 0) ctrl->fjb_cmp = k;
+  if (b == 0 && tid == 0) { ctrl->fjb_cmp = k; ctrl->micro_thres2 = thres2; }
 
   // ---- write the slab back and emit Vc ----
   const int kpad = (k + 7) & ~7;
@@ -589,7 +592,8 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_tall(qrdm_prob P, in
   // squared stop threshold (carried across the sub-panels in ctrl->tall_thres): the test runs on ||x||^2 and the
   // reflector needs ONE square root, beta^2 = alpha^2 + ||x||^2 — the same scalar chain as k_panel_reg (the
   // sqrt + hypot pair of the first version cost more than the sweep of a slab-resident sub-panel)
-  double thres2 = (sub_s == 0) ? P.thres0 * P.thres0 : ctrl->tall_thres;
+  const bool cont = ctrl->micro_t > 0;  // nb > 64: the panel continues a wider block (k_wide.cu)
+  double thres2 = (sub_s == 0) ? (cont ? ctrl->micro_thres2 : P.thres0 * P.thres0) : ctrl->tall_thres;
   int k = fjb;
   for (int i = 0; i < fjb; ++i) {
     const int cur = i & 1, nxt = cur ^ 1;
@@ -636,7 +640,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_tall(qrdm_prob P, in
     const int len = rows - i;
     double tau = 0.0, beta = alpha, scale = 1.0;
     if (len > 1) {
-      if (sub_s + i > 0 && xn2 < thres2 && !forced) { k = i; break; }  // DM early stop (never for fixed columns)
+      if ((sub_s + i > 0 || cont) && xn2 < thres2 && !forced) { k = i; break; }  // DM early stop (never for fixed columns)
       if (xn2 != 0.0) {
         const double h = sqrt(fma(alpha, alpha, xn2));
         beta = (alpha >= 0.0) ? -h : h;
@@ -644,7 +648,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_tall(qrdm_prob P, in
         scale = 1.0 / (alpha - beta);
       }
     }
-    if (sub_s + i == 0 && fjb_main > 1 && P.tau_ > 0.0) { const double th = P.tau_ * fabs(beta); thres2 = th * th; }
+    if (sub_s + i == 0 && !cont && fjb_main > 1 && P.tau_ > 0.0) { const double th = P.tau_ * fabs(beta); thres2 = th * th; }
     if (b == 0 && tid == 0) {
       P.tau[j + i] = tau;
       if (tau != tau && ctrl->err == 0) ctrl->err = -8;
@@ -732,6 +736,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_tall(qrdm_prob P, in
     ctrl->tall_done = (k < fjb) ? 1 : 0;
     if (k < fjb) ctrl->tall_stop_s = sub_s;
     ctrl->tall_thres = thres2;
+    ctrl->micro_thres2 = thres2;
     ctrl->fjb_cmp = tk;
     if (MG) *pc.xseq = px0 + (unsigned)(k < fjb ? k + 1 : fjb);  // exchanges performed by this launch
   }

@@ -10,7 +10,10 @@
 extern "C" {
 #endif
 
-#define QRDM_KMAX 64       /* max block size / candidates (QRDM_NB_MAX) */
+#define QRDM_KMAX 64       /* width of the panel / trailing-update tiles: a block of up to 64 columns per pass */
+#define QRDM_CANDMAX 256   /* max nb = max candidates / selected columns per iteration (QRDM_NB_MAX); blocks wider than
+                              QRDM_KMAX are factored in micro-panels of QRDM_KMAX columns (k_wide.cu) */
+#define QRDM_WIDE_ROWCTAS 148 /* row chunks of the wide Gram kernel */
 #define QRDM_MAXEX 160     /* max column exchanges planned per iteration (<= 2*KMAX, see k_pick) */
 #define QRDM_MAXPOS 320    /* max column positions touched by those exchanges */
 #define QRDM_SELCAP 1024   /* capacity of the top-k candidate list in k_select */
@@ -47,9 +50,9 @@ typedef struct qrdm_ctrl {
   int tall_done;          /* 1 once the early stop fired: later sub-panels are no-ops */
   int tall_stop_s;        /* panel column at which the sub-panel that stopped early starts (valid when tall_done) */
   double tall_thres;      /* SQUARED stop threshold (set by the panel's first column), carried across sub-panels */
-  int cand[QRDM_KMAX];        /* candidate column offsets (relative to j), by norm descending */
-  double candnrm[QRDM_KMAX];  /* their partial norms */
-  int sel[QRDM_KMAX];         /* accepted offsets, acceptance order */
+  int cand[QRDM_CANDMAX];        /* candidate column offsets (relative to j), by norm descending */
+  double candnrm[QRDM_CANDMAX];  /* their partial norms */
+  int sel[QRDM_CANDMAX];         /* accepted offsets, acceptance order */
   int cyc_start[QRDM_MAXPOS + 1];
   int cyc_pos[QRDM_MAXPOS];   /* cycle c: new[p_k] = old[p_{k+1}], new[p_last] = old[p_0] */
   /* deferred ("lazy") trailing update: block reflector whose pass 2 has not been applied to the bulk
@@ -60,6 +63,14 @@ typedef struct qrdm_ctrl {
   int forced;   /* 1: this iteration factors FIXED columns (jpvt != 0 on entry): the next columns as they stand, no DM
                    selection, no permutation, no early stop in the panel */
   long long stat_perm_cols; /* statistics: columns moved by k_permute since the start of the factorisation */
+  /* nb > 64: the selected block is factored in micro-panels of QRDM_KMAX columns (k_wide.cu) */
+  int w_j0, w_fjb;     /* j and fjb of the whole block */
+  int w_k;             /* reflectors produced by the micro-panels finished so far */
+  int w_stop;          /* a micro-panel stopped early: the block ends there */
+  int w_pending;       /* a micro-panel has run and is not yet accounted for */
+  int micro_t;         /* index of the current micro-panel (> 0: the panel continues a block — stop test from its first
+                          column on, threshold carried in micro_thres2) */
+  double micro_thres2; /* squared DM stop threshold carried across micro-panels */
 } qrdm_ctrl;
 #define QRDM_MAILBOX_BYTES 64
 
@@ -193,6 +204,12 @@ int qrdm_rt_peer_available(void);              /* number of ranks of the open pe
 int qrdm_k_peer_allreduce(double *buf, size_t count, void *stream);
 int qrdm_k_panel_tall_mg(const qrdm_prob *p, int j_host, void *stream); /* sharded sub-panel, exchange inside the kernel */
 int qrdm_k_skinny_update_mg(const qrdm_prob *p, int rows_hint, void *stream); /* sharded skinny update, cross-GPU sum inside k_sub_w2 */
+/* nb > 64 (k_wide.cu): part = [pairs][QRDM_WIDE_ROWCTAS][4096], G = [QRDM_CANDMAX][QRDM_CANDMAX], marks = [n] zeroed once,
+ * swaps = [2 * (2 * QRDM_CANDMAX + 4) + 1] */
+int qrdm_k_gram_wide(const qrdm_prob *p, double *part, double *G, int rows_hint, void *stream);
+int qrdm_k_pick_wide(const qrdm_prob *p, const double *G, int *marks, int *swaps, void *stream);
+int qrdm_k_micro_begin(const qrdm_prob *p, int t, void *stream);
+int qrdm_k_micro_end(const qrdm_prob *p, void *stream);
 const char *qrdm_rt_errstr(int code);
 long long qrdm_rt_launch_count(void);
 double qrdm_rt_fp64_peak(int use_dmma, void *stream);

@@ -50,7 +50,7 @@ def test_argument_errors_return_minus_one(lib, kw, entry, capfd):
 
 
 def test_unsupported_inputs(lib, capfd):
-    assert _call(lib, 4, 4, nb=65) == -102
+    assert _call(lib, 4, 4, nb=257) == -102   # QRDM_NB_MAX = 256 (64 < nb <= 256 runs in micro-panels of 64 columns)
     capfd.readouterr()
 
 
