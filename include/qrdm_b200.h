@@ -26,7 +26,7 @@ extern "C" {
  * LAPACKE_dlarft / LAPACKE_dlarfb_mia, reference src/dlarfb.c:73-86) */
 #define QRDM_ERR_CUDA (-100)       /* CUDA runtime failure (no device, launch error, OOM) */
 #define QRDM_ERR_COMM (-101)       /* NCCL failure in the row-sharded path */
-#define QRDM_ERR_UNSUPPORTED (-102) /* jpvt[j] != 0 on entry (fixed columns), nb > QRDM_NB_MAX */
+#define QRDM_ERR_UNSUPPORTED (-102) /* nb > QRDM_NB_MAX (nb > 64 in the row-sharded and batched entry points) */
 
 /* Threading: the reference keeps no global state (src/dgeqrdm_work.c:650-665, 816-826) and may be called from
  * several host threads at once.  Here the device workspace is per process; every entry point below takes one
@@ -39,12 +39,16 @@ extern "C" {
  *   a              m x n, column-major, lda >= m, HOST memory; overwritten with R (upper
  *                  triangle of the first r = sum(ncols) columns), the Householder vectors below
  *                  it (dgeqrf convention) and the Q'-updated R12/R22 in columns >= r
- *   jpvt[n]        in: all zero (free columns).  out: 1-based permutation
+ *   jpvt[n]        in: zero = free column, non-zero = FIXED column (LAPACK dgeqp3 convention, reference
+ *                  src/dgeqrdm_work.c:592-635): fixed columns are moved to the front with the reference's swap sequence,
+ *                  factored without pivoting, and DM pivoting runs on the rest.  out: 1-based permutation
  *   tau[min(m,n)]  out: reflector scalars, first r entries
  *   ncols[n]       in: ncols[0] = stop rule (0 none, 1 eps*n, 2 eps*sqrt(n), 3 thres[2]);
- *                  out: ncols[it] = columns triangularised in iteration it; revealed rank = sum
+ *                  out: ncols[it] = columns triangularised in DM iteration it; revealed rank = (number of fixed
+ *                  columns) + sum (the reference counts DM iterations only); at least min(m, n) entries
  *   thres          thres[0] = delta (cosine bound), thres[1] = tau_ (norm fraction), [2] = eta
- *   nb             maximum block size / number of candidates, 1..QRDM_NB_MAX
+ *   nb             maximum block size / number of candidates, 1..QRDM_NB_MAX (= 256; above 64 the selected block is
+ *                  factored in micro-panels of 64 columns)
  * Returns info as the reference does (0; -1 after an xerbla-style message for bad arguments;
  * -8/-6/-13 when NaNs reach the block reflector). */
 int dgeqrdm(int matrix_layout, int m, int n, double *a, int lda, int *jpvt, double *tau, int *ncols,
