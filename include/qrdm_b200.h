@@ -131,6 +131,11 @@ typedef struct qrdm_b200_stats {
   /* algorithmic bytes per stage, summed by the host from the mailbox: K1 8mn; K3b 8*m_r*nc;
    * K3d 32*m per exchange; K4 16*m_r*fjb; K2 8*k*n_r; K6 16*m_r*n_c (deferred schedule) or 24*m_r*n_c */
   double stage_bytes[12];
+  /* look-ahead: FLOPs of the pending blocks' pass 2 that the side stream applied beside the selection / panel of the
+   * next block (part of trailing_flops; NOT executed inside the trailing stage, whose time is ms_stage[TRAILING]); the
+   * side kernels' own event time is ms_stage[RANKK] (includes their waits for SMs: they run at the least priority) */
+  double side_flops;
+  long long side_launches;
 } qrdm_b200_stats;
 
 enum {

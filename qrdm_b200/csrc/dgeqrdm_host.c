@@ -49,6 +49,11 @@ typedef struct {
   void *ev_stage[2];
   void *compute_stream, *copy_stream; /* non-blocking streams of the host-pointer entry points */
   void *h2d_stream;                   /* third stream of the batched pipeline (created on first use) */
+  void *side_stream;                  /* look-ahead: pass 2 of the pending block beside the next selection / panel (LEAST priority) */
+  void *hp_stream;                    /* look-ahead: the factorisation itself runs here (GREATEST priority), see factor_device */
+  void *ev_hop[2];                    /* caller's stream -> hp_stream at entry, hp_stream -> caller's stream at exit */
+  void *ev_side[2];                   /* [0] main -> side (stamps are set), [1] side -> main (side update finished) */
+  int side_busy;                      /* a side launch is in flight that the main stream has not waited for yet */
   qrdm_hostio *io;                    /* bounce pipeline for pageable host buffers (created on first use) */
 } qrdm_workspace;
 
@@ -143,6 +148,10 @@ static void shutdown_impl(void) {
   if (w->compute_stream) qrdm_rt_stream_destroy(w->compute_stream);
   if (w->copy_stream) qrdm_rt_stream_destroy(w->copy_stream);
   if (w->h2d_stream) qrdm_rt_stream_destroy(w->h2d_stream);
+  if (w->side_stream) qrdm_rt_stream_destroy(w->side_stream);
+  if (w->hp_stream) qrdm_rt_stream_destroy(w->hp_stream);
+  for (int i = 0; i < 2; ++i) if (w->ev_side[i]) qrdm_rt_event_destroy(w->ev_side[i]);
+  for (int i = 0; i < 2; ++i) if (w->ev_hop[i]) qrdm_rt_event_destroy(w->ev_hop[i]);
   if (w->io) qrdm_hostio_destroy(w->io);
   memset(w, 0, sizeof(*w));
   if (cur >= 0 && cur != w->device) qrdm_rt_set_device(cur);
@@ -178,6 +187,11 @@ static int init_impl(int device) {
   for (int i = 0; i < 2; ++i) CU(qrdm_rt_event_create(&w->ev_stage[i]));
   CU(qrdm_rt_stream_create(&w->compute_stream));
   CU(qrdm_rt_stream_create(&w->copy_stream));
+  CU(qrdm_rt_stream_create_prio(&w->side_stream, 0));
+  CU(qrdm_rt_stream_create_prio(&w->hp_stream, 1));
+  for (int i = 0; i < 2; ++i) CU(qrdm_rt_event_create(&w->ev_side[i]));
+  for (int i = 0; i < 2; ++i) CU(qrdm_rt_event_create(&w->ev_hop[i]));
+  w->side_busy = 0;
   w->ready = 1;
   if (g_profile < 0) {
     const char *e = getenv("QRDM_B200_PROFILE");
@@ -250,7 +264,7 @@ static int g_ev_used = 0, g_ev_created = 0;
 
 static int stage_begin(int stage, void *stream) {
   if (g_profile == 1) return qrdm_rt_event_record(g_ws.ev_stage[0], stream);
-  if (g_profile == 2 && (stage == QRDM_STAGE_PANEL || stage == QRDM_STAGE_VTC) && g_ev_used + 2 <= EV_POOL) {
+  if (g_profile == 2 && (stage == QRDM_STAGE_PANEL || stage == QRDM_STAGE_VTC || stage == QRDM_STAGE_RANKK) && g_ev_used + 2 <= EV_POOL) {
     while (g_ev_created < g_ev_used + 2) {
       int e = qrdm_rt_event_create(&g_ev_pool[g_ev_created]);
       if (e) return e;
@@ -262,7 +276,7 @@ static int stage_begin(int stage, void *stream) {
   return 0;
 }
 static int stage_end(int stage, long long launches_before, void *stream) {
-  if (g_profile == 2 && (stage == QRDM_STAGE_PANEL || stage == QRDM_STAGE_VTC) && g_ev_used + 2 <= EV_POOL) {
+  if (g_profile == 2 && (stage == QRDM_STAGE_PANEL || stage == QRDM_STAGE_VTC || stage == QRDM_STAGE_RANKK) && g_ev_used + 2 <= EV_POOL) {
     int e = qrdm_rt_event_record(g_ev_pool[g_ev_used + 1], stream);
     g_ev_used += 2;
     g_stats.stage_launches[stage] += qrdm_rt_launch_count() - launches_before;
@@ -375,9 +389,37 @@ static int ws_ensure_wide(int n) {
 }
 
 /* The factorisation proper on device-resident data. */
+static int factor_device_impl(int m, int n, double *d_a, int lda, int *d_jpvt, double *d_tau, int *ncols,
+                              const double *thres, int nb, void *stream, qrdm_writeback *wb,
+                              const qrdm_shard *sh, int nfxd_in);
+
+/* The factorisation runs on the library's own GREATEST-priority stream, ordered after everything the caller has put on
+ * `stream` and before everything the caller puts there afterwards (two event hops).  That is what lets the look-ahead's
+ * side stream (LEAST priority, many short CTAs) share the GPU with it: the block scheduler serves the pending CTAs of
+ * the selection / panel kernels first — it even keeps whole SMs free for a panel CTA while side CTAs would still fit
+ * (measured, tools/prio_probe.cu: 120 full-SM CTAs of a high-priority kernel all start within 11 us of their launch
+ * into a saturated GPU, and the low-priority grid carries on on the 28 SMs they leave; with equal priorities they wait
+ * for the whole low grid).  On every exit, error paths included, the caller's stream waits for both streams. */
 static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double *d_tau, int *ncols,
                          const double *thres, int nb, void *stream, qrdm_writeback *wb,
                          const qrdm_shard *sh, int nfxd_in) {
+  int rc = init_impl(-1);
+  if (rc) return rc;
+  qrdm_workspace *w = &g_ws;
+  CU(qrdm_rt_event_record(w->ev_hop[0], stream));
+  CU(qrdm_rt_stream_wait_event(w->hp_stream, w->ev_hop[0]));
+  rc = factor_device_impl(m, n, d_a, lda, d_jpvt, d_tau, ncols, thres, nb, w->hp_stream, wb, sh, nfxd_in);
+  if (w->side_busy) { /* an error return left a side launch in flight */
+    if (qrdm_rt_stream_wait_event(w->hp_stream, w->ev_side[1]) == 0) w->side_busy = 0;
+  }
+  CU(qrdm_rt_event_record(w->ev_hop[1], w->hp_stream));
+  CU(qrdm_rt_stream_wait_event(stream, w->ev_hop[1]));
+  return rc;
+}
+
+static int factor_device_impl(int m, int n, double *d_a, int lda, int *d_jpvt, double *d_tau, int *ncols,
+                              const double *thres, int nb, void *stream, qrdm_writeback *wb,
+                              const qrdm_shard *sh, int nfxd_in) {
   qrdm_workspace *w = &g_ws;
   const double eps = DBL_EPSILON * 0.5; /* dlamch('e'), src/dgeqrdm_work.c:528 */
   /* row-sharded over several GPUs (QRDM_B200_FORCE_MG=1 exercises that path on a 1-rank communicator) */
@@ -424,7 +466,9 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
    * QRDM_B200_LAZY_MIN overrides the threshold (tests force it on tiny matrices). */
   /* measured on B200 (16384^2): the fused kernel saves ~0.5 ms x (size/16384)^2 per iteration against
    * k_vtc + k_rankk, the eager completion costs ~0.09 ms: break-even near a 7000 x 7000 trailing matrix */
-  int lazy_min = 7168;
+  /* with the look-ahead (below) pass 2 of small trailing matrices disappears into the selection / panel window
+   * altogether, which moves the break-even down: 8192^2 84.4 -> 81.7 ms, 16384^2 324.4 -> 322.1 ms with 2048 */
+  int lazy_min = (getenv("QRDM_B200_SIDE") && atoi(getenv("QRDM_B200_SIDE")) == 0) ? 7168 : 2048;
   { const char *e = getenv("QRDM_B200_LAZY_MIN"); if (e) lazy_min = atoi(e); if (lazy_min < 1) lazy_min = 1; }
   /* nb > 64: selection at full width, factorisation in micro-panels of 64 columns (k_wide.cu); eager schedule only */
   const int wide = nb > QRDM_KMAX;
@@ -440,6 +484,30 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
   const int lazy_on = !mg && !wide && !(getenv("QRDM_B200_LAZY") && atoi(getenv("QRDM_B200_LAZY")) == 0);
   int pending = 0, pend_j = 0, stamp = 0;
   double *vcbuf[2] = {w->vc, w->vc + (size_t)w->ldv * 64};
+  /* Look-ahead.  DM selects on the norms AFTER the whole block has been applied, so the next panel cannot
+   * start before pass 1 over the full trailing matrix; what can leave the critical path is pass 2 of the pending block:
+   * as soon as the stamps of the eager set are written (after k_select + the eager completion), the side stream applies
+   * it to the last columns of the matrix (k_rankk, side mode: many short CTAs at the least stream priority) while this
+   * stream (greatest priority) syncs the mailbox and runs the next Gram / pick / permutation / panel — the side CTAs
+   * fill whatever the latency-bound kernels of the chain leave idle.  The next k_fused then makes pass 1 only on those
+   * columns (qrdm_prob::pre_col0).  The share is sized from the idle SM-time of the window:
+   *   QRDM_B200_SIDE_US      microseconds of (nearly) the whole chip before the panel starts            [default 100]
+   *   QRDM_B200_SIDE_COL_US  microseconds per panel column, on the SMs the panel does not occupy        [default 3.3]
+   *   QRDM_B200_SIDE_EFF     side rate per SM relative to k_rankk's 24 TFLOP/s on the whole chip        [default 0.8]
+   * QRDM_B200_SIDE=0 switches the look-ahead off, QRDM_B200_SIDE_PANEL=0 ends the side update before the panel. */
+  int side_on = lazy_on, side_over_panel = 1, side_upc = 1;
+  double side_us = 100.0, side_col_us = 3.3, side_eff = 0.8;
+  { const char *e = getenv("QRDM_B200_SIDE"); if (e && atoi(e) == 0) side_on = 0; }
+  { const char *e = getenv("QRDM_B200_SIDE_US"); if (e) side_us = atof(e); }
+  { const char *e = getenv("QRDM_B200_SIDE_PANEL"); if (e) side_over_panel = atoi(e); }
+  { const char *e = getenv("QRDM_B200_SIDE_COL_US"); if (e) side_col_us = atof(e); }
+  { const char *e = getenv("QRDM_B200_SIDE_EFF"); if (e) side_eff = atof(e); }
+  { const char *e = getenv("QRDM_B200_SIDE_UPC"); if (e && atoi(e) >= 1) side_upc = atoi(e); }
+  int pend_pre = 0; /* first column the side stream owns for the pending block (0: none) */
+  if (w->side_busy) { /* a previous call left early with a side launch in flight: it still uses the workspace */
+    CU(qrdm_rt_stream_wait_event(stream, w->ev_side[1]));
+    w->side_busy = 0;
+  }
 
   memset(&g_stats, 0, sizeof(g_stats));
   g_ev_used = 0;
@@ -518,6 +586,10 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
       STAGE(QRDM_STAGE_GRAM, qrdm_k_gram(&P, 0, m - jr, stream));
       STAGE(QRDM_STAGE_PICK, qrdm_k_pick(&P, stream));
       STAGE(QRDM_STAGE_PERMUTE, qrdm_k_permute(&P, stream));
+      if (w->side_busy && !side_over_panel) { /* the panel needs every SM: the side update ends here */
+        CU(qrdm_rt_stream_wait_event(stream, w->ev_side[1]));
+        w->side_busy = 0;
+      }
       STAGE(QRDM_STAGE_PANEL, qrdm_k_panel(&P, j, stream));
       /* both dimensions must be large as well: with few trailing columns (tall-skinny, C4) the eager set of
        * <= 128 columns is a large share of the matrix and the deferred schedule buys nothing */
@@ -531,11 +603,18 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
         long long lb = qrdm_rt_launch_count();
         CU(stage_begin(QRDM_STAGE_VTC, stream));
         const int bn = pending ? 64 : 128; /* tile width of the partial-W slots */
+        if (w->side_busy) { /* columns >= pend_pre of the pending block come from the side stream */
+          CU(qrdm_rt_stream_wait_event(stream, w->ev_side[1]));
+          w->side_busy = 0;
+        }
+        P.pre_col0 = pending ? pend_pre : 0; /* k_fused / k_tinv / k_wapply share one unit partition, which depends on it */
         if (pending) CU(qrdm_k_fused(&P, j, &vt_stride, &vt_grid, stream)); /* pass 2 of block it-1 + pass 1 of block it */
         else CU(qrdm_k_vtc_only(&P, j, &vt_stride, &vt_grid, stream));
         pending = 0;
         /* lazy: k_wapply also finishes the k new R rows; everything below them waits for the next k_fused */
         if (vt_stride > 0) CU(qrdm_k_w2(&P, j, vt_grid, vt_stride, bn | (lazy ? 1 : 0), stream));
+        P.pre_col0 = 0;
+        pend_pre = 0;
         if (!lazy) CU(qrdm_k_rankk(&P, j, stream));
         CU(stage_end(QRDM_STAGE_VTC, lb, stream));
       }
@@ -637,6 +716,39 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
       STAGE(QRDM_STAGE_VTC, qrdm_k_colupd(&P, 0, j, stream));
       pending = 1;
       pend_j = j;
+      pend_pre = 0;
+      if (side_on) {
+        /* columns for the side stream: the idle SM-time of the window at k_rankk's rate (24 TFLOP/s on the whole chip =
+         * 187500 elements per us at k = 64, i.e. ~1267 per SM and us); never the leading 128 columns behind the block
+         * (eager set, next panel) */
+        const double rows_s = (double)(m - j - 1);
+        const int kmax_next = nb < n - j - 1 ? nb : n - j - 1;
+        double sm_us = side_us * (double)(w->sm_count > 4 ? w->sm_count - 4 : 1);
+        if (side_over_panel) {
+          const int free_sms = w->sm_count - qrdm_k_panel_ctas(&P, m - j - 1);
+          if (free_sms > 0) sm_us += side_col_us * (double)kmax_next * (double)free_sms;
+        }
+        long long nside = rows_s > 0 ? (long long)(sm_us * side_eff * (187500.0 / 148.0) / rows_s) : 0;
+        nside = nside / 32 * 32;
+        int c0s = n - (nside > n ? n : (int)nside);
+        if (c0s < j + 128) c0s = j + 128;
+        if (n - c0s >= 64) {
+          qrdm_prob Ps = P;
+          Ps.side_col0 = c0s;
+          CU(qrdm_rt_event_record(w->ev_side[0], stream));
+          CU(qrdm_rt_stream_wait_event(w->side_stream, w->ev_side[0]));
+          {
+            long long lbs = qrdm_rt_launch_count();
+            CU(stage_begin(QRDM_STAGE_RANKK, w->side_stream));
+            CU(qrdm_k_side(&Ps, j, side_upc, w->side_stream));
+            CU(stage_end(QRDM_STAGE_RANKK, lbs, w->side_stream));
+          }
+          CU(qrdm_rt_event_record(w->ev_side[1], w->side_stream));
+          w->side_busy = 1;
+          pend_pre = c0s;
+          ++g_stats.side_launches;
+        }
+      }
     }
     {
       long long lb = qrdm_rt_launch_count();
@@ -658,6 +770,8 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
       break;
     }
     g_stats.trailing_flops += 4.0 * (double)(m - jr) * (double)(cols - k) * (double)k;
+    if (pend_pre > 0 && pending) /* this block's pass 2 on the columns >= pend_pre went to the side stream (stamped columns aside) */
+      g_stats.side_flops += 2.0 * (double)(m - jr - k) * (double)(n - pend_pre) * (double)k;
     g_stats.stage_bytes[QRDM_STAGE_PANEL] += 16.0 * (double)(m - jr) * (double)k; /* >= 16 m_r k: k <= fjb columns read + written once */
     g_stats.stage_bytes[QRDM_STAGE_NORM_UPDATE] += 8.0 * (double)k * (double)(cols - k);
     g_stats.stage_bytes[QRDM_STAGE_VTC] += (lazy ? 16.0 : 24.0) * (double)(m - jr) * (double)(cols - k);
@@ -683,9 +797,15 @@ static int factor_device(int m, int n, double *d_a, int lda, int *d_jpvt, double
     }
     if (stop_mode && mb->maxnrm * sqrt((double)(cols - k)) <= eta) break; /* :782-785 */
   }
+  if (w->side_busy) {
+    CU(qrdm_rt_stream_wait_event(stream, w->ev_side[1]));
+    w->side_busy = 0;
+  }
   if (pending) { /* early exit (stop rule / error) with a block still deferred: finish it */
     P.vc_prev = vcbuf[(sweep - 1) & 1];
+    P.pre_col0 = pend_pre; /* the side stream's columns are done */
     STAGE(QRDM_STAGE_VTC, qrdm_k_flush(&P, pend_j, stream));
+    P.pre_col0 = 0;
   }
   if (in_scale != 1.0) CU(qrdm_k_scale(&P, 1.0 / in_scale, 1, j, stream)); /* R back to the caller's scale */
   CU(qrdm_rt_event_record(w->ev[1], stream));

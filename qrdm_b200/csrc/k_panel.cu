@@ -818,10 +818,49 @@ extern "C" int qrdm_k_panel_tall_mg(const qrdm_prob* p, int j_host, void* stream
   return es == cudaSuccess ? 0 : (int)es;
 }
 
+static int cl_max_ctas = -1;  // CTAs that fit as whole clusters of PANEL_CL (per device; queried on first use)
+// Rows per CTA (32 x RI) and exchange mode by a measured cost model (us per column, B200, square Gaussian
+// inputs): ~0.3 per RI (the in-CTA sweep) + 0.0045 per CTA (skew / fan-in of the LL exchange); the one-hop
+// exchange (<= 32 CTAs) saves 0.45 (1000 rows: 2.90 -> 2.44), the cluster exchange 0.3 (8192 rows: 3.58 -> 3.27).
+static void panel_plan(int rows, int gmax, int* per_out, int* mode_out) {
+  static const char* e_ag = getenv("QRDM_PANEL_AG");  // experiment switch: 0 disables the one-hop exchange
+  const bool ag_ok = !(e_ag && atoi(e_ag) == 0);
+  const int clmax = cl_max_ctas < 0 ? 0 : cl_max_ctas;
+  int per = 256, mode = 0;
+  double best = 1e30;
+  for (int ri = 1; ri <= 8; ri *= 2) {
+    const int g = (rows + 32 * ri - 1) / (32 * ri);
+    if (g > gmax) continue;
+    const int gpad = (g + PANEL_CL - 1) / PANEL_CL * PANEL_CL;
+    const int md = (ag_ok && g <= 32) ? 1 : (gpad <= clmax ? 2 : 0);
+    const double cost = 0.30 * ri + 0.0045 * g - (md == 1 ? 0.45 : md == 2 ? 0.30 : 0.0);
+    if (cost < best) { best = cost; per = 32 * ri; mode = md; }
+  }
+  const char* e = getenv("QRDM_PANEL_PER");  // experiment switch
+  if (e) {
+    const int v = atoi(e);
+    if ((v == 32 || v == 64 || v == 128 || v == 256) && rows <= v * gmax) {
+      per = v;
+      const int g = (rows + v - 1) / v, gpad = (g + PANEL_CL - 1) / PANEL_CL * PANEL_CL;
+      mode = (ag_ok && g <= 32) ? 1 : (gpad <= clmax ? 2 : 0);
+    }
+  }
+  *per_out = per; *mode_out = mode;
+}
+// SMs the panel of `rows` rows will occupy (one CTA per SM): what the look-ahead's side stream cannot count on
+extern "C" int qrdm_k_panel_ctas(const qrdm_prob* p, int rows) {
+  const int gmax = p->sm_count < QRDM_PANEL_MAXCTA ? p->sm_count : QRDM_PANEL_MAXCTA;
+  if (rows <= 0) return 0;
+  if (rows > 256 * gmax) return gmax;
+  int per = 256, mode = 0;
+  panel_plan(rows, gmax, &per, &mode);
+  const int g = (rows + per - 1) / per;
+  return mode == 2 ? (g + PANEL_CL - 1) / PANEL_CL * PANEL_CL : g;
+}
+
 extern "C" int qrdm_k_panel(const qrdm_prob* p, int j_host, void* stream) {
   static int attr_gen = -1;  // per-device function attributes: re-applied when the library moves to another device
   static int rows_per_cta = 128;
-  static int cl_max_ctas = -1;
   const int smem_cap = 200 * 1024;
   if (attr_gen != qrdm_rt_device_generation()) {
     cudaFuncSetAttribute(k_panel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap);
@@ -834,9 +873,7 @@ extern "C" int qrdm_k_panel(const qrdm_prob* p, int j_host, void* stream) {
   if (rows <= 0) return 0;
   const int gmax = p->sm_count < QRDM_PANEL_MAXCTA ? p->sm_count : QRDM_PANEL_MAXCTA;
   if (rows <= 256 * gmax && !getenv("QRDM_PANEL_NOREG")) {  // register-resident slabs, 32 ... 256 rows per CTA
-    static const char* e_ag = getenv("QRDM_PANEL_AG");  // experiment switches: 0 disables the one-hop exchange
-    static const char* e_cl = getenv("QRDM_PANEL_CL");  //                      0 disables the cluster exchange
-    const bool ag_ok = !(e_ag && atoi(e_ag) == 0);
+    static const char* e_cl = getenv("QRDM_PANEL_CL");  // experiment switch: 0 disables the cluster exchange
     // clusters of PANEL_CL CTAs (MODE 2): how many CTAs can be co-resident as whole clusters (GPC granularity:
     // 33 clusters of 4 = 132 CTAs on a 148-SM B200, only 15 clusters of 8); queried once
     static cudaLaunchAttribute cl_attrs[2];
@@ -862,30 +899,8 @@ extern "C" int qrdm_k_panel(const qrdm_prob* p, int j_host, void* stream) {
         if (cl_max_ctas > 35 * PANEL_CL) cl_max_ctas = 35 * PANEL_CL;  // gather width of the MODE 2 kernel
       }
     }
-    // Rows per CTA (32 x RI) and exchange mode by a measured cost model (us per column, B200, square Gaussian
-    // inputs): ~0.3 per RI (the in-CTA sweep) + 0.0045 per CTA (skew / fan-in of the LL exchange); the one-hop
-    // exchange (<= 32 CTAs) saves 0.45 (1000 rows: 2.90 -> 2.44), the cluster exchange 0.3 (8192 rows: 3.58 -> 3.27).
     int per = 256, mode = 0;
-    {
-      double best = 1e30;
-      for (int ri = 1; ri <= 8; ri *= 2) {
-        const int g = (rows + 32 * ri - 1) / (32 * ri);
-        if (g > gmax) continue;
-        const int gpad = (g + PANEL_CL - 1) / PANEL_CL * PANEL_CL;
-        const int md = (ag_ok && g <= 32) ? 1 : (gpad <= cl_max_ctas ? 2 : 0);
-        const double cost = 0.30 * ri + 0.0045 * g - (md == 1 ? 0.45 : md == 2 ? 0.30 : 0.0);
-        if (cost < best) { best = cost; per = 32 * ri; mode = md; }
-      }
-      static const char* e = getenv("QRDM_PANEL_PER");  // experiment switch
-      if (e) {
-        const int v = atoi(e);
-        if ((v == 32 || v == 64 || v == 128 || v == 256) && rows <= v * gmax) {
-          per = v;
-          const int g = (rows + v - 1) / v, gpad = (g + PANEL_CL - 1) / PANEL_CL * PANEL_CL;
-          mode = (ag_ok && g <= 32) ? 1 : (gpad <= cl_max_ctas ? 2 : 0);
-        }
-      }
-    }
+    panel_plan(rows, gmax, &per, &mode);
     int Gr = (rows + per - 1) / per, rpcr = (rows + Gr - 1) / Gr;
     unsigned epoch_r = panel_next_epoch(g_epoch_reg, 0x400000, 0x7fffff, p, stream);
     qrdm_prob prob_r = *p;

@@ -42,8 +42,15 @@ __device__ __forceinline__ int vt_sw(int col, int rowpair_idx) { return col * VT
 
 struct VtGeom {
   int j, jr, fjb, k, nc, kpad, jal, NCH, CT, voff;  // j: columns done; jr: first active LOCAL row; CT counts the V'V tile
-  long long U;
+  int Tpre;         // k_fused: tiles T >= Tpre already hold the pending update (look-ahead, P.pre_col0): pass 1 only
+  long long U;      // units = CT * NCH
+  long long Usplit; // = Tpre * NCH (== U without look-ahead): units beyond it cost VT_WB instead of VT_WA
+  long long Ctot;   // total cost
 };
+// Relative cost of a k_fused unit with / without phase A (measured: k_fused 2.08 ms against k_vtc 1.20 ms for the same
+// trailing matrix).  The CTAs take contiguous unit ranges of EQUAL COST, so a mix of both kinds stays balanced.
+#define VT_WA 7
+#define VT_WB 4
 __device__ __forceinline__ VtGeom vt_geom(const qrdm_prob& P, int bn = VT_BN) {
   VtGeom g;
   const QrdmGeom q = qrdm_geom(P);
@@ -56,16 +63,31 @@ __device__ __forceinline__ VtGeom vt_geom(const qrdm_prob& P, int bn = VT_BN) {
   g.NCH = (mpad - g.jal) / VT_BK;
   g.CT = 1 + (g.nc > 0 ? (g.nc + bn - 1) / bn : 0);
   g.U = (long long)g.CT * g.NCH;
+  g.Tpre = g.CT;
+  if (P.pre_col0 > 0 && !P.pend && P.sub == 0) {  // first tile whose first column is >= pre_col0
+    const int d = P.pre_col0 - (g.j + g.fjb);
+    const int tp = d <= 0 ? 1 : (d + bn - 1) / bn + 1;
+    if (tp < g.CT) g.Tpre = tp;
+  }
+  g.Usplit = (long long)g.Tpre * g.NCH;
+  g.Ctot = VT_WA * g.Usplit + VT_WB * (g.U - g.Usplit);
   return g;
 }
-__device__ __forceinline__ long long vt_lo(long long U, int G, int b) { return U * b / G; }
+__device__ __forceinline__ long long vt_cost(const VtGeom& ge, long long u) {
+  return u <= ge.Usplit ? VT_WA * u : VT_WA * ge.Usplit + VT_WB * (u - ge.Usplit);
+}
+// first unit of CTA b: the units are cut where the accumulated cost passes b/G of the total (lo(0) = 0, lo(G) = U)
+__device__ __forceinline__ long long vt_lo(const VtGeom& ge, int G, int b) {
+  const long long x = ge.Ctot * b / G;
+  return x <= VT_WA * ge.Usplit ? x / VT_WA : ge.Usplit + (x - VT_WA * ge.Usplit) / VT_WB;
+}
 // first CTA whose unit range reaches into tile T
-__device__ __forceinline__ int vt_bfirst(long long U, int G, int NCH, int T) {
-  const long long X = (long long)T * NCH;
-  int b = (int)(X * G / U);
+__device__ __forceinline__ int vt_bfirst(const VtGeom& ge, int G, int T) {
+  const long long X = (long long)T * ge.NCH;
+  int b = (int)(vt_cost(ge, X) * G / ge.Ctot);
   if (b >= G) b = G - 1;
-  while (b > 0 && vt_lo(U, G, b) > X) --b;
-  while (b + 1 < G && vt_lo(U, G, b + 1) <= X) ++b;
+  while (b > 0 && vt_lo(ge, G, b) > X) --b;
+  while (b + 1 < G && vt_lo(ge, G, b + 1) <= X) ++b;
   return b;
 }
 
@@ -86,7 +108,7 @@ template <bool VEC16, bool FULLK>
 __device__ __forceinline__ void vtc_body(const qrdm_prob& P, const VtGeom& ge, int wslot_stride_cols, double* sm) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
   const int G = gridDim.x, b = blockIdx.x;
-  const long long lo = vt_lo(ge.U, G, b), hi = vt_lo(ge.U, G, b + 1);
+  const long long lo = vt_lo(ge, G, b), hi = vt_lo(ge, G, b + 1);
   if (lo >= hi) return;
   const int MT = FULLK ? 8 : (ge.kpad >> 3);
   const double* Cg = P.a + (size_t)(ge.j + ge.fjb) * P.lda;
@@ -123,7 +145,7 @@ __device__ __forceinline__ void vtc_body(const qrdm_prob& P, const VtGeom& ge, i
     }
   };
   auto flush = [&](int T) {
-    const int slot = b - vt_bfirst(ge.U, G, ge.NCH, T);
+    const int slot = b - vt_bfirst(ge, G, T);
     double* W = P.wp + (size_t)slot * 64 * wslot_stride_cols + (size_t)T * VT_BN;
 #pragma unroll
     for (int mt = 0; mt < 8; ++mt) {
@@ -209,12 +231,12 @@ __global__ void __launch_bounds__(256, 2) k_vtc(qrdm_prob P, int wslot_stride_co
 
 __device__ __forceinline__ int vt_slot_list(const VtGeom& ge, int vt_grid, int T, int* list, int cap) {
   // indices b - bfirst of the CTAs that wrote a partial for tile T, in fixed (ascending) order
-  const int bf = vt_bfirst(ge.U, vt_grid, ge.NCH, T);
+  const int bf = vt_bfirst(ge, vt_grid, T);
   const long long Tend = (long long)(T + 1) * ge.NCH;
   int n = 0;
   (void)cap;
-  for (int b = bf; b < vt_grid && vt_lo(ge.U, vt_grid, b) < Tend && n < cap; ++b)
-    if (vt_lo(ge.U, vt_grid, b + 1) > vt_lo(ge.U, vt_grid, b)) list[n++] = b - bf;
+  for (int b = bf; b < vt_grid && vt_lo(ge, vt_grid, b) < Tend && n < cap; ++b)
+    if (vt_lo(ge, vt_grid, b + 1) > vt_lo(ge, vt_grid, b)) list[n++] = b - bf;
   return n;
 }
 
@@ -462,6 +484,12 @@ __global__ void __launch_bounds__(RK_THREADS, 2) k_rankk(qrdm_prob P) {
     __syncthreads();
     nc = 64 + ncand;
   }
+  // side mode (look-ahead, with P.pend): only the columns >= side_col0, and among them only those nobody else owns —
+  // a column stamped in upd_eager / upd_flag was completed eagerly and may be permuted or factored by the main stream
+  // while this kernel runs, so it is never stored here (not even with its old value)
+  const bool side = !LIST && P.side_col0 > 0;
+  int coff = 0;
+  if (side) { coff = P.side_col0 - (jc + fjb); if (coff < 0) coff = 0; nc -= coff; }
   if (nc <= 0 || k <= 0) return;
   (void)ctrl;
   const int j = qrdm_jr(P, jc);  // first active local row (== jc on a single GPU)
@@ -472,7 +500,7 @@ __global__ void __launch_bounds__(RK_THREADS, 2) k_rankk(qrdm_prob P) {
   const long long U = (long long)RB * CT;
   const long long lo = U * blockIdx.x / gridDim.x, hi = U * (blockIdx.x + 1) / gridDim.x;
   if (lo >= hi) return;
-  double* Cg = P.a + (size_t)(jc + fjb) * P.lda;
+  double* Cg = P.a + (size_t)(jc + fjb + coff) * P.lda;
   const size_t lda = (size_t)P.lda;
   // warp wr owns rows wr*32..+31 of the tile, all 32 columns: DMMA M = columns (4 tiles), N = rows (4)
   // lane element (mt, nt, e): column c0 + mt*8 + g, rows R0 + wr*32 + nt*8 + 2t + e
@@ -492,8 +520,28 @@ __global__ void __launch_bounds__(RK_THREADS, 2) k_rankk(qrdm_prob P) {
       }
       return;
     }
-    const double* src = P.w2 + (size_t)w_q * P.ldw + ct * RK_BN + w_cp;
+    const double* src = P.w2 + (size_t)w_q * P.ldw + coff + ct * RK_BN + w_cp;
+    if (coff & 1) {  // side mode with an odd column offset: the W2 rows are only 8-byte aligned
+      for (int i = 0; i < w_iters; ++i) {
+        cp_async8(dst + i * 8 * RK_LDW, src + (size_t)i * 8 * P.ldw, 8);
+        cp_async8(dst + i * 8 * RK_LDW + 1, src + (size_t)i * 8 * P.ldw + 1, 8);
+      }
+      return;
+    }
     for (int i = 0; i < w_iters; ++i) cp_async16(dst + i * 8 * RK_LDW, src + (size_t)i * 8 * P.ldw, 16);
+  };
+  // side mode: bit mt = the lane's column c0 + mt*8 + g may be stored; bit 4 = every column of the tile may (warp-uniform)
+  auto keep_mask = [&](int ct) -> int {
+    if (!side) return 31;
+    int mk = 0;
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+      const int c = ct * RK_BN + mt * 8 + g;
+      const int col = jc + fjb + coff + c;
+      if (c >= nc || (P.upd_eager[col] != P.stamp && P.upd_flag[col] != P.stamp)) mk |= 1 << mt;
+    }
+    if (__all_sync(0xffffffffu, mk == 15)) mk |= 16;
+    return mk;
   };
   auto issue_v = [&](int rb) {
     const int R0 = jal + rb * RK_BM;
@@ -572,12 +620,12 @@ __global__ void __launch_bounds__(RK_THREADS, 2) k_rankk(qrdm_prob P) {
       }
     }
   };
-  auto store_c = [&](int rb, int ct, double (&src)[4][4][2]) {
+  auto store_c = [&](int rb, int ct, double (&src)[4][4][2], int mk) {
     if (LIST) { list_rw(rb, ct, src, true); return; }
     if (P.debug & 1) return;
     const int R0 = jal + rb * RK_BM, c0 = ct * RK_BN;
     double* base = Cg + (size_t)c0 * lda + R0 + lane_off;
-    if (interior(rb, ct)) {
+    if (interior(rb, ct) && (mk & 16)) {
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
@@ -591,8 +639,8 @@ __global__ void __launch_bounds__(RK_THREADS, 2) k_rankk(qrdm_prob P) {
         for (int nt = 0; nt < 4; ++nt) {
           const int r = R0 + wr * 32 + nt * 8 + 2 * t;
           double* ptr = base + (size_t)(mt * 8) * lda + nt * 8;
-          if (c < nc && r >= j && r < P.m) ptr[0] = src[mt][nt][0];
-          if (c < nc && r + 1 >= j && r + 1 < P.m) ptr[1] = src[mt][nt][1];
+          if (c < nc && ((mk >> mt) & 1) && r >= j && r < P.m) ptr[0] = src[mt][nt][0];
+          if (c < nc && ((mk >> mt) & 1) && r + 1 >= j && r + 1 < P.m) ptr[1] = src[mt][nt][1];
         }
       }
     }
@@ -603,7 +651,7 @@ __global__ void __launch_bounds__(RK_THREADS, 2) k_rankk(qrdm_prob P) {
   const int a_off = t * RK_LDW + g;             // A[m=c][k=q] = W[q][c]
   const int b_off = t * RK_LDV + wr * 32 + g;   // B[k=q][n=r] = V[r][q]
   // one unit: X holds C(u) (prefetched), Y receives C(u+1) while the MMAs of u run
-  auto step = [&](double (&X)[4][4][2], double (&Y)[4][4][2]) {
+  auto step = [&](double (&X)[4][4][2], double (&Y)[4][4][2], int& mkX, int& mkY) {
     cp_async_wait<0>();
     __syncthreads();  // W(u) (and V) landed for everyone; everyone is done with W(u-1)
     const bool more = left > 1;
@@ -630,9 +678,9 @@ __global__ void __launch_bounds__(RK_THREADS, 2) k_rankk(qrdm_prob P) {
     // The prefetch of C(u+1) is issued only after the first use of X (see k_fused: a wait for X that sits
     // behind freshly issued loads on the same scoreboard costs a full memory latency per unit).
     ksteps(0, 2);
-    if (more) load_c(nrb, nct, Y);
+    if (more) { load_c(nrb, nct, Y); mkY = keep_mask(nct); }
     ksteps(2, kpad / 4);
-    store_c(rb, ct, X);
+    store_c(rb, ct, X, mkX);
     if (more && nrb != rb) {
       __syncthreads();  // all warps finished reading the old V tile
       issue_v(nrb);
@@ -647,9 +695,10 @@ __global__ void __launch_bounds__(RK_THREADS, 2) k_rankk(qrdm_prob P) {
   issue_w(ct, 0);
   cp_async_commit();
   load_c(rb, ct, accA);
+  int mkA = keep_mask(ct), mkB = 31;
   while (left > 0) {
-    step(accA, accB);
-    if (left > 0) step(accB, accA);
+    step(accA, accB, mkA, mkB);
+    if (left > 0) step(accB, accA, mkB, mkA);
   }
 }
 
@@ -724,9 +773,10 @@ __device__ __forceinline__ void fused_body(const qrdm_prob& P, const VtGeom& ge,
   const qrdm_ctrl* ctrl = P.ctrl;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
   const int G = gridDim.x, b = blockIdx.x;
-  const long long lo = vt_lo(ge.U, G, b), hi = vt_lo(ge.U, G, b + 1);
+  const long long lo = vt_lo(ge, G, b), hi = vt_lo(ge, G, b + 1);
   if (lo >= hi) return;
   const int kp_prev = (ctrl->pend_k + 7) & ~7, pend_c0 = ctrl->pend_c0;
+  const int pre_c0 = (P.pre_col0 > 0 && P.pre_col0 < P.n) ? P.pre_col0 : P.n;  // look-ahead: columns >= pre_c0 are done
   const int ccol0 = ge.j + ge.fjb;  // first trailing column
   const int jrow = ge.jr;           // first active row
   const size_t lda = (size_t)P.lda;
@@ -748,7 +798,7 @@ __device__ __forceinline__ void fused_body(const qrdm_prob& P, const VtGeom& ge,
       const int q = id >> 4, rp = (id & 15) * 2;
       cp_async16(Vn + q * FU_LDN + rp, Vn_g + (size_t)q * P.ldv + r0 + rp, 16);
     }
-    if (T > 0)
+    if (T > 0 && T < ge.Tpre)
       for (int id = tid; id < kp_prev * 16; id += FU_THREADS) {
         const int q = id >> 4, rp = (id & 15) * 2;
         cp_async16(Vp + q * FU_LDP + rp, P.vc_prev + (size_t)q * P.ldv + r0 + rp, 16);
@@ -760,7 +810,7 @@ __device__ __forceinline__ void fused_body(const qrdm_prob& P, const VtGeom& ge,
       const int q = e >> 6, c = e & 63;
       const int col = ccol0 + c0 + c, idx = col - pend_c0;
       double v = 0.0;
-      if (idx >= 0 && col < P.n && P.upd_eager[col] != P.stamp && P.upd_flag[col] != P.stamp) v = P.w2[(size_t)q * P.ldw + idx];
+      if (idx >= 0 && col < pre_c0 && P.upd_eager[col] != P.stamp && P.upd_flag[col] != P.stamp) v = P.w2[(size_t)q * P.ldw + idx];
       W2s[q * FU_LDW + c] = v;
     }
   };
@@ -832,7 +882,7 @@ __device__ __forceinline__ void fused_body(const qrdm_prob& P, const VtGeom& ge,
     }
   };
   auto flush = [&](int T) {
-    const int slot = b - vt_bfirst(ge.U, G, ge.NCH, T);
+    const int slot = b - vt_bfirst(ge, G, T);
     double* W = P.wp + (size_t)slot * 64 * wslot_stride_cols + (size_t)T * FU_BN;
 #pragma unroll
     for (int mt = 0; mt < 8; ++mt) {
@@ -850,7 +900,7 @@ __device__ __forceinline__ void fused_body(const qrdm_prob& P, const VtGeom& ge,
   int left = (int)(hi - lo), st = 0;
   int T = (int)(lo / ge.NCH), chunk = (int)(lo - (long long)T * ge.NCH);
   int curT = T;
-  if (curT > 0) load_w2(curT);
+  if (curT > 0 && curT < ge.Tpre) load_w2(curT);
   issue(T, chunk, 0);
   cp_async_commit();
   const int KSA = FULLK ? 16 : (kp_prev >> 2);  // k-steps of phase A
@@ -862,8 +912,10 @@ __device__ __forceinline__ void fused_body(const qrdm_prob& P, const VtGeom& ge,
     if (T != curT) {
       flush(curT);
       curT = T;
-      load_w2(T);
-      __syncthreads();
+      if (T < ge.Tpre) {
+        load_w2(T);
+        __syncthreads();
+      }
     }
     int nT = T, nchunk = chunk + 1;
     if (nchunk == ge.NCH) { nchunk = 0; ++nT; }
@@ -874,10 +926,11 @@ __device__ __forceinline__ void fused_body(const qrdm_prob& P, const VtGeom& ge,
     const double* Vp = stage0 + (size_t)st * FU_STAGE_DOUBLES;
     const double* Vn = Vp + 64 * FU_LDP;
     // phase B: acc[q][c] += sum_r V_cur[r][q] X[c][r]     (M = q, N = columns, K = rows {2t+e})
-    auto phase_b = [&]() {
+    auto phase_b = [&](bool prefetch_mid) {  // prefetch_mid (a literal): fetch C(u+1) after the first row group
       const double* ap = Vn + g * FU_LDN + 2 * t;
 #pragma unroll
       for (int rt = 0; rt < 4; ++rt) {
+        if (prefetch_mid && rt == 1 && left > 1) load_c(nT, nchunk, Y);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {  // 4 q-tiles at a time
           double2 a[4];
@@ -906,7 +959,7 @@ __device__ __forceinline__ void fused_body(const qrdm_prob& P, const VtGeom& ge,
     // first use of X that sits behind freshly issued loads of Y — which is what the merge point of the two
     // paths looked like to the compiler — waits a full memory latency per unit (ncu: 8-10% of all stall
     // samples on one DMMA).
-    if (T > 0) {
+    if (T > 0 && T < ge.Tpre) {
       // phase A: X[c][r] += sum_q W2[q][c] V_prev[r][q]   (M = columns, N = rows, K = q)
       const double* ap = W2s + t * FU_LDW + wid * 16 + g;
       const double* bp = Vp + t * FU_LDP + g;
@@ -927,9 +980,13 @@ __device__ __forceinline__ void fused_body(const qrdm_prob& P, const VtGeom& ge,
       for (int ks = 0; ks < KSA; ++ks) kstep(ks);
       store_c(T, chunk, X);
       if (left > 1) load_c(nT, nchunk, Y);
-      phase_b();
+      phase_b(false);
+    } else if (T > 0) {
+      // look-ahead tile: the pending update was applied by the side stream (k_rankk, side mode) — pass 1 only.
+      // Same rule as above: the prefetch goes out after the first use of X, the rest of the MMAs cover its latency.
+      phase_b(true);
     } else {
-      phase_b();
+      phase_b(false);
       if (left > 1) load_c(nT, nchunk, Y);
     }
     T = nT; chunk = nchunk; st ^= 1; --left;
@@ -947,7 +1004,10 @@ __device__ __forceinline__ void fused_body(const qrdm_prob& P, const VtGeom& ge,
 template <bool VEC16>
 __global__ void __launch_bounds__(FU_THREADS, 2) k_fused(qrdm_prob P, int wslot_stride_cols) {
   extern __shared__ __align__(16) double sm[];
-  const VtGeom ge = vt_geom(P, FU_BN);
+  // the geometry lives in shared memory: the body needs most of it only at tile changes, and 255 registers are all taken
+  __shared__ VtGeom ge;
+  if (threadIdx.x == 0) ge = vt_geom(P, FU_BN);
+  __syncthreads();
   if (ge.k <= 0 || ge.nc <= 0 || ge.jr >= P.m) return;
   if (ge.kpad == 64 && P.ctrl->pend_k > 56) fused_body<VEC16, true>(P, ge, wslot_stride_cols, sm);  // the common case: both blocks full, no predicates
   else fused_body<VEC16, false>(P, ge, wslot_stride_cols, sm);
@@ -1021,7 +1081,7 @@ __global__ void __launch_bounds__(256) k_w2mask(qrdm_prob P) {
   const int c0p = ctrl->pend_c0;
   const int col = c0p + blockIdx.x * 256 + threadIdx.x;
   if (col >= P.n) return;
-  if (P.upd_eager[col] == P.stamp || P.upd_flag[col] == P.stamp)
+  if (P.upd_eager[col] == P.stamp || P.upd_flag[col] == P.stamp || (P.pre_col0 > 0 && col >= P.pre_col0))
     for (int q = 0; q < 64; ++q) P.w2[(size_t)q * P.ldw + (col - c0p)] = 0.0;
 }
 
@@ -1180,6 +1240,33 @@ extern "C" int qrdm_k_colupd(const qrdm_prob* p, int mode, int j_host, void* str
     q.vc_prev = p->vc;
     k_colupd<<<dim3(gx, gx >= 64 ? 4 : 16), CU_ROWS, 0, (cudaStream_t)stream>>>(q);
   }
+  QRDM_LAUNCH_CHECK();
+  return 0;
+}
+
+// Look-ahead: pass 2 of the pending block on the columns >= p->side_col0, launched on the LEAST-priority
+// side stream while the main stream runs the next block's Gram / pick / permutation / panel.  Called in the iteration
+// that created the pending block (its V is still p->vc), after k_select and the eager completion (all stamps are set).
+// Unlike every other launch of k_rankk this one is NOT persistent: ~units_per_cta units (128 rows x 32 columns, ~6.5 us
+// each) per CTA, so that CTA slots come free every few microseconds and the block scheduler can hand them to the main
+// stream's kernels the moment those are launched.
+extern "C" int qrdm_k_side(const qrdm_prob* p, int j_host, int units_per_cta, void* stream) {
+  trailing_attrs();
+  cudaStream_t s = (cudaStream_t)stream;
+  const int ncols = p->n - p->side_col0;
+  if (p->side_col0 <= 0 || ncols <= 0) return 0;
+  const int jal = host_jr(p, j_host) & ~(QRDM_ROWALIGN - 1);
+  if (p->m - jal <= 0) return 0;
+  qrdm_prob q = *p;
+  q.pend = 1;
+  q.pre_col0 = 0;
+  const long long units = (long long)((ncols + RK_BN - 1) / RK_BN) * ((p->m - jal + RK_BM - 1) / RK_BM);
+  if (units_per_cta < 1) units_per_cta = 1;
+  long long grid = (units + units_per_cta - 1) / units_per_cta;
+  if (grid < 1) grid = 1;
+  if (grid > 0x7fffffffLL) grid = 0x7fffffffLL;
+  if (p->vec16) k_rankk<true, false><<<(unsigned)grid, RK_THREADS, RK_SMEM, s>>>(q);
+  else k_rankk<false, false><<<(unsigned)grid, RK_THREADS, RK_SMEM, s>>>(q);
   QRDM_LAUNCH_CHECK();
   return 0;
 }

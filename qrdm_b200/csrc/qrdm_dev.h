@@ -117,6 +117,12 @@ typedef struct qrdm_prob {
   int keep_jpvt;      /* 1: d_jpvt holds the caller's initial permutation, K1 must not reset it to the identity */
   double thres0;      /* the panel's initial absolute stop threshold 5e-14 (src/dgeqr2.c:40) times the power-of-two input
                          scale (1 unless the matrix was pre-scaled, see qrdm_k_scale) */
+  /* look-ahead of the deferred update: while the selection / Gram / pick / permutation (and, on SMs the
+   * panel leaves free, the panel) of the next block run, a second stream applies pass 2 of the pending block to the
+   * columns >= side_col0 that nobody touches in that window (k_rankk in side mode skips stamped columns); the next
+   * k_fused / k_tinv / k_wapply are told so through pre_col0: those columns need pass 1 only. */
+  int side_col0;      /* side launch: first absolute column it owns (0 = not a side launch) */
+  int pre_col0;       /* k_fused & co: columns >= pre_col0 already hold the pending update (0 = none) */
   double inv_scale;   /* 1 / that scale (MUST be 1.0, never 0, for an unscaled matrix): the norm downdate evaluates its
                          sum of squares in the CALLER's scale, where the reference's unscaled sum (src/dgeqrdm_work.c:81-86)
                          underflows to 0 for ~1e-200 entries (no downdate) and overflows for ~1e+200 (forced recompute) */
@@ -133,6 +139,7 @@ int qrdm_k_gram(const qrdm_prob *p, int of_v, int rows_hint, void *stream); /* K
 int qrdm_k_pick(const qrdm_prob *p, void *stream);                          /* K3c + plan */
 int qrdm_k_permute(const qrdm_prob *p, void *stream);                       /* K3d */
 int qrdm_k_panel(const qrdm_prob *p, int j_host, void *stream);             /* K4 */
+int qrdm_k_panel_ctas(const qrdm_prob *p, int rows);  /* SMs the panel kernel will occupy for a panel of `rows` rows */
 int qrdm_k_trailing(const qrdm_prob *p, int j_host, void *stream);          /* K6: vtc, wsolve, rankk */
 int qrdm_k_norm_update(const qrdm_prob *p, int j_host, void *stream);       /* K2 */
 int qrdm_k_norm_recompute_all(const qrdm_prob *p, int j_host, void *stream); /* exact norms of every column right of the block (end of the fixed-column phase, src/dgeqrdm_work.c:672-682) */
@@ -152,6 +159,8 @@ int qrdm_k_rankk(const qrdm_prob *p, int j_host, void *stream);    /* pass 2 alo
 int qrdm_k_colupd(const qrdm_prob *p, int mode, int j_host, void *stream); /* 0: eager set (DMMA, gathered), 1: flagged-norm list (FMA) */
 int qrdm_k_norm_update_lazy(const qrdm_prob *p, int j_host, void *stream);
 int qrdm_k_flush(const qrdm_prob *p, int j_host, void *stream);    /* apply a pending block to the whole trailing matrix */
+/* look-ahead: pass 2 of the pending block on the columns >= p->side_col0 (unstamped ones), ~units_per_cta units per CTA */
+int qrdm_k_side(const qrdm_prob *p, int j_host, int units_per_cta, void *stream);
 int qrdm_k_vc_build(const qrdm_prob *p, const double *d_af, int ldf, int j0, int k, void *stream); /* Vc + ctrl of one block of a factored matrix */
 int qrdm_k_skinny_update(const qrdm_prob *p, int rows_hint, void *stream); /* tall panel: sub-panel -> rest of panel */
 int qrdm_k_skinny_part(const qrdm_prob *p, int rows_hint, void *stream);   /* row-sharded: before the all-reduce */
@@ -182,6 +191,7 @@ int qrdm_rt_h2d_2d(void *dst, size_t dpitch, const void *src, size_t spitch, siz
 int qrdm_rt_d2h_2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height, void *stream);
 int qrdm_rt_sync(void *stream);
 int qrdm_rt_stream_create(void **stream);
+int qrdm_rt_stream_create_prio(void **stream, int prio); /* > 0: greatest priority of the device, <= 0: least */
 int qrdm_rt_is_pinned(const void *ptr);
 int qrdm_rt_stream_wait_event(void *stream, void *ev);
 int qrdm_rt_event_create(void **ev);

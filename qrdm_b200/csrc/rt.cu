@@ -32,6 +32,15 @@ int qrdm_rt_d2h_2d(void* dst, size_t dpitch, const void* src, size_t spitch, siz
   return (int)cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
 }
 int qrdm_rt_stream_create(void** stream) { return (int)cudaStreamCreateWithFlags((cudaStream_t*)stream, cudaStreamNonBlocking); }
+// prio > 0: the device's greatest priority, prio <= 0: its least (B200: 0 = least, also the default; -5 = greatest).
+// The block scheduler serves pending CTAs of the highest-priority stream first and keeps SMs free for them even when a
+// lower-priority CTA would fit (tools/prio_probe.cu): the look-ahead's side stream lives on that.
+int qrdm_rt_stream_create_prio(void** stream, int prio) {
+  int least = 0, greatest = 0;
+  cudaError_t e = cudaDeviceGetStreamPriorityRange(&least, &greatest);
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaStreamCreateWithPriority((cudaStream_t*)stream, cudaStreamNonBlocking, prio > 0 ? greatest : least);
+}
 int qrdm_rt_is_pinned(const void* ptr) {
   cudaPointerAttributes at;
   if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return 0; }

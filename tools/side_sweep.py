@@ -1,0 +1,50 @@
+"""Look-ahead sweep on one device-resident matrix: ms_total / stage times per environment setting.
+usage: python tools/side_sweep.py m n "K=V,K=V;K=V;..." [reps]      (settings separated by ';', empty = defaults)"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import qrdm_b200
+
+m, n = int(sys.argv[1]), int(sys.argv[2])
+settings = sys.argv[3].split(";") if len(sys.argv) > 3 else [""]
+reps = int(sys.argv[4]) if len(sys.argv) > 4 else 2
+KEYS = ("QRDM_B200_SIDE", "QRDM_B200_SIDE_US", "QRDM_B200_SIDE_PANEL", "QRDM_B200_SIDE_COL_US", "QRDM_B200_SIDE_UPC", "QRDM_B200_SIDE_EFF", "QRDM_B200_LAZY_MIN",
+        "QRDM_B200_LAZY", "QRDM_PANEL_CL", "QRDM_PANEL_PER")
+dev = torch.device("cuda", 0)
+gen = torch.Generator(device=dev)
+gen.manual_seed(1234)
+A0 = torch.randn((n, m), dtype=torch.float64, device=dev, generator=gen)
+A = A0.clone()
+jp = torch.zeros(n, dtype=torch.int32, device=dev)
+tau = torch.zeros(min(m, n), dtype=torch.float64, device=dev)
+qrdm_b200.set_profile(2)
+ref = None
+for s in settings:
+    for k in KEYS:
+        os.environ.pop(k, None)
+    for kv in filter(None, s.split(",")):
+        k, v = kv.split("=")
+        os.environ[k] = v
+    best = None
+    for r in range(reps + 1):  # first run of a setting is a warm-up
+        A.copy_(A0)
+        torch.cuda.synchronize()
+        info, nc = qrdm_b200.dgeqrdm_device(A, m, n, m, jp, tau)
+        st = qrdm_b200.stats()
+        if r > 0 and (best is None or st["ms_total"] < best["ms_total"]):
+            best = st
+    st = best
+    d = torch.abs(torch.diagonal(A.T)[: min(m, n)]).clone()
+    same = ""
+    if ref is None:
+        ref = (jp.clone(), d, A.clone())
+    else:
+        same = (f" jpvt_equal={bool(torch.equal(jp, ref[0]))} max_rel_diag_diff={float(torch.max(torch.abs(d - ref[1]) / ref[1])):.1e}"
+                f" bitwise={bool(torch.equal(A, ref[2]))}")
+    ms = st["ms_stage"]
+    tf = st["trailing_flops"] / ((ms["trailing"] + ms["rankk"]) * 1e-3) / 1e12
+    print(f"{m}x{n} [{s or 'defaults'}]: info {info} rank {int(nc.sum())} ms_total {st['ms_total']:.2f} panel {ms['panel']:.2f} "
+          f"trailing {ms['trailing']:.2f} side {ms['rankk']:.2f} ms -> K6 {tf:.2f} TFLOP/s, launches {st['launches']}{same}", flush=True)
