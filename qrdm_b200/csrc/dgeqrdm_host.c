@@ -175,10 +175,10 @@ static int init_impl(int device) {
   CU(qrdm_rt_malloc((void **)&w->ctrl, sizeof(qrdm_ctrl)));
   CU(qrdm_rt_malloc((void **)&w->gram_part, sizeof(double) * 4096 * QRDM_GRAM_MAXCTA));
   CU(qrdm_rt_malloc((void **)&w->gram, sizeof(double) * 4096));
-  CU(qrdm_rt_malloc((void **)&w->panel_part, 16 * 2 * QRDM_PANEL_MAXCTA * 64)); /* LL packets */
-  CU(qrdm_rt_memset(w->panel_part, 0, 16 * 2 * QRDM_PANEL_MAXCTA * 64, NULL));
-  CU(qrdm_rt_malloc((void **)&w->panel_row, 16 * 2 * 128));
-  CU(qrdm_rt_memset(w->panel_row, 0, 16 * 2 * 128, NULL));
+  CU(qrdm_rt_malloc((void **)&w->panel_part, 16 * (QRDM_PANEL_PART_PKTS + QRDM_PANEL_GPART_PKTS))); /* LL packets */
+  CU(qrdm_rt_memset(w->panel_part, 0, 16 * (QRDM_PANEL_PART_PKTS + QRDM_PANEL_GPART_PKTS), NULL));
+  CU(qrdm_rt_malloc((void **)&w->panel_row, 16 * (QRDM_PANEL_ROW_PKTS + QRDM_PANEL_GROW_PKTS)));
+  CU(qrdm_rt_memset(w->panel_row, 0, 16 * (QRDM_PANEL_ROW_PKTS + QRDM_PANEL_GROW_PKTS), NULL));
   CU(qrdm_rt_malloc((void **)&w->mg_buf, sizeof(double) * (512 + 128 * 2 * 160)));
   CU(qrdm_rt_malloc((void **)&w->mg_cnt, 64));
   CU(qrdm_rt_memset(w->mg_cnt, 0, 64, NULL));

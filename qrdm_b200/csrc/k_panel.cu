@@ -495,6 +495,376 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_reg(qrdm_prob P, int
 }
 
 // ---------------------------------------------------------------------------------------------
+// Grouped register panel: ONE cross-CTA exchange per group of up to S columns instead of one per column.
+//
+// The per-column kernel above spends its 3.9 us per column (16384 rows, 128 CTAs) almost entirely on the exchange that
+// turns the CTAs' partial sums into [||x||^2, x'C] — 64 dependent exchanges per panel.  But everything a reflector
+// needs besides the slab itself is a handful of inner products, and inner products can be carried through a
+// Householder update algebraically.  For a group that starts at panel column i0 the exchange delivers, for its columns
+// u = 0..S-1 and every remaining column jj >= i0,
+//     M[u][jj]  = sum over rows R > i0 of  c_{i0+u}[R] c_jj[R]        (S rows of the panel's Gram matrix)
+//     Rw[u][jj] = c_jj[i0+u]                                          (the group's S pivot rows)
+// and every CTA then runs the same scalar recurrence on these replicated numbers.  Step t (column col = i0 + t) takes
+// alpha = Rw[t][col], ||x||^2 = M[t][col], forms beta, tau, scale and w_jj = tau (Rw[t][jj] + scale M[t][jj]) exactly
+// as dlarfg/dlarf do (src/dlarfg.c:120-185, src/dlarf.c:173-184), sweeps the slab registers with H = I - tau v v', and
+// carries the state to step t + 1 (v = scale x below the diagonal, sums over R > col):
+//     Rw'[u][jj] = Rw[u][jj] - (scale Rw[u][col]) w_jj                                              (the sweep, row i0+u)
+//     M~[u][jj]  = M[u][jj] - w_jj (scale M[t][cu]) - w_cu (scale M[t][jj]) + w_cu w_jj scale^2 M[t][col]   (cu = i0+u)
+//     M'[u][jj]  = M~[u][jj] - Rw'[t+1][cu] Rw'[t+1][jj]                            (row col + 1 leaves the sums)
+// The pivot-row recurrence repeats the sweep's own operations, so alpha is bit-identical to the slab's entry; the
+// downdated sums are exact up to eps times the ORIGINAL column norms, i.e. they lose accuracy only when a column
+// loses most of its norm inside the group.  That is tested: if ||x||^2 comes out below 2^-7 of the column's sum at the
+// start of the group, the group ends there and a fresh exchange delivers exact sums (same decision on every CTA:
+// all of them hold the same numbers).  Error amplification is therefore bounded by ~2^7 in ||x||^2 (1.4e-14
+// relative) and ~11 in w; Gaussian panels never trip the test, DM-selected panels rarely (their columns are far from
+// parallel by construction).  Exchanges are numbered (tag, buffer parity) by a counter, not by the column index.
+// MODE 1 (<= 32 CTAs) / 2 (clusters) as in k_panel_reg; larger grids without clusters keep the per-column kernel.
+#define GRP_GUARD 0x1p-7
+__device__ __forceinline__ void bar_sync_64() { asm volatile("bar.sync 1, 64;\n" ::: "memory"); }  // warps 0-1 only
+template <int RI, int MODE, int S>
+__global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_grp(qrdm_prob P, int rpc, unsigned epoch) {
+  static_assert(MODE == 1 || MODE == 2, "all-gather exchange only");
+  static_assert(S == 2 || S == 4, "group width");
+  constexpr int NV = S * 64;                 // values per exchange
+  constexpr int NGRP = PANEL_THREADS / NV;   // gather groups (4 / 2)
+  constexpr int GB = 6;                      // packet loads a thread keeps in flight
+  __shared__ double red[NGRP][NV];
+  __shared__ double cpart[MODE == 2 ? 2 : 1][MODE == 2 ? PANEL_CL : 1][NV];  // leader's copy: [buf][rank][value]
+  // the group's Gram rows / pivot rows, double-buffered by step parity (a step reads [t & 1], writes the rows u > t of [~t & 1])
+  __shared__ double Mx[2][S][64], Rw[2][S][64];
+  __shared__ double Wt[S][64 + S], SC[S][4];  // per step: w (0 for columns <= i and beyond the panel), and {tau, beta, scale}
+  __shared__ double SEFF[64], BETA[64];   // per finished column: the scale of its reflector (1 when tau = 0) and beta
+  __shared__ int ginfo[2];                // reflectors produced by the group, DM stop flag
+  __shared__ double xbuf[S][32 * RI];
+  qrdm_ctrl* ctrl = P.ctrl;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int j = ctrl->j, fjb = ctrl->fjb;
+  if (fjb <= 0) return;
+  const bool forced = ctrl->forced != 0;
+  const int rows = P.m - j, lda = P.lda;
+  const int G = gridDim.x, b = blockIdx.x;
+  const int r0 = min(rows, b * rpc), r1 = min(rows, r0 + rpc), nr = r1 - r0;
+  double* Ap = P.a + (size_t)j * lda + j;
+  LLPacket* part = reinterpret_cast<LLPacket*>(P.panel_part) + QRDM_PANEL_PART_PKTS;  // [2][MAXCTA][NV]
+  LLPacket* brow = reinterpret_cast<LLPacket*>(P.panel_row) + QRDM_PANEL_ROW_PKTS;    // [2][NV]
+  const unsigned tag_base = epoch << 8;
+  const int crank = MODE == 2 ? (int)cooperative_groups::this_cluster().block_rank() : 0;
+  const int pub = MODE == 2 ? b / PANEL_CL : b, GP = MODE == 2 ? G / PANEL_CL : G;
+  double* cpart_leader = MODE == 2 ? cooperative_groups::this_cluster().map_shared_rank(&cpart[0][0][0], 0) : nullptr;
+  if (MODE == 2) cooperative_groups::this_cluster().sync();  // DSMEM rule, see k_panel_reg
+
+  double reg[RI][4];  // [ri][c]: row r0 + lane + 32*ri, column wid + 16*c
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int ri = 0; ri < RI; ++ri) {
+      const int r = lane + 32 * ri, jj = wid + 16 * c;
+      reg[ri][c] = (r < nr && jj < fjb) ? Ap[(size_t)jj * lda + r0 + r] : 0.0;
+    }
+  double xg[S][RI];  // this thread's rows of the group's columns (private copy, swept along with the slab)
+
+  // ---- local part of exchange e for the group that starts at column i0: partial Gram rows + the pivot rows ----
+  auto contribute = [&](int i0, int sg, int e) {
+    const int buf = e & 1;
+    const unsigned tag = tag_base + e + 1;
+#pragma unroll
+    for (int u = 0; u < S; ++u) {  // the group's columns through smem (their owner warps hold them)
+      const int cu = i0 + u;
+      if (u < sg && wid == (cu & 15)) {
+        const int cs = cu >> 4;  // (selects, not a dynamic index: the slab must stay in registers)
+#pragma unroll
+        for (int ri = 0; ri < RI; ++ri)
+          xbuf[u][lane + 32 * ri] = cs == 0 ? reg[ri][0] : (cs == 1 ? reg[ri][1] : (cs == 2 ? reg[ri][2] : reg[ri][3]));
+      }
+    }
+    __syncthreads();
+    double acc[S][4];
+#pragma unroll
+    for (int u = 0; u < S; ++u)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[u][c] = 0.0;
+#pragma unroll
+    for (int ri = 0; ri < RI; ++ri) {
+      const int r = lane + 32 * ri, R = r0 + r;
+#pragma unroll
+      for (int u = 0; u < S; ++u) xg[u][ri] = (u < sg && r < nr) ? xbuf[u][r] : 0.0;
+      if (r < nr && R >= i0) {
+        if (R > i0) {
+#pragma unroll
+          for (int u = 0; u < S; ++u)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[u][c] = fma(xg[u][ri], reg[ri][c], acc[u][c]);
+        }
+        if (R < i0 + sg) {  // pivot row R - i0 of the group
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int jj = wid + 16 * c;
+            if (jj >= i0 && jj < fjb) ll_store(&brow[(size_t)buf * NV + (R - i0) * 64 + jj], reg[ri][c], tag);
+          }
+        }
+      }
+    }
+    // Transposing warp reduction of the 4S accumulators: each butterfly stage halves the number of values a lane
+    // carries (it keeps the half selected by its lane bit and adds the partner's partial of that half), so the 4S
+    // sums cost 4S shuffles instead of 5 x 4S, and they end up on 4S different lanes, which publish in parallel.
+    {
+      constexpr int NA = 4 * S;
+      double a[NA];
+#pragma unroll
+      for (int u = 0; u < S; ++u)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) a[u * 4 + c] = acc[u][c];
+      int idx = 0;  // index of the value this lane ends up with
+#pragma unroll
+      for (int half = NA / 2, o = 16; half >= 1; half >>= 1, o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int q = 0; q < half; ++q) {
+          const double send = up ? a[q] : a[q + half];
+          const double keep = up ? a[q + half] : a[q];
+          a[q] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+        idx = idx * 2 + (up ? 1 : 0);
+      }
+      // remaining lane bits (2 for S = 2, 1 for S = 4): plain butterfly on the single value left
+#pragma unroll
+      for (int o = (S == 4 ? 1 : 2); o >= 1; o >>= 1) a[0] += __shfl_xor_sync(0xffffffffu, a[0], o);
+      const int u = idx >> 2, jj = wid + 16 * (idx & 3);
+      const bool first = (lane & (S == 4 ? 1 : 3)) == 0;  // one of the lanes that hold the same total
+      if (first && u < sg && jj >= i0 && jj < fjb) {
+        if (MODE == 2) cpart_leader[((size_t)buf * PANEL_CL + crank) * NV + u * 64 + jj] = a[0];
+        else ll_store(&part[((size_t)buf * QRDM_PANEL_MAXCTA + b) * NV + u * 64 + jj], a[0], tag);
+      }
+    }
+    if (MODE == 2) {
+      cooperative_groups::this_cluster().sync();
+      if (crank == 0 && tid < NV) {
+        const int u = tid >> 6, jj = tid & 63;
+        if (u < sg && jj >= i0 && jj < fjb) {
+          double t = 0.0;
+#pragma unroll
+          for (int r = 0; r < PANEL_CL; ++r) t += cpart[buf][r][tid];
+          ll_store(&part[((size_t)buf * QRDM_PANEL_MAXCTA + pub) * NV + tid], t, tag);
+        }
+      }
+    }
+  };
+  // ---- gather exchange e: the same packets added in the same order everywhere => identical M / Rw in every CTA.
+  // MODE 1: every CTA reads all G x NV packets.  MODE 2: that all-gather is L2-bandwidth bound (124 CTAs x 31
+  // publishers x 256 packets x 16 B = 15.7 MB per exchange), so the CTAs of a cluster share it: CTA r totals the r-th
+  // quarter of the values and stores its totals into the Mx of all four CTAs through DSMEM (+ one cluster barrier) ----
+  constexpr int QV = MODE == 2 ? NV / PANEL_CL : NV;   // values this CTA totals
+  constexpr int QGRP = PANEL_THREADS / QV;             // publisher groups (threads per value)
+  double* mx_peer[PANEL_CL];
+#pragma unroll
+  for (int rr = 0; rr < PANEL_CL; ++rr)
+    mx_peer[rr] = MODE == 2 ? cooperative_groups::this_cluster().map_shared_rank(&Mx[0][0][0], rr) : &Mx[0][0][0];
+  double* redq = &red[0][0];  // [QGRP][QV], same storage
+  auto gather = [&](int i0, int sg, int e) {
+    const int buf = e & 1;
+    const unsigned tag = tag_base + e + 1;
+    const int xq = tid % QV, grp = tid / QV;
+    const int x = (MODE == 2 ? crank * QV : 0) + xq, u = x >> 6, jj = x & 63;
+    const bool live = u < sg && jj >= i0 && jj < fjb;
+    double v = 0.0;
+    if (live) {
+      const LLPacket* base = &part[(size_t)buf * QRDM_PANEL_MAXCTA * NV + x];
+      for (int c0 = grp; c0 < GP; c0 += QGRP * GB) {  // publishers grp, grp + QGRP, ...: GB loads in flight
+        unsigned lo[GB], t0[GB], hi[GB], t1[GB];
+#pragma unroll
+        for (int q = 0; q < GB; ++q) {
+          const int c = c0 + q * QGRP;
+          if (c < GP)
+            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];\n"
+                         : "=r"(lo[q]), "=r"(t0[q]), "=r"(hi[q]), "=r"(t1[q]) : "l"(base + (size_t)c * NV) : "memory");
+        }
+#pragma unroll
+        for (int q = 0; q < GB; ++q) {
+          const int c = c0 + q * QGRP;
+          if (c < GP) {
+            unsigned spins = 0;
+            while (t0[q] != tag || t1[q] != tag) {
+              asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];\n"
+                           : "=r"(lo[q]), "=r"(t0[q]), "=r"(hi[q]), "=r"(t1[q]) : "l"(base + (size_t)c * NV) : "memory");
+              if (++spins > LL_SPIN_LIMIT) __trap();
+            }
+            v += __longlong_as_double((long long)(((unsigned long long)hi[q] << 32) | lo[q]));
+          }
+        }
+      }
+    }
+    redq[grp * QV + xq] = v;
+    if (tid < NV) {  // pivot row i0 + u' (rows beyond the panel do not exist: zero); every CTA reads all of them
+      const int u2 = tid >> 6, j2 = tid & 63;
+      double rv = 0.0;
+      if (u2 < sg && j2 >= i0 && j2 < fjb && i0 + u2 < rows) rv = ll_load(&brow[(size_t)buf * NV + tid], tag);
+      Rw[0][u2][j2] = rv;
+    }
+    __syncthreads();
+    if (tid < QV) {
+      double t = redq[tid];
+#pragma unroll
+      for (int q = 1; q < QGRP; ++q) t += redq[q * QV + tid];
+      const int xo = (MODE == 2 ? crank * QV : 0) + tid;  // index into Mx[0] viewed as [NV]
+#pragma unroll
+      for (int rr = 0; rr < (MODE == 2 ? PANEL_CL : 1); ++rr) mx_peer[rr][xo] = t;
+    }
+    if (MODE == 2) cooperative_groups::this_cluster().sync();
+    else __syncthreads();
+  };
+
+  const bool cont = ctrl->micro_t > 0;
+  double thres2 = cont ? ctrl->micro_thres2 : P.thres0 * P.thres0;  // (reference src/dgeqr2.c:40)^2; kept by warps 0-1
+  int k = fjb, e = 0, i0 = 0;
+  bool stopped = false;
+  long long tph[6] = {0, 0, 0, 0, 0, 0};  // QRDM_B200_DEBUG & 8: per-phase cycle counts of one CTA
+  const bool timing = (P.debug & 8) && b == (G > 40 ? 40 : 0) && tid == 0;
+  long long tq0 = timing ? clock64() : 0;
+#define GRP_TICK(slot) do { if (timing) { const long long tq = clock64(); tph[slot] += tq - tq0; tq0 = tq; } } while (0)
+  while (i0 < fjb && !stopped) {
+    const int sg = min(S, fjb - i0);
+    contribute(i0, sg, e);  // (single call site: the lambda must be inlined, it works on the register slab)
+    GRP_TICK(0);
+    gather(i0, sg, e);
+    GRP_TICK(1);
+    // ---- the scalar recurrence of the whole group, on replicated numbers only (no slab access): warps 0-1, one
+    // 64-thread barrier per step; thread jj carries column jj and recomputes what it needs of the group's own columns ----
+    if (tid < 64) {
+      const int jj = tid;
+      int t = 0;
+      bool stop = false;
+      double d0[S];  // the group columns' own sums at the start of the group
+#pragma unroll
+      for (int u = 0; u < S; ++u) d0[u] = (u < sg) ? Mx[0][u][i0 + u] : 0.0;
+      for (; t < sg; ++t) {
+        const int i = i0 + t, pb = t & 1;
+        const double alpha = Rw[pb][t][i], xn2 = Mx[pb][t][i];
+        // a column that lost most of its norm inside the group: its downdated sums are no longer trustworthy
+        double d0t = d0[0];
+#pragma unroll
+        for (int u = 1; u < S; ++u) d0t = (t == u) ? d0[u] : d0t;
+        if (t > 0 && !(xn2 >= GRP_GUARD * d0t)) break;
+        const int len = rows - i;
+        double tau = 0.0, beta = alpha, scale = 1.0;
+        if (len > 1) {
+          if ((i > 0 || cont) && xn2 < thres2 && !forced) { stop = true; break; }  // DM early stop: column i left untouched
+          if (xn2 != 0.0) {  // dlarfg_mia, src/dlarfg.c:120-185: one sqrt, two divisions
+            const double h = sqrt(fma(alpha, alpha, xn2));
+            beta = (alpha >= 0.0) ? -h : h;
+            tau = (beta - alpha) / beta;
+            scale = 1.0 / (alpha - beta);
+          }
+        }
+        if (i == 0 && !cont && fjb > 1 && P.tau_ > 0.0) { const double th = P.tau_ * fabs(beta); thres2 = th * th; }
+        if (jj == 0) {
+          SC[t][0] = tau; SC[t][1] = beta; SC[t][2] = scale;
+          SEFF[i] = tau != 0.0 ? scale : 1.0; BETA[i] = beta;
+          if (b == 0) {
+            P.tau[j + i] = tau;
+            if (tau != tau && ctrl->err == 0) ctrl->err = -8;  // LAPACKE_dlarft's NaN screen of tau
+          }
+        }
+        if (!(jj > i && jj < fjb)) Wt[t][jj] = 0.0;  // finished / own / absent columns: the sweep's FMA leaves them alone
+        if (jj < S) Wt[t][64 + jj] = 0.0;
+        if (jj > i && jj < fjb) {
+          const double w_j = __dmul_rn(tau, __fma_rn(Mx[pb][t][jj], scale, Rw[pb][t][jj]));  // tau (c_jj[i] + scale x'c_jj) = tau v'c_jj
+          Wt[t][jj] = w_j;
+          if (t + 1 < sg) {
+            const double sc = tau != 0.0 ? scale : 0.0;  // tau == 0: H = I, only the row leaves the sums
+            const double vs = tau != 0.0 ? scale : 1.0;
+            const double sv_j = __dmul_rn(sc, Mx[pb][t][jj]), vv = sc * sc * xn2;
+            // row i0 + t + 1 after H_i, for this column and (below) for the group's columns
+            const double vr1 = Rw[pb][t + 1][i] * vs;
+            const double r1_j = __fma_rn(-vr1, w_j, Rw[pb][t + 1][jj]);
+#pragma unroll
+            for (int u = 1; u < S; ++u)
+              if (u > t && u < sg) {
+                const int cu = i0 + u;
+                const double w_u = __dmul_rn(tau, __fma_rn(Mx[pb][t][cu], scale, Rw[pb][t][cu]));
+                const double sv_u = __dmul_rn(sc, Mx[pb][t][cu]);
+                const double r1_u = __fma_rn(-vr1, w_u, Rw[pb][t + 1][cu]);
+                const double vr = Rw[pb][u][i] * vs;
+                Rw[pb ^ 1][u][jj] = __fma_rn(-vr, w_j, Rw[pb][u][jj]);  // the sweep's own operation on the replicated row
+                double mnew = Mx[pb][u][jj] - w_j * sv_u - w_u * sv_j + w_u * w_j * vv;
+                mnew -= r1_u * r1_j;
+                Mx[pb ^ 1][u][jj] = mnew;
+              }
+          }
+        }
+        bar_sync_64();
+      }
+      if (jj == 0) { ginfo[0] = t; ginfo[1] = stop ? 1 : 0; }
+    }
+    GRP_TICK(2);
+    __syncthreads();
+    GRP_TICK(3);
+    const int nsteps = ginfo[0];
+    stopped = ginfo[1] != 0;
+    // ---- apply the group's reflectors to the slab registers, one after the other, no barrier in between.  The code
+    // is kept lean on purpose (16 warps issue every instruction of it): unconditional FMAs against w = 0 for the
+    // columns that must not change; a reflector's own column keeps the raw x in the slab (its private copy xg feeds
+    // the later steps) and is scaled / gets beta only when the slab is written back (SEFF, BETA) ----
+#pragma unroll
+    for (int t = 0; t < S; ++t) {
+      if (t < nsteps) {
+        const int i = i0 + t;
+        const double seff = SC[t][0] != 0.0 ? SC[t][2] : 1.0;
+        double wreg[4], wg[S];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) wreg[c] = Wt[t][wid + 16 * c];
+#pragma unroll
+        for (int u = 0; u < S; ++u) wg[u] = u > t ? Wt[t][i0 + u] : 0.0;
+#pragma unroll
+        for (int ri = 0; ri < RI; ++ri) {
+          const int r = lane + 32 * ri, R = r0 + r;
+          // rows beyond this CTA's slab hold zeros in xg, so R > i needs no r < nr test
+          const double v = R > i ? xg[t][ri] * seff : ((R == i && r < nr) ? 1.0 : 0.0);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) reg[ri][c] = fma(-v, wreg[c], reg[ri][c]);
+#pragma unroll
+          for (int u = 0; u < S; ++u)
+            if (u > t) xg[u][ri] = fma(-v, wg[u], xg[u][ri]);
+        }
+      }
+    }
+    GRP_TICK(4);
+    i0 += nsteps;
+    if (stopped) k = i0;
+    ++e;
+  }
+#undef GRP_TICK
+  if (timing && j == 640)
+    printf("panel_grp<S=%d> j=%d G=%d rpc=%d fjb=%d exchanges=%d cycles: contribute %lld gather %lld recurrence %lld sync %lld sweeps %lld\n",
+           S, j, G, rpc, fjb, e, tph[0], tph[1], tph[2], tph[3], tph[4]);
+  __syncthreads();
+  if (b == 0 && tid == 0) { ctrl->fjb_cmp = k; ctrl->micro_thres2 = thres2; }
+
+  // ---- write the slab back and emit Vc ----
+  const int kpad = (k + 7) & ~7;
+  const int jal = j & ~(QRDM_ROWALIGN - 1);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int jj = wid + 16 * c;
+    const double sf = jj < k ? SEFF[jj] : 1.0, bt = jj < k ? BETA[jj] : 0.0;
+#pragma unroll
+    for (int ri = 0; ri < RI; ++ri) {
+      const int r = lane + 32 * ri, R = r0 + r;
+      double val = reg[ri][c];
+      if (jj < k) val = R > jj ? val * sf : (R == jj ? bt : val);  // the reflector itself: v below the diagonal, beta on it
+      if (r < nr && jj < fjb) Ap[(size_t)jj * lda + R] = val;
+      if (r < nr && jj < kpad) {
+        double v = 0.0;
+        if (jj < k) v = (R > jj) ? val : (R == jj ? 1.0 : 0.0);
+        P.vc[(size_t)jj * P.ldv + j + R] = v;
+      }
+    }
+    if (b == 0 && jj < kpad)
+      for (int g = jal + lane; g < j; g += 32) P.vc[(size_t)jj * P.ldv + g] = 0.0;
+  }
+  if (MODE == 2) cooperative_groups::this_cluster().sync();  // no CTA of a cluster leaves while its shared memory may still be addressed
+}
+
+// ---------------------------------------------------------------------------------------------
 // Sub-panel kernel of the blocked tall panel: QRDM_TALL_B (= 8) columns, slab in global memory.
 // With so few columns the row dimension is what has to be parallel: threads <-> rows (coalesced,
 // several independent rows in flight per thread), the <= 8 column values of a row live in registers
@@ -775,6 +1145,18 @@ static unsigned panel_next_epoch(unsigned& e, unsigned lo, unsigned hi, const qr
   return e;
 }
 static unsigned g_epoch_tall = 0, g_epoch_plain = 0x200000, g_epoch_reg = 0x400000;
+// the grouped register panel has its own packet regions (behind the per-column ones) and its own epoch range [2^23, 2^24)
+static unsigned g_epoch_grp = 0x800000;
+static unsigned panel_grp_epoch(const qrdm_prob* p, void* stream) {
+  if (g_epoch_grp + 1 >= 0xffffffu) {
+    cudaMemsetAsync(reinterpret_cast<LLPacket*>(p->panel_part) + QRDM_PANEL_PART_PKTS, 0, (size_t)16 * QRDM_PANEL_GPART_PKTS, (cudaStream_t)stream);
+    cudaMemsetAsync(reinterpret_cast<LLPacket*>(p->panel_row) + QRDM_PANEL_ROW_PKTS, 0, (size_t)16 * QRDM_PANEL_GROW_PKTS, (cudaStream_t)stream);
+    g_epoch_grp = 0x800000;
+  } else {
+    ++g_epoch_grp;
+  }
+  return g_epoch_grp;
+}
 // dynamic shared memory of the slab-resident sub-panel kernel for `rpc` rows per CTA, or 0 when the slab does not fit
 #define TALL_SLAB_CAP (200 * 1024)
 static size_t tall_slab_bytes(int rpc) {
@@ -902,6 +1284,33 @@ extern "C" int qrdm_k_panel(const qrdm_prob* p, int j_host, void* stream) {
     int per = 256, mode = 0;
     panel_plan(rows, gmax, &per, &mode);
     int Gr = (rows + per - 1) / per, rpcr = (rows + Gr - 1) / Gr;
+    // columns per exchange: 2 (default) or 4 = the grouped kernel k_panel_grp, 1 = one exchange per column (k_panel_reg)
+    const char* e_s = getenv("QRDM_PANEL_S");
+    int grp_s = (mode == 0) ? 1 : (e_s ? atoi(e_s) : 2);
+    if (per == 256) grp_s = 1;  // 256-row slabs + the group's private columns and accumulators do not fit in 128 registers
+    if (grp_s == 2 || grp_s == 4) {
+      unsigned epoch_g = panel_grp_epoch(p, stream);
+      qrdm_prob prob_g = *p;
+      void* args_g[] = {(void*)&prob_g, (void*)&rpcr, (void*)&epoch_g};
+#define PANEL_GFN(MODE, S) (per == 32 ? (void*)k_panel_grp<1, MODE, S> : per == 64 ? (void*)k_panel_grp<2, MODE, S> \
+                            : per == 128 ? (void*)k_panel_grp<4, MODE, S> : (void*)k_panel_grp<8, MODE, S>)
+      if (mode == 2) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((Gr + PANEL_CL - 1) / PANEL_CL * PANEL_CL);  // padded with CTAs that own no rows
+        cfg.blockDim = dim3(PANEL_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = (cudaStream_t)stream;
+        cfg.attrs = cl_attrs; cfg.numAttrs = 2;
+        const cudaError_t e2 = cudaLaunchKernelExC(&cfg, grp_s == 2 ? PANEL_GFN(2, 2) : PANEL_GFN(2, 4), args_g);
+        if (e2 == cudaSuccess) { ++g_qrdm_launches; return 0; }
+        (void)cudaGetLastError();  // fall through to the per-column kernels below (they handle a failing cluster launch)
+      } else {
+        cudaError_t eg = cudaLaunchCooperativeKernel(grp_s == 2 ? PANEL_GFN(1, 2) : PANEL_GFN(1, 4), dim3(Gr), dim3(PANEL_THREADS),
+                                                     args_g, 0, (cudaStream_t)stream);
+        ++g_qrdm_launches;
+        return eg == cudaSuccess ? 0 : (int)eg;
+      }
+#undef PANEL_GFN
+    }
     unsigned epoch_r = panel_next_epoch(g_epoch_reg, 0x400000, 0x7fffff, p, stream);
     qrdm_prob prob_r = *p;
     void* args_r[] = {(void*)&prob_r, (void*)&rpcr, (void*)&epoch_r};

@@ -19,6 +19,13 @@ extern "C" {
 #define QRDM_SELCAP 1024   /* capacity of the top-k candidate list in k_select */
 #define QRDM_GRAM_MAXCTA 296
 #define QRDM_PANEL_MAXCTA 148
+/* LL packet buffers of the panel kernels (16-byte packets): the per-column kernels use the first region of each buffer,
+ * the grouped kernel (k_panel_grp: one exchange per QRDM_PANEL_SMAX columns at most) the second */
+#define QRDM_PANEL_SMAX 4
+#define QRDM_PANEL_PART_PKTS (2 * QRDM_PANEL_MAXCTA * 64)
+#define QRDM_PANEL_GPART_PKTS (2 * QRDM_PANEL_MAXCTA * 64 * QRDM_PANEL_SMAX)
+#define QRDM_PANEL_ROW_PKTS (2 * 128)
+#define QRDM_PANEL_GROW_PKTS (2 * 64 * QRDM_PANEL_SMAX)
 #define QRDM_ERR_INTERNAL (-103) /* planner overflow: cannot happen for nb <= QRDM_KMAX */
 #define QRDM_TALL_B 8     /* sub-panel width of the blocked panel used when the slab does not fit on chip */
 #define QRDM_ROWALIGN 32   /* row tiles of the trailing kernels start at multiples of this */

@@ -12,7 +12,7 @@ m, n = int(sys.argv[1]), int(sys.argv[2])
 settings = sys.argv[3].split(";") if len(sys.argv) > 3 else [""]
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 2
 KEYS = ("QRDM_B200_SIDE", "QRDM_B200_SIDE_US", "QRDM_B200_SIDE_PANEL", "QRDM_B200_SIDE_COL_US", "QRDM_B200_SIDE_UPC", "QRDM_B200_SIDE_EFF", "QRDM_B200_LAZY_MIN",
-        "QRDM_B200_LAZY", "QRDM_PANEL_CL", "QRDM_PANEL_PER")
+        "QRDM_B200_LAZY", "QRDM_PANEL_CL", "QRDM_PANEL_PER", "QRDM_PANEL_S")
 dev = torch.device("cuda", 0)
 gen = torch.Generator(device=dev)
 gen.manual_seed(1234)
