@@ -521,6 +521,15 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_reg(qrdm_prob P, int
 // MODE 1 (<= 32 CTAs) / 2 (clusters) as in k_panel_reg; larger grids without clusters keep the per-column kernel.
 #define GRP_GUARD 0x1p-7
 __device__ __forceinline__ void bar_sync_64() { asm volatile("bar.sync 1, 64;\n" ::: "memory"); }  // warps 0-1 only
+// w_c = tau v'c = tau (c[i] + scale x'c) for a column with pivot-row entry r and sum m; and the carry of a Gram entry
+// through H_i (see the header of k_panel_grp).  Fixed rounding: both phases of the recurrence call exactly these.
+__device__ __forceinline__ double grp_w(double tau, double scale, double m, double r) { return __dmul_rn(tau, __fma_rn(m, scale, r)); }
+__device__ __forceinline__ double grp_m_update(double m_uj, double w_j, double sv_j, double r1_j, double w_u, double sv_u, double r1_u, double vv) {
+  double t = __fma_rn(-w_j, sv_u, m_uj);
+  t = __fma_rn(-w_u, sv_j, t);
+  t = __fma_rn(__dmul_rn(w_u, w_j), vv, t);
+  return __fma_rn(-r1_u, r1_j, t);
+}
 template <int RI, int MODE, int S>
 __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_grp(qrdm_prob P, int rpc, unsigned epoch) {
   static_assert(MODE == 1 || MODE == 2, "all-gather exchange only");
@@ -531,8 +540,9 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_grp(qrdm_prob P, int
   __shared__ double red[NGRP][NV];
   __shared__ double cpart[MODE == 2 ? 2 : 1][MODE == 2 ? PANEL_CL : 1][NV];  // leader's copy: [buf][rank][value]
   // the group's Gram rows / pivot rows, double-buffered by step parity (a step reads [t & 1], writes the rows u > t of [~t & 1])
-  __shared__ double Mx[2][S][64], Rw[2][S][64];
-  __shared__ double Wt[S][64 + S], SC[S][4];  // per step: w (0 for columns <= i and beyond the panel), and {tau, beta, scale}
+  __shared__ double Mx[S][64], Rw[S][64];  // the group's Gram rows / pivot rows as delivered by the exchange
+  __shared__ double Wt[S][64 + S], SC[S][4], SCX[S][2];  // per step: w (0 for columns <= i and beyond the panel), {tau, beta, scale, vv}, {vr1, sc}
+  __shared__ double GW[S][S], GSV[S][S], GR1[S][S], GVR[S][S];  // per step, per group column u: w_u, sv_u, r1_u, vr_u
   __shared__ double SEFF[64], BETA[64];   // per finished column: the scale of its reflector (1 when tau = 0) and beta
   __shared__ int ginfo[2];                // reflectors produced by the group, DM stop flag
   __shared__ double xbuf[S][32 * RI];
@@ -658,7 +668,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_grp(qrdm_prob P, int
   double* mx_peer[PANEL_CL];
 #pragma unroll
   for (int rr = 0; rr < PANEL_CL; ++rr)
-    mx_peer[rr] = MODE == 2 ? cooperative_groups::this_cluster().map_shared_rank(&Mx[0][0][0], rr) : &Mx[0][0][0];
+    mx_peer[rr] = MODE == 2 ? cooperative_groups::this_cluster().map_shared_rank(&Mx[0][0], rr) : &Mx[0][0];
   double* redq = &red[0][0];  // [QGRP][QV], same storage
   auto gather = [&](int i0, int sg, int e) {
     const int buf = e & 1;
@@ -698,14 +708,14 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_grp(qrdm_prob P, int
       const int u2 = tid >> 6, j2 = tid & 63;
       double rv = 0.0;
       if (u2 < sg && j2 >= i0 && j2 < fjb && i0 + u2 < rows) rv = ll_load(&brow[(size_t)buf * NV + tid], tag);
-      Rw[0][u2][j2] = rv;
+      Rw[u2][j2] = rv;
     }
     __syncthreads();
     if (tid < QV) {
       double t = redq[tid];
 #pragma unroll
       for (int q = 1; q < QGRP; ++q) t += redq[q * QV + tid];
-      const int xo = (MODE == 2 ? crank * QV : 0) + tid;  // index into Mx[0] viewed as [NV]
+      const int xo = (MODE == 2 ? crank * QV : 0) + tid;  // index into Mx viewed as [NV]
 #pragma unroll
       for (int rr = 0; rr < (MODE == 2 ? PANEL_CL : 1); ++rr) mx_peer[rr][xo] = t;
     }
@@ -727,73 +737,100 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_grp(qrdm_prob P, int
     GRP_TICK(0);
     gather(i0, sg, e);
     GRP_TICK(1);
-    // ---- the scalar recurrence of the whole group, on replicated numbers only (no slab access): warps 0-1, one
-    // 64-thread barrier per step; thread jj carries column jj and recomputes what it needs of the group's own columns ----
+    // ---- the scalar recurrence of the whole group, on replicated numbers only (no slab access), in two phases.
+    // Phase 1 (warp 0, critical path): the reflector scalars of all steps depend only on the S x S block of the
+    // group's own columns; lane (u, u') carries M[u][cu'] and Rw[u][cu'] in registers and fetches what it needs of
+    // row t by shuffles — no shared-memory round trip, no barrier between steps.  Per step it publishes the scalars and
+    // the group-column terms (w_u, sv_u, r1_u, vr_u) that every column's update needs.
+    // Phase 2 (warps 0-1, one thread per column): each column runs its own S-step recurrence in registers against
+    // those published terms and produces w for the sweep.  Both phases evaluate grp_w / grp_m_update with the same
+    // rounding, so a group column's phase-2 values are bit-identical to the block's. ----
     if (tid < 64) {
       const int jj = tid;
-      int t = 0;
-      bool stop = false;
-      double d0[S];  // the group columns' own sums at the start of the group
+      double m[S], rw[S];
 #pragma unroll
-      for (int u = 0; u < S; ++u) d0[u] = (u < sg) ? Mx[0][u][i0 + u] : 0.0;
-      for (; t < sg; ++t) {
-        const int i = i0 + t, pb = t & 1;
-        const double alpha = Rw[pb][t][i], xn2 = Mx[pb][t][i];
-        // a column that lost most of its norm inside the group: its downdated sums are no longer trustworthy
-        double d0t = d0[0];
+      for (int u = 0; u < S; ++u) { m[u] = Mx[u][jj]; rw[u] = Rw[u][jj]; }
+      if (wid == 0) {
+        const int u = lane / S, up = lane % S;
+        const bool inblk = lane < S * S && u < sg && up < sg;
+        double gm = inblk ? Mx[u][i0 + up] : 0.0, grw = inblk ? Rw[u][i0 + up] : 0.0;
+        const double gm0 = gm;
+        int t = 0;
+        bool stop = false, go = true;
 #pragma unroll
-        for (int u = 1; u < S; ++u) d0t = (t == u) ? d0[u] : d0t;
-        if (t > 0 && !(xn2 >= GRP_GUARD * d0t)) break;
-        const int len = rows - i;
-        double tau = 0.0, beta = alpha, scale = 1.0;
-        if (len > 1) {
-          if ((i > 0 || cont) && xn2 < thres2 && !forced) { stop = true; break; }  // DM early stop: column i left untouched
-          if (xn2 != 0.0) {  // dlarfg_mia, src/dlarfg.c:120-185: one sqrt, two divisions
-            const double h = sqrt(fma(alpha, alpha, xn2));
-            beta = (alpha >= 0.0) ? -h : h;
-            tau = (beta - alpha) / beta;
-            scale = 1.0 / (alpha - beta);
+        for (int tt = 0; tt < S; ++tt) {
+          if (tt < sg && go) {
+            const int i = i0 + tt;
+            const double alpha = __shfl_sync(0xffffffffu, grw, tt * S + tt), xn2 = __shfl_sync(0xffffffffu, gm, tt * S + tt);
+            const double d0t = __shfl_sync(0xffffffffu, gm0, tt * S + tt);
+            // a column that lost most of its norm inside the group: its downdated sums are no longer trustworthy
+            if (tt > 0 && !(xn2 >= GRP_GUARD * d0t)) go = false;
+            const int len = rows - i;
+            if (go && len > 1 && (i > 0 || cont) && xn2 < thres2 && !forced) { stop = true; go = false; }  // DM early stop
+            if (go) {
+              double tau = 0.0, beta = alpha, scale = 1.0;
+              if (len > 1 && xn2 != 0.0) {  // dlarfg_mia, src/dlarfg.c:120-185: one sqrt, two divisions
+                const double h = sqrt(fma(alpha, alpha, xn2));
+                beta = (alpha >= 0.0) ? -h : h;
+                tau = (beta - alpha) / beta;
+                scale = 1.0 / (alpha - beta);
+              }
+              if (i == 0 && !cont && fjb > 1 && P.tau_ > 0.0) { const double th = P.tau_ * fabs(beta); thres2 = th * th; }
+              const double sc = tau != 0.0 ? scale : 0.0;  // tau == 0: H = I, only the row leaves the sums
+              const double vs = tau != 0.0 ? scale : 1.0;
+              const double vv = sc * sc * xn2;
+              // row tt of the block for this lane's two columns, row tt + 1, and column i of rows u and tt + 1
+              const double Mt_u = __shfl_sync(0xffffffffu, gm, (tt * S + u) & 31), Mt_up = __shfl_sync(0xffffffffu, gm, tt * S + up);
+              const double Rt_u = __shfl_sync(0xffffffffu, grw, (tt * S + u) & 31), Rt_up = __shfl_sync(0xffffffffu, grw, tt * S + up);
+              const double R1_u = __shfl_sync(0xffffffffu, grw, ((tt + 1) * S + u) & 31), R1_up = __shfl_sync(0xffffffffu, grw, ((tt + 1) * S + up) & 31);
+              const double Ru_i = __shfl_sync(0xffffffffu, grw, (u * S + tt) & 31), R1_i = __shfl_sync(0xffffffffu, grw, ((tt + 1) * S + tt) & 31);
+              const double vr1 = R1_i * vs, vr_u = Ru_i * vs;
+              const double w_u = grp_w(tau, scale, Mt_u, Rt_u), w_up = grp_w(tau, scale, Mt_up, Rt_up);
+              const double sv_u = __dmul_rn(sc, Mt_u), sv_up = __dmul_rn(sc, Mt_up);
+              const double r1_u = __fma_rn(-vr1, w_u, R1_u), r1_up = __fma_rn(-vr1, w_up, R1_up);
+              if (lane == 0) {
+                SC[tt][0] = tau; SC[tt][1] = beta; SC[tt][2] = scale; SC[tt][3] = vv;
+                SCX[tt][0] = vr1; SCX[tt][1] = sc;
+                SEFF[i] = vs; BETA[i] = beta;
+                if (b == 0) {
+                  P.tau[j + i] = tau;
+                  if (tau != tau && ctrl->err == 0) ctrl->err = -8;  // LAPACKE_dlarft's NaN screen of tau
+                }
+              }
+              if (lane < S * S && up == 0) { GW[tt][u] = w_u; GSV[tt][u] = sv_u; GR1[tt][u] = r1_u; GVR[tt][u] = vr_u; }
+              if (u > tt && up > tt) {  // the block after H_i, row i0 + tt + 1 out of the sums
+                grw = __fma_rn(-vr_u, w_up, grw);
+                gm = grp_m_update(gm, w_up, sv_up, r1_up, w_u, sv_u, r1_u, vv);
+              }
+              t = tt + 1;
+            }
           }
         }
-        if (i == 0 && !cont && fjb > 1 && P.tau_ > 0.0) { const double th = P.tau_ * fabs(beta); thres2 = th * th; }
-        if (jj == 0) {
-          SC[t][0] = tau; SC[t][1] = beta; SC[t][2] = scale;
-          SEFF[i] = tau != 0.0 ? scale : 1.0; BETA[i] = beta;
-          if (b == 0) {
-            P.tau[j + i] = tau;
-            if (tau != tau && ctrl->err == 0) ctrl->err = -8;  // LAPACKE_dlarft's NaN screen of tau
-          }
-        }
-        if (!(jj > i && jj < fjb)) Wt[t][jj] = 0.0;  // finished / own / absent columns: the sweep's FMA leaves them alone
-        if (jj < S) Wt[t][64 + jj] = 0.0;
-        if (jj > i && jj < fjb) {
-          const double w_j = __dmul_rn(tau, __fma_rn(Mx[pb][t][jj], scale, Rw[pb][t][jj]));  // tau (c_jj[i] + scale x'c_jj) = tau v'c_jj
+        if (lane == 0) { ginfo[0] = t; ginfo[1] = stop ? 1 : 0; }
+      }
+      if (timing) { tph[5] += clock64() - tq0; }
+      bar_sync_64();
+      const int nst = ginfo[0];
+#pragma unroll
+      for (int t = 0; t < S; ++t) {
+        if (t < nst) {
+          const int i = i0 + t;
+          const double tau = SC[t][0], scale = SC[t][2], vv = SC[t][3], vr1 = SCX[t][0], sc = SCX[t][1];
+          const double w_j = (jj > i && jj < fjb) ? grp_w(tau, scale, m[t], rw[t]) : 0.0;  // 0: the sweep's FMA leaves the column alone
           Wt[t][jj] = w_j;
-          if (t + 1 < sg) {
-            const double sc = tau != 0.0 ? scale : 0.0;  // tau == 0: H = I, only the row leaves the sums
-            const double vs = tau != 0.0 ? scale : 1.0;
-            const double sv_j = __dmul_rn(sc, Mx[pb][t][jj]), vv = sc * sc * xn2;
-            // row i0 + t + 1 after H_i, for this column and (below) for the group's columns
-            const double vr1 = Rw[pb][t + 1][i] * vs;
-            const double r1_j = __fma_rn(-vr1, w_j, Rw[pb][t + 1][jj]);
+          if (jj < S) Wt[t][64 + jj] = 0.0;
+          if (t + 1 < S) {
+            const double sv_j = __dmul_rn(sc, m[t]);
+            const double r1_j = __fma_rn(-vr1, w_j, rw[t + 1]);
 #pragma unroll
             for (int u = 1; u < S; ++u)
-              if (u > t && u < sg) {
-                const int cu = i0 + u;
-                const double w_u = __dmul_rn(tau, __fma_rn(Mx[pb][t][cu], scale, Rw[pb][t][cu]));
-                const double sv_u = __dmul_rn(sc, Mx[pb][t][cu]);
-                const double r1_u = __fma_rn(-vr1, w_u, Rw[pb][t + 1][cu]);
-                const double vr = Rw[pb][u][i] * vs;
-                Rw[pb ^ 1][u][jj] = __fma_rn(-vr, w_j, Rw[pb][u][jj]);  // the sweep's own operation on the replicated row
-                double mnew = Mx[pb][u][jj] - w_j * sv_u - w_u * sv_j + w_u * w_j * vv;
-                mnew -= r1_u * r1_j;
-                Mx[pb ^ 1][u][jj] = mnew;
+              if (u > t) {
+                rw[u] = __fma_rn(-GVR[t][u], w_j, rw[u]);  // the sweep's own operation on the replicated row
+                m[u] = grp_m_update(m[u], w_j, sv_j, r1_j, GW[t][u], GSV[t][u], GR1[t][u], vv);
               }
           }
         }
-        bar_sync_64();
       }
-      if (jj == 0) { ginfo[0] = t; ginfo[1] = stop ? 1 : 0; }
     }
     GRP_TICK(2);
     __syncthreads();
@@ -834,8 +871,8 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_grp(qrdm_prob P, int
   }
 #undef GRP_TICK
   if (timing && j == 640)
-    printf("panel_grp<S=%d> j=%d G=%d rpc=%d fjb=%d exchanges=%d cycles: contribute %lld gather %lld recurrence %lld sync %lld sweeps %lld\n",
-           S, j, G, rpc, fjb, e, tph[0], tph[1], tph[2], tph[3], tph[4]);
+    printf("panel_grp<S=%d> j=%d G=%d rpc=%d fjb=%d exchanges=%d cycles: contribute %lld gather %lld recurrence %lld (phase 1: %lld) sync %lld sweeps %lld\n",
+           S, j, G, rpc, fjb, e, tph[0], tph[1], tph[2], tph[5], tph[3], tph[4]);
   __syncthreads();
   if (b == 0 && tid == 0) { ctrl->fjb_cmp = k; ctrl->micro_thres2 = thres2; }
 
@@ -1284,17 +1321,23 @@ extern "C" int qrdm_k_panel(const qrdm_prob* p, int j_host, void* stream) {
     int per = 256, mode = 0;
     panel_plan(rows, gmax, &per, &mode);
     int Gr = (rows + per - 1) / per, rpcr = (rows + Gr - 1) / Gr;
-    // columns per exchange: 2 (default) or 4 = the grouped kernel k_panel_grp, 1 = one exchange per column (k_panel_reg)
+    // columns per exchange: 4 (default) or 2 = the grouped kernel k_panel_grp, 1 = one exchange per column (k_panel_reg)
     const char* e_s = getenv("QRDM_PANEL_S");
-    int grp_s = (mode == 0) ? 1 : (e_s ? atoi(e_s) : 2);
+    int grp_s = e_s ? atoi(e_s) : 4;
     if (per == 256) grp_s = 1;  // 256-row slabs + the group's private columns and accumulators do not fit in 128 registers
+    // No cluster launch available for this grid (more than 132 CTAs, QRDM_PANEL_CL=0, or a failed cluster launch earlier):
+    // the grouped kernel runs its plain all-gather exchange (MODE 1) on any grid — more L2 traffic per exchange, but still
+    // one exchange per 4 columns.  This is also the variant Nsight Compute can profile: under ncu the cooperative +
+    // cluster launch of 31 clusters does not become co-resident and the run ends in the spin-limit trap.
+    const int gmode = (mode == 0 && (grp_s == 2 || grp_s == 4)) ? 1 : mode;
     if (grp_s == 2 || grp_s == 4) {
       unsigned epoch_g = panel_grp_epoch(p, stream);
       qrdm_prob prob_g = *p;
       void* args_g[] = {(void*)&prob_g, (void*)&rpcr, (void*)&epoch_g};
 #define PANEL_GFN(MODE, S) (per == 32 ? (void*)k_panel_grp<1, MODE, S> : per == 64 ? (void*)k_panel_grp<2, MODE, S> \
                             : per == 128 ? (void*)k_panel_grp<4, MODE, S> : (void*)k_panel_grp<8, MODE, S>)
-      if (mode == 2) {
+      bool plain = gmode != 2;
+      if (gmode == 2) {
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3((Gr + PANEL_CL - 1) / PANEL_CL * PANEL_CL);  // padded with CTAs that own no rows
@@ -1302,8 +1345,11 @@ extern "C" int qrdm_k_panel(const qrdm_prob* p, int j_host, void* stream) {
         cfg.attrs = cl_attrs; cfg.numAttrs = 2;
         const cudaError_t e2 = cudaLaunchKernelExC(&cfg, grp_s == 2 ? PANEL_GFN(2, 2) : PANEL_GFN(2, 4), args_g);
         if (e2 == cudaSuccess) { ++g_qrdm_launches; return 0; }
-        (void)cudaGetLastError();  // fall through to the per-column kernels below (they handle a failing cluster launch)
-      } else {
+        (void)cudaGetLastError();
+        cl_max_ctas = 0;  // no cluster launches from now on
+        plain = true;
+      }
+      if (plain) {
         cudaError_t eg = cudaLaunchCooperativeKernel(grp_s == 2 ? PANEL_GFN(1, 2) : PANEL_GFN(1, 4), dim3(Gr), dim3(PANEL_THREADS),
                                                      args_g, 0, (cudaStream_t)stream);
         ++g_qrdm_launches;
