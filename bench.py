@@ -560,18 +560,21 @@ def main():
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches = 0
-    trailing_ms = panel_ms = trailing_flops = side_flops = side_ms = 0.0
-    trailing_launches = side_launches = 0
+    trailing_ms = panel_ms = trailing_flops = side_flops = side_ms = fused_ms = fused_flops = 0.0
+    trailing_launches = side_launches = fused_launches = 0
     torch.cuda.synchronize()
     e0.record(stream)
     for _ in range(args.steps):
         ncols = one_step()
         st = qrdm_b200.stats()
         launches += st["launches"]
-        trailing_ms += st["ms_stage"]["trailing"]
+        trailing_ms += st["ms_stage"]["trailing"] + st["ms_stage"]["vtv"]   # vtv = the k_fused launches, timed on their own
+        fused_ms += st["ms_stage"]["vtv"]
+        fused_flops += st["fused_flops"]
+        fused_launches += st["fused_launches"]
         panel_ms += st["ms_stage"]["panel"]
         trailing_flops += st["trailing_flops"]
-        trailing_launches += st["stage_launches"]["trailing"]
+        trailing_launches += st["stage_launches"]["trailing"] + st["stage_launches"]["vtv"]
         side_flops += st["side_flops"]          # look-ahead: pass-2 FLOPs applied by the side stream, outside the stage
         side_ms += st["ms_stage"]["rankk"]
         side_launches += st["side_launches"]
@@ -738,8 +741,8 @@ def main():
                     st = qrdm_b200.stats()
                     if best is None or st["ms_total"] < best:
                         best = st["ms_total"]
-                        k6 = (st["trailing_flops"] - st["side_flops"], st["ms_stage"]["trailing"], st["ms_stage"]["panel"],
-                              st["side_flops"])
+                        k6 = (st["trailing_flops"] - st["side_flops"], st["ms_stage"]["trailing"] + st["ms_stage"]["vtv"],
+                              st["ms_stage"]["panel"], st["side_flops"], st["fused_flops"], st["ms_stage"]["vtv"])
                 qrdm_b200.set_profile(0)
                 ork = int(oncols.sum())
                 k6_tf = k6[0] / (k6[1] * 1e-3) / 1e12 if k6 and k6[1] > 0 else None
@@ -749,6 +752,8 @@ def main():
                                             "unit": "TFLOP/s", "frac": (k6_tf / peak_dmma) if k6_tf else None,
                                             "ms": k6[1] if k6 else None, "panel_ms": k6[2] if k6 else None,
                                             "flops_in_stage": k6[0] if k6 else None,
+                                            "k_fused_alone": ({"tflops": k6[4] / (k6[5] * 1e-3) / 1e12, "frac": k6[4] / (k6[5] * 1e-3) / 1e12 / peak_dmma,
+                                                               "ms": k6[5]} if k6 and k6[5] > 0 else None),
                                             "flops_on_side_stream": k6[3] if k6 else None,
                                             "whole_step_frac_of_peak": flops(om, on, ork) / (best * 1e-3) / 1e12 / peak_dmma},
                                "timing": "best of 3 after 1 warm-up, device-resident (CUDA events inside dgeqrdm_dev)"}
@@ -767,8 +772,12 @@ def main():
         peaks_file = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    # FLOPs the look-ahead moved to the side stream are not executed inside the timed stage: they do not count for it
-    achieved = (trailing_flops - side_flops) / (trailing_ms * 1e-3) / 1e12 if trailing_ms > 0 else None
+    # Dominant kernel: k_fused (k_vtc for the first deferred block), its own CUDA-event pairs inside the timed steps and
+    # the FLOPs executed inside those launches.  The whole K6 stage (+ k_tinv, k_wapply, the eager k_rankk<list>, and
+    # k_vtc + k_rankk below the break-even) is reported beside it; FLOPs the look-ahead moved to the side stream are
+    # executed outside the stage and do not count for either.
+    achieved = fused_flops / (fused_ms * 1e-3) / 1e12 if fused_ms > 0 else None
+    stage_achieved = (trailing_flops - side_flops) / (trailing_ms * 1e-3) / 1e12 if trailing_ms > 0 else None
     line = {
         "metric": "dgeqrdm_fp64_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -784,28 +793,34 @@ def main():
                 "steps": e2e_steps, "api": "dgeqrdm (C ABI, pinned host buffers, wall clock around the blocking call)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"kernel": "K6 trailing update stage on the main stream: k_fused (deferred pass 2 + pass 1; pass 1 only on the "
-                               "columns the look-ahead's side stream completed) + k_tinv + k_wapply + eager k_rankk<list> "
-                               "(DMMA.8x8x4); k_vtc/k_rankk below the 2048^2 break-even", "bound": "tensor",
+        "roofline": {"kernel": "k_fused (K6, DMMA.8x8x4): pass 2 of the pending block fused into pass 1 of the current one; pass 1 only "
+                               "on the columns the look-ahead's side stream completed", "bound": "tensor",
                      "achieved": achieved, "peak": peak_dmma, "unit": "TFLOP/s",
                      "frac": (achieved / peak_dmma) if achieved else None,
                      "peak_source": "FP64 DMMA peak measured live by qrdm_b200_measure_fp64_peak "
                                     f"(DFMA pipe: {peak_dfma:.2f}); MEASURED_PEAKS.json has no FP64 entry "
                                     f"(hbm_gbs={peaks_file.get('hbm_gbs')})",
-                     "algorithmic_flops_per_step": (trailing_flops - side_flops) / args.steps,
-                     "launches_per_step": trailing_launches / args.steps,
+                     "algorithmic_flops_per_step": fused_flops / args.steps,
+                     "launches_per_step": fused_launches / args.steps,
+                     "avg_launch_ms": fused_ms / fused_launches if fused_launches else None,
+                     "k6_stage": {"what": "the whole trailing-update stage on the main stream: k_fused + k_tinv + k_wapply + eager "
+                                          "k_rankk<list>, and k_vtc + k_rankk below the 2048^2 break-even",
+                                  "achieved": stage_achieved, "frac": (stage_achieved / peak_dmma) if stage_achieved else None,
+                                  "algorithmic_flops_per_step": (trailing_flops - side_flops) / args.steps,
+                                  "launches_per_step": trailing_launches / args.steps, "ms_per_step": trailing_ms / args.steps},
                      "lookahead": {"what": "pass 2 of the pending block on the last columns, applied by k_rankk (side mode) on a "
                                            "least-priority stream beside the next selection / panel (SURVEY 8f-2); its FLOPs are "
                                            "excluded from `achieved` above, its event time (waits for SMs included) is reported here",
                                    "flops_per_step": side_flops / args.steps, "launches_per_step": side_launches / args.steps,
                                    "side_stream_ms_per_step": side_ms / args.steps,
                                    "share_of_k6_flops": side_flops / trailing_flops if trailing_flops > 0 else None},
-                     "ms_per_step": trailing_ms / args.steps, "share_of_step": trailing_ms / ms,
-                     "traffic": None,
-                     "traffic_note": "ncu --set full at iteration 10 (m_r=15744): k_fused 2.03 GB read + 1.93 GB written "
-                                     "(algorithmic 1.97 + 1.97; the unfused pair k_vtc + k_rankk moved 4.1 GB read + 1.9 GB "
-                                     "written): no wasted re-reads; per-launch traffic shrinks with the trailing matrix, "
-                                     "see profiles/r01_ncu_fused_v3.txt"},
+                     "ms_per_step": fused_ms / args.steps, "share_of_step": fused_ms / ms,
+                     "traffic": 2.075419e9 + 1.768631e9,
+                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, ncu --set full at iteration 10 (m_r = 15744, "
+                                     "15680 trailing columns): 2.075 GB read + 1.769 GB written; algorithmic for that launch: 1.975 GB "
+                                     "read (every trailing element once) + ~1.77 GB written (the columns the side stream completed are "
+                                     "read for pass 1 but not written): ratio 1.03, no wasted re-reads; traffic shrinks with the trailing "
+                                     "matrix, `achieved` is the average over all launches of a step; profiles/r02_ncu_lookahead_and_grouped_panel.txt"},
         "stages": {"panel_ms_per_step": panel_ms / args.steps, "trailing_ms_per_step": trailing_ms / args.steps},
     }
     if e2e_pg is not None:

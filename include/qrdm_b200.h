@@ -136,6 +136,11 @@ typedef struct qrdm_b200_stats {
    * side kernels' own event time is ms_stage[RANKK] (includes their waits for SMs: they run at the least priority) */
   double side_flops;
   long long side_launches;
+  /* the dominant kernel alone: FLOPs executed inside the k_fused launches (pass 1 of the current block on all trailing
+   * columns + pass 2 of the pending block on the columns neither the eager set nor the side stream completed; k_vtc for
+   * the first deferred block), whose own event time is ms_stage[VTV] in profile mode 2 */
+  double fused_flops;
+  long long fused_launches;
 } qrdm_b200_stats;
 
 enum {

@@ -17,7 +17,8 @@ class Stats(C.Structure):
                 ("ms_total", C.c_double), ("ms_h2d", C.c_double), ("ms_d2h", C.c_double),
                 ("ms_stage", C.c_double * 12), ("stage_launches", C.c_longlong * 12),
                 ("trailing_flops", C.c_double), ("panel_cols", C.c_double),
-                ("stage_bytes", C.c_double * 12), ("side_flops", C.c_double), ("side_launches", C.c_longlong)]
+                ("stage_bytes", C.c_double * 12), ("side_flops", C.c_double), ("side_launches", C.c_longlong),
+                ("fused_flops", C.c_double), ("fused_launches", C.c_longlong)]
 
 
 STAGES = ["norm_init", "select", "gram", "pick", "permute", "panel", "vtv", "trailing", "wsolve",
@@ -96,4 +97,5 @@ def stats() -> dict:
                 ms_stage={STAGES[i]: s.ms_stage[i] for i in range(12)},
                 stage_launches={STAGES[i]: s.stage_launches[i] for i in range(12)},
                 stage_bytes={STAGES[i]: s.stage_bytes[i] for i in range(12)},
-                side_flops=s.side_flops, side_launches=s.side_launches)
+                side_flops=s.side_flops, side_launches=s.side_launches,
+                fused_flops=s.fused_flops, fused_launches=s.fused_launches)

@@ -264,7 +264,7 @@ static int g_ev_used = 0, g_ev_created = 0;
 
 static int stage_begin(int stage, void *stream) {
   if (g_profile == 1) return qrdm_rt_event_record(g_ws.ev_stage[0], stream);
-  if (g_profile == 2 && (stage == QRDM_STAGE_PANEL || stage == QRDM_STAGE_VTC || stage == QRDM_STAGE_RANKK) && g_ev_used + 2 <= EV_POOL) {
+  if (g_profile == 2 && (stage == QRDM_STAGE_PANEL || stage == QRDM_STAGE_VTC || stage == QRDM_STAGE_RANKK || stage == QRDM_STAGE_VTV) && g_ev_used + 2 <= EV_POOL) {
     while (g_ev_created < g_ev_used + 2) {
       int e = qrdm_rt_event_create(&g_ev_pool[g_ev_created]);
       if (e) return e;
@@ -276,7 +276,7 @@ static int stage_begin(int stage, void *stream) {
   return 0;
 }
 static int stage_end(int stage, long long launches_before, void *stream) {
-  if (g_profile == 2 && (stage == QRDM_STAGE_PANEL || stage == QRDM_STAGE_VTC || stage == QRDM_STAGE_RANKK) && g_ev_used + 2 <= EV_POOL) {
+  if (g_profile == 2 && (stage == QRDM_STAGE_PANEL || stage == QRDM_STAGE_VTC || stage == QRDM_STAGE_RANKK || stage == QRDM_STAGE_VTV) && g_ev_used + 2 <= EV_POOL) {
     int e = qrdm_rt_event_record(g_ev_pool[g_ev_used + 1], stream);
     g_ev_used += 2;
     g_stats.stage_launches[stage] += qrdm_rt_launch_count() - launches_before;
@@ -493,17 +493,22 @@ static int factor_device_impl(int m, int n, double *d_a, int lda, int *d_jpvt, d
    * columns (qrdm_prob::pre_col0).  The share is sized from the idle SM-time of the window:
    *   QRDM_B200_SIDE_US      microseconds of (nearly) the whole chip before the panel starts            [default 100]
    *   QRDM_B200_SIDE_COL_US  microseconds per panel column, on the SMs the panel does not occupy        [default 3.3]
-   *   QRDM_B200_SIDE_EFF     side rate per SM relative to k_rankk's 24 TFLOP/s on the whole chip        [default 0.8]
+   *   QRDM_B200_SIDE_EFF     side rate per SM relative to k_rankk's 24 TFLOP/s on the whole chip        [default 0.6]
+   * (measured with the grouped panel, 16384^2: 0.6 -> 295.3 ms, 0.8 -> 298.9, 1.1 -> 304.6, look-ahead off 296.3: a side
+   * update that is still running when the next k_fused is due costs more than the share it took off that kernel)
    * QRDM_B200_SIDE=0 switches the look-ahead off, QRDM_B200_SIDE_PANEL=0 ends the side update before the panel. */
   int side_on = lazy_on, side_over_panel = 1, side_upc = 1;
-  double side_us = 100.0, side_col_us = 3.3, side_eff = 0.8;
+  double side_us = 100.0, side_col_us = 3.3, side_eff = 0.6;
   { const char *e = getenv("QRDM_B200_SIDE"); if (e && atoi(e) == 0) side_on = 0; }
   { const char *e = getenv("QRDM_B200_SIDE_US"); if (e) side_us = atof(e); }
   { const char *e = getenv("QRDM_B200_SIDE_PANEL"); if (e) side_over_panel = atoi(e); }
   { const char *e = getenv("QRDM_B200_SIDE_COL_US"); if (e) side_col_us = atof(e); }
   { const char *e = getenv("QRDM_B200_SIDE_EFF"); if (e) side_eff = atof(e); }
   { const char *e = getenv("QRDM_B200_SIDE_UPC"); if (e && atoi(e) >= 1) side_upc = atoi(e); }
+  { const char *e = getenv("QRDM_B200_VT_WB"); P.vt_wb = e ? atoi(e) : 0; } /* experiment: cost of a pass-1-only unit (of 7) */
   int pend_pre = 0; /* first column the side stream owns for the pending block (0: none) */
+  int fused_timed = 0, fused_prev_k = 0; /* bookkeeping of the separately timed k_fused launches (stats.fused_flops) */
+  double fused_prev_cols = 0.0;
   if (w->side_busy) { /* a previous call left early with a side launch in flight: it still uses the workspace */
     CU(qrdm_rt_stream_wait_event(stream, w->ev_side[1]));
     w->side_busy = 0;
@@ -601,15 +606,26 @@ static int factor_device_impl(int m, int n, double *d_a, int lda, int *d_jpvt, d
       } else {
         int vt_stride = 0, vt_grid = 0;
         long long lb = qrdm_rt_launch_count();
-        CU(stage_begin(QRDM_STAGE_VTC, stream));
+        /* the dominant kernel gets its own event pair (stage VTV): k_fused, or k_vtc for the first deferred block */
+        CU(stage_begin(QRDM_STAGE_VTV, stream));
         const int bn = pending ? 64 : 128; /* tile width of the partial-W slots */
         if (w->side_busy) { /* columns >= pend_pre of the pending block come from the side stream */
           CU(qrdm_rt_stream_wait_event(stream, w->ev_side[1]));
           w->side_busy = 0;
         }
         P.pre_col0 = pending ? pend_pre : 0; /* k_fused / k_tinv / k_wapply share one unit partition, which depends on it */
+        fused_prev_cols = 0.0;
+        if (pending) { /* phase-A columns of this k_fused: up to the side stream's share, minus the eager set (>= 128 columns) */
+          const int cend = pend_pre > 0 ? pend_pre : n;
+          fused_prev_cols = (double)(cend - j - 128 > 0 ? cend - j - 128 : 0);
+          fused_prev_k = w->mailbox->last_k;
+        }
+        fused_timed = 1;
         if (pending) CU(qrdm_k_fused(&P, j, &vt_stride, &vt_grid, stream)); /* pass 2 of block it-1 + pass 1 of block it */
         else CU(qrdm_k_vtc_only(&P, j, &vt_stride, &vt_grid, stream));
+        CU(stage_end(QRDM_STAGE_VTV, lb, stream));
+        lb = qrdm_rt_launch_count();
+        CU(stage_begin(QRDM_STAGE_VTC, stream));
         pending = 0;
         /* lazy: k_wapply also finishes the k new R rows; everything below them waits for the next k_fused */
         if (vt_stride > 0) CU(qrdm_k_w2(&P, j, vt_grid, vt_stride, bn | (lazy ? 1 : 0), stream));
@@ -770,6 +786,12 @@ static int factor_device_impl(int m, int n, double *d_a, int lda, int *d_jpvt, d
       break;
     }
     g_stats.trailing_flops += 4.0 * (double)(m - jr) * (double)(cols - k) * (double)k;
+    if (fused_timed) { /* FLOPs inside the separately timed k_fused / k_vtc launch: pass 1 of this block + pass 2 of the pending one */
+      g_stats.fused_flops += 2.0 * (double)(m - jr) * (double)(cols - k) * (double)k
+                             + 2.0 * (double)(m - jr) * fused_prev_cols * (double)fused_prev_k;
+      ++g_stats.fused_launches;
+      fused_timed = 0;
+    }
     if (pend_pre > 0 && pending) /* this block's pass 2 on the columns >= pend_pre went to the side stream (stamped columns aside) */
       g_stats.side_flops += 2.0 * (double)(m - jr - k) * (double)(n - pend_pre) * (double)k;
     g_stats.stage_bytes[QRDM_STAGE_PANEL] += 16.0 * (double)(m - jr) * (double)k; /* >= 16 m_r k: k <= fjb columns read + written once */

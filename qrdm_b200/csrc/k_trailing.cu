@@ -46,6 +46,7 @@ struct VtGeom {
   long long U;      // units = CT * NCH
   long long Usplit; // = Tpre * NCH (== U without look-ahead): units beyond it cost VT_WB instead of VT_WA
   long long Ctot;   // total cost
+  int wb;           // cost of a unit beyond Usplit (VT_WB unless overridden)
 };
 // Relative cost of a k_fused unit with / without phase A (measured: k_fused 2.08 ms against k_vtc 1.20 ms for the same
 // trailing matrix).  The CTAs take contiguous unit ranges of EQUAL COST, so a mix of both kinds stays balanced.
@@ -70,16 +71,17 @@ __device__ __forceinline__ VtGeom vt_geom(const qrdm_prob& P, int bn = VT_BN) {
     if (tp < g.CT) g.Tpre = tp;
   }
   g.Usplit = (long long)g.Tpre * g.NCH;
-  g.Ctot = VT_WA * g.Usplit + VT_WB * (g.U - g.Usplit);
+  g.wb = P.vt_wb > 0 ? P.vt_wb : VT_WB;
+  g.Ctot = VT_WA * g.Usplit + g.wb * (g.U - g.Usplit);
   return g;
 }
 __device__ __forceinline__ long long vt_cost(const VtGeom& ge, long long u) {
-  return u <= ge.Usplit ? VT_WA * u : VT_WA * ge.Usplit + VT_WB * (u - ge.Usplit);
+  return u <= ge.Usplit ? VT_WA * u : VT_WA * ge.Usplit + ge.wb * (u - ge.Usplit);
 }
 // first unit of CTA b: the units are cut where the accumulated cost passes b/G of the total (lo(0) = 0, lo(G) = U)
 __device__ __forceinline__ long long vt_lo(const VtGeom& ge, int G, int b) {
   const long long x = ge.Ctot * b / G;
-  return x <= VT_WA * ge.Usplit ? x / VT_WA : ge.Usplit + (x - VT_WA * ge.Usplit) / VT_WB;
+  return x <= VT_WA * ge.Usplit ? x / VT_WA : ge.Usplit + (x - VT_WA * ge.Usplit) / ge.wb;
 }
 // first CTA whose unit range reaches into tile T
 __device__ __forceinline__ int vt_bfirst(const VtGeom& ge, int G, int T) {

@@ -130,6 +130,7 @@ typedef struct qrdm_prob {
    * k_fused / k_tinv / k_wapply are told so through pre_col0: those columns need pass 1 only. */
   int side_col0;      /* side launch: first absolute column it owns (0 = not a side launch) */
   int pre_col0;       /* k_fused & co: columns >= pre_col0 already hold the pending update (0 = none) */
+  int vt_wb;          /* relative cost of a pass-1-only unit of k_fused against VT_WA = 7 for a full one (0: the default, 4) */
   double inv_scale;   /* 1 / that scale (MUST be 1.0, never 0, for an unscaled matrix): the norm downdate evaluates its
                          sum of squares in the CALLER's scale, where the reference's unscaled sum (src/dgeqrdm_work.c:81-86)
                          underflows to 0 for ~1e-200 entries (no downdate) and overflows for ~1e+200 (forced recompute) */

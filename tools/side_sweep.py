@@ -12,7 +12,7 @@ m, n = int(sys.argv[1]), int(sys.argv[2])
 settings = sys.argv[3].split(";") if len(sys.argv) > 3 else [""]
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 2
 KEYS = ("QRDM_B200_SIDE", "QRDM_B200_SIDE_US", "QRDM_B200_SIDE_PANEL", "QRDM_B200_SIDE_COL_US", "QRDM_B200_SIDE_UPC", "QRDM_B200_SIDE_EFF", "QRDM_B200_LAZY_MIN",
-        "QRDM_B200_LAZY", "QRDM_PANEL_CL", "QRDM_PANEL_PER", "QRDM_PANEL_S")
+        "QRDM_B200_LAZY", "QRDM_PANEL_CL", "QRDM_PANEL_PER", "QRDM_PANEL_S", "QRDM_B200_VT_WB")
 dev = torch.device("cuda", 0)
 gen = torch.Generator(device=dev)
 gen.manual_seed(1234)
@@ -45,6 +45,6 @@ for s in settings:
         same = (f" jpvt_equal={bool(torch.equal(jp, ref[0]))} max_rel_diag_diff={float(torch.max(torch.abs(d - ref[1]) / ref[1])):.1e}"
                 f" bitwise={bool(torch.equal(A, ref[2]))}")
     ms = st["ms_stage"]
-    tf = st["trailing_flops"] / ((ms["trailing"] + ms["rankk"]) * 1e-3) / 1e12
+    tf = st["fused_flops"] / (ms["vtv"] * 1e-3) / 1e12 if ms["vtv"] > 0 else 0.0
     print(f"{m}x{n} [{s or 'defaults'}]: info {info} rank {int(nc.sum())} ms_total {st['ms_total']:.2f} panel {ms['panel']:.2f} "
-          f"trailing {ms['trailing']:.2f} side {ms['rankk']:.2f} ms -> K6 {tf:.2f} TFLOP/s, launches {st['launches']}{same}", flush=True)
+          f"k_fused {ms['vtv']:.2f} rest-of-K6 {ms['trailing']:.2f} side {ms['rankk']:.2f} ms -> k_fused {tf:.2f} TFLOP/s, launches {st['launches']}{same}", flush=True)
