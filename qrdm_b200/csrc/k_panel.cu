@@ -1167,6 +1167,318 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_tall(qrdm_prob P, in
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Grouped sub-panel kernel of the blocked tall panel: the whole 8-column sub-panel with ONE exchange (normally).
+// Same algebra as k_panel_grp with S = 8 = all columns of the sub-panel: pass 1 streams the CTA's rows once and
+// accumulates the upper triangle of the 8 x 8 Gram matrix of the rows below the first pivot row (36 sums) and
+// publishes the 8 pivot rows; one exchange (within the GPU: all-gather of the G partials; MG: + one LL exchange with
+// the other GPUs over NVLink peer memory — ONE per sub-panel instead of one per column); the scalar recurrence on
+// the replicated 8 x 8 numbers gives all tau / beta / scale / w; pass 2 streams the rows again and applies the
+// reflectors to the row's 8 values in registers (read once, written once).  The per-column kernel above made 8
+// read+write sweeps over the remaining columns and 8 exchanges.  The accuracy guard of k_panel_grp applies: a column
+// whose ||x||^2 falls below 2^-7 of its sum at the start of the round ends the round; the kernel then makes another
+// round (pass 1 / exchange / recurrence / pass 2) from that column on — every CTA (and every rank) takes the same
+// decision from the same numbers, so the number of exchanges is the same everywhere.
+#define TG_NSUM 36  // upper triangle of the 8 x 8 Gram block: index of (u, c), u <= c
+__device__ __forceinline__ constexpr int tg_idx(int u, int c) { return u * TALL_B - u * (u - 1) / 2 + (c - u); }
+template <bool MG, bool SM>
+__global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_tall_grp(qrdm_prob P, int rpc, unsigned epoch, PeerCtx pc) {
+  extern __shared__ __align__(16) double tall_slab[];  // SM: [TALL_B][lds]
+  __shared__ double sacc[PANEL_WARPS][TG_NSUM];
+  __shared__ double Gs[TG_NSUM], Rs[TALL_B][TALL_B];            // totals delivered by the exchange
+  __shared__ double Mb[2][TALL_B][TALL_B], Rb[2][TALL_B][TALL_B];  // recurrence state, double-buffered by step parity
+  __shared__ double Wt[TALL_B][TALL_B], SC[TALL_B][4];            // per step: w_t[c], {tau, beta, seff}
+  __shared__ int ginfo[2];
+  __shared__ double gth2;
+  qrdm_ctrl* ctrl = P.ctrl;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const QrdmGeom qg = qrdm_geom(P);
+  const int j = qg.j, fjb = qg.fjb, sub_s = P.sub - 1;
+  const int jmain = ctrl->j, fjb_main = ctrl->fjb;
+  if (fjb <= 0) return;
+  const bool forced = ctrl->forced != 0;
+  const int lr0 = qrdm_jr(P, j);
+  const int goff = P.row0 + lr0 - j;
+  const int rows_l = P.m - lr0;
+  const int rows = P.m_glob - j;
+  const int lda = P.lda;
+  const int G = gridDim.x, b = blockIdx.x;
+  const int r0 = min(rows_l, b * rpc), r1 = min(rows_l, r0 + rpc), nr = r1 - r0;
+  double* Ag = P.a + (size_t)j * lda + lr0 + r0;
+  const int ldp = SM ? ((rpc + 1) & ~1) : lda;
+  double* Ap = SM ? tall_slab : Ag;
+  if (SM) {
+    for (int c = 0; c < fjb; ++c)
+      for (int r = threadIdx.x; r < nr; r += PANEL_THREADS) Ap[(size_t)c * ldp + r] = Ag[(size_t)c * lda + r];
+    __syncthreads();
+  }
+  LLPacket* part = reinterpret_cast<LLPacket*>(P.panel_part);  // [2][PANEL_MAXCTA][64]
+  LLPacket* bcast = reinterpret_cast<LLPacket*>(P.panel_row);  // [2][128]: pivot rows at 64 + u * 8 + c
+  const unsigned tag_base = epoch << 8;
+  const int me = MG ? pc.rank : 0, NR = MG ? pc.nranks : 1;
+  const unsigned px0 = MG ? *pc.xseq : 0u;
+  const bool cont = ctrl->micro_t > 0;
+  double thres2 = (sub_s == 0) ? (cont ? ctrl->micro_thres2 : P.thres0 * P.thres0) : ctrl->tall_thres;
+  int k = fjb, i0 = 0, round = 0;
+  bool stopped = false, vc_done = false;
+  while (i0 < fjb && !stopped) {
+    const int cur = round & 1;
+    const unsigned tag = tag_base + round + 1;
+    // ---- pass 1: Gram block of the columns >= i0 over the rows below pivot row i0; the pivot rows i0 .. fjb-1 ----
+    {
+      double acc[TG_NSUM];
+#pragma unroll
+      for (int x = 0; x < TG_NSUM; ++x) acc[x] = 0.0;
+      auto row1 = [&](int r) {
+        const int R = goff + r0 + r;
+        if (R < i0) return;
+        double v[TALL_B];
+#pragma unroll
+        for (int c = 0; c < TALL_B; ++c) v[c] = (c >= i0 && c < fjb) ? Ap[(size_t)c * ldp + r] : 0.0;
+        if (R > i0) {
+#pragma unroll
+          for (int u = 0; u < TALL_B; ++u)
+#pragma unroll
+            for (int c = u; c < TALL_B; ++c) acc[tg_idx(u, c)] = fma(v[u], v[c], acc[tg_idx(u, c)]);
+        }
+        if (R < fjb) {
+#pragma unroll
+          for (int c = 0; c < TALL_B; ++c)
+            if (c >= i0 && c < fjb) ll_store(&bcast[cur * 128 + 64 + R * TALL_B + c], v[c], tag);
+        }
+      };
+      // two rows per trip below the pivot rows (16 independent loads in flight per thread; same accumulation order)
+      int r = tid;
+      for (; !SM && r + PANEL_THREADS < nr; r += 2 * PANEL_THREADS) {
+        const int rb = r + PANEL_THREADS;
+        if (goff + r0 + r < TALL_B) { row1(r); row1(rb); continue; }
+        double va[TALL_B], vb[TALL_B];
+#pragma unroll
+        for (int c = 0; c < TALL_B; ++c) {
+          const bool on = c >= i0 && c < fjb;
+          va[c] = on ? Ap[(size_t)c * ldp + r] : 0.0;
+          vb[c] = on ? Ap[(size_t)c * ldp + rb] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < TALL_B; ++u)
+#pragma unroll
+          for (int c = u; c < TALL_B; ++c) {
+            acc[tg_idx(u, c)] = fma(va[u], va[c], acc[tg_idx(u, c)]);
+            acc[tg_idx(u, c)] = fma(vb[u], vb[c], acc[tg_idx(u, c)]);
+          }
+      }
+      for (; r < nr; r += PANEL_THREADS) row1(r);
+#pragma unroll
+      for (int x = 0; x < TG_NSUM; ++x) acc[x] = warp_sum(acc[x]);
+      if (lane == 0) {
+#pragma unroll
+        for (int x = 0; x < TG_NSUM; ++x) sacc[wid][x] = acc[x];
+      }
+      __syncthreads();
+      if (tid < TG_NSUM) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < PANEL_WARPS; ++w) t += sacc[w][tid];
+        ll_store(&part[((size_t)cur * QRDM_PANEL_MAXCTA + b) * 64 + tid], t, tag);
+      }
+    }
+    // ---- exchange: totals of the 36 sums and the 8 x 8 pivot rows, the same numbers in every CTA (and rank) ----
+    if (!MG) {
+      for (int x = wid; x < TG_NSUM; x += PANEL_WARPS) {
+        double v = ll_gather_sum(&part[(size_t)cur * QRDM_PANEL_MAXCTA * 64 + x], 64, lane, G, tag);
+        v = warp_sum(v);
+        if (lane == 0) Gs[x] = v;
+      }
+      if (tid >= 256 && tid < 256 + 64) {
+        const int u = (tid - 256) >> 3, c = (tid - 256) & 7;
+        double rv = 0.0;
+        if (u >= i0 && u < fjb && c >= i0 && c < fjb && u < rows) rv = ll_load(&bcast[cur * 128 + 64 + u * TALL_B + c], tag);
+        Rs[u][c] = rv;
+      }
+    } else {
+      const unsigned ptag = px0 + (unsigned)round + 1u;
+      const int pcur = (int)((px0 + (unsigned)round) & 1u);
+      if (b == 0) {
+        // rank leader: totals of this rank's CTAs and the pivot-row entries this rank owns (exact zeros otherwise),
+        // one packet per (value, peer) over NVLink
+        for (int x = wid; x < TG_NSUM; x += PANEL_WARPS) {
+          double v = ll_gather_sum(&part[(size_t)cur * QRDM_PANEL_MAXCTA * 64 + x], 64, lane, G, tag);
+          v = warp_sum(v);
+          if (lane < NR) ll_store(peer_panel_slot(pc.recv[lane], pcur, me, x), v, ptag);
+        }
+        for (int x = wid; x < 64; x += PANEL_WARPS) {
+          const int u = x >> 3, c = x & 7;
+          const int grow = j + u;  // global row of pivot row u
+          double rv = 0.0;
+          if (u >= i0 && u < fjb && c >= i0 && c < fjb && grow >= P.row0 && grow < P.row0 + P.m) {
+            if (lane == 0) rv = ll_load(&bcast[cur * 128 + 64 + u * TALL_B + c], tag);
+            rv = __shfl_sync(0xffffffffu, rv, 0);
+          }
+          if (lane < NR) ll_store(peer_panel_slot(pc.recv[lane], pcur, me, 64 + x), rv, ptag);
+        }
+      }
+      // everybody: the nranks contributions from the local receive buffer, added in rank order
+      for (int x = wid; x < TG_NSUM + 64; x += PANEL_WARPS) {
+        const int e = x < TG_NSUM ? x : 64 + (x - TG_NSUM);
+        double v = 0.0;
+        if (lane < NR) v = ll_load(peer_panel_slot(pc.recv[me], pcur, lane, e), ptag);
+        double t = 0.0;
+        for (int r = 0; r < NR; ++r) t += __shfl_sync(0xffffffffu, v, r);
+        if (lane == 0) {
+          if (x < TG_NSUM) Gs[x] = t;
+          else Rs[(x - TG_NSUM) >> 3][(x - TG_NSUM) & 7] = t;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- scalar recurrence on the replicated 8 x 8 block: threads (u, c) of warps 0-1, one 64-thread barrier per step ----
+    if (tid < 64) {
+      const int u = tid >> 3, c = tid & 7;
+      Mb[0][u][c] = (u >= i0 && c >= i0 && u < fjb && c < fjb) ? Gs[u <= c ? tg_idx(u, c) : tg_idx(c, u)] : 0.0;
+      Rb[0][u][c] = Rs[u][c];
+      bar_sync_64();
+      const double d0 = Mb[0][c][c];  // (read before anything is overwritten; used as the guard reference of column c)
+      int t = i0;
+      bool stop = false;
+      for (; t < fjb; ++t) {
+        const int pb = (t - i0) & 1;
+        const double alpha = Rb[pb][t][t], xn2 = Mb[pb][t][t];
+        const double d0t = __shfl_sync(0xffffffffu, d0, t & 7, 8);  // lanes c = t of every group of 8 hold it
+        if (t > i0 && !(xn2 >= GRP_GUARD * d0t)) break;
+        const int len = rows - t;
+        double tau = 0.0, beta = alpha, scale = 1.0;
+        if (len > 1) {
+          if ((sub_s + t > 0 || cont) && xn2 < thres2 && !forced) { stop = true; break; }  // DM early stop
+          if (xn2 != 0.0) {
+            const double h = sqrt(fma(alpha, alpha, xn2));
+            beta = (alpha >= 0.0) ? -h : h;
+            tau = (beta - alpha) / beta;
+            scale = 1.0 / (alpha - beta);
+          }
+        }
+        if (sub_s + t == 0 && !cont && fjb_main > 1 && P.tau_ > 0.0) { const double th = P.tau_ * fabs(beta); thres2 = th * th; }
+        const double sc = tau != 0.0 ? scale : 0.0, vs = tau != 0.0 ? scale : 1.0, vv = sc * sc * xn2;
+        if (tid == 0) {
+          SC[t][0] = tau; SC[t][1] = beta; SC[t][2] = vs;
+          if (b == 0) {
+            P.tau[j + t] = tau;
+            if (tau != tau && ctrl->err == 0) ctrl->err = -8;
+          }
+        }
+        const double w_c = c > t ? grp_w(tau, scale, Mb[pb][t][c], Rb[pb][t][c]) : 0.0;
+        if (u == 0) Wt[t][c] = w_c;
+        if (u > t && c > t && t + 1 < fjb) {
+          const double w_u = grp_w(tau, scale, Mb[pb][t][u], Rb[pb][t][u]);
+          const double sv_c = __dmul_rn(sc, Mb[pb][t][c]), sv_u = __dmul_rn(sc, Mb[pb][t][u]);
+          const double vr1 = Rb[pb][t + 1][t] * vs, vr_u = Rb[pb][u][t] * vs;
+          const double r1_c = __fma_rn(-vr1, w_c, Rb[pb][t + 1][c]), r1_u = __fma_rn(-vr1, w_u, Rb[pb][t + 1][u]);
+          Rb[pb ^ 1][u][c] = __fma_rn(-vr_u, w_c, Rb[pb][u][c]);
+          Mb[pb ^ 1][u][c] = grp_m_update(Mb[pb][u][c], w_c, sv_c, r1_c, w_u, sv_u, r1_u, vv);
+        }
+        bar_sync_64();
+      }
+      if (tid == 0) { ginfo[0] = t - i0; ginfo[1] = stop ? 1 : 0; gth2 = thres2; }
+    }
+    __syncthreads();
+    const int nsteps = ginfo[0];
+    stopped = ginfo[1] != 0;
+    thres2 = gth2;
+    // ---- pass 2: apply the round's reflectors to every row of the slab (the row's values in registers).  In the
+    // common case — one round took the whole sub-panel — the clean copy Vc is written from the same registers ----
+    const bool emit_vc = round == 0 && nsteps == fjb && !SM;
+    if (emit_vc) vc_done = true;
+    if (nsteps > 0) {
+      const int kpad_e = min(TALL_B, 64 - qg.voff);
+      // (the small tables stay in shared memory: 28 w's + 16 scalars do not fit next to the row in 128 registers)
+      auto row2 = [&](int r, double (&v)[TALL_B]) {
+        const int R = goff + r0 + r;
+#pragma unroll
+        for (int t = 0; t < TALL_B; ++t) {
+          if (t >= i0 && t < i0 + nsteps && R >= t) {
+            const double vt = R > t ? v[t] * SC[t][2] : 1.0;
+#pragma unroll
+            for (int c = 0; c < TALL_B; ++c)
+              if (c > t) v[c] = fma(-vt, Wt[t][c], v[c]);
+            v[t] = R > t ? vt : SC[t][1];
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < TALL_B; ++c)
+          if (c >= i0 && c < fjb) Ap[(size_t)c * ldp + r] = v[c];
+        if (emit_vc) {
+#pragma unroll
+          for (int q = 0; q < TALL_B; ++q)
+            if (q < kpad_e) P.vc[(size_t)(qg.voff + q) * P.ldv + lr0 + r0 + r] = q < fjb ? (R > q ? v[q] : (R == q ? 1.0 : 0.0)) : 0.0;
+        }
+      };
+      int r = tid;
+      for (; !SM && r + PANEL_THREADS < nr; r += 2 * PANEL_THREADS) {
+        const int rb = r + PANEL_THREADS;
+        if (goff + r0 + r < i0) {  // (rows above the round's first pivot row: only at the top of the diagonal block)
+          for (int q = 0; q < 2; ++q) {
+            const int rr = q ? rb : r;
+            if (goff + r0 + rr < i0) continue;
+            double v[TALL_B];
+#pragma unroll
+            for (int c = 0; c < TALL_B; ++c) v[c] = (c >= i0 && c < fjb) ? Ap[(size_t)c * ldp + rr] : 0.0;
+            row2(rr, v);
+          }
+          continue;
+        }
+        double va[TALL_B], vb[TALL_B];
+#pragma unroll
+        for (int c = 0; c < TALL_B; ++c) {
+          const bool on = c >= i0 && c < fjb;
+          va[c] = on ? Ap[(size_t)c * ldp + r] : 0.0;
+          vb[c] = on ? Ap[(size_t)c * ldp + rb] : 0.0;
+        }
+        row2(r, va);
+        row2(rb, vb);
+      }
+      for (; r < nr; r += PANEL_THREADS) {
+        if (goff + r0 + r < i0) continue;
+        double v[TALL_B];
+#pragma unroll
+        for (int c = 0; c < TALL_B; ++c) v[c] = (c >= i0 && c < fjb) ? Ap[(size_t)c * ldp + r] : 0.0;
+        row2(r, v);
+      }
+    }
+    i0 += nsteps;
+    if (stopped) k = i0;
+    ++round;
+    __syncthreads();  // the small tables are rewritten by the next round
+  }
+  if (b == 0 && tid == 0) {
+    const int tk = (sub_s == 0 ? 0 : ctrl->tall_k) + k;
+    ctrl->sub_k = k;
+    ctrl->tall_k = tk;
+    ctrl->tall_done = (k < fjb) ? 1 : 0;
+    if (k < fjb) ctrl->tall_stop_s = sub_s;
+    ctrl->tall_thres = thres2;
+    ctrl->micro_thres2 = thres2;
+    ctrl->fjb_cmp = tk;
+    if (MG) *pc.xseq = px0 + (unsigned)round;  // exchanges performed by this launch
+  }
+  if (SM) {
+    for (int c = 0; c < fjb; ++c)
+      for (int r = tid; r < nr; r += PANEL_THREADS) Ag[(size_t)c * lda + r] = Ap[(size_t)c * ldp + r];
+  }
+  // ---- clean copy of the sub-panel's reflectors into Vc columns voff .. voff + 7 (Vc is indexed by LOCAL row) ----
+  const int kpad = min(TALL_B, 64 - qg.voff);
+  const int jal = qrdm_jr(P, jmain) & ~(QRDM_ROWALIGN - 1);
+  for (int q = 0; q < kpad; ++q) {
+    double* vcol = P.vc + (size_t)(qg.voff + q) * P.ldv + lr0 + r0;
+    for (int r = tid; r < nr && !vc_done; r += PANEL_THREADS) {
+      const int R = goff + r0 + r;
+      double v = 0.0;
+      if (q < k) v = (R > q) ? Ap[(size_t)q * ldp + r] : (R == q ? 1.0 : 0.0);
+      vcol[r] = v;
+    }
+    if (b == 0)
+      for (int g = jal + tid; g < lr0; g += PANEL_THREADS) P.vc[(size_t)(qg.voff + q) * P.ldv + g] = 0.0;
+  }
+}
+
 // LL tags = (epoch << 8) + step.  Three disjoint epoch ranges share the exchange buffers: [1, 2^21) blocked tall
 // panel, [2^21, 2^22) smem/global panel, [2^22, 2^23) register panel.  When a range wraps, packets of its previous
 // cycle could carry tags that match again, so the buffers are cleared (stream-ordered, between two panel launches no
@@ -1196,6 +1508,11 @@ static unsigned panel_grp_epoch(const qrdm_prob* p, void* stream) {
 }
 // dynamic shared memory of the slab-resident sub-panel kernel for `rpc` rows per CTA, or 0 when the slab does not fit
 #define TALL_SLAB_CAP (200 * 1024)
+// QRDM_TALL_S=1: the per-column sub-panel kernel (k_panel_tall); default: the grouped one (k_panel_tall_grp)
+static bool tall_grouped() {
+  const char* e = getenv("QRDM_TALL_S");
+  return !(e && atoi(e) == 1);
+}
 static size_t tall_slab_bytes(int rpc) {
   static int attr_gen = -1;
   static const char* e_off = getenv("QRDM_PANEL_TALL_SM");  // experiment switch: 0 = always stream from global memory
@@ -1205,6 +1522,8 @@ static size_t tall_slab_bytes(int rpc) {
   if (attr_gen != qrdm_rt_device_generation()) {
     cudaFuncSetAttribute(k_panel_tall<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TALL_SLAB_CAP);
     cudaFuncSetAttribute(k_panel_tall<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TALL_SLAB_CAP);
+    cudaFuncSetAttribute(k_panel_tall_grp<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TALL_SLAB_CAP);
+    cudaFuncSetAttribute(k_panel_tall_grp<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TALL_SLAB_CAP);
     attr_gen = qrdm_rt_device_generation();
   }
   return bytes;
@@ -1231,8 +1550,11 @@ extern "C" int qrdm_k_panel_tall_mg(const qrdm_prob* p, int j_host, void* stream
   PeerCtx pcv = *pc;
   void* args_s[] = {(void*)&prob_s, (void*)&rpcs, (void*)&epoch, (void*)&pcv};
   const size_t slab = tall_slab_bytes(rpcs);
-  cudaError_t es = slab ? cudaLaunchCooperativeKernel((void*)k_panel_tall<true, true>, dim3(Gs), dim3(PANEL_THREADS), args_s, slab, (cudaStream_t)stream)
-                        : cudaLaunchCooperativeKernel((void*)k_panel_tall<true, false>, dim3(Gs), dim3(PANEL_THREADS), args_s, 0, (cudaStream_t)stream);
+  const bool grp = tall_grouped();
+  void* fn_sm = grp ? (void*)k_panel_tall_grp<true, true> : (void*)k_panel_tall<true, true>;
+  void* fn_gl = grp ? (void*)k_panel_tall_grp<true, false> : (void*)k_panel_tall<true, false>;
+  cudaError_t es = slab ? cudaLaunchCooperativeKernel(fn_sm, dim3(Gs), dim3(PANEL_THREADS), args_s, slab, (cudaStream_t)stream)
+                        : cudaLaunchCooperativeKernel(fn_gl, dim3(Gs), dim3(PANEL_THREADS), args_s, 0, (cudaStream_t)stream);
   ++g_qrdm_launches;
   return es == cudaSuccess ? 0 : (int)es;
 }
@@ -1407,8 +1729,11 @@ extern "C" int qrdm_k_panel(const qrdm_prob* p, int j_host, void* stream) {
       prob_s.sub = sb + 1;
       void* args_s[] = {(void*)&prob_s, (void*)&rpcs, (void*)&epoch_t, (void*)&nopeer};
       const size_t slab = tall_slab_bytes(rpcs);
-      cudaError_t es = slab ? cudaLaunchCooperativeKernel((void*)k_panel_tall<false, true>, dim3(Gs), dim3(PANEL_THREADS), args_s, slab, (cudaStream_t)stream)
-                            : cudaLaunchCooperativeKernel((void*)k_panel_tall<false, false>, dim3(Gs), dim3(PANEL_THREADS), args_s, 0, (cudaStream_t)stream);
+      const bool grp = tall_grouped();
+      void* fn_sm = grp ? (void*)k_panel_tall_grp<false, true> : (void*)k_panel_tall<false, true>;
+      void* fn_gl = grp ? (void*)k_panel_tall_grp<false, false> : (void*)k_panel_tall<false, false>;
+      cudaError_t es = slab ? cudaLaunchCooperativeKernel(fn_sm, dim3(Gs), dim3(PANEL_THREADS), args_s, slab, (cudaStream_t)stream)
+                            : cudaLaunchCooperativeKernel(fn_gl, dim3(Gs), dim3(PANEL_THREADS), args_s, 0, (cudaStream_t)stream);
       ++g_qrdm_launches;
       if (es != cudaSuccess) return (int)es;
       if (sb + QRDM_TALL_B < kmax_h) {  // apply the sub-panel's reflectors to the rest of the panel
