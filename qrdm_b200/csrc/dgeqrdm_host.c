@@ -213,7 +213,9 @@ static int ws_ensure(int m, int n) {
   w->ldw = roundup(cn, 128) + 128;           /* k_rankk / k_vtc column tiles overhang likewise */
   w->nrm_splits = 64;
   /* partial-W capacity: enough splits for ~2 CTAs per SM at any trailing width (see k_trailing) */
-  w->wp_elems = (size_t)64 * w->ldw * 16 + (size_t)64 * 256 * (2 * (size_t)w->sm_count + 2);
+  /* (second term: with the V'V tile skipped (qrdm_prob::no_vtv) a single 128-column tile can carry all 2 x SMs slots:
+   * slots x 64 x stride <= 64 x 128 x (grid / t + 2)(t + 2) for t real tiles, largest at t = 1) */
+  w->wp_elems = (size_t)64 * w->ldw * 16 + (size_t)64 * 128 * (6 * (size_t)w->sm_count + 64);
   CU(qrdm_rt_malloc((void **)&w->vn1, sizeof(double) * cn));
   CU(qrdm_rt_malloc((void **)&w->vn2, sizeof(double) * cn));
   CU(qrdm_rt_malloc((void **)&w->vc, sizeof(double) * (size_t)w->ldv * 64 * 2)); /* two buffers: current / pending block */

@@ -147,7 +147,9 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 // kernel re-read V once per 8 columns and spent more shuffles on its per-chunk reductions than FMAs on the product
 // (402 us per call at 2,000,000 rows against 98 us of HBM time, profiles/r02_launches_c4_summary.txt).
 // Output: the CTA's partial in the layout k_sub_w2 folds, gram_part[cta * 512 + group * 64 + q * 8 + c].
-template <int NB8, bool SUBW>
+// SRC: 0 = the candidates of the selection, 1 = SUBW (above), 2 = the block's clean reflectors Vc (V'V for k_tinv when
+// the trailing update of a tall-skinny matrix skips its V'V tile, see k_trailing.cu: P.no_vtv)
+template <int NB8, int SRC>
 __global__ void __launch_bounds__(GT_THREADS, 1) k_gram_tma(qrdm_prob P, int chunk) {
   extern __shared__ __align__(128) unsigned char gt_smem[];
   double* stage = reinterpret_cast<double*>(gt_smem);
@@ -156,8 +158,15 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gram_tma(qrdm_prob P, int chu
   __shared__ const double* scolp[64];  // column c of X, local row 0
   const qrdm_ctrl* ctrl = P.ctrl;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  constexpr bool SUBW = SRC == 1;
   int nc, r_lo;
-  if (SUBW) {
+  if (SRC == 2) {
+    const QrdmGeom q = qrdm_geom(P);
+    if (q.k <= 0) return;
+    nc = (q.k + 7) & ~7;
+    r_lo = qrdm_jr(P, q.j);
+    if (tid < 64) scolp[tid] = P.vc + (size_t)(q.voff + (tid < nc ? tid : 0)) * P.ldv;
+  } else if (SUBW) {
     const QrdmGeom q = qrdm_geom(P);
     const int c0 = q.j + q.fjb, ncp = q.n_end - c0;
     if (q.fjb <= 0 || q.k <= 0 || ncp <= 0) return;  // dead sub-panel / nothing behind it (k_sub_w2 returns alike)
@@ -292,10 +301,32 @@ __global__ void __launch_bounds__(64) k_gram_reduce(qrdm_prob P, int of_v, int n
 }
 
 static void gram_tma_attrs() {
-  cudaFuncSetAttribute(k_gram_tma<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM);
-  cudaFuncSetAttribute(k_gram_tma<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM);
-  cudaFuncSetAttribute(k_gram_tma<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM);
-  cudaFuncSetAttribute(k_gram_tma<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM);
+  cudaFuncSetAttribute(k_gram_tma<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM);
+  cudaFuncSetAttribute(k_gram_tma<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM);
+  cudaFuncSetAttribute(k_gram_tma<8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM);
+  cudaFuncSetAttribute(k_gram_tma<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM);
+  cudaFuncSetAttribute(k_gram_tma<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM);
+}
+
+// V'V of the current block's clean reflectors on the TMA + DMMA path -> p->gram (64 x 64, zero beyond kpad).  Used by
+// the trailing update of tall-skinny matrices instead of its V'V tile (P.no_vtv): one pass over V at HBM speed against
+// a full 128-wide DMMA tile per 32 rows.  Returns -1 when Vc cannot be bulk-copied (never: Vc is library-allocated).
+extern "C" int qrdm_k_vtv(const qrdm_prob* p, int rows_hint, void* stream) {
+  static int attr_gen = -1;
+  if (attr_gen != qrdm_rt_device_generation()) {
+    gram_tma_attrs();
+    attr_gen = qrdm_rt_device_generation();
+  }
+  int gt = (rows_hint + 1 + GT_TR - 1) / GT_TR;
+  if (gt > p->sm_count) gt = p->sm_count;
+  if (gt < 1) gt = 1;
+  int chunk = (rows_hint + 1 + gt - 1) / gt;
+  chunk = (chunk + GT_TR - 1) / GT_TR * GT_TR;
+  k_gram_tma<8, 2><<<gt, GT_THREADS, GT_SMEM, (cudaStream_t)stream>>>(*p, chunk);
+  QRDM_LAUNCH_CHECK();
+  k_gram_reduce<<<64, 64, 0, (cudaStream_t)stream>>>(*p, 1, gt);
+  QRDM_LAUNCH_CHECK();
+  return 0;
 }
 
 // Skinny product of the blocked tall panel on the TMA + DMMA path; *nparts = number of 512-double partials written to
@@ -314,7 +345,7 @@ extern "C" int qrdm_k_subw_tma(const qrdm_prob* p, int rows_hint, int* nparts, v
   if (gt < 1) gt = 1;
   int chunk = (rows_hint + 1 + gt - 1) / gt;
   chunk = (chunk + GT_TR - 1) / GT_TR * GT_TR;
-  k_gram_tma<8, true><<<gt, GT_THREADS, GT_SMEM, (cudaStream_t)stream>>>(*p, chunk);
+  k_gram_tma<8, 1><<<gt, GT_THREADS, GT_SMEM, (cudaStream_t)stream>>>(*p, chunk);
   QRDM_LAUNCH_CHECK();
   *nparts = gt;
   return 0;
@@ -345,9 +376,9 @@ extern "C" int qrdm_k_gram(const qrdm_prob* p, int of_v, int rows_hint, void* st
     // nc is only known on the device: the widest variant is always correct (narrower ones are an optimisation the
     // host can take when nb bounds the candidate count)
     const int nbmax = p->nb < QRDM_KMAX ? p->nb : QRDM_KMAX;
-    if (nbmax <= 16) k_gram_tma<2, false><<<gt, GT_THREADS, GT_SMEM, s>>>(*p, chunk);
-    else if (nbmax <= 32) k_gram_tma<4, false><<<gt, GT_THREADS, GT_SMEM, s>>>(*p, chunk);
-    else k_gram_tma<8, false><<<gt, GT_THREADS, GT_SMEM, s>>>(*p, chunk);
+    if (nbmax <= 16) k_gram_tma<2, 0><<<gt, GT_THREADS, GT_SMEM, s>>>(*p, chunk);
+    else if (nbmax <= 32) k_gram_tma<4, 0><<<gt, GT_THREADS, GT_SMEM, s>>>(*p, chunk);
+    else k_gram_tma<8, 0><<<gt, GT_THREADS, GT_SMEM, s>>>(*p, chunk);
     QRDM_LAUNCH_CHECK();
     k_gram_reduce<<<64, 64, 0, s>>>(*p, of_v, gt);
     QRDM_LAUNCH_CHECK();

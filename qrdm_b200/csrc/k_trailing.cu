@@ -42,6 +42,7 @@ __device__ __forceinline__ int vt_sw(int col, int rowpair_idx) { return col * VT
 
 struct VtGeom {
   int j, jr, fjb, k, nc, kpad, jal, NCH, CT, voff;  // j: columns done; jr: first active LOCAL row; CT counts the V'V tile
+  int T0;           // first tile the unit walk covers: 0 = the V'V tile, 1 when P.no_vtv (V'V comes from qrdm_k_vtv)
   int Tpre;         // k_fused: tiles T >= Tpre already hold the pending update (look-ahead, P.pre_col0): pass 1 only
   long long U;      // units = CT * NCH
   long long Usplit; // = Tpre * NCH (== U without look-ahead): units beyond it cost VT_WB instead of VT_WA
@@ -63,14 +64,15 @@ __device__ __forceinline__ VtGeom vt_geom(const qrdm_prob& P, int bn = VT_BN) {
   const int mpad = (P.m + VT_BK - 1) / VT_BK * VT_BK;
   g.NCH = (mpad - g.jal) / VT_BK;
   g.CT = 1 + (g.nc > 0 ? (g.nc + bn - 1) / bn : 0);
-  g.U = (long long)g.CT * g.NCH;
+  g.T0 = (P.no_vtv && !P.pend && P.sub == 0 && g.CT > 1) ? 1 : 0;
+  g.U = (long long)(g.CT - g.T0) * g.NCH;
   g.Tpre = g.CT;
   if (P.pre_col0 > 0 && !P.pend && P.sub == 0) {  // first tile whose first column is >= pre_col0
     const int d = P.pre_col0 - (g.j + g.fjb);
     const int tp = d <= 0 ? 1 : (d + bn - 1) / bn + 1;
     if (tp < g.CT) g.Tpre = tp;
   }
-  g.Usplit = (long long)g.Tpre * g.NCH;
+  g.Usplit = (long long)(g.Tpre - g.T0) * g.NCH;
   g.wb = P.vt_wb > 0 ? P.vt_wb : VT_WB;
   g.Ctot = VT_WA * g.Usplit + g.wb * (g.U - g.Usplit);
   return g;
@@ -85,7 +87,7 @@ __device__ __forceinline__ long long vt_lo(const VtGeom& ge, int G, int b) {
 }
 // first CTA whose unit range reaches into tile T
 __device__ __forceinline__ int vt_bfirst(const VtGeom& ge, int G, int T) {
-  const long long X = (long long)T * ge.NCH;
+  const long long X = (long long)(T - ge.T0) * ge.NCH;
   int b = (int)(vt_cost(ge, X) * G / ge.Ctot);
   if (b >= G) b = G - 1;
   while (b > 0 && vt_lo(ge, G, b) > X) --b;
@@ -122,7 +124,7 @@ __device__ __forceinline__ void vtc_body(const qrdm_prob& P, const VtGeom& ge, i
     for (int c = 0; c < 2; ++c) acc[a][c][0] = acc[a][c][1] = 0.0;
 
   auto issue = [&](long long u, int stage) {
-    const int T = (int)(u / ge.NCH), chunk = (int)(u - (long long)T * ge.NCH);
+    const int T = ge.T0 + (int)(u / ge.NCH), chunk = (int)(u - (long long)(T - ge.T0) * ge.NCH);
     double* Vs = sm + (size_t)stage * VT_STAGE_DOUBLES;
     double* Cs = Vs + 64 * VT_LD;
     const int r0 = ge.jal + chunk * VT_BK;
@@ -165,9 +167,9 @@ __device__ __forceinline__ void vtc_body(const qrdm_prob& P, const VtGeom& ge, i
   const int nmy = (int)(hi - lo);
   issue(lo, 0);
   cp_async_commit();
-  int curT = (int)(lo / ge.NCH);
+  int curT = ge.T0 + (int)(lo / ge.NCH);
   for (int it = 0; it < nmy; ++it) {
-    const int T = (int)((lo + it) / ge.NCH);
+    const int T = ge.T0 + (int)((lo + it) / ge.NCH);
     if (T != curT) { flush(curT); curT = T; }
     cp_async_wait<0>();
     __syncthreads();
@@ -233,8 +235,9 @@ __global__ void __launch_bounds__(256, 2) k_vtc(qrdm_prob P, int wslot_stride_co
 
 __device__ __forceinline__ int vt_slot_list(const VtGeom& ge, int vt_grid, int T, int* list, int cap) {
   // indices b - bfirst of the CTAs that wrote a partial for tile T, in fixed (ascending) order
+  if (T < ge.T0) return 0;
   const int bf = vt_bfirst(ge, vt_grid, T);
-  const long long Tend = (long long)(T + 1) * ge.NCH;
+  const long long Tend = (long long)(T - ge.T0 + 1) * ge.NCH;
   int n = 0;
   (void)cap;
   for (int b = bf; b < vt_grid && vt_lo(ge, vt_grid, b) < Tend && n < cap; ++b)
@@ -260,7 +263,9 @@ __global__ void __launch_bounds__(TI_THREADS) k_tinv(qrdm_prob P, int vt_grid, i
   for (int e = tid; e < 4096; e += TI_THREADS) {
     const int s = e >> 6, i = e & 63;  // (V'V)[s][i], needed for s < i < k
     double g = 0.0;
-    if (s < i && i < k) {
+    if (P.no_vtv && ge.T0 == 1) {  // V'V was formed by qrdm_k_vtv (reduced 64 x 64 block in P.gram; overwritten with M below)
+      if (s < i && i < k) g = P.gram[s * 64 + i];
+    } else if (s < i && i < k) {
       const double* src = P.wp + (size_t)s * wslot_stride_cols + i;
       for (int q = 0; q < nslots; q += 4) {  // up to 4 slot loads in flight; fixed summation order
         double v[4];
@@ -717,7 +722,7 @@ __global__ void __launch_bounds__(256) k_wreduce(qrdm_prob P, int vt_grid, int w
   __shared__ int nslots;
   const VtGeom ge = vt_geom(P);
   const int T = blockIdx.x;
-  if (ge.k <= 0 || T >= ge.CT) return;
+  if (ge.k <= 0 || T >= ge.CT || T < ge.T0) return;
   const bool have_rows = ge.jr < P.m && ge.nc > 0;
   if (threadIdx.x == 0) nslots = have_rows ? vt_slot_list(ge, vt_grid, T, slots, QRDM_PANEL_MAXCTA * 2 + 8) : 0;
   __syncthreads();
@@ -1184,8 +1189,22 @@ extern "C" int qrdm_k_trailing_finish(const qrdm_prob* p, int j_host, int vt_gri
   return qrdm_k_rankk(p, j_host, stream);
 }
 
-extern "C" int qrdm_k_trailing(const qrdm_prob* p, int j_host, void* stream) {
+extern "C" int qrdm_k_trailing(const qrdm_prob* p_in, int j_host, void* stream) {
   int stride = 0, grid = 0;
+  // Tall-skinny trailing matrices: k_vtc's V'V tile is a full 128-wide DMMA tile per 32 rows of which half is padding —
+  // 1.2 of the 5.4 ms of the first iteration of configs[3] (ncu: DMMA pipe 82 % active on 30 % padding + V'V work).
+  // There V'V comes from one pass over V at HBM speed (qrdm_k_vtv: TMA + DMMA upper triangle, 0.25 ms) instead.
+  qrdm_prob pv = *p_in;
+  {
+    const int rows = p_in->m - host_jr(p_in, j_host), ncmax = p_in->n - j_host - 1;
+    static const char* e = getenv("QRDM_B200_NO_VTV");  // experiment switch: 0 keeps the V'V tile everywhere
+    pv.no_vtv = (!p_in->sub && !p_in->pend && p_in->nranks == 1 && p_in->vec16 && rows >= 65536 && ncmax <= 1024 && !(e && atoi(e) == 0)) ? 1 : 0;
+  }
+  const qrdm_prob* p = &pv;
+  if (p->no_vtv) {
+    const int rcv = qrdm_k_vtv(p, p->m - host_jr(p, j_host), stream);
+    if (rcv) return rcv;
+  }
   int rc = qrdm_k_vtc_only(p, j_host, &stride, &grid, stream);
   if (rc) return rc;
   // tall-skinny: many CTAs per column tile => fold the partial-W slots in parallel first (see k_wreduce)

@@ -130,6 +130,7 @@ typedef struct qrdm_prob {
    * k_fused / k_tinv / k_wapply are told so through pre_col0: those columns need pass 1 only. */
   int side_col0;      /* side launch: first absolute column it owns (0 = not a side launch) */
   int pre_col0;       /* k_fused & co: columns >= pre_col0 already hold the pending update (0 = none) */
+  int no_vtv;         /* 1: k_vtc skips its V'V tile (tile numbering starts at 1), k_tinv takes V'V from p->gram (qrdm_k_vtv): tall-skinny matrices */
   int vt_wb;          /* relative cost of a pass-1-only unit of k_fused against VT_WA = 7 for a full one (0: the default, 4) */
   double inv_scale;   /* 1 / that scale (MUST be 1.0, never 0, for an unscaled matrix): the norm downdate evaluates its
                          sum of squares in the CALLER's scale, where the reference's unscaled sum (src/dgeqrdm_work.c:81-86)
@@ -144,6 +145,7 @@ int qrdm_k_amax(const qrdm_prob *p, double *out, int *nparts, void *stream);
 int qrdm_k_scale(const qrdm_prob *p, double s, int mode, int r, void *stream);
 int qrdm_k_select(const qrdm_prob *p, void *stream);                        /* K3a */
 int qrdm_k_gram(const qrdm_prob *p, int of_v, int rows_hint, void *stream); /* K3b / K5 */
+int qrdm_k_vtv(const qrdm_prob *p, int rows_hint, void *stream);            /* V'V of the block -> p->gram (TMA + DMMA), for p->no_vtv */
 int qrdm_k_pick(const qrdm_prob *p, void *stream);                          /* K3c + plan */
 int qrdm_k_permute(const qrdm_prob *p, void *stream);                       /* K3d */
 int qrdm_k_panel(const qrdm_prob *p, int j_host, void *stream);             /* K4 */
