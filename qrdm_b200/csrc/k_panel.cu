@@ -769,10 +769,21 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) k_panel_grp(qrdm_prob P, int
             if (go && len > 1 && (i > 0 || cont) && xn2 < thres2 && !forced) { stop = true; go = false; }  // DM early stop
             if (go) {
               double tau = 0.0, beta = alpha, scale = 1.0;
-              if (len > 1 && xn2 != 0.0) {  // dlarfg_mia, src/dlarfg.c:120-185: one sqrt, two divisions
-                const double h = sqrt(fma(alpha, alpha, xn2));
-                beta = (alpha >= 0.0) ? -h : h;
-                tau = (beta - alpha) / beta;
+              if (len > 1 && xn2 != 0.0) {
+                // dlarfg_mia, src/dlarfg.c:120-185.  The serial chain of the panel runs through these scalars once per
+                // column: one reciprocal square root + one reciprocal (206 cycles) instead of sqrt + two divisions (345,
+                // tools/fp64_lat.cu): h = s2 * rsqrt(s2), 1/beta = -+rsqrt(s2); beta and tau differ from the divided
+                // forms by at most an ulp or two, far inside the 1e-10 parity tolerance
+                const double s2 = fma(alpha, alpha, xn2);
+                if (s2 > 0x1p-1000 && s2 < 0x1p1000) {
+                  const double rh = rsqrt(s2), h = s2 * rh;
+                  beta = (alpha >= 0.0) ? -h : h;
+                  tau = (beta - alpha) * ((alpha >= 0.0) ? -rh : rh);
+                } else {  // (never with the driver's pre-scaling; keeps Inf / NaN behaviour of the plain formulas)
+                  const double h = sqrt(s2);
+                  beta = (alpha >= 0.0) ? -h : h;
+                  tau = (beta - alpha) / beta;
+                }
                 scale = 1.0 / (alpha - beta);
               }
               if (i == 0 && !cont && fjb > 1 && P.tau_ > 0.0) { const double th = P.tau_ * fabs(beta); thres2 = th * th; }
