@@ -592,6 +592,22 @@ def main():
     value = world * args.steps * flops(m, n, rk) / (ms * 1e-3) / 1e9
     qrdm_b200.set_profile(0)
 
+    # ---- QRCP on the same device: LAPACK dgeqp3's blocked algorithm on the GPU, one run, same matrix ----
+    qrcp_gpu = None
+    if rank == 0 and not args.no_other_configs:
+        try:
+            A.copy_(A0)
+            torch.cuda.synchronize()
+            qinfo = qrdm_b200.dgeqp3_device(A, m, n, lda, d_jpvt, d_tau, stream=stream.cuda_stream)
+            qst = qrdm_b200.stats()
+            qrcp_gpu = {"what": "qrdm_b200_dgeqp3_dev: blocked Householder QR with classical column pivoting (dlaqps) on the same "
+                                "device-resident matrix, CUDA events inside the call, one run",
+                        "info": qinfo, "seconds": qst["ms_total"] * 1e-3, "launches": qst["launches"],
+                        "gflops": flops(m, n, minmn) / (qst["ms_total"] * 1e-3) / 1e9,
+                        "dgeqrdm_speedup_same_device": (qst["ms_total"] / (ms / args.steps)) if ms > 0 else None}
+        except Exception as exc:  # noqa: BLE001
+            qrcp_gpu = {"error": str(exc)[:200]}
+
     # ---- end to end through the reference-facing C ABI with pinned host buffers ----
     hA0 = torch.empty((n, m), dtype=torch.float64, pin_memory=True)
     hA0.copy_(A0[:, :m])
@@ -825,6 +841,8 @@ def main():
     }
     if e2e_pg is not None:
         line["e2e_pageable"] = e2e_pg
+    if qrcp_gpu is not None:
+        line["qrcp_same_device"] = qrcp_gpu
     # ---- HBM rooflines of the bandwidth-bound stages, measured on configs[3] (one GPU) ----
     if row_sharded is not None and isinstance(row_sharded.get("stage_profile"), dict) and "ms_stage" in row_sharded["stage_profile"]:
         sp = row_sharded["stage_profile"]

@@ -115,6 +115,14 @@ int qrdm_b200_dormqr_dev(char trans, int m, int n, int k, const double *d_a, int
                          int ldc, void *stream);
 int qrdm_b200_dormqr(char trans, int m, int n, int k, const double *a, int lda, const double *tau, double *c, int ldc);
 
+/* QR with classical column pivoting on the GPU: LAPACK dgeqp3's blocked algorithm (dlaqps) — what the
+ * reference exports as dgeqp3 (src/dgeqp3.c:39-93, a renamed LAPACKE_dgeqp3) and its wrapper calls as QP3
+ * (QRDM_wrapper.c:15-41) — so that dgeqrdm is compared with QRCP on the same device.  Column-major, all columns free
+ * (the host variant rejects jpvt[c] != 0 on entry with QRDM_ERR_UNSUPPORTED); on exit A holds R and the Householder
+ * vectors, tau the min(m, n) scalars, jpvt the 1-based permutation.  _dev: device pointers. */
+int qrdm_b200_dgeqp3(int m, int n, double *a, int lda, int *jpvt, double *tau);
+int qrdm_b200_dgeqp3_dev(int m, int n, double *d_a, int lda, int *d_jpvt, double *d_tau, void *stream);
+
 /* Addition: per-call statistics of the last dgeqrdm*() on this thread's device. */
 typedef struct qrdm_b200_stats {
   int iterations;        /* DM iterations (= number of ncols entries written) */

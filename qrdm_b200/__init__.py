@@ -12,7 +12,7 @@ from . import generators  # noqa: F401
 def __getattr__(name):
     # lazy so that `from qrdm_b200 import generators` works before the library is built
     if name in ("dgeqrdm", "dgeqrdm_device", "dgeqrdm_batched", "dgeqrdm_batched_device", "dormqr", "dormqr_device", "low_rank", "stats",
-                "set_profile", "fp64_peak", "copy_gbs"):
+                "set_profile", "fp64_peak", "copy_gbs", "dgeqp3", "dgeqp3_device"):
         from . import api
         return getattr(api, name)
     if name in ("QRDM", "api", "_lib", "sharded"):

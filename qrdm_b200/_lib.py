@@ -80,6 +80,10 @@ def _load():
     lib.qrdm_b200_dormqr_dev.restype = C.c_int
     lib.qrdm_b200_dormqr_dev.argtypes = [C.c_char, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                          C.c_int, C.c_void_p]
+    lib.qrdm_b200_dgeqp3.restype = C.c_int
+    lib.qrdm_b200_dgeqp3.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.qrdm_b200_dgeqp3_dev.restype = C.c_int
+    lib.qrdm_b200_dgeqp3_dev.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.qrdm_b200_dormqr.restype = C.c_int
     lib.qrdm_b200_dormqr.argtypes = [C.c_char, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                      C.c_int]

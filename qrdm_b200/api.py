@@ -119,6 +119,25 @@ def dormqr_device(trans, m, n, k, dA, lda, d_tau, dC, ldc, stream=None):
                                              ptr(dC), int(ldc), C.c_void_p(int(stream))))
 
 
+def dgeqp3(A):
+    """QR with classical column pivoting on the GPU (LAPACK dgeqp3's blocked algorithm): the comparator the
+    reference's wrapper exposes as QP3 (QRDM_wrapper.c:15-41).  Returns dict(info, A, jpvt (1-based), tau)."""
+    A = np.asarray(A, dtype=np.float64)
+    m, n = A.shape
+    F = np.asfortranarray(A.copy())
+    jpvt = np.zeros(n, dtype=np.int32)
+    tau = np.zeros(min(m, n), dtype=np.float64)
+    info = _lib.lib.qrdm_b200_dgeqp3(m, n, F.ctypes.data, m, jpvt.ctypes.data, tau.ctypes.data)
+    return dict(info=int(info), A=F, jpvt=jpvt, tau=tau)
+
+
+def dgeqp3_device(dA, m, n, lda, d_jpvt, d_tau, stream=None):
+    """Device-resident variant: dA is an (n, lda) row-major float64 CUDA tensor (= column-major m x n)."""
+    def ptr(x):
+        return x.data_ptr() if hasattr(x, "data_ptr") else int(x)
+    return int(_lib.lib.qrdm_b200_dgeqp3_dev(m, n, ptr(dA), lda, ptr(d_jpvt), ptr(d_tau), stream or 0))
+
+
 def stats():
     return _lib.stats()
 

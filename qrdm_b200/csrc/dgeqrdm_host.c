@@ -1080,6 +1080,93 @@ int qrdm_b200_dormqr_dev(char trans, int m, int n, int k, const double *d_a, int
   API_BODY(dormqr_dev_locked(trans, m, n, k, d_a, lda, d_tau, d_c, ldc, stream));
 }
 
+/* ---- QR with classical column pivoting on the device: the comparator the reference exports as dgeqp3
+ * (src/dgeqp3.c:39-93 -> LAPACKE_dgeqp3_work) and its wrapper calls as QP3 (QRDM_wrapper.c:15-41), here as LAPACK's
+ * blocked algorithm (dlaqps) on the GPU (k_qp3.cu).  All columns are free: jpvt is output only (1-based). ---- */
+static int dgeqp3_dev_locked(int m, int n, double *d_a, int lda, int *d_jpvt, double *d_tau, void *stream) {
+  if (m <= 0) return bad_argument(2);
+  if (n <= 0) return bad_argument(3);
+  if (lda < m) return bad_argument(5);
+  int rc = ws_ensure(m, n);
+  if (rc) return rc;
+  qrdm_workspace *w = &g_ws;
+  qrdm_prob P;
+  memset(&P, 0, sizeof(P));
+  P.m = m; P.n = n; P.lda = lda; P.nb = QRDM_KMAX;
+  P.a = d_a; P.jpvt = d_jpvt; P.tau = d_tau;
+  P.vn1 = w->vn1; P.vn2 = w->vn2; P.ctrl = w->ctrl;
+  P.gram_part = w->gram_part; P.gram = w->gram;
+  P.vc = w->vc; P.vc_prev = w->vc; P.ldv = w->ldv;
+  P.wp = w->wp; P.wp_elems = w->wp_elems; P.w2 = w->w2; P.ldw = w->ldw;
+  P.nrm_part = w->nrm_part; P.nrm_splits = w->nrm_splits; P.flag_list = w->flag_list;
+  P.upd_flag = w->upd_marks; P.upd_eager = w->upd_marks + w->cap_n;
+  P.sm_count = w->sm_count;
+  P.vec16 = (((size_t)d_a & 15) == 0 && (lda & 1) == 0) ? 1 : 0;
+  P.m_glob = m; P.nranks = 1; P.inv_scale = 1.0; P.thres0 = 5e-14;
+  memset(&g_stats, 0, sizeof(g_stats));
+  const long long launches0 = qrdm_rt_launch_count();
+  CU(qrdm_rt_event_record(w->ev[0], stream));
+  CU(qrdm_rt_memset(w->vc, 0, sizeof(double) * (size_t)w->ldv * 64, stream));
+  CU(qrdm_rt_memset(w->upd_marks, 0, sizeof(int) * (size_t)w->cap_n * 2, stream));
+  CU(qrdm_qp3_dev(&P, w->mailbox, stream));
+  CU(qrdm_rt_event_record(w->ev[1], stream));
+  CU(qrdm_rt_event_sync(w->ev[1]));
+  g_stats.ms_total = qrdm_rt_event_ms(w->ev[0], w->ev[1]);
+  g_stats.rank = m < n ? m : n;
+  g_stats.launches = qrdm_rt_launch_count() - launches0;
+  return 0;
+}
+int qrdm_b200_dgeqp3_dev(int m, int n, double *d_a, int lda, int *d_jpvt, double *d_tau, void *stream) {
+  API_BODY(dgeqp3_dev_locked(m, n, d_a, lda, d_jpvt, d_tau, stream));
+}
+static int dgeqp3_locked(int m, int n, double *a, int lda, int *jpvt, double *tau) {
+  if (m <= 0) return bad_argument(2);
+  if (n <= 0) return bad_argument(3);
+  if (lda < (m > 1 ? m : 1)) return bad_argument(5);
+  for (int c = 0; c < n; ++c)
+    if (jpvt[c] != 0) {
+      fprintf(stderr, "qrdm_b200_dgeqp3: fixed columns (jpvt[%d] != 0 on entry) are not supported\n", c);
+      return QRDM_ERR_UNSUPPORTED;
+    }
+  int rc = init_impl(-1);
+  if (rc) return rc;
+  void *stream = g_ws.compute_stream;
+  const int ldd = (m + 1) & ~1, minmn = m < n ? m : n;
+  double *d_a = NULL, *d_tau = NULL;
+  int *d_jpvt = NULL;
+  int info = QRDM_ERR_CUDA;
+#define CUX(call)                                                                             \
+  do {                                                                                        \
+    int e__ = (call);                                                                         \
+    if (e__ != 0) {                                                                           \
+      fprintf(stderr, "qrdm_b200: CUDA error %d (%s) at %s:%d\n", e__, qrdm_rt_errstr(e__), \
+              __FILE__, __LINE__);                                                            \
+      info = QRDM_ERR_CUDA;                                                                   \
+      goto done;                                                                              \
+    }                                                                                         \
+  } while (0)
+  CUX(qrdm_rt_malloc((void **)&d_a, sizeof(double) * (size_t)ldd * n));
+  CUX(qrdm_rt_malloc((void **)&d_tau, sizeof(double) * minmn));
+  CUX(qrdm_rt_malloc((void **)&d_jpvt, sizeof(int) * n));
+  CUX(qrdm_rt_memset(d_a, 0, sizeof(double) * (size_t)ldd * n, stream));
+  CUX(qrdm_rt_h2d_2d(d_a, sizeof(double) * ldd, a, sizeof(double) * lda, sizeof(double) * m, n, stream));
+  info = dgeqp3_dev_locked(m, n, d_a, ldd, d_jpvt, d_tau, stream);
+  if (info == 0) {
+    CUX(qrdm_rt_d2h_2d(a, sizeof(double) * lda, d_a, sizeof(double) * ldd, sizeof(double) * m, n, stream));
+    CUX(qrdm_rt_d2h(tau, d_tau, sizeof(double) * minmn, stream));
+    CUX(qrdm_rt_d2h(jpvt, d_jpvt, sizeof(int) * n, stream));
+    info = 0;
+  }
+done:
+  qrdm_rt_sync(stream);
+  if (d_a) qrdm_rt_free(d_a);
+  if (d_tau) qrdm_rt_free(d_tau);
+  if (d_jpvt) qrdm_rt_free(d_jpvt);
+  return info;
+#undef CUX
+}
+int qrdm_b200_dgeqp3(int m, int n, double *a, int lda, int *jpvt, double *tau) { API_BODY(dgeqp3_locked(m, n, a, lda, jpvt, tau)); }
+
 /* Host-pointer variant: A (m x k reflector columns, as returned by dgeqrdm/dgeqrf), tau and C in host memory. */
 static int dormqr_locked(char trans, int m, int n, int k, const double *a, int lda, const double *tau, double *c, int ldc) {
   int rc = init_impl(-1);

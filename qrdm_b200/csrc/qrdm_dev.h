@@ -230,6 +230,8 @@ int qrdm_k_gram_wide(const qrdm_prob *p, double *part, double *G, int rows_hint,
 int qrdm_k_pick_wide(const qrdm_prob *p, const double *G, int *marks, int *swaps, void *stream);
 int qrdm_k_micro_begin(const qrdm_prob *p, int t, void *stream);
 int qrdm_k_micro_end(const qrdm_prob *p, void *stream);
+/* blocked QR with classical column pivoting (k_qp3.cu): the whole factorisation, one 64-byte mailbox read per panel */
+int qrdm_qp3_dev(const qrdm_prob *p, void *mailbox, void *stream);
 const char *qrdm_rt_errstr(int code);
 long long qrdm_rt_launch_count(void);
 double qrdm_rt_fp64_peak(int use_dmma, void *stream);
