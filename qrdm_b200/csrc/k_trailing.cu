@@ -1197,7 +1197,7 @@ extern "C" int qrdm_k_trailing(const qrdm_prob* p_in, int j_host, void* stream) 
   qrdm_prob pv = *p_in;
   {
     const int rows = p_in->m - host_jr(p_in, j_host), ncmax = p_in->n - j_host - 1;
-    static const char* e = getenv("QRDM_B200_NO_VTV");  // experiment switch: 0 keeps the V'V tile everywhere
+    const char* e = getenv("QRDM_B200_NO_VTV");  // experiment switch: 0 keeps the V'V tile everywhere
     pv.no_vtv = (!p_in->sub && !p_in->pend && p_in->nranks == 1 && p_in->vec16 && rows >= 65536 && ncmax <= 1024 && !(e && atoi(e) == 0)) ? 1 : 0;
   }
   const qrdm_prob* p = &pv;

@@ -64,6 +64,17 @@ def kahan(n: int, theta: float = 1.25, perturb: float = 0.0, seed: int | None = 
     return np.asfortranarray(K)
 
 
+def planted(m: int, n: int, seed: int = 0, eps: float = 1e-9) -> np.ndarray:
+    """Gaussian columns among which every third one is (almost) the sum of its two left neighbours: pairwise cosines stay
+    below 0.9 (0.707), so Deviation Maximisation may select such triples into one block — inside the block the third column
+    then loses all but `eps` of its norm, which is what the panel's early stop (and the grouped panels' accuracy guard) exist for."""
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((m, n))
+    for c in range(2, n, 3):
+        A[:, c] = A[:, c - 1] + A[:, c - 2] + eps * rng.standard_normal(m)
+    return np.asfortranarray(A)
+
+
 def flops(m: int, n: int, r: int) -> float:
     """Algorithmic FLOPs of a rank-r Householder QR of an m x n matrix:
     ``4mnr - 2(m+n)r^2 + (4/3)r^3`` (= ``2mn^2 - (2/3)n^3`` for r = n <= m)."""
