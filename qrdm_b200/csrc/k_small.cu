@@ -38,7 +38,7 @@ __device__ long long g_pt[12];
 #define SM_PT(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long t_ = clock64(); if ((i) > 0) g_pt[i] += t_ - S.ptq; S.ptq = t_; } } while (0)
 #define SM_TDECL long long tph_[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, tq_ = 0
 #define SM_T(i) do { const long long t_ = clock64(); if ((i) > 0) tph_[i] += t_ - tq_; tq_ = t_; } while (0)
-#define SM_TPRINT do { if (tid == 0 && blockIdx.x == 0) printf("cycles: cosines %lld pick %lld permute %lld panel %lld tfactor %lld trailing %lld normupd %lld select %lld\n", tph_[1], tph_[2], tph_[3], tph_[4], tph_[5], tph_[6], tph_[7], tph_[8]); printf("panel: load+dots %lld steps %lld writeback %lld blockupd %lld\n", g_pt[1], g_pt[2], g_pt[3], g_pt[4]); printf("step: scalars %lld update+dots %lld sync1 %lld reduce %lld sync2 %lld\n", g_pt[5], g_pt[6], g_pt[7], g_pt[8], g_pt[9]); } while (0)
+#define SM_TPRINT do { if (tid == 0 && blockIdx.x == 0) { printf("cycles: cosines %lld pick %lld permute %lld panel %lld tfactor %lld trailing %lld normupd %lld select %lld\n", tph_[1], tph_[2], tph_[3], tph_[4], tph_[5], tph_[6], tph_[7], tph_[8]); printf("panel: load+dots %lld steps %lld writeback %lld blockupd %lld\n", g_pt[1], g_pt[2], g_pt[3], g_pt[4]); printf("step: scalars %lld update+dots %lld sync1 %lld reduce %lld sync2 %lld\n", g_pt[5], g_pt[6], g_pt[7], g_pt[8], g_pt[9]); } } while (0)
 #else
 #define SM_PT(i)
 #define SM_PS(i)
